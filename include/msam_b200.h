@@ -1,0 +1,68 @@
+/* msam_b200.h -- C ABI of libmsam_b200.so: the B200 (sm_100a) SAM inference core behind micro-sam's predictor seam.
+ *
+ * The reference (micro-sam) has no FFI; its seam is the Python `SamPredictor`/`Sam` duck type returned by
+ * micro_sam/util.py:318 (get_sam_model).  Each entry point below names the reference call it replaces.
+ * Conventions: opaque handle; int return code (0 = ok, <0 = error, text via msam_last_error()); plain pointers and
+ * sizes only.  Unless stated otherwise pointers are DEVICE pointers on the handle's CUDA device, `stream` is a
+ * cudaStream_t passed as void*, calls are asynchronous on that stream.  One handle = one predictor = one stream at a
+ * time (the reference predictor is stateful and not re-entrant either).
+ */
+#ifndef MSAM_B200_H
+#define MSAM_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct msam_handle msam_handle;
+
+/* Architecture, mirrors the constructor arguments of micro_sam/models/build_sam.py:87-142 (_build_sam). */
+typedef struct msam_config {
+  int32_t embed_dim;          /* 768 / 1024 / 1280 */
+  int32_t depth;              /* 12 / 24 / 32 */
+  int32_t num_heads;          /* 12 / 16 / 16  (head_dim must be 64 or 80) */
+  int32_t global_attn[8];     /* indexes of global-attention blocks, -1 terminated */
+  int32_t window_size;        /* 14 */
+  int32_t image_size;         /* 1024 */
+  int32_t patch_size;         /* 16 */
+  int32_t out_chans;          /* 256 */
+  int32_t max_batch;          /* tiles per msam_encode call the workspace is sized for */
+  int32_t max_prompts;        /* prompts per msam_decode call the workspace is sized for */
+} msam_config;
+
+const char* msam_last_error(void);
+/* number of CUDA kernels this library has launched from the calling thread since load */
+int64_t msam_launch_count(void);
+
+/* util.get_sam_model (util.py:441-458): build the model on `device`. */
+int msam_create(const msam_config* cfg, int device, msam_handle** out);
+int msam_destroy(msam_handle* h);
+
+/* sam.load_state_dict (util.py:457): one tensor, upstream SAM key name (e.g. "image_encoder.blocks.0.attn.qkv.weight"),
+ * fp32, HOST pointer, row-major, `shape[ndim]`.  Call once per tensor, then msam_finalize_weights. */
+int msam_load_weight(msam_handle* h, const char* name, const float* host_data, const int64_t* shape, int ndim);
+int msam_finalize_weights(msam_handle* h);
+
+/* ImageEncoderViT.forward as called from util.py:674 (_compute_embeddings_batched) / SamPredictor.set_torch_image:
+ * (B,3,S,S) fp32 preprocessed (normalised + padded) NCHW -> (B,256,64,64) fp32 NCHW. */
+int msam_encode_f32(msam_handle* h, const float* nchw, int B, float* out, void* stream);
+/* Same, fusing Sam.preprocess (util.py:670; trainable_sam.py:24-47): B resized uint8 HWC images, each (hh, ww, 3)
+ * with max(hh, ww) <= S, contiguous [B, hh, ww, 3]. */
+int msam_encode_u8(msam_handle* h, const uint8_t* hwc, int B, int hh, int ww, float* out, void* stream);
+
+/* ---- single-op entry points (unit tests / profiling; the same kernels the calls above are built from) ---- */
+/* out[M,N] = act(A[M,K] @ W[N,K]^T + bias) + residual[row % res_rows];  A, W bf16; bias/residual fp32 or NULL;
+ * out bf16 (out_fp32=0) or fp32; act: 0 none, 1 GELU(erf), 2 ReLU. */
+int msam_op_gemm(const void* A, const void* W, int M, int N, int K, const float* bias, const float* residual,
+                 int res_rows, void* out, int out_fp32, int act, void* stream);
+/* LayerNorm over rows of fp32 x[rows, D] -> bf16; window_mode=1 scatters into the 14x14 window-partitioned layout. */
+int msam_op_layernorm(const float* x, int rows, int D, const float* gamma, const float* beta, float eps, void* out_bf16,
+                      int window_mode, void* stream);
+/* Encoder attention on a packed qkv buffer (see csrc/attention.cu). rel_table: bf16 [NT, 64*ceil(hd/64)]. */
+int msam_op_attention(const void* qkv_bf16, const void* rel_table_bf16, void* out_bf16, int batch, int heads, int head_dim,
+                      int window, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,394 @@
+// C-ABI implementation (include/msam_b200.h): model container, weight packing, workspace, encoder forward.
+#include "engine.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace msam {
+
+// ------------------------------------------------------------------------------------------------ error / counters
+static thread_local char g_err[1024] = "";
+static thread_local int64_t g_launches = 0;
+
+int set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return -1;
+}
+void count_launch() { ++g_launches; }
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(gptr) & 15) != 0 || (ld * 2) % 16 != 0)
+    return set_error("tensor map: base/stride must be 16-byte aligned (ptr=%p ld=%llu)", gptr, (unsigned long long)ld);
+  if (box_rows > 256) return set_error("tensor map: box_rows=%u > 256", box_rows);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box_rows=%u", (int)r,
+                     (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ device memory
+void* Engine::dalloc(size_t bytes, bool zero) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 16;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    set_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  if (zero) cudaMemset(p, 0, bytes);
+  allocs.push_back(p);
+  return p;
+}
+
+const std::vector<float>* Engine::host(const std::string& name, std::initializer_list<int64_t> shape) {
+  auto it = host_weights.find(name);
+  if (it == host_weights.end()) {
+    set_error("missing weight '%s'", name.c_str());
+    return nullptr;
+  }
+  int64_t n = 1;
+  for (auto s : shape) n *= s;
+  if ((int64_t)it->second.data.size() != n) {
+    set_error("weight '%s' has %zu elements, expected %lld", name.c_str(), it->second.data.size(), (long long)n);
+    return nullptr;
+  }
+  return &it->second.data;
+}
+
+__nv_bfloat16* Engine::upload_bf16(const float* src, size_t n) {
+  std::vector<__nv_bfloat16> tmp(n);
+  for (size_t i = 0; i < n; ++i) tmp[i] = __float2bfloat16(src[i]);
+  auto* d = static_cast<__nv_bfloat16*>(dalloc(n * 2));
+  if (!d) return nullptr;
+  if (cudaMemcpy(d, tmp.data(), n * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("H2D copy failed");
+    return nullptr;
+  }
+  return d;
+}
+float* Engine::upload_f32(const float* src, size_t n) {
+  auto* d = static_cast<float*>(dalloc(n * 4));
+  if (!d) return nullptr;
+  if (cudaMemcpy(d, src, n * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("H2D copy failed");
+    return nullptr;
+  }
+  return d;
+}
+__nv_bfloat16* Engine::up_bf16(const std::string& name, std::initializer_list<int64_t> shape) {
+  const auto* h = host(name, shape);
+  return h ? upload_bf16(h->data(), h->size()) : nullptr;
+}
+float* Engine::up_f32(const std::string& name, std::initializer_list<int64_t> shape) {
+  const auto* h = host(name, shape);
+  return h ? upload_f32(h->data(), h->size()) : nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+#define CHK(p) do { if (!(p)) return -1; } while (0)
+
+int Engine::finalize_encoder() {
+  const int D = cfg.embed_dim, hd = D / cfg.num_heads, g = cfg.image_size / cfg.patch_size;
+  const std::string e = "image_encoder.";
+  CHK(enc.patch_w = up_bf16(e + "patch_embed.proj.weight", {D, 3, 16, 16}));
+  CHK(enc.patch_b = up_f32(e + "patch_embed.proj.bias", {D}));
+  CHK(enc.pos_embed = up_f32(e + "pos_embed", {1, g, g, D}));
+  enc.blocks.resize(cfg.depth);
+  for (int i = 0; i < cfg.depth; ++i) {
+    EncBlock& b = enc.blocks[i];
+    const std::string p = e + "blocks." + std::to_string(i) + ".";
+    b.global = false;
+    for (int k = 0; k < 8 && cfg.global_attn[k] >= 0; ++k) b.global |= (cfg.global_attn[k] == i);
+    const int S = b.global ? g : cfg.window_size;
+    CHK(b.ln1_g = up_f32(p + "norm1.weight", {D}));
+    CHK(b.ln1_b = up_f32(p + "norm1.bias", {D}));
+    CHK(b.qkv_w = up_bf16(p + "attn.qkv.weight", {3 * D, D}));
+    CHK(b.qkv_b = up_f32(p + "attn.qkv.bias", {3 * D}));
+    CHK(b.proj_w = up_bf16(p + "attn.proj.weight", {D, D}));
+    CHK(b.proj_b = up_f32(p + "attn.proj.bias", {D}));
+    CHK(b.ln2_g = up_f32(p + "norm2.weight", {D}));
+    CHK(b.ln2_b = up_f32(p + "norm2.bias", {D}));
+    CHK(b.fc1_w = up_bf16(p + "mlp.lin1.weight", {4 * D, D}));
+    CHK(b.fc1_b = up_f32(p + "mlp.lin1.bias", {4 * D}));
+    CHK(b.fc2_w = up_bf16(p + "mlp.lin2.weight", {D, 4 * D}));
+    CHK(b.fc2_b = up_f32(p + "mlp.lin2.bias", {D}));
+    // relative-position table tile: rows [0,2S-1) = rel_pos_h, rows [WOFF, WOFF+2S-1) = rel_pos_w, zero elsewhere;
+    // columns padded to a multiple of 64 (csrc/attention.cu).  get_rel_pos's interpolation branch (table length
+    // != 2S-1, only hit when image_size != 1024) is not supported.
+    const auto* rh = host(p + "attn.rel_pos_h", {2 * S - 1, hd});
+    const auto* rw = host(p + "attn.rel_pos_w", {2 * S - 1, hd});
+    CHK(rh && rw);
+    const int NT = b.global ? 256 : 64, WOFF = b.global ? 128 : 32, cols = ((hd + 63) / 64) * 64;
+    std::vector<float> tab((size_t)NT * cols, 0.f);
+    for (int r = 0; r < 2 * S - 1; ++r)
+      for (int c = 0; c < hd; ++c) {
+        tab[(size_t)r * cols + c] = (*rh)[(size_t)r * hd + c];
+        tab[(size_t)(WOFF + r) * cols + c] = (*rw)[(size_t)r * hd + c];
+      }
+    CHK(b.rel_table = upload_bf16(tab.data(), tab.size()));
+  }
+  const int C = cfg.out_chans;
+  CHK(enc.neck_conv1 = up_bf16(e + "neck.0.weight", {C, D, 1, 1}));
+  CHK(enc.neck_ln1_g = up_f32(e + "neck.1.weight", {C}));
+  CHK(enc.neck_ln1_b = up_f32(e + "neck.1.bias", {C}));
+  {
+    const auto* w = host(e + "neck.2.weight", {C, C, 3, 3});
+    CHK(w);
+    std::vector<float> r((size_t)C * 9 * C);
+    for (int o = 0; o < C; ++o)
+      for (int c = 0; c < C; ++c)
+        for (int k = 0; k < 9; ++k) r[((size_t)o * 9 + k) * C + c] = (*w)[((size_t)o * C + c) * 9 + k];
+    CHK(enc.neck_conv2 = upload_bf16(r.data(), r.size()));
+  }
+  CHK(enc.neck_ln2_g = up_f32(e + "neck.3.weight", {C}));
+  CHK(enc.neck_ln2_b = up_f32(e + "neck.3.bias", {C}));
+  return 0;
+}
+
+int Engine::alloc_encoder_ws() {
+  const int D = cfg.embed_dim, g = cfg.image_size / cfg.patch_size, T = g * g, B = cfg.max_batch, C = cfg.out_chans;
+  const int wpr = (g + cfg.window_size - 1) / cfg.window_size;
+  const size_t Tw = (size_t)wpr * wpr * cfg.window_size * cfg.window_size;  // 4900 window-partitioned rows / image
+  CHK(ws.patches = (__nv_bfloat16*)dalloc((size_t)B * T * 768 * 2));
+  CHK(ws.x = (float*)dalloc((size_t)B * T * D * 4));
+  CHK(ws.xn = (__nv_bfloat16*)dalloc((size_t)B * T * D * 2));
+  CHK(ws.xn_win = (__nv_bfloat16*)dalloc((size_t)B * Tw * D * 2, /*zero=*/true));  // pad rows stay zero forever
+  CHK(ws.qkv = (__nv_bfloat16*)dalloc((size_t)B * Tw * 3 * D * 2));
+  CHK(ws.attn = (__nv_bfloat16*)dalloc((size_t)B * T * D * 2));
+  CHK(ws.hidden = (__nv_bfloat16*)dalloc((size_t)B * T * 4 * D * 2));
+  CHK(ws.neck1 = (float*)dalloc((size_t)B * T * C * 4));
+  CHK(ws.neck1b = (__nv_bfloat16*)dalloc((size_t)B * T * C * 2));
+  CHK(ws.neck_col = (__nv_bfloat16*)dalloc((size_t)B * T * 9 * C * 2));
+  CHK(ws.neck2 = (float*)dalloc((size_t)B * T * C * 4));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ encoder forward
+int Engine::encode(const uint8_t* u8, const float* f32, int B, int hh, int ww, float* out, cudaStream_t st) {
+  if (!finalized) return set_error("msam_encode: weights not finalized");
+  if (B <= 0) return set_error("msam_encode: empty batch");
+  const int D = cfg.embed_dim, hd = D / cfg.num_heads, g = cfg.image_size / cfg.patch_size, T = g * g, C = cfg.out_chans;
+  const int wpr = (g + cfg.window_size - 1) / cfg.window_size;
+  const int Tw = wpr * wpr * cfg.window_size * cfg.window_size;
+  if (u8 && (hh > cfg.image_size || ww > cfg.image_size || hh <= 0 || ww <= 0))
+    return set_error("msam_encode_u8: image %dx%d exceeds %d", hh, ww, cfg.image_size);
+  static const float mean[3] = {123.675f, 116.28f, 103.53f}, stdv[3] = {58.395f, 57.12f, 57.375f};
+  for (int b0 = 0; b0 < B; b0 += cfg.max_batch) {
+    const int nb = (B - b0 < cfg.max_batch) ? (B - b0) : cfg.max_batch;
+    const int M = nb * T;
+    const uint8_t* u8p = u8 ? u8 + (size_t)b0 * hh * ww * 3 : nullptr;
+    const float* f32p = f32 ? f32 + (size_t)b0 * 3 * cfg.image_size * cfg.image_size : nullptr;
+    if (launch_patchify(u8p, f32p, nb, hh, ww, cfg.image_size, mean, stdv, ws.patches, st)) return -1;
+    {  // patch embed: conv 16x16/16 == GEMM, + bias + pos_embed (row % T)
+      GemmArgs a;
+      a.A = ws.patches; a.W = enc.patch_w; a.M = M; a.N = D; a.K = 768; a.lda = 768; a.ldw = 768;
+      a.bias = enc.patch_b; a.residual = enc.pos_embed; a.res_rows = T; a.out = ws.x; a.out_fp32 = 1;
+      if (launch_gemm(a, num_sms, st)) return -1;
+    }
+    for (const EncBlock& b : enc.blocks) {
+      LnArgs l;
+      l.x = ws.x; l.rows = M; l.D = D; l.gamma = b.ln1_g; l.beta = b.ln1_b; l.eps = 1e-6f;
+      l.grid = g; l.ws = cfg.window_size;
+      if (b.global) { l.out = ws.xn; } else { l.out = ws.xn_win; l.window_mode = 1; }
+      if (launch_layernorm(l, st)) return -1;
+      const int Mq = b.global ? M : nb * Tw;
+      {
+        GemmArgs a;
+        a.A = b.global ? ws.xn : ws.xn_win; a.W = b.qkv_w; a.M = Mq; a.N = 3 * D; a.K = D; a.lda = D; a.ldw = D;
+        a.bias = b.qkv_b; a.out = ws.qkv;
+        if (launch_gemm(a, num_sms, st)) return -1;
+      }
+      {
+        AttnArgs a;
+        a.qkv = ws.qkv; a.rel_table = b.rel_table; a.out = ws.attn; a.batch = nb; a.heads = cfg.num_heads;
+        a.head_dim = hd; a.grid = g; a.window = b.global ? 0 : cfg.window_size; a.scale = 1.0f / sqrtf((float)hd);
+        if (launch_attention(a, st)) return -1;
+      }
+      {
+        GemmArgs a;
+        a.A = ws.attn; a.W = b.proj_w; a.M = M; a.N = D; a.K = D; a.lda = D; a.ldw = D;
+        a.bias = b.proj_b; a.residual = ws.x; a.out = ws.x; a.out_fp32 = 1;
+        if (launch_gemm(a, num_sms, st)) return -1;
+      }
+      l = LnArgs();
+      l.x = ws.x; l.rows = M; l.D = D; l.gamma = b.ln2_g; l.beta = b.ln2_b; l.eps = 1e-6f; l.out = ws.xn;
+      if (launch_layernorm(l, st)) return -1;
+      {
+        GemmArgs a;
+        a.A = ws.xn; a.W = b.fc1_w; a.M = M; a.N = 4 * D; a.K = D; a.lda = D; a.ldw = D;
+        a.bias = b.fc1_b; a.act = 1; a.out = ws.hidden;
+        if (launch_gemm(a, num_sms, st)) return -1;
+      }
+      {
+        GemmArgs a;
+        a.A = ws.hidden; a.W = b.fc2_w; a.M = M; a.N = D; a.K = 4 * D; a.lda = 4 * D; a.ldw = 4 * D;
+        a.bias = b.fc2_b; a.residual = ws.x; a.out = ws.x; a.out_fp32 = 1;
+        if (launch_gemm(a, num_sms, st)) return -1;
+      }
+    }
+    // neck: conv1x1 -> LN2d -> conv3x3 (im2col GEMM) -> LN2d (NCHW out)
+    if (launch_cast_bf16(ws.x, (long)M * D, ws.xn, st)) return -1;
+    {
+      GemmArgs a;
+      a.A = ws.xn; a.W = enc.neck_conv1; a.M = M; a.N = C; a.K = D; a.lda = D; a.ldw = D; a.out = ws.neck1; a.out_fp32 = 1;
+      if (launch_gemm(a, num_sms, st)) return -1;
+    }
+    {
+      LnArgs l;
+      l.x = ws.neck1; l.rows = M; l.D = C; l.gamma = enc.neck_ln1_g; l.beta = enc.neck_ln1_b; l.eps = 1e-6f; l.out = ws.neck1b;
+      if (launch_layernorm(l, st)) return -1;
+    }
+    if (launch_im2col3x3(ws.neck1b, nb, g, C, ws.neck_col, st)) return -1;
+    {
+      GemmArgs a;
+      a.A = ws.neck_col; a.W = enc.neck_conv2; a.M = M; a.N = C; a.K = 9 * C; a.lda = 9 * C; a.ldw = 9 * C;
+      a.out = ws.neck2; a.out_fp32 = 1;
+      if (launch_gemm(a, num_sms, st)) return -1;
+    }
+    if (launch_layernorm2d_nchw(ws.neck2, nb, T, enc.neck_ln2_g, enc.neck_ln2_b, 1e-6f, out + (size_t)b0 * C * T, st))
+      return -1;
+  }
+  return 0;
+}
+
+}  // namespace msam
+
+// =================================================================================================== C ABI
+using namespace msam;
+
+struct msam_handle {
+  Engine eng;
+};
+
+extern "C" {
+
+const char* msam_last_error(void) { return g_err; }
+int64_t msam_launch_count(void) { return g_launches; }
+
+int msam_create(const msam_config* cfg, int device, msam_handle** out) {
+  if (!cfg || !out) return set_error("msam_create: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return set_error("msam_create: no CUDA device available (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return set_error("msam_create: bad device %d (have %d)", device, ndev);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) return set_error("msam_create: device %d is sm_%d%d; this library is sm_100a only", device, prop.major, prop.minor);
+  if (cfg->embed_dim % cfg->num_heads != 0) return set_error("embed_dim %% num_heads != 0");
+  const int hd = cfg->embed_dim / cfg->num_heads;
+  if (hd != 64 && hd != 80) return set_error("head_dim %d unsupported (64 or 80)", hd);
+  if (cfg->image_size != 1024 || cfg->patch_size != 16 || cfg->window_size != 14 || cfg->out_chans != 256)
+    return set_error("only image_size 1024 / patch 16 / window 14 / out_chans 256 are supported");
+  if (cfg->embed_dim % 32 != 0 || cfg->embed_dim > 1280) return set_error("embed_dim %d unsupported", cfg->embed_dim);
+  if (cudaSetDevice(device) != cudaSuccess) return set_error("cudaSetDevice(%d) failed", device);
+  auto* h = new msam_handle();
+  h->eng.cfg = *cfg;
+  if (h->eng.cfg.max_batch <= 0) h->eng.cfg.max_batch = 1;
+  if (h->eng.cfg.max_prompts <= 0) h->eng.cfg.max_prompts = 64;
+  h->eng.device = device;
+  h->eng.num_sms = prop.multiProcessorCount;
+  *out = h;
+  return 0;
+}
+
+int msam_destroy(msam_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->eng.device);
+  cudaDeviceSynchronize();
+  for (void* p : h->eng.allocs) cudaFree(p);
+  delete h;
+  return 0;
+}
+
+int msam_load_weight(msam_handle* h, const char* name, const float* host_data, const int64_t* shape, int ndim) {
+  if (!h || !name || !host_data || !shape) return set_error("msam_load_weight: null argument");
+  int64_t n = 1;
+  HostTensor t;
+  for (int i = 0; i < ndim; ++i) { n *= shape[i]; t.shape.push_back(shape[i]); }
+  t.data.assign(host_data, host_data + n);
+  h->eng.host_weights[name] = std::move(t);
+  return 0;
+}
+
+int msam_finalize_weights(msam_handle* h) {
+  if (!h) return set_error("null handle");
+  cudaSetDevice(h->eng.device);
+  if (h->eng.finalize_encoder()) return -1;
+  if (h->eng.alloc_encoder_ws()) return -1;
+  if (h->eng.finalize_decoder()) return -1;
+  h->eng.host_weights.clear();
+  if (cudaDeviceSynchronize() != cudaSuccess) return set_error("finalize: %s", cudaGetErrorString(cudaGetLastError()));
+  h->eng.finalized = true;
+  return 0;
+}
+
+int msam_encode_f32(msam_handle* h, const float* nchw, int B, float* out, void* stream) {
+  if (!h || !nchw || !out) return set_error("msam_encode_f32: null argument");
+  return h->eng.encode(nullptr, nchw, B, h->eng.cfg.image_size, h->eng.cfg.image_size, out, (cudaStream_t)stream);
+}
+int msam_encode_u8(msam_handle* h, const uint8_t* hwc, int B, int hh, int ww, float* out, void* stream) {
+  if (!h || !hwc || !out) return set_error("msam_encode_u8: null argument");
+  return h->eng.encode(hwc, nullptr, B, hh, ww, out, (cudaStream_t)stream);
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+int msam_op_gemm(const void* A, const void* W, int M, int N, int K, const float* bias, const float* residual,
+                 int res_rows, void* out, int out_fp32, int act, void* stream) {
+  GemmArgs a;
+  a.A = (const __nv_bfloat16*)A; a.W = (const __nv_bfloat16*)W; a.M = M; a.N = N; a.K = K; a.lda = K; a.ldw = K;
+  a.bias = bias; a.residual = residual; a.res_rows = res_rows; a.out = out; a.out_fp32 = out_fp32; a.act = act;
+  return launch_gemm(a, sm_count(), (cudaStream_t)stream);
+}
+
+int msam_op_layernorm(const float* x, int rows, int D, const float* gamma, const float* beta, float eps, void* out_bf16,
+                      int window_mode, void* stream) {
+  LnArgs l;
+  l.x = x; l.rows = rows; l.D = D; l.gamma = gamma; l.beta = beta; l.eps = eps; l.out = (__nv_bfloat16*)out_bf16;
+  l.window_mode = window_mode;
+  return launch_layernorm(l, (cudaStream_t)stream);
+}
+
+int msam_op_attention(const void* qkv, const void* rel_table, void* out, int batch, int heads, int head_dim, int window,
+                      float scale, void* stream) {
+  AttnArgs a;
+  a.qkv = (const __nv_bfloat16*)qkv; a.rel_table = (const __nv_bfloat16*)rel_table; a.out = (__nv_bfloat16*)out;
+  a.batch = batch; a.heads = heads; a.head_dim = head_dim; a.grid = 64; a.window = window; a.scale = scale;
+  return launch_attention(a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

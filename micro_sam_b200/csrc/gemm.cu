@@ -1,0 +1,262 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] * W[N,K]^T)
+//   * operands: TMA (SWIZZLE_128B boxes of 64 K-elements) -> shared memory ring (mbarrier full/empty)
+//   * math:     tcgen05.mma cta_group::1 kind::f16, M=128 x N=BN x K=16, fp32 accumulators in TMEM (2 stages)
+//   * epilogue: 8 warps, tcgen05.ld 32x32b -> bias / GELU(erf) / ReLU / fp32 residual (row modulus) -> bf16 or fp32
+// One CTA per SM; tiles are distributed round-robin, N-block fastest so that the CTAs that run concurrently share the
+// same A row-block through L2.
+//
+// Replaces (on the B200 path) the nn.Linear / 1x1-conv / patch-embed conv calls inside segment_anything's
+// ImageEncoderViT / MaskDecoder that micro_sam reaches through util.py:674 (image_encoder) and
+// SamPredictor.predict_torch (inference.py:248, instance_segmentation.py:361).
+#include "kernels.h"
+#include "ptx.cuh"
+#include "tensormap.h"
+
+namespace msam {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 384;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4..11 epilogue
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN;  // power of two >= 32 for BN in {64,128,256}
+};
+
+struct GemmParams {
+  int M, N, K;
+  const float* bias;      // [N] or null
+  const float* residual;  // fp32 [res_rows, ldr] or null; row index = row % res_rows
+  int res_rows, ldr;
+  void* out;              // bf16 or fp32 [M, ldc]
+  int ldc;
+  int out_fp32;
+  int act;                // 0 none, 1 GELU(erf), 2 ReLU
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == 1) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  if (act == 2) return fmaxf(x, 0.0f);
+  return x;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_blocks = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int n_blocks = (p.N + BN - 1) / BN;
+  const int k_blocks = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int num_tiles = m_blocks * n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1, 2);  // epilogue drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t da = make_desc_sw128(sa, 0, 1024);
+          const uint64_t db = make_desc_sw128(sb, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // +32 B per K=16 step inside the 128-B swizzle atom -> +2 on the encoded (>>4) start address
+            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs have read it
+          if (kb == k_blocks - 1) umma_commit(&tfull_bar[as]);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue: TMEM -> regs -> global
+    const int ew = warp - 4;         // 0..7
+    const int quad = warp & 3;       // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;        // column half of the tile
+    constexpr int COLS_PER_WARP = BN / 2;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase, 4);
+      tc_fence_after();
+      const int row = m_blk * GEMM_BM + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const float* res_row = nullptr;
+      if (p.residual && row_ok) res_row = p.residual + (size_t)(row % p.res_rows) * p.ldr;
+#pragma unroll 1
+      for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
+        const int col0 = n_blk * BN + half * COLS_PER_WARP + c * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + half * COLS_PER_WARP + c * 32), v);
+        tmem_ld_wait();
+        if (c == COLS_PER_WARP / 32 - 1) {
+          // all TMEM reads of this accumulator stage by this warp are complete -> hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        if (row_ok && col0 < p.N) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            }
+          }
+          if (p.act) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+          }
+          if (res_row) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 r = *reinterpret_cast<const float4*>(res_row + col0 + j);
+              f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
+            }
+          }
+          if (p.out_fp32) {
+            float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldc + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldc + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u;
+              u.x = pack_bf16(f[j], f[j + 1]);
+              u.y = pack_bf16(f[j + 2], f[j + 3]);
+              u.z = pack_bf16(f[j + 4], f[j + 5]);
+              u.w = pack_bf16(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = u;
+            }
+          }
+        }
+        __syncwarp();  // reconverge before the next warp-collective tcgen05.ld
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  if (make_tmap_bf16_2d(&tmA, a.A, a.M, a.K, a.lda, GEMM_BM)) return -1;
+  if (make_tmap_bf16_2d(&tmB, a.W, a.N, a.K, a.ldw, BN)) return -1;
+  GemmParams p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.bias = a.bias;
+  p.residual = a.residual;
+  p.res_rows = a.res_rows > 0 ? a.res_rows : a.M;
+  p.ldr = a.ldr > 0 ? a.ldr : a.N;
+  p.out = a.out;
+  p.ldc = a.ldc > 0 ? a.ldc : a.N;
+  p.out_fp32 = a.out_fp32;
+  p.act = a.act;
+  const int tiles = ((a.M + GEMM_BM - 1) / GEMM_BM) * ((a.N + BN - 1) / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("gemm launch failed: %s", cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
+int launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) return set_error("gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
+  if (a.N % 32 != 0) return set_error("gemm: N=%d must be a multiple of 32", a.N);
+  if (a.K % 8 != 0 || a.lda % 8 != 0 || a.ldw % 8 != 0)
+    return set_error("gemm: K/lda/ldw must be multiples of 8 (16-byte TMA strides)");
+  // BN=256 keeps the tensor pipe at its 1-CTA rate with the fewest smem bytes per flop; fall back to 128 / 64 when N is
+  // not a multiple (or is small), to avoid wasted columns.
+  if (a.N % 256 == 0) return launch_gemm_bn<256>(a, num_sms, stream);
+  if (a.N % 128 == 0) return launch_gemm_bn<128>(a, num_sms, stream);
+  return launch_gemm_bn<64>(a, num_sms, stream);
+}
+
+}  // namespace msam

@@ -1,0 +1,63 @@
+// Internal kernel launch interface (host side).  All pointers are device pointers.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace msam {
+
+int set_error(const char* fmt, ...);  // records msam_last_error(); returns -1
+void count_launch();                  // per-thread launch counter (msam_launch_count)
+
+// ---- gemm.cu :  out[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual[row % res_rows])
+struct GemmArgs {
+  const __nv_bfloat16* A = nullptr;  // [M, lda]
+  const __nv_bfloat16* W = nullptr;  // [N, ldw]
+  int M = 0, N = 0, K = 0, lda = 0, ldw = 0;
+  const float* bias = nullptr;
+  const float* residual = nullptr;
+  int res_rows = 0, ldr = 0;
+  void* out = nullptr;
+  int ldc = 0;
+  int out_fp32 = 0;
+  int act = 0;  // 0 none, 1 GELU(erf), 2 ReLU
+};
+int launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream);
+
+// ---- attention.cu : ViT encoder attention with decomposed relative-position bias
+struct AttnArgs {
+  const __nv_bfloat16* qkv = nullptr;  // [groups*G, 3*D] rows = tokens (window-partitioned incl. pad tokens, or global)
+  const __nv_bfloat16* rel_table = nullptr;  // [NT, hd_pad] : rows [0,2S-1) rel_pos_h, rows [S_off, S_off+2S-1) rel_pos_w
+  __nv_bfloat16* out = nullptr;        // [B*grid*grid, D] in image token order
+  int batch = 0;      // images
+  int heads = 0;
+  int head_dim = 0;   // 64 or 80
+  int grid = 0;       // tokens per image side (64)
+  int window = 0;     // 0 = global attention, else window size (14)
+  float scale = 0.f;
+};
+int launch_attention(const AttnArgs& a, cudaStream_t stream);
+
+// ---- elementwise.cu
+int launch_patchify(const uint8_t* u8, const float* f32, int B, int h, int w, int img, const float* mean,
+                    const float* stdv, __nv_bfloat16* out, cudaStream_t stream);
+struct LnArgs {
+  const float* x = nullptr;  // [rows, D] fp32
+  int rows = 0, D = 0;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  float eps = 1e-6f;
+  __nv_bfloat16* out = nullptr;  // bf16 [rows(or window-partitioned rows), D] (optional)
+  float* out_f32 = nullptr;      // fp32 copy of the normalised rows (optional)
+  int window_mode = 0, grid = 64, ws = 14;
+  const float* add = nullptr;    // [add_rows, D] fp32 added after the affine for out2 (optional)
+  int add_rows = 1;
+  __nv_bfloat16* out2 = nullptr;
+};
+int launch_layernorm(const LnArgs& a, cudaStream_t stream);
+int launch_layernorm2d_nchw(const float* x, int B, int T, const float* gamma, const float* beta, float eps, float* out,
+                            cudaStream_t stream);
+int launch_cast_bf16(const float* x, long n, __nv_bfloat16* out, cudaStream_t stream);
+int launch_im2col3x3(const __nv_bfloat16* x, int B, int g, int C, __nv_bfloat16* out, cudaStream_t stream);
+
+}  // namespace msam

@@ -1,0 +1,256 @@
+"""Bring-up diagnostics for the CUDA ops (run on a B200 via gpurun).  Prints one line per check and never stops at the
+first failure, so that a single GPU call yields a complete picture.  Usage: python tests/gpu_diag.py [section ...]"""
+import math
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from micro_sam_b200 import _lib  # noqa: E402
+
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+DEV = "cuda" if torch.cuda.is_available() else "cpu"
+RESULTS = []
+
+
+def report(name, got, ref, tol):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    rel = (got - ref).norm() / (ref.norm() + 1e-12)
+    ok = bool(rel < tol) and bool(torch.isfinite(got).all())
+    RESULTS.append(ok)
+    print(f"[{'OK ' if ok else 'BAD'}] {name}: rel_l2={rel:.3e} max_abs={err.max():.3e} ref_absmax={ref.abs().max():.3e} "
+          f"finite={bool(torch.isfinite(got).all())}", flush=True)
+    if not ok:
+        bad = (err > 10 * tol * ref.abs().max()).nonzero()
+        print(f"      n_bad={len(bad)} of {got.numel()}  first bad idx: {bad[:8].tolist()}", flush=True)
+        if got.ndim == 2:
+            rows = torch.unique(bad[:, 0])[:16].tolist()
+            cols = torch.unique(bad[:, 1])[:16].tolist()
+            print(f"      bad rows(first16)={rows} bad cols(first16)={cols}", flush=True)
+            print(f"      got[0,:8]={got[0,:8].tolist()}\n      ref[0,:8]={ref[0,:8].tolist()}", flush=True)
+    return ok
+
+
+def gemm(A, W, bias=None, residual=None, res_rows=0, out_fp32=False, act=0):
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.empty(M, N, device=DEV, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    L = _lib.lib()
+    _lib.check(L.msam_op_gemm(_lib.ptr(A), _lib.ptr(W), M, N, K, _lib.ptr(bias), _lib.ptr(residual), res_rows,
+                              _lib.ptr(out), int(out_fp32), act, _lib.cur_stream()))
+    torch.cuda.synchronize()
+    return out
+
+
+def sec_gemm():
+    g = torch.Generator(device="cpu").manual_seed(0)
+    cases = [
+        # M, N, K, bias, act, residual(res_rows), out_fp32
+        (128, 256, 64, False, 0, 0, True),
+        (128, 256, 128, False, 0, 0, True),
+        (256, 256, 256, True, 0, 0, True),
+        (4096, 768, 768, True, 1, 0, False),
+        (1000, 2304, 768, True, 0, 0, False),
+        (4096, 768, 3072, True, 0, 4096, True),
+        (8192, 768, 768, True, 0, 4096, True),
+        (300, 128, 256, True, 2, 0, False),
+        (300, 96, 128, True, 0, 0, True),
+        (4096, 256, 2304, False, 0, 0, True),
+        (2 * 4900, 480, 160, True, 0, 0, False),
+        (4096 * 4, 3072, 768, True, 1, 0, False),
+    ]
+    for (M, N, K, hb, act, rr, f32) in cases:
+        A = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()
+        W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).bfloat16()
+        bias = torch.randn(N, generator=g).to(DEV) if hb else None
+        res = torch.randn(rr, N, generator=g).to(DEV) if rr else None
+        try:
+            out = gemm(A, W, bias, res, rr, f32, act)
+        except Exception as e:  # noqa: BLE001
+            RESULTS.append(False)
+            print(f"[BAD] gemm M={M} N={N} K={K}: EXCEPTION {e}", flush=True)
+            continue
+        ref = A.float() @ W.float().t()
+        if hb:
+            ref = ref + bias
+        if act == 1:
+            ref = torch.nn.functional.gelu(ref)
+        elif act == 2:
+            ref = torch.relu(ref)
+        if rr:
+            ref = ref + res.repeat(M // rr, 1)
+        report(f"gemm M={M} N={N} K={K} bias={hb} act={act} res={rr} f32={f32}", out, ref, 1e-5 if f32 else 5e-3)
+    # timing of a big one
+    M, N, K = 16 * 4096, 3072, 768
+    A = torch.randn(M, K, device=DEV).bfloat16()
+    W = torch.randn(N, K, device=DEV).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    for name, kw in (("fc1+gelu bf16out", dict(act=1)), ("plain bf16out", dict())):
+        gemm(A, W, bias, **kw)
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+        L = _lib.lib()
+        t0.record()
+        for _ in range(5):
+            L.msam_op_gemm(_lib.ptr(A), _lib.ptr(W), M, N, K, _lib.ptr(bias), None, 0, _lib.ptr(out), 0, kw.get("act", 0),
+                           _lib.cur_stream())
+        t1.record()
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1) / 5
+        print(f"[perf] gemm {name} M={M} N={N} K={K}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    (A @ W.t())
+    t0.record()
+    for _ in range(5):
+        (A @ W.t())
+    t1.record(); torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / 5
+    print(f"[perf] cublas same shape: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+
+
+def sec_ln():
+    L = _lib.lib()
+    for D in (768, 1280, 256, 160):
+        x = torch.randn(2 * 4096, D, device=DEV) * 2 + 0.5
+        gam = torch.randn(D, device=DEV)
+        bet = torch.randn(D, device=DEV)
+        out = torch.empty(2 * 4096, D, device=DEV, dtype=torch.bfloat16)
+        _lib.check(L.msam_op_layernorm(_lib.ptr(x), x.shape[0], D, _lib.ptr(gam), _lib.ptr(bet), 1e-6, _lib.ptr(out), 0,
+                                       _lib.cur_stream()))
+        torch.cuda.synchronize()
+        ref = torch.nn.functional.layer_norm(x, (D,), gam, bet, 1e-6)
+        report(f"layernorm D={D}", out, ref, 5e-3)
+    D = 768
+    x = torch.randn(2 * 4096, D, device=DEV)
+    gam = torch.randn(D, device=DEV); bet = torch.randn(D, device=DEV)
+    out = torch.zeros(2 * 25 * 196, D, device=DEV, dtype=torch.bfloat16)
+    _lib.check(L.msam_op_layernorm(_lib.ptr(x), x.shape[0], D, _lib.ptr(gam), _lib.ptr(bet), 1e-6, _lib.ptr(out), 1,
+                                   _lib.cur_stream()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (D,), gam, bet, 1e-6).view(2, 64, 64, D)
+    ref = torch.nn.functional.pad(ref, (0, 0, 0, 6, 0, 6)).view(2, 5, 14, 5, 14, D).permute(0, 1, 3, 2, 4, 5).reshape(-1, D)
+    report("layernorm window-partition", out, ref, 5e-3)
+
+
+def attn_ref(qkv, rel_h, rel_w, B, heads, hd, S, groups_tokens):
+    """qkv: [groups*G, 3*D] (bf16 values as float).  Returns [groups, G, D] fp32 following sam_ref.Attention."""
+    D = heads * hd
+    G = S * S
+    x = qkv.view(-1, G, 3, heads, hd).permute(2, 0, 3, 1, 4)  # 3, groups, heads, G, hd
+    q, k, v = x[0], x[1], x[2]
+    attn = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    idx = torch.arange(S, device=qkv.device)
+    rel = idx[:, None] - idx[None, :] + (S - 1)
+    Rh, Rw = rel_h[rel], rel_w[rel]  # S,S,hd
+    rq = q.reshape(q.shape[0], heads, S, S, hd)
+    bh = torch.einsum("ghywc,ykc->ghywk", rq, Rh)
+    bw = torch.einsum("ghywc,wkc->ghywk", rq, Rw)
+    attn = (attn.view(-1, heads, S, S, S, S) + bh[..., :, None] + bw[..., None, :]).view(-1, heads, G, G)
+    attn = attn.softmax(-1)
+    return (attn @ v).permute(0, 2, 1, 3).reshape(-1, G, D)
+
+
+def sec_attn(which=("w64", "g64", "w80", "g80")):
+    L = _lib.lib()
+    for tag in which:
+        window = tag[0] == "w"
+        hd = int(tag[1:])
+        heads, B = 2, 1
+        D = heads * hd
+        S = 14 if window else 64
+        groups = B * 25 if window else B
+        G = S * S
+        g = torch.Generator().manual_seed(1)
+        qkv = (torch.randn(groups * G, 3 * D, generator=g) * 1.0).to(DEV).bfloat16()
+        rel_h = (torch.randn(2 * S - 1, hd, generator=g) * 0.3).to(DEV).bfloat16()
+        rel_w = (torch.randn(2 * S - 1, hd, generator=g) * 0.3).to(DEV).bfloat16()
+        NT, WOFF = (64, 32) if window else (256, 128)
+        cols = ((hd + 63) // 64) * 64
+        tab = torch.zeros(NT, cols, device=DEV, dtype=torch.bfloat16)
+        tab[: 2 * S - 1, :hd] = rel_h
+        tab[WOFF: WOFF + 2 * S - 1, :hd] = rel_w
+        out = torch.zeros(B * 4096, D, device=DEV, dtype=torch.bfloat16)
+        try:
+            _lib.check(L.msam_op_attention(_lib.ptr(qkv), _lib.ptr(tab), _lib.ptr(out), B, heads, hd, 14 if window else 0,
+                                           hd ** -0.5, _lib.cur_stream()))
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            RESULTS.append(False)
+            print(f"[BAD] attention {tag}: EXCEPTION {e}", flush=True)
+            continue
+        ref = attn_ref(qkv.float(), rel_h.float(), rel_w.float(), B, heads, hd, S, None)
+        if window:
+            ref = ref.view(B, 5, 5, 14, 14, D).permute(0, 1, 3, 2, 4, 5).reshape(B, 70, 70, D)[:, :64, :64].reshape(-1, D)
+        else:
+            ref = ref.reshape(-1, D)
+        report(f"attention {tag} (heads={heads}, hd={hd})", out, ref, 1.5e-2)
+        for h in range(heads):
+            report(f"   head {h}", out[:, h * hd:(h + 1) * hd], ref[:, h * hd:(h + 1) * hd], 1.5e-2)
+
+
+def build_engine(model_type, sd, max_batch=1):
+    from oracle import sam_ref
+    a = sam_ref.ARCH[model_type]
+    L = _lib.lib()
+    import ctypes
+    ga = list(a["global_attn_indexes"]) + [-1] * (8 - len(a["global_attn_indexes"]))
+    cfg = _lib.MsamConfig(a["embed_dim"], a["depth"], a["num_heads"], (ctypes.c_int32 * 8)(*ga), 14, 1024, 16, 256,
+                          max_batch, 64)
+    h = ctypes.c_void_p()
+    _lib.check(L.msam_create(ctypes.byref(cfg), 0, ctypes.byref(h)))
+    for k, v in sd.items():
+        v = v.detach().float().contiguous().cpu()
+        shape = (ctypes.c_int64 * v.ndim)(*v.shape)
+        _lib.check(L.msam_load_weight(h, k.encode(), ctypes.c_void_p(v.data_ptr()), shape, v.ndim))
+    _lib.check(L.msam_finalize_weights(h))
+    return h
+
+
+def sec_encoder(types=("vit_test", "vit_test80")):
+    from oracle import sam_ref
+    L = _lib.lib()
+    for mt in types:
+        sd = sam_ref.seeded_state_dict(mt, seed=1)
+        sam = sam_ref.build_sam(mt)
+        sam.load_state_dict(sd)
+        try:
+            h = build_engine(mt, sd, max_batch=2)
+            torch.manual_seed(0)
+            x = torch.rand(2, 3, 1024, 1024) * 255
+            xin = sam.preprocess(x)
+            t = time.time()
+            with torch.no_grad():
+                ref = sam.image_encoder(xin)
+            tcpu = time.time() - t
+            out = torch.empty(2, 256, 64, 64, device=DEV)
+            xd = xin.to(DEV).contiguous()
+            _lib.check(L.msam_encode_f32(h, _lib.ptr(xd), 2, _lib.ptr(out), _lib.cur_stream()))
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            RESULTS.append(False)
+            print(f"[BAD] encoder {mt}: EXCEPTION {e}", flush=True)
+            continue
+        report(f"encoder {mt} vs fp32 oracle (cpu {tcpu:.1f}s)", out.cpu(), ref, 2e-2)
+        L.msam_destroy(h)
+
+
+SECTIONS = {"gemm": sec_gemm, "ln": sec_ln, "attn": sec_attn, "encoder": sec_encoder}
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(SECTIONS)
+    print("device:", torch.cuda.get_device_name(0), flush=True)
+    for n in names:
+        print(f"==== {n}", flush=True)
+        n, _, sub = n.partition(":")
+        try:
+            SECTIONS[n](tuple(sub.split(","))) if sub else SECTIONS[n]()
+        except Exception as e:  # noqa: BLE001
+            RESULTS.append(False)
+            print(f"[BAD] section {n}: EXCEPTION {type(e).__name__}: {e}", flush=True)
+    print(f"==== {sum(RESULTS)}/{len(RESULTS)} checks ok", flush=True)
