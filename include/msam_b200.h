@@ -50,6 +50,39 @@ int msam_encode_f32(msam_handle* h, const float* nchw, int B, float* out, void* 
  * with max(hh, ww) <= S, contiguous [B, hh, ww, 3]. */
 int msam_encode_u8(msam_handle* h, const uint8_t* hwc, int B, int hh, int ww, float* out, void* stream);
 
+/* SamPredictor.features assignment (util.py:676-679 / set_precomputed util.py:1248-1256): bind a (256,64,64) fp32
+ * NCHW image embedding as the decoder's current image; precomputes the prompt-independent layer-0 projections. */
+int msam_set_image_embedding(msam_handle* h, const float* feat_256x64x64, void* stream);
+
+/* SamPredictor.predict_torch up to the low-res logits (inference.py:248, instance_segmentation.py:361):
+ * prompt_encoder(points=(coords,labels)|None, boxes|None, masks=None) -> mask_decoder(multimask_output).
+ * points [P,n_points,2] / labels [P,n_points] (fp32; -1 pad, 0 neg, 1 pos) in the 1024-frame (already
+ * ResizeLongestSide.apply_coords'ed), boxes [P,4] xyxy; either may be NULL, not both.
+ * Outputs: low_res [P,M,256,256] fp32, iou [P,M] fp32, M = 3 (multimask) or 1.  mask_input is not supported. */
+int msam_decode(msam_handle* h, const float* points, const float* labels, int n_points, const float* boxes, int P,
+                int multimask, float* low_res, float* iou, void* stream);
+
+/* Sam.postprocess_masks + calculate_stability_score + threshold + batched_mask_to_box + area, fused, never
+ * materialising the upsampled logits (instance_segmentation.py:229-255; inference.py:137-151; _vendored.py:33-85).
+ * low_res [n,256,256]; boxes int32 [n,4] xyxy ([0,0,0,0] if empty); stability fp32 [n]; area int32 [n]. */
+int msam_mask_stats(const float* low_res, int n_masks, int in_h, int in_w, int orig_h, int orig_w, float mask_threshold,
+                    float stability_offset, int32_t* boxes_xyxy, float* stability, int32_t* area, void* stream);
+/* Sam.postprocess_masks materialised for the selected masks `sel` (int32 [n_sel] device, or NULL = first n_sel):
+ * logits fp32 [n_sel,H,W] and/or binary uint8 [n_sel,H,W] (either may be NULL). */
+int msam_upsample_masks(const float* low_res, const int32_t* sel, int n_sel, int in_h, int in_w, int orig_h, int orig_w,
+                        float mask_threshold, float* logits, uint8_t* binary, void* stream);
+/* util.mask_data_to_segmentation painting loop (util.py:1799-1829): paint masks sel[0..n_sel) in that order with ids
+ * seg_ids[k] into label (uint32, row pitch ld_label); exclusive=1: first painter wins, 0: last wins (AMG). */
+int msam_paint(const float* low_res, const int32_t* sel, const int32_t* boxes_xyxy, const int32_t* seg_ids, int n_sel,
+               int in_h, int in_w, int orig_h, int orig_w, float mask_threshold, int exclusive, uint32_t* label,
+               int ld_label, void* stream);
+/* AMGBase._postprocess_batch (instance_segmentation.py:99-132): iou_pred > t, stability >= t, not
+ * is_box_near_crop_edge(atol 20), then torchvision-semantics greedy box NMS by iou_pred.  crop/orig boxes are HOST
+ * int32[4] xyxy.  keep: int32 [n] device (descending score order), n_keep: int32 [1] device.  use_filters=0: NMS only. */
+int msam_amg_filter_nms(const int32_t* boxes_xyxy, const float* iou_preds, const float* stability, int n, int use_filters,
+                        float pred_iou_thresh, float stability_thresh, float box_nms_thresh, const int32_t* crop_box_host,
+                        const int32_t* orig_box_host, int32_t* keep, int32_t* n_keep, void* stream);
+
 /* ---- single-op entry points (unit tests / profiling; the same kernels the calls above are built from) ---- */
 /* out[M,N] = act(A[M,K] @ W[N,K]^T + bias) + residual[row % res_rows];  A, W bf16; bias/residual fp32 or NULL;
  * out bf16 (out_fp32=0) or fp32; act: 0 none, 1 GELU(erf), 2 ReLU. */

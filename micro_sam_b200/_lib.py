@@ -42,6 +42,16 @@ def lib() -> ctypes.CDLL:
                                    c_int, c_void_p]
         L.msam_op_layernorm.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p]
         L.msam_op_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]
+        L.msam_set_image_embedding.argtypes = [c_void_p, c_void_p, c_void_p]
+        L.msam_decode.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
+        L.msam_mask_stats.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]
+        L.msam_upsample_masks.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                                          c_void_p, c_void_p]
+        L.msam_paint.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+                                 c_void_p, c_int, c_void_p]
+        L.msam_amg_filter_nms.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float,
+                                          POINTER(c_int32), POINTER(c_int32), c_void_p, c_void_p, c_void_p]
         _lib = L
     return _lib
 

@@ -1,5 +1,678 @@
-// placeholder until the decoder lands
+// Prompt encoder + two-way-transformer mask decoder (segment_anything PromptEncoder / MaskDecoder / TwoWayTransformer,
+// restated in oracle/sam_ref.py) batched over P prompts of one image embedding.
+//
+// Layout: image tokens are rows (token-major [4096, 256]); per-prompt image-side tensors are [P*4096, C].  All dense
+// projections run on the tcgen05 GEMM (gemm.cu); this file adds the small fused CUDA-core kernels around them
+// (prompt PE, 7-token self attention, token->image and image->token attention cores, hyper-network mask product).
+// Exact algebraic hoist: in layer 0 the image-side projections (k/v of token->image, q of image->token) act on
+// `image_embedding + dense (+ pe)`, identical for every prompt when no mask prompt is given -> computed once per
+// image in set_image_embedding.
 #include "engine.h"
+
+#include <cmath>
+
 namespace msam {
-int Engine::finalize_decoder() { return 0; }
+
+constexpr int DC = 256;     // transformer dim
+constexpr int DI = 128;     // cross-attention internal dim
+constexpr int NHEAD = 8;
+constexpr int TMAX = 16;    // max tokens per prompt (5 output tokens + sparse prompt tokens)
+
+struct AttnW {  // one SamAttention: q,k,v [inner, 256], out [256, inner]
+  __nv_bfloat16 *q = nullptr, *k = nullptr, *v = nullptr, *o = nullptr, *qk = nullptr, *qkv = nullptr;
+  float *qb = nullptr, *kb = nullptr, *vb = nullptr, *ob = nullptr, *qkb = nullptr, *qkvb = nullptr;
+};
+struct DecLayer {
+  AttnW self_attn, t2i, i2t;
+  float *n1g, *n1b, *n2g, *n2b, *n3g, *n3b, *n4g, *n4b;
+  __nv_bfloat16 *mlp1, *mlp2;
+  float *mlp1b, *mlp2b;
+};
+struct Mlp3 {
+  __nv_bfloat16* w[3];
+  float* b[3];
+};
+
+struct DecoderState {
+  // prompt encoder
+  float *gauss = nullptr, *point_emb = nullptr /*[4,256]*/, *not_a_point = nullptr, *no_mask = nullptr;
+  float* pos = nullptr;  // dense PE, token-major [4096, 256]
+  // mask decoder
+  float* out_tokens = nullptr;  // [5, 256] = iou_token ; mask_tokens
+  DecLayer layers[2];
+  AttnW final_t2i;
+  float *nfg, *nfb;
+  __nv_bfloat16 *ct1 = nullptr, *ct2 = nullptr;  // conv-transpose weights as GEMM operands
+  float *ct1b = nullptr, *ct2b = nullptr, *upln_g = nullptr, *upln_b = nullptr;
+  Mlp3 hyper[4], iou_head;
+  // per-image state (set_image_embedding)
+  bool image_set = false;
+  float* src = nullptr;               // [4096,256] image embedding + no_mask_embed (fp32, residual of layer 0)
+  __nv_bfloat16 *src_bf = nullptr, *src_pe_bf = nullptr;
+  __nv_bfloat16 *k0 = nullptr, *v0 = nullptr, *q0 = nullptr;  // hoisted layer-0 projections [4096,128]
+  // per-chunk workspace (P = max_prompts)
+  float *tok0 = nullptr, *queries = nullptr, *tok_f32 = nullptr;
+  __nv_bfloat16 *tok0_bf = nullptr, *q_bf = nullptr, *qpe_bf = nullptr, *t_qkv = nullptr, *t_att = nullptr, *t_mlp = nullptr;
+  __nv_bfloat16 *t_q128 = nullptr, *t_k128 = nullptr, *t_v128 = nullptr, *t_att128 = nullptr;
+  __nv_bfloat16 *keys = nullptr, *keys_pe = nullptr, *img_a = nullptr, *img_b = nullptr, *img_att = nullptr;
+  float* img_f32 = nullptr;           // [P*4096, 256] fp32 scratch (out_proj result before norm4 / conv-transpose 1)
+  __nv_bfloat16 *up1 = nullptr, *up2 = nullptr;
+  __nv_bfloat16 *h1 = nullptr, *h2 = nullptr;
+  float *hyper_in = nullptr, *iou_out = nullptr;
+};
+
+// ================================================================================================ kernels
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pk2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
 }
+
+// Dense PE of the 64x64 pixel-centre grid (PositionEmbeddingRandom.forward) -> token-major [g*g, 256].
+__global__ void dense_pe_kernel(const float* __restrict__ G, int g, float* __restrict__ pos) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g * g * 128) return;
+  const int f = idx % 128, t = idx / 128, y = t / g, x = t % g;
+  const float cx = 2.f * (((float)x + 0.5f) / (float)g) - 1.f, cy = 2.f * (((float)y + 0.5f) / (float)g) - 1.f;
+  const float v = 6.283185307179586f * (cx * G[f] + cy * G[128 + f]);
+  pos[(long)t * 256 + f] = sinf(v);
+  pos[(long)t * 256 + 128 + f] = cosf(v);
+}
+
+// NCHW fp32 image embedding [256, T] -> token-major src = emb + no_mask_embed (fp32, bf16) and src + pos (bf16).
+__global__ void set_image_kernel(const float* __restrict__ feat, const float* __restrict__ no_mask,
+                                 const float* __restrict__ pos, int T, float* __restrict__ src,
+                                 __nv_bfloat16* __restrict__ src_bf, __nv_bfloat16* __restrict__ src_pe_bf) {
+  __shared__ float tile[32][33];
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) tile[i][tx] = feat[(long)(c0 + i) * T + t0 + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    const float v = tile[tx][i] + no_mask[c];
+    src[(long)t * 256 + c] = v;
+    src_bf[(long)t * 256 + c] = __float2bfloat16(v);
+    src_pe_bf[(long)t * 256 + c] = __float2bfloat16(v + pos[(long)t * 256 + c]);
+  }
+}
+
+// Tokens [P, T, 256] = [iou_token, mask_tokens(4), sparse prompt embeddings].  Sparse = points (+ pad point when no
+// box) then box corners (PromptEncoder._embed_points/_embed_boxes).  grid = (T-5, P), block = 128.
+__global__ void prompt_tokens_kernel(const float* __restrict__ points, const float* __restrict__ labels, int np,
+                                     const float* __restrict__ boxes, int T, float img_size,
+                                     const float* __restrict__ G, const float* __restrict__ point_emb,
+                                     const float* __restrict__ not_a_point, const float* __restrict__ out_tokens,
+                                     float* __restrict__ tok, __nv_bfloat16* __restrict__ tok_bf) {
+  const int p = blockIdx.y, s = blockIdx.x, f = threadIdx.x;
+  const int n_pts = points ? np + (boxes ? 0 : 1) : 0;
+  float* dst = tok + ((long)p * T + 5 + s) * 256;
+  __nv_bfloat16* dstb = tok_bf + ((long)p * T + 5 + s) * 256;
+  float x, y;
+  int kind;  // -1 not-a-point, 0/1 point labels, 2/3 box corners
+  if (s < n_pts) {
+    if (s < np) {
+      x = points[((long)p * np + s) * 2];
+      y = points[((long)p * np + s) * 2 + 1];
+      const int lb = (int)labels[(long)p * np + s];
+      kind = (lb == -1) ? -1 : ((lb == 0 || lb == 1) ? lb : 4);  // other labels: plain PE (upstream adds nothing)
+    } else {
+      x = 0.f; y = 0.f; kind = -1;
+    }
+  } else {
+    const int c = s - n_pts;
+    x = boxes[(long)p * 4 + 2 * c];
+    y = boxes[(long)p * 4 + 2 * c + 1];
+    kind = 2 + c;
+  }
+  const float cx = 2.f * ((x + 0.5f) / img_size) - 1.f, cy = 2.f * ((y + 0.5f) / img_size) - 1.f;
+  const float v = 6.283185307179586f * (cx * G[f] + cy * G[128 + f]);
+  float e0 = sinf(v), e1 = cosf(v);
+  if (kind < 0) {
+    e0 = not_a_point[f];
+    e1 = not_a_point[128 + f];
+  } else if (kind < 4) {
+    e0 += point_emb[kind * 256 + f];
+    e1 += point_emb[kind * 256 + 128 + f];
+  }
+  dst[f] = e0; dst[128 + f] = e1;
+  dstb[f] = __float2bfloat16(e0); dstb[128 + f] = __float2bfloat16(e1);
+  if (s == 0) {  // also write the 5 output tokens of this prompt
+    float* d0 = tok + (long)p * T * 256;
+    __nv_bfloat16* d0b = tok_bf + (long)p * T * 256;
+    for (int i = f; i < 5 * 256; i += 128) {
+      d0[i] = out_tokens[i];
+      d0b[i] = __float2bfloat16(out_tokens[i]);
+    }
+  }
+}
+
+// Token self attention: T x T per (prompt, head), 8 heads x 32 dims.  One warp per (prompt, head); lane t = query t.
+__global__ void token_self_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k,
+                                       int ldk, const __nv_bfloat16* __restrict__ v, int ldv, int P, int T,
+                                       __nv_bfloat16* __restrict__ out) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= P * NHEAD) return;
+  const int p = w / NHEAD, h = w % NHEAD;
+  __shared__ float sk[4][TMAX][33], sv[4][TMAX][33];
+  const int wib = threadIdx.x >> 5;
+  for (int i = lane; i < T * 32; i += 32) {
+    const int t = i / 32, d = i % 32;
+    sk[wib][t][d] = __bfloat162float(k[((long)p * T + t) * ldk + h * 32 + d]);
+    sv[wib][t][d] = __bfloat162float(v[((long)p * T + t) * ldv + h * 32 + d]);
+  }
+  __syncwarp();
+  if (lane < T) {
+    float qv[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) qv[d] = __bfloat162float(q[((long)p * T + lane) * ldq + h * 32 + d]);
+    float s[TMAX], m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < TMAX; ++j) {
+      s[j] = -INFINITY;
+      if (j < T) {
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < 32; ++d) a += qv[d] * sk[wib][j][d];
+        s[j] = a * 0.17677669529663687f;  // 1/sqrt(32)
+        m = fmaxf(m, s[j]);
+      }
+    }
+    float l = 0.f, o[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < TMAX; ++j) {
+      if (j < T) {
+        const float pj = expf(s[j] - m);
+        l += pj;
+#pragma unroll
+        for (int d = 0; d < 32; ++d) o[d] += pj * sv[wib][j][d];
+      }
+    }
+    const float inv = 1.f / l;
+    __nv_bfloat16* dst = out + ((long)p * T + lane) * 256 + h * 32;
+#pragma unroll
+    for (int d = 0; d < 32; d += 2) *reinterpret_cast<uint32_t*>(dst + d) = pk2(o[d] * inv, o[d + 1] * inv);
+  }
+}
+
+// token -> image attention core.  q [P*T,128] (bf16, projected), k/v [*,128] image-side (kv_stride = 0 rows when shared
+// by all prompts, else 4096 rows per prompt).  One CTA per prompt, warp = head (16 dims), lane = slice of image tokens,
+// online softmax per (token, lane), combined across lanes at the end.  Tokens handled in groups of 8.
+__global__ void __launch_bounds__(256)
+t2i_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                const __nv_bfloat16* __restrict__ v, long kv_stride_rows, int T, int NI,
+                __nv_bfloat16* __restrict__ out) {
+  const int p = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float sq[TMAX][DI];
+  for (int i = threadIdx.x; i < T * DI; i += 256) sq[i / DI][i % DI] = __bfloat162float(q[(long)p * T * DI + i]) * 0.25f;
+  __syncthreads();
+  const __nv_bfloat16* kp = k + (long)p * kv_stride_rows * DI + h * 16;
+  const __nv_bfloat16* vp = v + (long)p * kv_stride_rows * DI + h * 16;
+  for (int t0 = 0; t0 < T; t0 += 8) {
+    const int nt = (T - t0 < 8) ? (T - t0) : 8;
+    float m[8], l[8], acc[8][16];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      m[t] = -INFINITY; l[t] = 0.f;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) acc[t][d] = 0.f;
+    }
+    for (int n = lane; n < NI; n += 32) {
+      const uint4 ka = *reinterpret_cast<const uint4*>(kp + (long)n * DI), kb = *reinterpret_cast<const uint4*>(kp + (long)n * DI + 8);
+      const uint4 va = *reinterpret_cast<const uint4*>(vp + (long)n * DI), vb = *reinterpret_cast<const uint4*>(vp + (long)n * DI + 8);
+      const uint32_t kw[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+      const uint32_t vw[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+      float kf[16], vf[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        kf[2 * i] = bf_lo(kw[i]); kf[2 * i + 1] = bf_hi(kw[i]);
+        vf[2 * i] = bf_lo(vw[i]); vf[2 * i + 1] = bf_hi(vw[i]);
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        if (t < nt) {
+          float s = 0.f;
+#pragma unroll
+          for (int d = 0; d < 16; ++d) s += sq[t0 + t][h * 16 + d] * kf[d];
+          const float mn = fmaxf(m[t], s);
+          const float corr = __expf(m[t] - mn), pj = __expf(s - mn);
+          m[t] = mn;
+          l[t] = l[t] * corr + pj;
+#pragma unroll
+          for (int d = 0; d < 16; ++d) acc[t][d] = acc[t][d] * corr + pj * vf[d];
+        }
+      }
+    }
+    // combine the 32 lanes
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (t < nt) {
+        float mm = m[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+        const float sc = (m[t] == -INFINITY) ? 0.f : __expf(m[t] - mm);
+        float ll = l[t] * sc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
+        const float inv = 1.f / ll;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+          float a = acc[t][d] * sc;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+          if (lane == d) out[((long)p * T + t0 + t) * DI + h * 16 + d] = __float2bfloat16(a * inv);
+        }
+      }
+    }
+  }
+}
+
+// image -> token attention core.  q_img [*,128] (q_stride_rows = 0 when shared), k_tok / v_tok [P*T,128].
+// grid = (NI/32, P), block = 256: thread = (image token n = blockIdx.x*32 + tid/8, head = tid%8).
+__global__ void __launch_bounds__(256)
+i2t_attn_kernel(const __nv_bfloat16* __restrict__ qimg, long q_stride_rows, const __nv_bfloat16* __restrict__ ktok,
+                const __nv_bfloat16* __restrict__ vtok, int T, int NI, __nv_bfloat16* __restrict__ out) {
+  const int p = blockIdx.y;
+  __shared__ float sk[TMAX][NHEAD][17], sv[TMAX][NHEAD][17];
+  for (int i = threadIdx.x; i < T * DI; i += 256) {
+    const int t = i / DI, c = i % DI;
+    sk[t][c / 16][c % 16] = __bfloat162float(ktok[((long)p * T + t) * DI + c]);
+    sv[t][c / 16][c % 16] = __bfloat162float(vtok[((long)p * T + t) * DI + c]);
+  }
+  __syncthreads();
+  const int h = threadIdx.x & 7, n = blockIdx.x * 32 + (threadIdx.x >> 3);
+  const __nv_bfloat16* qp = qimg + ((long)p * q_stride_rows + n) * DI + h * 16;
+  const uint4 qa = *reinterpret_cast<const uint4*>(qp), qb = *reinterpret_cast<const uint4*>(qp + 8);
+  const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+  float qf[16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { qf[2 * i] = bf_lo(qw[i]) * 0.25f; qf[2 * i + 1] = bf_hi(qw[i]) * 0.25f; }
+  float s[TMAX], m = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < TMAX; ++t) {
+    s[t] = -INFINITY;
+    if (t < T) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) a += qf[d] * sk[t][h][d];
+      s[t] = a;
+      m = fmaxf(m, a);
+    }
+  }
+  float l = 0.f, o[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) o[d] = 0.f;
+#pragma unroll
+  for (int t = 0; t < TMAX; ++t) {
+    if (t < T) {
+      const float pj = __expf(s[t] - m);
+      l += pj;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) o[d] += pj * sv[t][h][d];
+    }
+  }
+  const float inv = 1.f / l;
+  uint4 o0, o1;
+  o0.x = pk2(o[0] * inv, o[1] * inv); o0.y = pk2(o[2] * inv, o[3] * inv);
+  o0.z = pk2(o[4] * inv, o[5] * inv); o0.w = pk2(o[6] * inv, o[7] * inv);
+  o1.x = pk2(o[8] * inv, o[9] * inv); o1.y = pk2(o[10] * inv, o[11] * inv);
+  o1.z = pk2(o[12] * inv, o[13] * inv); o1.w = pk2(o[14] * inv, o[15] * inv);
+  __nv_bfloat16* dst = out + ((long)p * NI + n) * DI + h * 16;
+  *reinterpret_cast<uint4*>(dst) = o0;
+  *reinterpret_cast<uint4*>(dst + 8) = o1;
+}
+
+// masks[p, mi, Y, X] = sum_ch hyper_in[p, m0+mi, ch] * up2[p, tok(y,x), sub(dy,dx), subsub(ey,ex), ch]
+// with Y = 4y + 2dy + ey, X = 4x + 2dx + ex.  up2 row = (p*4096 + tok)*4 + sub, 128 cols = subsub*32 + ch.
+// grid = (256 /*Y*/, P), block = 256 /*X*/.
+__global__ void __launch_bounds__(256)
+mask_product_kernel(const __nv_bfloat16* __restrict__ up2, const float* __restrict__ hyper_in, int m0, int nm,
+                    float* __restrict__ masks) {
+  const int p = blockIdx.y, Y = blockIdx.x, X = threadIdx.x;
+  __shared__ float sh[4][32];
+  if (threadIdx.x < nm * 32) sh[threadIdx.x / 32][threadIdx.x % 32] = hyper_in[((long)p * 4 + m0 + threadIdx.x / 32) * 32 + threadIdx.x % 32];
+  __syncthreads();
+  const int y = Y >> 2, dy = (Y >> 1) & 1, ey = Y & 1, x = X >> 2, dx = (X >> 1) & 1, ex = X & 1;
+  const __nv_bfloat16* src = up2 + (((long)p * 4096 + y * 64 + x) * 4 + dy * 2 + dx) * 128 + (ey * 2 + ex) * 32;
+  float u[32];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 w = *reinterpret_cast<const uint4*>(src + 8 * i);
+    u[8 * i] = bf_lo(w.x); u[8 * i + 1] = bf_hi(w.x); u[8 * i + 2] = bf_lo(w.y); u[8 * i + 3] = bf_hi(w.y);
+    u[8 * i + 4] = bf_lo(w.z); u[8 * i + 5] = bf_hi(w.z); u[8 * i + 6] = bf_lo(w.w); u[8 * i + 7] = bf_hi(w.w);
+  }
+  for (int mi = 0; mi < nm; ++mi) {
+    float a = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) a += sh[mi][c] * u[c];
+    masks[(((long)p * nm + mi) * 256 + Y) * 256 + X] = a;
+  }
+}
+
+__global__ void gather_iou_kernel(const float* __restrict__ iou32, int P, int m0, int nm, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P * nm) out[i] = iou32[(long)(i / nm) * 32 + m0 + i % nm];
+}
+
+#define LAUNCH_CHECK(name)                                                                        \
+  do {                                                                                            \
+    cudaError_t e_ = cudaGetLastError();                                                          \
+    if (e_ != cudaSuccess) return set_error(name " launch failed: %s", cudaGetErrorString(e_)); \
+    count_launch();                                                                               \
+  } while (0)
+#define CHK(p) do { if (!(p)) return -1; } while (0)
+
+// ================================================================================================ weights
+static int load_attn(Engine& E, const std::string& p, int inner, AttnW& w, bool fuse_qkv) {
+  CHK(w.q = E.up_bf16(p + "q_proj.weight", {inner, DC}));
+  CHK(w.k = E.up_bf16(p + "k_proj.weight", {inner, DC}));
+  CHK(w.v = E.up_bf16(p + "v_proj.weight", {inner, DC}));
+  CHK(w.o = E.up_bf16(p + "out_proj.weight", {DC, inner}));
+  CHK(w.qb = E.up_f32(p + "q_proj.bias", {inner}));
+  CHK(w.kb = E.up_f32(p + "k_proj.bias", {inner}));
+  CHK(w.vb = E.up_f32(p + "v_proj.bias", {inner}));
+  CHK(w.ob = E.up_f32(p + "out_proj.bias", {DC}));
+  if (fuse_qkv) {  // [q;k;v] and [q;k] stacked along the output dim for single-GEMM projections
+    const auto *hq = E.host(p + "q_proj.weight", {inner, DC}), *hk = E.host(p + "k_proj.weight", {inner, DC}),
+               *hv = E.host(p + "v_proj.weight", {inner, DC});
+    const auto *bq = E.host(p + "q_proj.bias", {inner}), *bk = E.host(p + "k_proj.bias", {inner}),
+               *bv = E.host(p + "v_proj.bias", {inner});
+    std::vector<float> cat, catb;
+    cat.insert(cat.end(), hq->begin(), hq->end());
+    cat.insert(cat.end(), hk->begin(), hk->end());
+    catb.insert(catb.end(), bq->begin(), bq->end());
+    catb.insert(catb.end(), bk->begin(), bk->end());
+    CHK(w.qk = E.upload_bf16(cat.data(), cat.size()));
+    CHK(w.qkb = E.upload_f32(catb.data(), catb.size()));
+    cat.insert(cat.end(), hv->begin(), hv->end());
+    catb.insert(catb.end(), bv->begin(), bv->end());
+    CHK(w.qkv = E.upload_bf16(cat.data(), cat.size()));
+    CHK(w.qkvb = E.upload_f32(catb.data(), catb.size()));
+  }
+  return 0;
+}
+
+static int load_mlp3(Engine& E, const std::string& p, int out_dim, Mlp3& m) {
+  CHK(m.w[0] = E.up_bf16(p + "layers.0.weight", {DC, DC}));
+  CHK(m.b[0] = E.up_f32(p + "layers.0.bias", {DC}));
+  CHK(m.w[1] = E.up_bf16(p + "layers.1.weight", {DC, DC}));
+  CHK(m.b[1] = E.up_f32(p + "layers.1.bias", {DC}));
+  const auto* w2 = E.host(p + "layers.2.weight", {out_dim, DC});
+  const auto* b2 = E.host(p + "layers.2.bias", {out_dim});
+  CHK(w2 && b2);
+  std::vector<float> wp((size_t)32 * DC, 0.f), bp(32, 0.f);  // pad the output dim to 32 (GEMM N granularity)
+  std::copy(w2->begin(), w2->end(), wp.begin());
+  std::copy(b2->begin(), b2->end(), bp.begin());
+  CHK(m.w[2] = E.upload_bf16(wp.data(), wp.size()));
+  CHK(m.b[2] = E.upload_f32(bp.data(), bp.size()));
+  return 0;
+}
+
+int Engine::finalize_decoder() {
+  if (host_weights.find("mask_decoder.iou_token.weight") == host_weights.end()) return 0;  // encoder-only model
+  dec = new DecoderState();
+  DecoderState& d = *dec;
+  const int g = cfg.image_size / cfg.patch_size, NI = g * g;
+  const std::string pe = "prompt_encoder.", md = "mask_decoder.";
+  CHK(d.gauss = up_f32(pe + "pe_layer.positional_encoding_gaussian_matrix", {2, 128}));
+  {
+    std::vector<float> pts;
+    for (int i = 0; i < 4; ++i) {
+      const auto* h = host(pe + "point_embeddings." + std::to_string(i) + ".weight", {1, DC});
+      CHK(h);
+      pts.insert(pts.end(), h->begin(), h->end());
+    }
+    CHK(d.point_emb = upload_f32(pts.data(), pts.size()));
+  }
+  CHK(d.not_a_point = up_f32(pe + "not_a_point_embed.weight", {1, DC}));
+  CHK(d.no_mask = up_f32(pe + "no_mask_embed.weight", {1, DC}));
+  {
+    const auto *it = host(md + "iou_token.weight", {1, DC}), *mt = host(md + "mask_tokens.weight", {4, DC});
+    CHK(it && mt);
+    std::vector<float> t(it->begin(), it->end());
+    t.insert(t.end(), mt->begin(), mt->end());
+    CHK(d.out_tokens = upload_f32(t.data(), t.size()));
+  }
+  for (int l = 0; l < 2; ++l) {
+    DecLayer& L = d.layers[l];
+    const std::string p = md + "transformer.layers." + std::to_string(l) + ".";
+    if (load_attn(*this, p + "self_attn.", DC, L.self_attn, true)) return -1;
+    if (load_attn(*this, p + "cross_attn_token_to_image.", DI, L.t2i, false)) return -1;
+    if (load_attn(*this, p + "cross_attn_image_to_token.", DI, L.i2t, false)) return -1;
+    CHK(L.n1g = up_f32(p + "norm1.weight", {DC})); CHK(L.n1b = up_f32(p + "norm1.bias", {DC}));
+    CHK(L.n2g = up_f32(p + "norm2.weight", {DC})); CHK(L.n2b = up_f32(p + "norm2.bias", {DC}));
+    CHK(L.n3g = up_f32(p + "norm3.weight", {DC})); CHK(L.n3b = up_f32(p + "norm3.bias", {DC}));
+    CHK(L.n4g = up_f32(p + "norm4.weight", {DC})); CHK(L.n4b = up_f32(p + "norm4.bias", {DC}));
+    CHK(L.mlp1 = up_bf16(p + "mlp.lin1.weight", {2048, DC})); CHK(L.mlp1b = up_f32(p + "mlp.lin1.bias", {2048}));
+    CHK(L.mlp2 = up_bf16(p + "mlp.lin2.weight", {DC, 2048})); CHK(L.mlp2b = up_f32(p + "mlp.lin2.bias", {DC}));
+  }
+  if (load_attn(*this, md + "transformer.final_attn_token_to_image.", DI, d.final_t2i, false)) return -1;
+  CHK(d.nfg = up_f32(md + "transformer.norm_final_attn.weight", {DC}));
+  CHK(d.nfb = up_f32(md + "transformer.norm_final_attn.bias", {DC}));
+  {  // ConvTranspose2d(256->64,k2,s2): W[c,o,dy,dx] -> GEMM weight [(dy*2+dx)*64 + o][c], bias[(.)*64 + o] = b[o]
+    const auto *w = host(md + "output_upscaling.0.weight", {DC, 64, 2, 2}), *b = host(md + "output_upscaling.0.bias", {64});
+    CHK(w && b);
+    std::vector<float> W((size_t)256 * DC), B(256);
+    for (int c = 0; c < DC; ++c)
+      for (int o = 0; o < 64; ++o)
+        for (int s = 0; s < 4; ++s) W[((size_t)s * 64 + o) * DC + c] = (*w)[((size_t)c * 64 + o) * 4 + s];
+    for (int s = 0; s < 4; ++s)
+      for (int o = 0; o < 64; ++o) B[s * 64 + o] = (*b)[o];
+    CHK(d.ct1 = upload_bf16(W.data(), W.size()));
+    CHK(d.ct1b = upload_f32(B.data(), B.size()));
+  }
+  CHK(d.upln_g = up_f32(md + "output_upscaling.1.weight", {64}));
+  CHK(d.upln_b = up_f32(md + "output_upscaling.1.bias", {64}));
+  {  // ConvTranspose2d(64->32,k2,s2) -> GEMM weight [(ey*2+ex)*32 + o][c]
+    const auto *w = host(md + "output_upscaling.3.weight", {64, 32, 2, 2}), *b = host(md + "output_upscaling.3.bias", {32});
+    CHK(w && b);
+    std::vector<float> W((size_t)128 * 64), B(128);
+    for (int c = 0; c < 64; ++c)
+      for (int o = 0; o < 32; ++o)
+        for (int s = 0; s < 4; ++s) W[((size_t)s * 32 + o) * 64 + c] = (*w)[((size_t)c * 32 + o) * 4 + s];
+    for (int s = 0; s < 4; ++s)
+      for (int o = 0; o < 32; ++o) B[s * 32 + o] = (*b)[o];
+    CHK(d.ct2 = upload_bf16(W.data(), W.size()));
+    CHK(d.ct2b = upload_f32(B.data(), B.size()));
+  }
+  for (int i = 0; i < 4; ++i)
+    if (load_mlp3(*this, md + "output_hypernetworks_mlps." + std::to_string(i) + ".", 32, d.hyper[i])) return -1;
+  if (load_mlp3(*this, md + "iou_prediction_head.", 4, d.iou_head)) return -1;
+
+  // dense PE + per-image buffers
+  CHK(d.pos = (float*)dalloc((size_t)NI * DC * 4));
+  dense_pe_kernel<<<(NI * 128 + 255) / 256, 256>>>(d.gauss, g, d.pos);
+  LAUNCH_CHECK("dense_pe");
+  CHK(d.src = (float*)dalloc((size_t)NI * DC * 4));
+  CHK(d.src_bf = (__nv_bfloat16*)dalloc((size_t)NI * DC * 2));
+  CHK(d.src_pe_bf = (__nv_bfloat16*)dalloc((size_t)NI * DC * 2));
+  CHK(d.k0 = (__nv_bfloat16*)dalloc((size_t)NI * DI * 2));
+  CHK(d.v0 = (__nv_bfloat16*)dalloc((size_t)NI * DI * 2));
+  CHK(d.q0 = (__nv_bfloat16*)dalloc((size_t)NI * DI * 2));
+  // per-chunk workspace
+  const size_t P = cfg.max_prompts, PT = P * TMAX, PN = P * NI;
+  CHK(d.tok0 = (float*)dalloc(PT * DC * 4));
+  CHK(d.tok0_bf = (__nv_bfloat16*)dalloc(PT * DC * 2));
+  CHK(d.queries = (float*)dalloc(PT * DC * 4));
+  CHK(d.tok_f32 = (float*)dalloc(PT * DC * 4));
+  CHK(d.q_bf = (__nv_bfloat16*)dalloc(PT * DC * 2));
+  CHK(d.qpe_bf = (__nv_bfloat16*)dalloc(PT * DC * 2));
+  CHK(d.t_qkv = (__nv_bfloat16*)dalloc(PT * 3 * DC * 2));
+  CHK(d.t_att = (__nv_bfloat16*)dalloc(PT * DC * 2));
+  CHK(d.t_mlp = (__nv_bfloat16*)dalloc(PT * 2048 * 2));
+  CHK(d.t_q128 = (__nv_bfloat16*)dalloc(PT * DI * 2));
+  CHK(d.t_k128 = (__nv_bfloat16*)dalloc(PT * DI * 2));
+  CHK(d.t_v128 = (__nv_bfloat16*)dalloc(PT * DI * 2));
+  CHK(d.t_att128 = (__nv_bfloat16*)dalloc(PT * DI * 2));
+  CHK(d.keys = (__nv_bfloat16*)dalloc(PN * DC * 2));
+  CHK(d.keys_pe = (__nv_bfloat16*)dalloc(PN * DC * 2));
+  CHK(d.img_a = (__nv_bfloat16*)dalloc(PN * DI * 2));
+  CHK(d.img_b = (__nv_bfloat16*)dalloc(PN * DI * 2));
+  CHK(d.img_att = (__nv_bfloat16*)dalloc(PN * DI * 2));
+  CHK(d.img_f32 = (float*)dalloc(PN * DC * 4));
+  CHK(d.up1 = (__nv_bfloat16*)dalloc(PN * 4 * 64 * 2));
+  CHK(d.up2 = (__nv_bfloat16*)dalloc(PN * 4 * 128 * 2));
+  CHK(d.h1 = (__nv_bfloat16*)dalloc(P * DC * 2));
+  CHK(d.h2 = (__nv_bfloat16*)dalloc(P * DC * 2));
+  CHK(d.hyper_in = (float*)dalloc(P * 4 * 32 * 4));
+  CHK(d.iou_out = (float*)dalloc(P * 32 * 4));
+  return 0;
+}
+
+// ================================================================================================ forward
+static int gemm(Engine& E, cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int M, int N, int K,
+                const float* bias, void* out, int ldc, int out_fp32, int act = 0, const void* residual = nullptr,
+                int res_rows = 0, int res_bf16 = 0) {
+  GemmArgs a;
+  a.A = A; a.W = W; a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldw = K; a.bias = bias; a.out = out; a.ldc = ldc;
+  a.out_fp32 = out_fp32; a.act = act; a.residual = residual; a.res_rows = res_rows; a.res_bf16 = res_bf16;
+  return launch_gemm(a, E.num_sms, st);
+}
+static int ln(cudaStream_t st, const float* x, int rows, int D, const float* g, const float* b, float eps,
+              __nv_bfloat16* out, float* out_f32 = nullptr, const float* add = nullptr, int add_rows = 1,
+              __nv_bfloat16* out2 = nullptr, int act = 0) {
+  LnArgs l;
+  l.x = x; l.rows = rows; l.D = D; l.gamma = g; l.beta = b; l.eps = eps; l.out = out; l.out_f32 = out_f32;
+  l.add = add; l.add_rows = add_rows; l.out2 = out2; l.act = act;
+  return launch_layernorm(l, st);
+}
+
+int Engine::set_image_embedding(const float* feat, cudaStream_t st) {
+  if (!finalized || !dec) return set_error("set_image_embedding: decoder weights not loaded");
+  DecoderState& d = *dec;
+  const int g = cfg.image_size / cfg.patch_size, NI = g * g;
+  set_image_kernel<<<dim3(NI / 32, DC / 32), dim3(32, 8), 0, st>>>(feat, d.no_mask, d.pos, NI, d.src, d.src_bf, d.src_pe_bf);
+  LAUNCH_CHECK("set_image");
+  const DecLayer& L0 = d.layers[0];
+  if (gemm(*this, st, d.src_pe_bf, DC, L0.t2i.k, NI, DI, DC, L0.t2i.kb, d.k0, DI, 0)) return -1;
+  if (gemm(*this, st, d.src_bf, DC, L0.t2i.v, NI, DI, DC, L0.t2i.vb, d.v0, DI, 0)) return -1;
+  if (gemm(*this, st, d.src_pe_bf, DC, L0.i2t.q, NI, DI, DC, L0.i2t.qb, d.q0, DI, 0)) return -1;
+  d.image_set = true;
+  return 0;
+}
+
+// One chunk of P <= max_prompts prompts.
+static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const float* labels, int np, const float* boxes,
+                        int P, int multimask, float* low_res, float* iou) {
+  DecoderState& d = *E.dec;
+  const int NI = 4096;
+  const int n_sparse = (points ? np + (boxes ? 0 : 1) : 0) + (boxes ? 2 : 0);
+  const int T = 5 + n_sparse, PT = P * T, PN = P * NI;
+  if (n_sparse <= 0) return set_error("decode: need points and/or boxes");
+  if (T > TMAX) return set_error("decode: %d tokens per prompt exceeds the supported %d", T, TMAX);
+
+  prompt_tokens_kernel<<<dim3(n_sparse, P), 128, 0, st>>>(points, labels, np, boxes, T, (float)E.cfg.image_size, d.gauss,
+                                                          d.point_emb, d.not_a_point, d.out_tokens, d.tok0, d.tok0_bf);
+  LAUNCH_CHECK("prompt_tokens");
+
+  const __nv_bfloat16 *keys = nullptr, *keys_pe = nullptr;  // per-prompt image tokens (null = shared src of layer 0)
+  for (int l = 0; l < 2; ++l) {
+    const DecLayer& L = d.layers[l];
+    // ---- (1) token self attention
+    if (l == 0) {
+      if (gemm(E, st, d.tok0_bf, DC, L.self_attn.qkv, PT, 3 * DC, DC, L.self_attn.qkvb, d.t_qkv, 3 * DC, 0)) return -1;
+      token_self_attn_kernel<<<(P * NHEAD + 3) / 4, 128, 0, st>>>(d.t_qkv, 3 * DC, d.t_qkv + DC, 3 * DC, d.t_qkv + 2 * DC,
+                                                                    3 * DC, P, T, d.t_att);
+      LAUNCH_CHECK("token_self_attn");
+      // skip_first_layer_pe: the attention output REPLACES the tokens (no residual)
+      if (gemm(E, st, d.t_att, DC, L.self_attn.o, PT, DC, DC, L.self_attn.ob, d.tok_f32, DC, 1)) return -1;
+    } else {
+      if (gemm(E, st, d.qpe_bf, DC, L.self_attn.qk, PT, 2 * DC, DC, L.self_attn.qkb, d.t_qkv, 2 * DC, 0)) return -1;
+      if (gemm(E, st, d.q_bf, DC, L.self_attn.v, PT, DC, DC, L.self_attn.vb, d.t_mlp, DC, 0)) return -1;
+      token_self_attn_kernel<<<(P * NHEAD + 3) / 4, 128, 0, st>>>(d.t_qkv, 2 * DC, d.t_qkv + DC, 2 * DC, d.t_mlp, DC, P, T,
+                                                                    d.t_att);
+      LAUNCH_CHECK("token_self_attn");
+      if (gemm(E, st, d.t_att, DC, L.self_attn.o, PT, DC, DC, L.self_attn.ob, d.tok_f32, DC, 1, 0, d.queries, PT)) return -1;
+    }
+    if (ln(st, d.tok_f32, PT, DC, L.n1g, L.n1b, 1e-5f, d.q_bf, d.queries, d.tok0, PT, d.qpe_bf)) return -1;
+    // ---- (2) token -> image cross attention
+    if (gemm(E, st, d.qpe_bf, DC, L.t2i.q, PT, DI, DC, L.t2i.qb, d.t_q128, DI, 0)) return -1;
+    if (l == 0) {
+      t2i_attn_kernel<<<P, 256, 0, st>>>(d.t_q128, d.k0, d.v0, 0, T, NI, d.t_att128);
+    } else {
+      if (gemm(E, st, keys_pe, DC, L.t2i.k, PN, DI, DC, L.t2i.kb, d.img_a, DI, 0)) return -1;
+      if (gemm(E, st, keys, DC, L.t2i.v, PN, DI, DC, L.t2i.vb, d.img_b, DI, 0)) return -1;
+      t2i_attn_kernel<<<P, 256, 0, st>>>(d.t_q128, d.img_a, d.img_b, NI, T, NI, d.t_att128);
+    }
+    LAUNCH_CHECK("t2i_attn");
+    if (gemm(E, st, d.t_att128, DI, L.t2i.o, PT, DC, DI, L.t2i.ob, d.tok_f32, DC, 1, 0, d.queries, PT)) return -1;
+    if (ln(st, d.tok_f32, PT, DC, L.n2g, L.n2b, 1e-5f, d.q_bf, d.queries)) return -1;
+    // ---- (3) MLP (ReLU)
+    if (gemm(E, st, d.q_bf, DC, L.mlp1, PT, 2048, DC, L.mlp1b, d.t_mlp, 2048, 0, 2)) return -1;
+    if (gemm(E, st, d.t_mlp, 2048, L.mlp2, PT, DC, 2048, L.mlp2b, d.tok_f32, DC, 1, 0, d.queries, PT)) return -1;
+    if (ln(st, d.tok_f32, PT, DC, L.n3g, L.n3b, 1e-5f, d.q_bf, d.queries, d.tok0, PT, d.qpe_bf)) return -1;
+    // ---- (4) image -> token cross attention (updates all image tokens of every prompt)
+    if (gemm(E, st, d.qpe_bf, DC, L.i2t.k, PT, DI, DC, L.i2t.kb, d.t_k128, DI, 0)) return -1;
+    if (gemm(E, st, d.q_bf, DC, L.i2t.v, PT, DI, DC, L.i2t.vb, d.t_v128, DI, 0)) return -1;
+    if (l == 0) {
+      i2t_attn_kernel<<<dim3(NI / 32, P), 256, 0, st>>>(d.q0, 0, d.t_k128, d.t_v128, T, NI, d.img_att);
+    } else {
+      if (gemm(E, st, keys_pe, DC, L.i2t.q, PN, DI, DC, L.i2t.qb, d.img_a, DI, 0)) return -1;
+      i2t_attn_kernel<<<dim3(NI / 32, P), 256, 0, st>>>(d.img_a, NI, d.t_k128, d.t_v128, T, NI, d.img_att);
+    }
+    LAUNCH_CHECK("i2t_attn");
+    if (l == 0) {
+      if (gemm(E, st, d.img_att, DI, L.i2t.o, PN, DC, DI, L.i2t.ob, d.img_f32, DC, 1, 0, d.src, NI)) return -1;
+    } else {
+      if (gemm(E, st, d.img_att, DI, L.i2t.o, PN, DC, DI, L.i2t.ob, d.img_f32, DC, 1, 0, keys, PN, 1)) return -1;
+    }
+    if (ln(st, d.img_f32, PN, DC, L.n4g, L.n4b, 1e-5f, d.keys, nullptr, d.pos, NI, d.keys_pe)) return -1;
+    keys = d.keys;
+    keys_pe = d.keys_pe;
+  }
+  // ---- final token -> image attention
+  {
+    const AttnW& A = d.final_t2i;
+    if (gemm(E, st, d.qpe_bf, DC, A.q, PT, DI, DC, A.qb, d.t_q128, DI, 0)) return -1;
+    if (gemm(E, st, keys_pe, DC, A.k, PN, DI, DC, A.kb, d.img_a, DI, 0)) return -1;
+    if (gemm(E, st, keys, DC, A.v, PN, DI, DC, A.vb, d.img_b, DI, 0)) return -1;
+    t2i_attn_kernel<<<P, 256, 0, st>>>(d.t_q128, d.img_a, d.img_b, NI, T, NI, d.t_att128);
+    LAUNCH_CHECK("t2i_attn");
+    if (gemm(E, st, d.t_att128, DI, A.o, PT, DC, DI, A.ob, d.tok_f32, DC, 1, 0, d.queries, PT)) return -1;
+    if (ln(st, d.tok_f32, PT, DC, d.nfg, d.nfb, 1e-5f, d.q_bf)) return -1;
+  }
+  // ---- heads: IoU MLP on token 0, hyper-network MLPs on tokens 1..4 (rows p*T + i, lda = T*256)
+  {
+    const Mlp3& m = d.iou_head;
+    if (gemm(E, st, d.q_bf, T * DC, m.w[0], P, DC, DC, m.b[0], d.h1, DC, 0, 2)) return -1;
+    if (gemm(E, st, d.h1, DC, m.w[1], P, DC, DC, m.b[1], d.h2, DC, 0, 2)) return -1;
+    if (gemm(E, st, d.h2, DC, m.w[2], P, 32, DC, m.b[2], d.iou_out, 32, 1)) return -1;
+    for (int i = 0; i < 4; ++i) {
+      const Mlp3& hm = d.hyper[i];
+      if (gemm(E, st, d.q_bf + (1 + i) * DC, T * DC, hm.w[0], P, DC, DC, hm.b[0], d.h1, DC, 0, 2)) return -1;
+      if (gemm(E, st, d.h1, DC, hm.w[1], P, DC, DC, hm.b[1], d.h2, DC, 0, 2)) return -1;
+      if (gemm(E, st, d.h2, DC, hm.w[2], P, 32, DC, hm.b[2], d.hyper_in + i * 32, 128, 1)) return -1;
+    }
+  }
+  // ---- output upscaling: convT(256->64) -> LN2d(64) -> GELU -> convT(64->32) -> GELU, then the hyper product
+  if (gemm(E, st, keys, DC, d.ct1, PN, 256, DC, d.ct1b, d.img_f32, 256, 1)) return -1;
+  if (ln(st, d.img_f32, PN * 4, 64, d.upln_g, d.upln_b, 1e-6f, d.up1, nullptr, nullptr, 1, nullptr, /*gelu*/ 1)) return -1;
+  if (gemm(E, st, d.up1, 64, d.ct2, PN * 4, 128, 64, d.ct2b, d.up2, 128, 0, 1)) return -1;
+  const int m0 = multimask ? 1 : 0, nm = multimask ? 3 : 1;
+  mask_product_kernel<<<dim3(256, P), 256, 0, st>>>(d.up2, d.hyper_in, m0, nm, low_res);
+  LAUNCH_CHECK("mask_product");
+  gather_iou_kernel<<<(P * nm + 127) / 128, 128, 0, st>>>(d.iou_out, P, m0, nm, iou);
+  LAUNCH_CHECK("gather_iou");
+  return 0;
+}
+
+int Engine::decode(const float* points, const float* labels, int np, const float* boxes, int P, int multimask,
+                   float* low_res, float* iou, cudaStream_t st) {
+  if (!finalized || !dec) return set_error("decode: decoder weights not loaded");
+  if (!dec->image_set) return set_error("decode: no image embedding set (call msam_set_image_embedding first)");
+  if (P <= 0) return set_error("decode: empty prompt batch");
+  const int nm = multimask ? 3 : 1;
+  for (int p0 = 0; p0 < P; p0 += cfg.max_prompts) {
+    const int n = (P - p0 < cfg.max_prompts) ? (P - p0) : cfg.max_prompts;
+    if (decode_chunk(*this, st, points ? points + (size_t)p0 * np * 2 : nullptr, labels ? labels + (size_t)p0 * np : nullptr,
+                     np, boxes ? boxes + (size_t)p0 * 4 : nullptr, n, multimask, low_res + (size_t)p0 * nm * 65536,
+                     iou + (size_t)p0 * nm))
+      return -1;
+  }
+  return 0;
+}
+
+}  // namespace msam

@@ -76,7 +76,7 @@ constexpr int LN_MAX_V4 = 10;  // D <= 1280
 __global__ void layernorm_rows_kernel(const float* __restrict__ x, int rows, int D, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out,
                                       int mode, int grid, int ws, const float* __restrict__ add, int add_rows,
-                                      __nv_bfloat16* __restrict__ out2, float* __restrict__ out_f32) {
+                                      __nv_bfloat16* __restrict__ out2, float* __restrict__ out_f32, int act) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -128,6 +128,12 @@ __global__ void layernorm_rows_kernel(const float* __restrict__ x, int rows, int
       r.y = (v[i].y - mean) * rstd * g.y + bb.y;
       r.z = (v[i].z - mean) * rstd * g.z + bb.z;
       r.w = (v[i].w - mean) * rstd * g.w + bb.w;
+      if (act == 1) {
+        r.x = 0.5f * r.x * (1.0f + erff(r.x * 0.70710678118654752440f));
+        r.y = 0.5f * r.y * (1.0f + erff(r.y * 0.70710678118654752440f));
+        r.z = 0.5f * r.z * (1.0f + erff(r.z * 0.70710678118654752440f));
+        r.w = 0.5f * r.w * (1.0f + erff(r.w * 0.70710678118654752440f));
+      }
       if (out) *reinterpret_cast<uint2*>(out + orow * D + 4 * k) = make_uint2(pack2(r.x, r.y), pack2(r.z, r.w));
       if (out_f32) *reinterpret_cast<float4*>(out_f32 + orow * D + 4 * k) = r;
       if (out2) {
@@ -145,7 +151,7 @@ int launch_layernorm(const LnArgs& a, cudaStream_t stream) {
   const unsigned blocks = (unsigned)((a.rows + warps_per_block - 1) / warps_per_block);
   layernorm_rows_kernel<<<blocks, warps_per_block * 32, 0, stream>>>(a.x, a.rows, a.D, a.gamma, a.beta, a.eps, a.out,
                                                                     a.window_mode, a.grid, a.ws, a.add, a.add_rows,
-                                                                    a.out2, a.out_f32);
+                                                                    a.out2, a.out_f32, a.act);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("layernorm launch failed: %s", cudaGetErrorString(e));
   count_launch();

@@ -357,6 +357,39 @@ int msam_encode_u8(msam_handle* h, const uint8_t* hwc, int B, int hh, int ww, fl
   return h->eng.encode(hwc, nullptr, B, hh, ww, out, (cudaStream_t)stream);
 }
 
+int msam_set_image_embedding(msam_handle* h, const float* feat, void* stream) {
+  if (!h || !feat) return set_error("msam_set_image_embedding: null argument");
+  return h->eng.set_image_embedding(feat, (cudaStream_t)stream);
+}
+int msam_decode(msam_handle* h, const float* points, const float* labels, int n_points, const float* boxes, int P,
+                int multimask, float* low_res, float* iou, void* stream) {
+  if (!h || !low_res || !iou) return set_error("msam_decode: null argument");
+  if (!points && !boxes) return set_error("msam_decode: need points and/or boxes");
+  if (points && !labels) return set_error("msam_decode: points without labels");
+  return h->eng.decode(points, labels, points ? n_points : 0, boxes, P, multimask, low_res, iou, (cudaStream_t)stream);
+}
+int msam_mask_stats(const float* low_res, int n_masks, int in_h, int in_w, int orig_h, int orig_w, float mask_threshold,
+                    float stability_offset, int32_t* boxes_xyxy, float* stability, int32_t* area, void* stream) {
+  return post_mask_stats(low_res, n_masks, in_h, in_w, orig_h, orig_w, mask_threshold, stability_offset, boxes_xyxy,
+                         stability, area, (cudaStream_t)stream);
+}
+int msam_upsample_masks(const float* low_res, const int32_t* sel, int n_sel, int in_h, int in_w, int orig_h, int orig_w,
+                        float mask_threshold, float* logits, uint8_t* binary, void* stream) {
+  return post_upsample(low_res, sel, n_sel, in_h, in_w, orig_h, orig_w, mask_threshold, logits, binary, (cudaStream_t)stream);
+}
+int msam_paint(const float* low_res, const int32_t* sel, const int32_t* boxes_xyxy, const int32_t* seg_ids, int n_sel,
+               int in_h, int in_w, int orig_h, int orig_w, float mask_threshold, int exclusive, uint32_t* label,
+               int ld_label, void* stream) {
+  return post_paint(low_res, sel, boxes_xyxy, seg_ids, n_sel, in_h, in_w, orig_h, orig_w, mask_threshold, exclusive, label,
+                    ld_label, (cudaStream_t)stream);
+}
+int msam_amg_filter_nms(const int32_t* boxes_xyxy, const float* iou_preds, const float* stability, int n, int use_filters,
+                        float pred_iou_thresh, float stability_thresh, float box_nms_thresh, const int32_t* crop_box_host,
+                        const int32_t* orig_box_host, int32_t* keep, int32_t* n_keep, void* stream) {
+  return post_filter_nms(boxes_xyxy, iou_preds, stability, n, use_filters, pred_iou_thresh, stability_thresh,
+                         box_nms_thresh, crop_box_host, orig_box_host, keep, n_keep, (cudaStream_t)stream);
+}
+
 static int sm_count() {
   static int n = 0;
   if (!n) {

@@ -61,6 +61,20 @@ struct Engine {
   int alloc_encoder_ws();
   int finalize_decoder();  // decoder.cu
   int encode(const uint8_t* u8, const float* f32, int B, int hh, int ww, float* out, cudaStream_t st);
+  int set_image_embedding(const float* feat, cudaStream_t st);  // decoder.cu
+  int decode(const float* points, const float* labels, int np, const float* boxes, int P, int multimask, float* low_res,
+             float* iou, cudaStream_t st);  // decoder.cu
 };
+
+// postprocess.cu
+int post_mask_stats(const float* low_res, int n, int in_h, int in_w, int out_h, int out_w, float thr, float off,
+                    int32_t* boxes, float* stability, int32_t* area, cudaStream_t st);
+int post_upsample(const float* low_res, const int32_t* sel, int n_sel, int in_h, int in_w, int out_h, int out_w, float thr,
+                  float* logits, uint8_t* bin, cudaStream_t st);
+int post_paint(const float* low_res, const int32_t* sel, const int32_t* boxes, const int32_t* seg_ids, int n_sel, int in_h,
+               int in_w, int out_h, int out_w, float thr, int exclusive, uint32_t* label, int ld_label, cudaStream_t st);
+int post_filter_nms(const int32_t* boxes, const float* scores, const float* stab, int n, int use_filters, float iou_thresh,
+                    float stab_thresh, float nms_thresh, const int32_t* crop_box, const int32_t* orig_box, int32_t* keep,
+                    int32_t* n_keep, cudaStream_t st);
 
 }  // namespace msam

@@ -31,8 +31,8 @@ struct GemmCfg {
 struct GemmParams {
   int M, N, K;
   const float* bias;      // [N] or null
-  const float* residual;  // fp32 [res_rows, ldr] or null; row index = row % res_rows
-  int res_rows, ldr;
+  const void* residual;   // fp32 (or bf16 if res_bf16) [res_rows, ldr] or null; row index = row % res_rows
+  int res_rows, ldr, res_bf16;
   void* out;              // bf16 or fp32 [M, ldc]
   int ldc;
   int out_fp32;
@@ -150,7 +150,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row = m_blk * GEMM_BM + quad * 32 + lane;
       const bool row_ok = row < p.M;
       const float* res_row = nullptr;
-      if (p.residual && row_ok) res_row = p.residual + (size_t)(row % p.res_rows) * p.ldr;
+      const __nv_bfloat16* res_row_bf = nullptr;
+      if (p.residual && row_ok) {
+        const size_t off = (size_t)(row % p.res_rows) * p.ldr;
+        if (p.res_bf16) res_row_bf = reinterpret_cast<const __nv_bfloat16*>(p.residual) + off;
+        else res_row = reinterpret_cast<const float*>(p.residual) + off;
+      }
 #pragma unroll 1
       for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
         const int col0 = n_blk * BN + half * COLS_PER_WARP + c * 32;
@@ -183,6 +188,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 32; j += 4) {
               const float4 r = *reinterpret_cast<const float4*>(res_row + col0 + j);
               f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
+            }
+          } else if (res_row_bf) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 r = *reinterpret_cast<const uint4*>(res_row_bf + col0 + j);
+              const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                f[j + 2 * q] += __uint_as_float(w[q] << 16);
+                f[j + 2 * q + 1] += __uint_as_float(w[q] & 0xffff0000u);
+              }
             }
           }
           if (p.out_fp32) {
@@ -232,6 +248,7 @@ static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.bias = a.bias;
   p.residual = a.residual;
+  p.res_bf16 = a.res_bf16;
   p.res_rows = a.res_rows > 0 ? a.res_rows : a.M;
   p.ldr = a.ldr > 0 ? a.ldr : a.N;
   p.out = a.out;

@@ -15,8 +15,8 @@ struct GemmArgs {
   const __nv_bfloat16* W = nullptr;  // [N, ldw]
   int M = 0, N = 0, K = 0, lda = 0, ldw = 0;
   const float* bias = nullptr;
-  const float* residual = nullptr;
-  int res_rows = 0, ldr = 0;
+  const void* residual = nullptr;   // fp32, or bf16 when res_bf16
+  int res_rows = 0, ldr = 0, res_bf16 = 0;
   void* out = nullptr;
   int ldc = 0;
   int out_fp32 = 0;
@@ -50,6 +50,7 @@ struct LnArgs {
   __nv_bfloat16* out = nullptr;  // bf16 [rows(or window-partitioned rows), D] (optional)
   float* out_f32 = nullptr;      // fp32 copy of the normalised rows (optional)
   int window_mode = 0, grid = 64, ws = 14;
+  int act = 0;                   // 1: exact GELU after the affine
   const float* add = nullptr;    // [add_rows, D] fp32 added after the affine for out2 (optional)
   int add_rows = 1;
   __nv_bfloat16* out2 = nullptr;

@@ -1,1 +1,341 @@
+// Mask post-processing of automatic mask generation / batched inference, without ever materialising the full
+// resolution logits: everything is recomputed from the 256x256 low-res logits.
+//   mask_stats   : Sam.postprocess_masks (bilinear 256->1024, crop, bilinear -> original size, align_corners=False)
+//                  fused with calculate_stability_score, thresholding, batched_mask_to_box and area
+//                  (instance_segmentation.py:229-255, inference.py:137-151, _vendored.py:33-85)
+//   upsample     : the same interpolation, materialised on request (predict_torch's `masks` output / rle export)
+//   filter_nms   : AMGBase._postprocess_batch (instance_segmentation.py:99-132): pred-IoU / stability / crop-edge
+//                  filters + torchvision-semantics greedy box NMS, one CTA
+//   paint        : mask_data_to_segmentation's painting loop (util.py:1799-1829)
 #include "engine.h"
+
+namespace msam {
+
+struct Interp {  // one axis of F.interpolate(mode="bilinear", align_corners=False)
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ Interp interp_axis(int dst, float scale, int in_size) {
+  float src = scale * ((float)dst + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  Interp r;
+  r.i0 = (int)src;
+  if (r.i0 > in_size - 1) r.i0 = in_size - 1;
+  r.i1 = r.i0 + ((r.i0 < in_size - 1) ? 1 : 0);
+  r.l1 = src - (float)r.i0;
+  r.l0 = 1.f - r.l1;
+  return r;
+}
+__device__ __forceinline__ float bilerp(float v00, float v01, float v10, float v11, const Interp& y, const Interp& x) {
+  return y.l0 * (x.l0 * v00 + x.l1 * v01) + y.l1 * (x.l0 * v10 + x.l1 * v11);
+}
+
+struct PostGeom {
+  int lr;              // low-res side (256)
+  int img;             // model input side (1024)
+  int in_h, in_w;      // input_size (resized image before padding)
+  int out_h, out_w;    // original_size
+  float s1;            // lr / img
+  float s2y, s2x;      // in_h / out_h, in_w / out_w
+  int identity2;       // second interpolation is the identity (in == out)
+};
+
+// stage 1 value at (Y, X) of the img x img grid
+__device__ __forceinline__ float stage1(const float* __restrict__ lr, const PostGeom& g, int Y, int X) {
+  const Interp iy = interp_axis(Y, g.s1, g.lr), ix = interp_axis(X, g.s1, g.lr);
+  const float* r0 = lr + iy.i0 * g.lr;
+  const float* r1 = lr + iy.i1 * g.lr;
+  return bilerp(__ldg(r0 + ix.i0), __ldg(r0 + ix.i1), __ldg(r1 + ix.i0), __ldg(r1 + ix.i1), iy, ix);
+}
+__device__ __forceinline__ float full_res(const float* __restrict__ lr, const PostGeom& g, int y, int x) {
+  if (g.identity2) return stage1(lr, g, y, x);
+  const Interp iy = interp_axis(y, g.s2y, g.in_h), ix = interp_axis(x, g.s2x, g.in_w);
+  return bilerp(stage1(lr, g, iy.i0, ix.i0), stage1(lr, g, iy.i0, ix.i1), stage1(lr, g, iy.i1, ix.i0),
+                stage1(lr, g, iy.i1, ix.i1), iy, ix);
+}
+
+// One CTA per mask.  stats: cnt(v > thr+off), cnt(v > thr-off), area = cnt(v > thr), bbox of (v > thr).
+__global__ void __launch_bounds__(256)
+mask_stats_kernel(const float* __restrict__ low_res, PostGeom g, float thr, float off, int32_t* __restrict__ boxes,
+                  float* __restrict__ stability, int32_t* __restrict__ area) {
+  const long mi = blockIdx.x;
+  const float* lr = low_res + mi * g.lr * g.lr;
+  int hi = 0, lo = 0, ar = 0, x0 = 1 << 30, y0 = 1 << 30, x1 = -1, y1 = -1;
+  const float t_hi = thr + off, t_lo = thr - off;
+  for (int y = threadIdx.x >> 5; y < g.out_h; y += 8) {
+    for (int x = threadIdx.x & 31; x < g.out_w; x += 32) {
+      const float v = full_res(lr, g, y, x);
+      hi += v > t_hi;
+      lo += v > t_lo;
+      if (v > thr) {
+        ++ar;
+        x0 = min(x0, x); x1 = max(x1, x); y0 = min(y0, y); y1 = max(y1, y);
+      }
+    }
+  }
+  __shared__ int red[7][8];
+  int vals[7] = {hi, lo, ar, x0, y0, x1, y1};
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    int v = vals[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int w = __shfl_xor_sync(0xffffffffu, v, o);
+      v = (k < 3) ? v + w : ((k == 3 || k == 4) ? min(v, w) : max(v, w));
+    }
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int r[7];
+    for (int k = 0; k < 7; ++k) {
+      int v = red[k][0];
+      for (int w = 1; w < 8; ++w) v = (k < 3) ? v + red[k][w] : ((k == 3 || k == 4) ? min(v, red[k][w]) : max(v, red[k][w]));
+      r[k] = v;
+    }
+    stability[mi] = (float)r[0] / (float)r[1];  // 0/0 -> NaN like torch; NaN fails ">= thresh" downstream
+    area[mi] = r[2];
+    const bool empty = r[2] == 0;
+    boxes[mi * 4 + 0] = empty ? 0 : r[3];
+    boxes[mi * 4 + 1] = empty ? 0 : r[4];
+    boxes[mi * 4 + 2] = empty ? 0 : r[5];
+    boxes[mi * 4 + 3] = empty ? 0 : r[6];
+  }
+}
+
+// Materialise selected masks: logits (fp32) and/or thresholded (uint8 0/1), each [n_sel, out_h, out_w].
+__global__ void upsample_kernel(const float* __restrict__ low_res, const int32_t* __restrict__ sel, PostGeom g,
+                                float thr, float* __restrict__ logits, uint8_t* __restrict__ bin) {
+  const long k = blockIdx.y;
+  const long mi = sel ? sel[k] : k;
+  const float* lr = low_res + mi * g.lr * g.lr;
+  const long npx = (long)g.out_h * g.out_w;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long)gridDim.x * blockDim.x) {
+    const int y = i / g.out_w, x = i % g.out_w;
+    const float v = full_res(lr, g, y, x);
+    if (logits) logits[k * npx + i] = v;
+    if (bin) bin[k * npx + i] = v > thr;
+  }
+}
+
+// Paint `n_sel` masks (given in painting order) into a uint32 label image at (oy, ox) offsets of a larger canvas.
+// exclusive = 1: the first mask covering a pixel wins (merge_exclusively=True); 0: the last one wins (AMG).
+__global__ void paint_kernel(const float* __restrict__ low_res, const int32_t* __restrict__ sel,
+                             const int32_t* __restrict__ boxes /*xyxy per mask id*/, const int32_t* __restrict__ seg_ids,
+                             int n_sel, PostGeom g, float thr, int exclusive, uint32_t* __restrict__ label, int ld_label) {
+  extern __shared__ int32_t sbox[];  // [n_sel][4]
+  for (int i = threadIdx.x; i < n_sel * 4; i += blockDim.x) sbox[i] = boxes[(long)sel[i / 4] * 4 + (i % 4)];
+  __syncthreads();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= g.out_w) return;
+  uint32_t lab = 0;
+  for (int k = 0; k < n_sel; ++k) {
+    if (x < sbox[4 * k] || x > sbox[4 * k + 2] || y < sbox[4 * k + 1] || y > sbox[4 * k + 3]) continue;
+    const float v = full_res(low_res + (long)sel[k] * g.lr * g.lr, g, y, x);
+    if (v > thr) {
+      lab = (uint32_t)seg_ids[k];
+      if (exclusive) break;
+    }
+  }
+  if (lab) label[(long)y * ld_label + x] = lab;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused AMG filter + greedy box NMS (single CTA, N <= NMS_MAX).  keep[] receives indices in descending-score order.
+constexpr int NMS_MAX = 8192;
+
+struct NmsParams {
+  int n;
+  float iou_thresh, stab_thresh, nms_thresh;
+  int use_filters;
+  float crop[4], orig[4];  // xyxy
+  float edge_atol;
+};
+
+__device__ __forceinline__ uint32_t orderable(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(1024)
+filter_nms_kernel(const int32_t* __restrict__ boxes, const float* __restrict__ scores, const float* __restrict__ stab,
+                  NmsParams p, int32_t* __restrict__ keep, int32_t* __restrict__ n_keep) {
+  extern __shared__ unsigned long long skey[];  // [npow2] sort keys, then reused
+  __shared__ int s_cnt, s_cur;
+  int npow2 = 1;
+  while (npow2 < p.n) npow2 <<= 1;
+  float* bx = reinterpret_cast<float*>(skey + npow2);  // [n][4] boxes in sorted order
+  uint8_t* alive = reinterpret_cast<uint8_t*>(bx + 4 * (size_t)p.n);
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  for (int i = tid; i < npow2; i += nt) {
+    unsigned long long key = 0;  // sorts last
+    if (i < p.n) {
+      bool ok = true;
+      const float b0 = (float)boxes[4 * i], b1 = (float)boxes[4 * i + 1], b2 = (float)boxes[4 * i + 2], b3 = (float)boxes[4 * i + 3];
+      if (p.use_filters) {
+        if (p.iou_thresh > 0.f) ok = ok && (scores[i] > p.iou_thresh);
+        if (p.stab_thresh > 0.f) ok = ok && (stab[i] >= p.stab_thresh);
+        // is_box_near_crop_edge: boxes are in crop coordinates
+        const float u[4] = {b0 + p.crop[0], b1 + p.crop[1], b2 + p.crop[0], b3 + p.crop[1]};
+        bool near = false;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const bool nc = fabsf(u[c] - p.crop[c]) <= p.edge_atol, ni = fabsf(u[c] - p.orig[c]) <= p.edge_atol;
+          near = near || (nc && !ni);
+        }
+        ok = ok && !near;
+      }
+      if (ok) key = ((unsigned long long)orderable(scores[i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
+    }
+    skey[i] = key;
+  }
+  __syncthreads();
+  // bitonic sort, descending
+  for (int k = 2; k <= npow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < npow2; i += nt) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = skey[i], b = skey[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? (a < b) : (a > b)) { skey[i] = b; skey[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) { s_cnt = 0; }
+  __syncthreads();
+  // candidates are the non-zero keys at the front
+  int ncand = 0;
+  {
+    int lo = 0, hi = p.n;  // keys are sorted descending; find the first zero key
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (skey[mid] != 0ull) lo = mid + 1; else hi = mid; }
+    ncand = lo;
+  }
+  for (int i = tid; i < ncand; i += nt) {
+    const int idx = (int)(0xFFFFFFFFu - (uint32_t)(skey[i] & 0xFFFFFFFFull));
+    bx[4 * i] = (float)boxes[4 * idx]; bx[4 * i + 1] = (float)boxes[4 * idx + 1];
+    bx[4 * i + 2] = (float)boxes[4 * idx + 2]; bx[4 * i + 3] = (float)boxes[4 * idx + 3];
+    alive[i] = 1;
+  }
+  __syncthreads();
+  int cur = 0;
+  while (true) {
+    // next alive candidate (all threads scan identically; alive[] only changes between barriers)
+    while (cur < ncand && !alive[cur]) ++cur;
+    if (cur >= ncand) break;
+    if (tid == 0) {
+      keep[s_cnt] = (int)(0xFFFFFFFFu - (uint32_t)(skey[cur] & 0xFFFFFFFFull));
+      ++s_cnt;
+    }
+    const float ax0 = bx[4 * cur], ay0 = bx[4 * cur + 1], ax1 = bx[4 * cur + 2], ay1 = bx[4 * cur + 3];
+    const float aarea = (ax1 - ax0) * (ay1 - ay0);
+    __syncthreads();  // everyone has read alive[cur] / bx before anyone updates alive[]
+    for (int j = cur + 1 + tid; j < ncand; j += nt) {
+      if (!alive[j]) continue;
+      const float xx0 = fmaxf(ax0, bx[4 * j]), yy0 = fmaxf(ay0, bx[4 * j + 1]);
+      const float xx1 = fminf(ax1, bx[4 * j + 2]), yy1 = fminf(ay1, bx[4 * j + 3]);
+      const float w = fmaxf(0.f, xx1 - xx0), h = fmaxf(0.f, yy1 - yy0);
+      const float inter = w * h;
+      const float barea = (bx[4 * j + 2] - bx[4 * j]) * (bx[4 * j + 3] - bx[4 * j + 1]);
+      const float ovr = inter / (aarea + barea - inter);
+      if (ovr > p.nms_thresh) alive[j] = 0;
+    }
+    ++cur;
+    __syncthreads();
+  }
+  __syncthreads();
+  if (tid == 0) *n_keep = s_cnt;
+  (void)s_cur;
+}
+
+#define LAUNCH_CHECK(name)                                                                        \
+  do {                                                                                            \
+    cudaError_t e_ = cudaGetLastError();                                                          \
+    if (e_ != cudaSuccess) return set_error(name " launch failed: %s", cudaGetErrorString(e_)); \
+    count_launch();                                                                               \
+  } while (0)
+
+static int make_geom(int in_h, int in_w, int out_h, int out_w, PostGeom* g) {
+  if (in_h <= 0 || in_w <= 0 || out_h <= 0 || out_w <= 0 || in_h > 1024 || in_w > 1024)
+    return set_error("postprocess: bad sizes input=(%d,%d) original=(%d,%d)", in_h, in_w, out_h, out_w);
+  g->lr = 256; g->img = 1024; g->in_h = in_h; g->in_w = in_w; g->out_h = out_h; g->out_w = out_w;
+  g->s1 = 256.f / 1024.f;
+  g->s2y = (float)in_h / (float)out_h;
+  g->s2x = (float)in_w / (float)out_w;
+  g->identity2 = (in_h == out_h && in_w == out_w);
+  return 0;
+}
+
+int post_mask_stats(const float* low_res, int n, int in_h, int in_w, int out_h, int out_w, float thr, float off,
+                    int32_t* boxes, float* stability, int32_t* area, cudaStream_t st) {
+  PostGeom g;
+  if (make_geom(in_h, in_w, out_h, out_w, &g)) return -1;
+  if (n <= 0) return 0;
+  mask_stats_kernel<<<n, 256, 0, st>>>(low_res, g, thr, off, boxes, stability, area);
+  LAUNCH_CHECK("mask_stats");
+  return 0;
+}
+
+int post_upsample(const float* low_res, const int32_t* sel, int n_sel, int in_h, int in_w, int out_h, int out_w, float thr,
+                  float* logits, uint8_t* bin, cudaStream_t st) {
+  PostGeom g;
+  if (make_geom(in_h, in_w, out_h, out_w, &g)) return -1;
+  if (n_sel <= 0) return 0;
+  const long npx = (long)out_h * out_w;
+  int bx = (int)((npx + 255) / 256);
+  if (bx > 1024) bx = 1024;
+  for (int k0 = 0; k0 < n_sel; k0 += 32768) {  // gridDim.y limit
+    const int nk = (n_sel - k0 < 32768) ? n_sel - k0 : 32768;
+    upsample_kernel<<<dim3(bx, nk), 256, 0, st>>>(low_res + (sel ? 0 : (long)k0 * 65536), sel ? sel + k0 : nullptr, g, thr,
+                                                  logits ? logits + (long)k0 * npx : nullptr, bin ? bin + (long)k0 * npx : nullptr);
+    LAUNCH_CHECK("upsample");
+  }
+  return 0;
+}
+
+int post_paint(const float* low_res, const int32_t* sel, const int32_t* boxes, const int32_t* seg_ids, int n_sel, int in_h,
+               int in_w, int out_h, int out_w, float thr, int exclusive, uint32_t* label, int ld_label, cudaStream_t st) {
+  PostGeom g;
+  if (make_geom(in_h, in_w, out_h, out_w, &g)) return -1;
+  if (n_sel <= 0) return 0;
+  if ((size_t)n_sel * 16 > 200 * 1024) return set_error("paint: too many masks (%d)", n_sel);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(paint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  paint_kernel<<<dim3((out_w + 255) / 256, out_h), 256, (size_t)n_sel * 16, st>>>(low_res, sel, boxes, seg_ids, n_sel, g, thr,
+                                                                                  exclusive, label, ld_label);
+  LAUNCH_CHECK("paint");
+  return 0;
+}
+
+int post_filter_nms(const int32_t* boxes, const float* scores, const float* stab, int n, int use_filters, float iou_thresh,
+                    float stab_thresh, float nms_thresh, const int32_t* crop_box, const int32_t* orig_box, int32_t* keep,
+                    int32_t* n_keep, cudaStream_t st) {
+  if (n > NMS_MAX) return set_error("filter_nms: n=%d exceeds %d", n, NMS_MAX);
+  if (n <= 0) {
+    cudaMemsetAsync(n_keep, 0, 4, st);
+    return 0;
+  }
+  NmsParams p;
+  p.n = n; p.iou_thresh = iou_thresh; p.stab_thresh = stab_thresh; p.nms_thresh = nms_thresh; p.use_filters = use_filters;
+  for (int i = 0; i < 4; ++i) { p.crop[i] = crop_box ? (float)crop_box[i] : 0.f; p.orig[i] = orig_box ? (float)orig_box[i] : 0.f; }
+  p.edge_atol = 20.f;
+  int npow2 = 1;
+  while (npow2 < n) npow2 <<= 1;
+  const size_t smem = (size_t)npow2 * 8 + (size_t)n * 16 + n + 16;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(filter_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr = true;
+  }
+  filter_nms_kernel<<<1, 1024, smem, st>>>(boxes, scores, stab, p, keep, n_keep);
+  LAUNCH_CHECK("filter_nms");
+  return 0;
+}
+
+}  // namespace msam

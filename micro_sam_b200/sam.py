@@ -1,0 +1,331 @@
+"""`Sam` / `SamPredictor` duck types backed by libmsam_b200.so (include/msam_b200.h).
+
+micro-sam never touches SAM internals except through the predictor object that `util.get_sam_model` returns
+(reference: micro_sam/util.py:460-476; attribute census in SURVEY.md 8b).  `B200SamPredictor` offers exactly that
+surface -- `set_image`, `set_torch_image`, `predict`, `predict_torch`, `get_image_embedding`, `reset_image`, the mutable
+`features / original_size / input_size / is_image_set` attributes, `transform`, `device`, `model` -- while every FLOP
+runs in the hand-written sm_100a kernels.  There is no PyTorch fallback: without the library / a B200 it raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+# micro_sam/models/build_sam.py:40-76
+ARCH = {
+    "vit_b": dict(embed_dim=768, depth=12, num_heads=12, global_attn_indexes=(2, 5, 8, 11)),
+    "vit_l": dict(embed_dim=1024, depth=24, num_heads=16, global_attn_indexes=(5, 11, 17, 23)),
+    "vit_h": dict(embed_dim=1280, depth=32, num_heads=16, global_attn_indexes=(7, 15, 23, 31)),
+    # tiny shapes for tests only
+    "vit_test": dict(embed_dim=128, depth=2, num_heads=2, global_attn_indexes=(1,)),
+    "vit_test80": dict(embed_dim=160, depth=2, num_heads=2, global_attn_indexes=(1,)),
+}
+_EMBED_TO_TYPE = {768: "vit_b", 1024: "vit_l", 1280: "vit_h", 128: "vit_test", 160: "vit_test80"}
+
+
+def validate_model_type(state: Dict[str, torch.Tensor]) -> str:
+    """micro_sam/models/build_sam.py:24-37."""
+    if "image_encoder.patch_embed.proj.weight" in state:
+        return _EMBED_TO_TYPE[state["image_encoder.patch_embed.proj.weight"].shape[0]]
+    return "vit_t"
+
+
+def get_preprocess_shape(oldh: int, oldw: int, long_side: int) -> Tuple[int, int]:
+    scale = long_side * 1.0 / max(oldh, oldw)
+    return int(oldh * scale + 0.5), int(oldw * scale + 0.5)
+
+
+class ResizeLongestSide:
+    """segment_anything.utils.transforms.ResizeLongestSide (host side; used at util.py:663, inference.py:227-233)."""
+
+    def __init__(self, target_length: int):
+        self.target_length = target_length
+
+    def apply_image(self, image: np.ndarray) -> np.ndarray:
+        th, tw = get_preprocess_shape(image.shape[0], image.shape[1], self.target_length)
+        if (th, tw) == tuple(image.shape[:2]):
+            return np.ascontiguousarray(image)
+        from PIL import Image  # same PIL bilinear(+antialias) uint8 resize the reference reaches via torchvision
+        return np.array(Image.fromarray(image).resize((tw, th), Image.BILINEAR))
+
+    def apply_coords(self, coords: np.ndarray, original_size: Tuple[int, ...]) -> np.ndarray:
+        old_h, old_w = original_size
+        new_h, new_w = get_preprocess_shape(old_h, old_w, self.target_length)
+        coords = np.array(coords, dtype=float, copy=True)
+        coords[..., 0] = coords[..., 0] * (new_w / old_w)
+        coords[..., 1] = coords[..., 1] * (new_h / old_h)
+        return coords
+
+    def apply_boxes(self, boxes: np.ndarray, original_size: Tuple[int, ...]) -> np.ndarray:
+        return self.apply_coords(np.asarray(boxes).reshape(-1, 2, 2), original_size).reshape(-1, 4)
+
+    def apply_coords_torch(self, coords: torch.Tensor, original_size) -> torch.Tensor:
+        old_h, old_w = original_size
+        new_h, new_w = get_preprocess_shape(old_h, old_w, self.target_length)
+        coords = coords.clone().to(torch.float)
+        coords[..., 0] = coords[..., 0] * (new_w / old_w)
+        coords[..., 1] = coords[..., 1] * (new_h / old_h)
+        return coords
+
+    def apply_boxes_torch(self, boxes: torch.Tensor, original_size) -> torch.Tensor:
+        return self.apply_coords_torch(boxes.reshape(-1, 2, 2), original_size).reshape(-1, 4)
+
+
+class _ImageEncoder:
+    """Callable stand-in for `sam.image_encoder`: (B,3,1024,1024) fp32 preprocessed -> (B,256,64,64) fp32."""
+
+    def __init__(self, sam: "B200Sam"):
+        self._sam = sam
+        self.img_size = sam.image_size
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        sam = self._sam
+        if x.ndim != 4 or x.shape[1] != 3 or x.shape[2] != self.img_size or x.shape[3] != self.img_size:
+            raise ValueError(f"image_encoder expects (B,3,{self.img_size},{self.img_size}), got {tuple(x.shape)}")
+        x = x.to(device=sam.device, dtype=torch.float32).contiguous()
+        out = torch.empty(x.shape[0], 256, 64, 64, device=sam.device, dtype=torch.float32)
+        _lib.check(_lib.lib().msam_encode_f32(sam._h, _lib.ptr(x), x.shape[0], _lib.ptr(out), _lib.cur_stream()))
+        return out
+
+
+class _PromptEncoder:
+    embed_dim = 256
+
+    def __init__(self, sam: "B200Sam"):
+        self._sam = sam
+        g = sam.image_size // 16
+        self.image_embedding_size = (g, g)
+        self.input_image_size = (sam.image_size, sam.image_size)
+
+
+class B200Sam:
+    """The model object (`predictor.model`).  Holds the upstream-keyed state dict (CPU) and the device engine."""
+
+    mask_threshold: float = 0.0
+    image_format: str = "RGB"
+
+    def __init__(self, model_type: str, state_dict: Dict[str, torch.Tensor], device="cuda", max_batch: int = 16,
+                 max_prompts: int = 256, image_size: int = 1024):
+        if model_type not in ARCH:
+            raise ValueError(f"unsupported model type {model_type!r} (have {sorted(ARCH)})")
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError(f"micro_sam_b200 runs on a CUDA (sm_100a) device only; got device={device!r}")
+        if not torch.cuda.is_available():
+            raise RuntimeError("micro_sam_b200: no CUDA device available and there is no CPU fallback")
+        self.model_type = model_type
+        self.image_size = image_size
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        a = ARCH[model_type]
+        L = _lib.lib()
+        ga = list(a["global_attn_indexes"]) + [-1] * (8 - len(a["global_attn_indexes"]))
+        cfg = _lib.MsamConfig(a["embed_dim"], a["depth"], a["num_heads"], (ctypes.c_int32 * 8)(*ga), 14, image_size, 16,
+                              256, max_batch, max_prompts)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(L.msam_create(ctypes.byref(cfg), self.device.index, ctypes.byref(self._h)))
+            self._state = {}
+            for k, v in state_dict.items():
+                v = v.detach().to("cpu", torch.float32).contiguous()
+                self._state[k] = v
+                shape = (ctypes.c_int64 * max(v.ndim, 1))(*v.shape)
+                _lib.check(L.msam_load_weight(self._h, k.encode(), ctypes.c_void_p(v.data_ptr()), shape, v.ndim))
+            _lib.check(L.msam_finalize_weights(self._h))
+        self.pixel_mean = torch.tensor([123.675, 116.28, 103.53], device=self.device).view(-1, 1, 1)
+        self.pixel_std = torch.tensor([58.395, 57.12, 57.375], device=self.device).view(-1, 1, 1)
+        self.image_encoder = _ImageEncoder(self)
+        self.prompt_encoder = _PromptEncoder(self)
+
+    # --- nn.Module-ish surface used by micro-sam
+    def state_dict(self):
+        return dict(self._state)
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("micro_sam_b200 models live on a CUDA device")
+        return self
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().msam_destroy(self._h)
+                self._h = None
+        except Exception:  # noqa: BLE001
+            pass
+
+    def preprocess(self, x: torch.Tensor) -> torch.Tensor:
+        """Sam.preprocess: normalise + zero-pad to image_size (trainable_sam.py:24-47)."""
+        x = (x.to(self.device, torch.float32) - self.pixel_mean) / self.pixel_std
+        h, w = x.shape[-2:]
+        return torch.nn.functional.pad(x, (0, self.image_size - w, 0, self.image_size - h))
+
+    def encode_u8(self, images_u8: torch.Tensor) -> torch.Tensor:
+        """Fused preprocess + encoder for a batch of already-resized uint8 HWC images [B,h,w,3] (h,w <= 1024)."""
+        x = images_u8.to(self.device).contiguous()
+        if x.dtype != torch.uint8 or x.ndim != 4 or x.shape[-1] != 3:
+            raise ValueError("encode_u8 expects uint8 [B,h,w,3]")
+        out = torch.empty(x.shape[0], 256, 64, 64, device=self.device, dtype=torch.float32)
+        _lib.check(_lib.lib().msam_encode_u8(self._h, _lib.ptr(x), x.shape[0], x.shape[1], x.shape[2], _lib.ptr(out),
+                                             _lib.cur_stream()))
+        return out
+
+    def postprocess_masks(self, masks: torch.Tensor, input_size, original_size) -> torch.Tensor:
+        """Sam.postprocess_masks on (P,M,256,256) low-res logits -> (P,M,H,W) logits."""
+        P, M = masks.shape[:2]
+        lr = masks.to(self.device, torch.float32).contiguous().view(P * M, 256, 256)
+        out = torch.empty(P * M, original_size[0], original_size[1], device=self.device, dtype=torch.float32)
+        _lib.check(_lib.lib().msam_upsample_masks(_lib.ptr(lr), None, P * M, int(input_size[0]), int(input_size[1]),
+                                                  int(original_size[0]), int(original_size[1]), self.mask_threshold,
+                                                  _lib.ptr(out), None, _lib.cur_stream()))
+        return out.view(P, M, original_size[0], original_size[1])
+
+
+class B200SamPredictor:
+    """Drop-in for segment_anything.SamPredictor."""
+
+    def __init__(self, sam_model: B200Sam):
+        self.model = sam_model
+        self.transform = ResizeLongestSide(sam_model.image_size)
+        self._bound_features = None
+        self.reset_image()
+
+    @property
+    def device(self):
+        return self.model.device
+
+    def reset_image(self) -> None:
+        self.is_image_set = False
+        self.features = None
+        self.orig_h = self.orig_w = self.input_h = self.input_w = None
+
+    @torch.no_grad()
+    def set_image(self, image: np.ndarray, image_format: str = "RGB") -> None:
+        if image.dtype != np.uint8 or image.ndim != 3 or image.shape[-1] != 3:
+            raise ValueError("set_image expects an HxWx3 uint8 image")
+        if image_format != self.model.image_format:
+            image = image[..., ::-1]
+        x = self.transform.apply_image(image)
+        self.reset_image()
+        self.original_size = tuple(image.shape[:2])
+        self.input_size = tuple(x.shape[:2])
+        self.features = self.model.encode_u8(torch.from_numpy(np.ascontiguousarray(x))[None])
+        self.is_image_set = True
+
+    @torch.no_grad()
+    def set_torch_image(self, transformed_image: torch.Tensor, original_image_size: Tuple[int, ...]) -> None:
+        self.reset_image()
+        self.original_size = tuple(original_image_size)
+        self.input_size = tuple(transformed_image.shape[-2:])
+        self.features = self.model.image_encoder(self.model.preprocess(transformed_image))
+        self.is_image_set = True
+
+    def get_image_embedding(self) -> torch.Tensor:
+        if not self.is_image_set:
+            raise RuntimeError("An image must be set with .set_image(...) to generate an embedding.")
+        return self.features
+
+    # -- the engine caches prompt-independent decoder state per bound embedding; re-bind when `features` was reassigned
+    def _bind_features(self) -> None:
+        f = self.features
+        if f is None:
+            raise RuntimeError("An image must be set with .set_image(...) before mask prediction.")
+        key = (f.data_ptr(), f._version, tuple(f.shape))
+        if self._bound_features != key:
+            feat = f.to(self.device, torch.float32).contiguous()
+            if feat.numel() != 256 * 64 * 64:
+                raise ValueError(f"features must have shape (1,256,64,64), got {tuple(f.shape)}")
+            _lib.check(_lib.lib().msam_set_image_embedding(self.model._h, _lib.ptr(feat), _lib.cur_stream()))
+            self._bound_features = key
+            self._bound_tensor = feat  # keep alive
+
+    @torch.no_grad()
+    def decode_low_res(self, point_coords: Optional[torch.Tensor], point_labels: Optional[torch.Tensor],
+                       boxes: Optional[torch.Tensor] = None, multimask_output: bool = True):
+        """prompt_encoder + mask_decoder only: (low_res (P,M,256,256), iou (P,M)).  The hot AMG / batched-inference path
+        stops here and post-processes with msam_mask_stats instead of materialising (P,M,H,W) logits."""
+        if not self.is_image_set:
+            raise RuntimeError("An image must be set with .set_image(...) before mask prediction.")
+        self._bind_features()
+        dev = self.device
+        pts = lbl = bx = None
+        np_ = 0
+        if point_coords is not None:
+            if point_labels is None:
+                raise ValueError("point_labels must be supplied with point_coords")
+            pts = point_coords.to(dev, torch.float32).contiguous()
+            lbl = point_labels.to(dev, torch.float32).contiguous()
+            P, np_ = pts.shape[0], pts.shape[1]
+        if boxes is not None:
+            bx = boxes.to(dev, torch.float32).reshape(-1, 4).contiguous()
+            P = bx.shape[0]
+        if pts is None and bx is None:
+            raise ValueError("predict_torch needs point and/or box prompts (mask-only prompts are not supported)")
+        M = 3 if multimask_output else 1
+        low = torch.empty(P, M, 256, 256, device=dev, dtype=torch.float32)
+        iou = torch.empty(P, M, device=dev, dtype=torch.float32)
+        _lib.check(_lib.lib().msam_decode(self.model._h, _lib.ptr(pts), _lib.ptr(lbl), np_, _lib.ptr(bx), P,
+                                          int(multimask_output), _lib.ptr(low), _lib.ptr(iou), _lib.cur_stream()))
+        return low, iou
+
+    @torch.no_grad()
+    def predict_torch(self, point_coords, point_labels, boxes=None, mask_input=None, multimask_output: bool = True,
+                      return_logits: bool = False):
+        if mask_input is not None:
+            raise NotImplementedError("mask_input prompts are not supported by the B200 decoder yet")
+        low, iou = self.decode_low_res(point_coords, point_labels, boxes, multimask_output)
+        P, M = low.shape[:2]
+        H, W = self.original_size
+        lr = low.view(P * M, 256, 256)
+        if return_logits:
+            masks = torch.empty(P * M, H, W, device=self.device, dtype=torch.float32)
+            args = (_lib.ptr(masks), None)
+        else:
+            masks = torch.empty(P * M, H, W, device=self.device, dtype=torch.uint8)
+            args = (None, _lib.ptr(masks))
+        _lib.check(_lib.lib().msam_upsample_masks(_lib.ptr(lr), None, P * M, int(self.input_size[0]), int(self.input_size[1]),
+                                                  int(H), int(W), self.model.mask_threshold, *args, _lib.cur_stream()))
+        masks = masks.view(P, M, H, W)
+        if not return_logits:
+            masks = masks.bool()
+        return masks, iou, low
+
+    def predict(self, point_coords=None, point_labels=None, box=None, mask_input=None, multimask_output=True,
+                return_logits=False):
+        if not self.is_image_set:
+            raise RuntimeError("An image must be set with .set_image(...) before mask prediction.")
+        coords_t = labels_t = box_t = None
+        if point_coords is not None:
+            pc = self.transform.apply_coords(point_coords, self.original_size)
+            coords_t = torch.as_tensor(pc, dtype=torch.float, device=self.device)[None]
+            labels_t = torch.as_tensor(point_labels, dtype=torch.int, device=self.device)[None]
+        if box is not None:
+            box_t = torch.as_tensor(self.transform.apply_boxes(box, self.original_size), dtype=torch.float,
+                                    device=self.device).reshape(1, 4)
+        m, s, l = self.predict_torch(coords_t, labels_t, box_t, mask_input, multimask_output, return_logits)
+        return m[0].cpu().numpy(), s[0].cpu().numpy(), l[0].cpu().numpy()
+
+
+def mask_stats(low_res: torch.Tensor, input_size, original_size, mask_threshold: float = 0.0,
+               stability_offset: float = 1.0):
+    """Fused postprocess_masks + stability score + threshold + box + area on (N,256,256) low-res logits.
+    Returns (boxes int32 [N,4] xyxy, stability fp32 [N], area int32 [N]) on the device of `low_res`."""
+    lr = low_res.reshape(-1, 256, 256)
+    if not lr.is_cuda:
+        raise RuntimeError("mask_stats needs CUDA tensors")
+    lr = lr.to(torch.float32).contiguous()
+    n = lr.shape[0]
+    boxes = torch.empty(n, 4, device=lr.device, dtype=torch.int32)
+    stab = torch.empty(n, device=lr.device, dtype=torch.float32)
+    area = torch.empty(n, device=lr.device, dtype=torch.int32)
+    _lib.check(_lib.lib().msam_mask_stats(_lib.ptr(lr), n, int(input_size[0]), int(input_size[1]), int(original_size[0]),
+                                          int(original_size[1]), float(mask_threshold), float(stability_offset),
+                                          _lib.ptr(boxes), _lib.ptr(stab), _lib.ptr(area), _lib.cur_stream()))
+    return boxes, stab, area

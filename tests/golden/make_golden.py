@@ -1,0 +1,112 @@
+"""Generates tests/golden/*.npz by EXECUTING THE REFERENCE's own code in this container (run once here; the GPU box has
+no /root/reference).  Third-party imports the reference needs but this image lacks are stubbed only where the stubbed
+symbol is not on the executed path:
+  * micro_sam/_vendored.py is imported whole with a stub `bioimage_cpp.utils.compute_rle` (the numpy RLE implementation
+    of the same file, _vendored.py:104, is the one exercised: rle_implementation="numpy");
+  * micro_sam/util.py cannot be imported (zarr/elf/pooch/...), so the *source text* of the listed functions is extracted
+    with `ast` and exec'ed unchanged: _to_image, _overlap_matrix, _calculate_ious_between_pred_masks,
+    _calculate_iomin_between_pred_masks, _batched_mask_nms.
+Usage:  python tests/golden/make_golden.py
+"""
+import ast
+import importlib.util
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+
+REF = "/root/reference/micro_sam"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def load_vendored():
+    stub = types.ModuleType("bioimage_cpp")
+    stub.utils = types.ModuleType("bioimage_cpp.utils")
+    stub.utils.compute_rle = lambda mask: (_ for _ in ()).throw(RuntimeError("stub: bioimage_cpp not available"))
+    sys.modules["bioimage_cpp"] = stub
+    sys.modules["bioimage_cpp.utils"] = stub.utils
+    spec = importlib.util.spec_from_file_location("ref_vendored", os.path.join(REF, "_vendored.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def load_util_functions(names):
+    src = open(os.path.join(REF, "util.py")).read()
+    tree = ast.parse(src)
+    ns = {"np": np, "torch": torch, "warnings": warnings}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "util.py", "exec"), ns)
+    missing = [n for n in names if n not in ns]
+    assert not missing, missing
+    return ns
+
+
+def blobs(rng, n, h, w):
+    yy, xx = np.mgrid[:h, :w]
+    out = np.zeros((n, h, w), dtype=bool)
+    for i in range(n):
+        for _ in range(rng.integers(1, 4)):
+            cy, cx, r = rng.integers(0, h), rng.integers(0, w), rng.integers(2, max(3, min(h, w) // 3))
+            out[i] |= (yy - cy) ** 2 + (xx - cx) ** 2 < r * r
+    return out
+
+
+def main():
+    rng = np.random.default_rng(0)
+    ven = load_vendored()
+    res = {}
+    # --- batched_mask_to_box + mask_to_rle_pytorch (numpy implementation) on random blob masks, incl. empty / full
+    for tag, (n, h, w) in {"a": (6, 128, 256), "b": (5, 37, 53), "c": (4, 64, 64)}.items():
+        m = blobs(rng, n, h, w)
+        m[0] = False
+        m[1] = True
+        t = torch.from_numpy(m)
+        res[f"masks_{tag}"] = np.packbits(m, axis=-1)
+        res[f"shape_{tag}"] = np.array([n, h, w])
+        res[f"boxes_{tag}"] = ven.batched_mask_to_box(t).numpy()
+        rles = ven.mask_to_rle_pytorch(t, rle_implementation="numpy")
+        res[f"rle_counts_{tag}"] = np.concatenate([np.asarray(r["counts"], dtype=np.int64) for r in rles])
+        res[f"rle_lens_{tag}"] = np.array([len(r["counts"]) for r in rles])
+    np.savez_compressed(os.path.join(OUT, "vendored.npz"), **res)
+
+    fns = load_util_functions(["_to_image", "_overlap_matrix", "_calculate_ious_between_pred_masks",
+                               "_calculate_iomin_between_pred_masks", "_batched_mask_nms"])
+    res = {}
+    # --- _to_image
+    imgs = {
+        "gray_f32": rng.normal(100, 30, (40, 50)).astype("float32"),
+        "gray_u16": rng.integers(0, 60000, (33, 47)).astype("uint16"),
+        "one_ch": rng.random((20, 30, 1)).astype("float64"),
+        "two_ch": rng.integers(0, 255, (25, 25, 2)).astype("uint8"),
+        "rgb_u8": rng.integers(0, 255, (31, 29, 3)).astype("uint8"),
+        "const": np.full((16, 16), 7.0, dtype="float32"),
+    }
+    for k, v in imgs.items():
+        res[f"in_{k}"] = v
+        res[f"out_{k}"] = fns["_to_image"](v)
+    # --- mask NMS (IoU and IoMin), greedy order incl. ties
+    m = blobs(rng, 24, 64, 64)
+    m[5] = m[4]                      # exact duplicate
+    m[7] = m[6] & (rng.random((64, 64)) > 0.02)  # near duplicate
+    masks = torch.from_numpy(m)
+    boxes = ven.batched_mask_to_box(masks)
+    scores = torch.from_numpy(rng.random(24).astype("float32"))
+    scores[5] = scores[4]
+    res["nms_masks"] = np.packbits(m, axis=-1)
+    res["nms_boxes"] = boxes.numpy()
+    res["nms_scores"] = scores.numpy()
+    for thr in (0.3, 0.9):
+        res[f"nms_keep_iou_{thr}"] = fns["_batched_mask_nms"](masks, boxes, scores, thr, False).numpy()
+        res[f"nms_keep_iomin_{thr}"] = fns["_batched_mask_nms"](masks, boxes, scores, thr, True).numpy()
+    res["nms_iou_matrix"] = fns["_calculate_ious_between_pred_masks"](masks, boxes).numpy()
+    np.savez_compressed(os.path.join(OUT, "util.npz"), **res)
+    print("written", os.listdir(OUT))
+
+
+if __name__ == "__main__":
+    main()

@@ -240,7 +240,121 @@ def sec_encoder(types=("vit_test", "vit_test80")):
         L.msam_destroy(h)
 
 
-SECTIONS = {"gemm": sec_gemm, "ln": sec_ln, "attn": sec_attn, "encoder": sec_encoder}
+
+
+# ------------------------------------------------------------------------------------------------ decoder & post
+def _predictors(mt, seed=1):
+    from oracle import sam_ref
+    from micro_sam_b200.sam import B200Sam, B200SamPredictor
+    sd = sam_ref.seeded_state_dict(mt, seed=seed)
+    osam = sam_ref.build_sam(mt)
+    osam.load_state_dict(sd)
+    bsam = B200Sam(mt, sd, max_batch=2, max_prompts=64)
+    return sam_ref.SamPredictor(osam), B200SamPredictor(bsam)
+
+
+def sec_decoder(types=("vit_test",)):
+    for mt in types:
+        op, bp = _predictors(mt)
+        torch.manual_seed(0)
+        feat = torch.randn(1, 256, 64, 64)
+        for pr in (op, bp):
+            pr.features = feat.clone() if pr is op else feat.to(DEV)
+            pr.is_image_set = True
+            pr.original_size = pr.input_size = (1024, 1024)
+        g = torch.Generator().manual_seed(3)
+        pts = torch.rand(70, 1, 2, generator=g) * 1024
+        lbl = torch.ones(70, 1, dtype=torch.int)
+        _, iou_r, low_r = op.predict_torch(pts, lbl, multimask_output=True, return_logits=True)
+        low, iou = bp.decode_low_res(pts, lbl, None, True)
+        torch.cuda.synchronize()
+        report(f"decoder {mt} points multimask: low_res", low.cpu(), low_r, 3e-2)
+        report(f"decoder {mt} points multimask: iou", iou.cpu(), iou_r, 3e-2)
+        agree = ((low.cpu() > 0) == (low_r > 0)).float().mean()
+        print(f"      mask sign agreement {agree:.5f}", flush=True)
+        boxes = torch.tensor([[100.0, 120.0, 300.0, 400.0], [10.0, 20.0, 1000.0, 900.0], [500, 500, 600, 640.0]])
+        _, iou_r, low_r = op.predict_torch(None, None, boxes=boxes, multimask_output=False, return_logits=True)
+        low, iou = bp.decode_low_res(None, None, boxes, False)
+        report(f"decoder {mt} boxes single: low_res", low.cpu(), low_r, 3e-2)
+        report(f"decoder {mt} boxes single: iou", iou.cpu(), iou_r, 3e-2)
+        # box + 2 points
+        pts2 = torch.rand(3, 2, 2, generator=g) * 1024
+        lbl2 = torch.tensor([[1, 0], [1, 1], [0, 1]], dtype=torch.int)
+        _, iou_r, low_r = op.predict_torch(pts2, lbl2, boxes=boxes, multimask_output=True, return_logits=True)
+        low, iou = bp.decode_low_res(pts2, lbl2, boxes, True)
+        report(f"decoder {mt} box+2pts multimask: low_res", low.cpu(), low_r, 3e-2)
+        report(f"decoder {mt} box+2pts multimask: iou", iou.cpu(), iou_r, 3e-2)
+
+
+def sec_post():
+    from oracle import sam_ref
+    from micro_sam_b200 import sam as bsam
+    L = _lib.lib()
+    osam = sam_ref.build_sam("vit_test")
+    g = torch.Generator().manual_seed(5)
+    # smooth random low-res logits with both signs
+    low = torch.nn.functional.interpolate(torch.randn(12, 1, 16, 16, generator=g), (256, 256), mode="bicubic")[:, 0] * 3
+    low[3] = -5.0  # empty mask
+    low[4] = 5.0   # full mask
+    for (inp, orig) in (((1024, 1024), (1024, 1024)), ((1024, 683), (768, 512)), ((640, 1024), (500, 800))):
+        ref_full = osam.postprocess_masks(low[:, None], inp, orig)[:, 0]
+        boxes, stab, area = bsam.mask_stats(low.to(DEV), inp, orig, 0.0, 1.0)
+        full = torch.empty(12, orig[0], orig[1], device=DEV)
+        binm = torch.empty(12, orig[0], orig[1], device=DEV, dtype=torch.uint8)
+        _lib.check(L.msam_upsample_masks(_lib.ptr(low.to(DEV).contiguous()), None, 12, inp[0], inp[1], orig[0], orig[1], 0.0,
+                                         _lib.ptr(full), _lib.ptr(binm), _lib.cur_stream()))
+        torch.cuda.synchronize()
+        report(f"postprocess_masks {inp}->{orig}", full.cpu(), ref_full, 1e-5)
+        rb = ref_full > 0
+        mism = (binm.cpu().bool() != rb).sum().item()
+        inter = (ref_full > 1.0).flatten(1).sum(1).float()
+        union = (ref_full > -1.0).flatten(1).sum(1).float()
+        ok_area = bool((area.cpu() == rb.flatten(1).sum(1)).all()) or mism > 0
+        print(f"      binary mismatches={mism} area_equal={bool((area.cpu() == rb.flatten(1).sum(1)).all())} "
+              f"stab max diff={(stab.cpu() - inter / union).nan_to_num(0).abs().max():.2e}", flush=True)
+        # integer stages bit-exact GIVEN the GPU masks: boxes / area recomputed by the oracle from the GPU binary masks
+        from oracle import amg_ref
+        ref_boxes = amg_ref.batched_mask_to_box(binm.cpu().bool())
+        okb = bool((ref_boxes.to(torch.int32) == boxes.cpu()).all()) and bool((area.cpu() == binm.cpu().flatten(1).sum(1)).all())
+        RESULTS.append(okb)
+        print(f"[{'OK ' if okb else 'BAD'}] mask_stats boxes/area bit-exact vs oracle on GPU masks {inp}->{orig}", flush=True)
+
+
+def sec_nms():
+    import torchvision
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(7)
+    for n in (1, 5, 300, 3072):
+        xy = torch.randint(0, 900, (n, 2), generator=g)
+        wh = torch.randint(1, 200, (n, 2), generator=g)
+        boxes = torch.cat([xy, torch.minimum(xy + wh, torch.tensor(1023))], 1).to(torch.int32)
+        boxes[: n // 3] = boxes[n // 3: 2 * (n // 3)]  # many duplicates / heavy overlaps
+        boxes[: n // 3, 2:] += torch.randint(0, 4, (n // 3, 2), generator=g).to(torch.int32)
+        scores = torch.rand(n, generator=g)
+        stab = torch.rand(n, generator=g) * 0.2 + 0.85
+        keep = torch.empty(n, dtype=torch.int32, device=DEV)
+        nk = torch.zeros(1, dtype=torch.int32, device=DEV)
+        import ctypes
+        crop = (ctypes.c_int32 * 4)(0, 0, 1024, 1024)
+        for use_f in (0, 1):
+            _lib.check(L.msam_amg_filter_nms(_lib.ptr(boxes.to(DEV)), _lib.ptr(scores.to(DEV)), _lib.ptr(stab.to(DEV)), n, use_f,
+                                             0.5, 0.9, 0.7, crop, crop, _lib.ptr(keep), _lib.ptr(nk), _lib.cur_stream()))
+            torch.cuda.synchronize()
+            got = keep[: int(nk.item())].cpu().long()
+            if use_f:
+                from oracle import amg_ref
+                m = (scores > 0.5) & (stab >= 0.9) & ~amg_ref.is_box_near_crop_edge(boxes, [0, 0, 1024, 1024], [0, 0, 1024, 1024])
+                idx = m.nonzero()[:, 0]
+            else:
+                idx = torch.arange(n)
+            ref = idx[torchvision.ops.nms(boxes[idx].float(), scores[idx], 0.7)]
+            ok = got.tolist() == ref.tolist()
+            RESULTS.append(ok)
+            print(f"[{'OK ' if ok else 'BAD'}] filter_nms n={n} filters={use_f}: kept {len(got)} (ref {len(ref)})", flush=True)
+
+
+SECTIONS = {"gemm": sec_gemm, "ln": sec_ln, "attn": sec_attn, "encoder": sec_encoder, "decoder": sec_decoder,
+            "post": sec_post, "nms": sec_nms}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(SECTIONS)
