@@ -34,6 +34,12 @@ const char* msam_last_error(void);
 /* number of CUDA kernels this library has launched from the calling thread since load */
 int64_t msam_launch_count(void);
 
+/* bench instrumentation: when enabled, CUDA events are recorded on the launching stream around every GEMM / attention
+ * launch; msam_profile_summary synchronises and returns {ms, algorithmic flops, launches} per category
+ * (0 = tcgen05 GEMM, 1 = encoder attention) in out[6]. */
+int msam_profile(int enable);
+int msam_profile_summary(double* out);
+
 /* util.get_sam_model (util.py:441-458): build the model on `device`. */
 int msam_create(const msam_config* cfg, int device, msam_handle** out);
 int msam_destroy(msam_handle* h);

@@ -52,6 +52,8 @@ def lib() -> ctypes.CDLL:
                                  c_void_p, c_int, c_void_p]
         L.msam_amg_filter_nms.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float,
                                           POINTER(c_int32), POINTER(c_int32), c_void_p, c_void_p, c_void_p]
+        L.msam_profile.argtypes = [c_int]
+        L.msam_profile_summary.argtypes = [POINTER(ctypes.c_double)]
         _lib = L
     return _lib
 

@@ -418,7 +418,10 @@ static int launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
   p.grid = a.grid;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   dim3 grid(C::NKT, a.heads, groups);
+  // algorithmic FLOPs: QK^T + PV over the G keys of each group (+ the rel-pos dot products)
+  prof_begin(stream, PROF_ATTN, (double)groups * a.heads * (4.0 * C::G * C::G * D + 4.0 * C::G * S * D));
   attn_kernel<D, S><<<grid, ATT_THREADS, C::SMEM_BYTES, stream>>>(tmQKV, tmRT, p);
+  prof_end(stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("attention launch failed: %s", cudaGetErrorString(e));
   count_launch();

@@ -20,6 +20,24 @@ int set_error(const char* fmt, ...) {
 }
 void count_launch() { ++g_launches; }
 
+struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+void prof_begin(cudaStream_t st, int cat, double work) {
+  if (!g_prof_on) return;
+  ProfRec r;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  r.cat = cat;
+  r.work = work;
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t st) {
+  if (!g_prof_on || g_prof.empty()) return;
+  cudaEventRecord(g_prof.back().b, st);
+}
+
 // ------------------------------------------------------------------------------------------------ tensor maps
 PFN_encodeTiled get_encode_tiled() {
   static PFN_encodeTiled fn = nullptr;
@@ -290,6 +308,27 @@ extern "C" {
 
 const char* msam_last_error(void) { return g_err; }
 int64_t msam_launch_count(void) { return g_launches; }
+
+int msam_profile(int enable) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on = enable != 0;
+  return 0;
+}
+// out[3*cat + 0] = total ms, [3*cat + 1] = total work, [3*cat + 2] = launches.  Synchronises the device.
+int msam_profile_summary(double* out) {
+  if (!out) return set_error("msam_profile_summary: null argument");
+  if (cudaDeviceSynchronize() != cudaSuccess) return set_error("profile: %s", cudaGetErrorString(cudaGetLastError()));
+  for (int i = 0; i < 3 * PROF_NCAT; ++i) out[i] = 0.0;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+    out[3 * r.cat] += ms;
+    out[3 * r.cat + 1] += r.work;
+    out[3 * r.cat + 2] += 1.0;
+  }
+  return 0;
+}
 
 int msam_create(const msam_config* cfg, int device, msam_handle** out) {
   if (!cfg || !out) return set_error("msam_create: null argument");

@@ -9,6 +9,11 @@ namespace msam {
 int set_error(const char* fmt, ...);  // records msam_last_error(); returns -1
 void count_launch();                  // per-thread launch counter (msam_launch_count)
 
+// Optional per-kernel timing (bench.py roofline): CUDA events recorded on the launching stream around a launch.
+enum ProfCat { PROF_GEMM = 0, PROF_ATTN = 1, PROF_NCAT = 2 };
+void prof_begin(cudaStream_t st, int cat, double work);  // work = algorithmic FLOPs (or bytes) of the launch
+void prof_end(cudaStream_t st);
+
 // ---- gemm.cu :  out[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual[row % res_rows])
 struct GemmArgs {
   const __nv_bfloat16* A = nullptr;  // [M, lda]

@@ -1,0 +1,268 @@
+"""Automatic mask generation (AMG) with the reference's class surface and initialize/generate split
+(micro_sam/instance_segmentation.py:65-680), re-expressed so that no full-resolution logit, bool mask or RLE ever leaves
+the GPU unless asked for:
+
+* initialize(): encoder -> decoder over the point grid -> `msam_mask_stats` (fused upsample + stability + threshold + box
+  + area).  The per-crop state keeps the 256x256 low-res logits on the device instead of CPU RLEs (the reference's
+  `_to_mask_data` D2H-copies every mask for CPU RLE, instance_segmentation.py:229-255).
+* generate(): `msam_amg_filter_nms` (pred-IoU / stability / crop-edge filters + box NMS, one kernel) -> survivors are
+  painted straight from their low-res logits (`msam_paint`), then connected components / background removal / relabel
+  on the host like the reference (util.py:1831-1848).  RLEs / binary masks are produced lazily for the survivors only.
+"""
+from __future__ import annotations
+
+import ctypes
+from abc import ABC
+from typing import Any, Callable, Dict, List, Optional, Union
+
+import numpy as np
+import torch
+
+from . import _amg_utils as amg_utils
+from . import _lib, util
+from .sam import mask_stats
+
+DEFAULT_SEGMENTATION_MODE_WITH_DECODER = "ais"
+
+
+class AMGBase(ABC):
+    """instance_segmentation.py:65-285."""
+
+    def __init__(self):
+        self._is_initialized = False
+        self._crop_list = None
+        self._crop_boxes = None
+        self._original_size = None
+
+    @property
+    def is_initialized(self):
+        return self._is_initialized
+
+    @property
+    def crop_list(self):
+        return self._crop_list
+
+    @property
+    def crop_boxes(self):
+        return self._crop_boxes
+
+    @property
+    def original_size(self):
+        return self._original_size
+
+    # ---- device-side equivalents of _postprocess_batch (instance_segmentation.py:99-144)
+    def _filter_nms(self, data, crop_box, original_size, pred_iou_thresh, stability_score_thresh, box_nms_thresh):
+        orig_h, orig_w = original_size
+        n = int(data["iou_preds"].shape[0])
+        dev = data["iou_preds"].device
+        keep = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        n_keep = torch.zeros(1, dtype=torch.int32, device=dev)
+        crop = (ctypes.c_int32 * 4)(*[int(c) for c in crop_box])
+        orig = (ctypes.c_int32 * 4)(0, 0, int(orig_w), int(orig_h))
+        _lib.check(_lib.lib().msam_amg_filter_nms(
+            _lib.ptr(data["boxes"]), _lib.ptr(data["iou_preds"]), _lib.ptr(data["stability_score"]), n, 1,
+            float(pred_iou_thresh), float(stability_score_thresh), float(box_nms_thresh), crop, orig, _lib.ptr(keep),
+            _lib.ptr(n_keep), _lib.cur_stream()))
+        self._last_n_keep = int(n_keep.item())
+        return keep[: self._last_n_keep].long()
+
+    def _records(self, data, keep, crop_box, output_mode, geom):
+        """Annotation dicts for the kept masks (instance_segmentation.py:188-227)."""
+        x0, y0 = int(crop_box[0]), int(crop_box[1])
+        boxes = data["boxes"][keep].cpu().numpy().astype(np.int64) + np.array([x0, y0, x0, y0])
+        iou = data["iou_preds"][keep].cpu().numpy()
+        stab = data["stability_score"][keep].cpu().numpy()
+        area = data["area"][keep].cpu().numpy()
+        pts = data["points"][keep.cpu()].numpy() + np.array([x0, y0]) if "points" in data else None
+        segs = None
+        if output_mode in ("binary_mask", "rle", "coco_rle"):
+            H, W = geom["orig"]
+            sel = keep.to(torch.int32).contiguous()
+            binm = torch.empty(len(keep), H, W, dtype=torch.uint8, device=sel.device)
+            _lib.check(_lib.lib().msam_upsample_masks(_lib.ptr(data["low_res"]), _lib.ptr(sel), len(keep), geom["inp"][0],
+                                                      geom["inp"][1], H, W, 0.0, None, _lib.ptr(binm), _lib.cur_stream()))
+            segs = binm.cpu().numpy().astype(bool)
+            if output_mode != "binary_mask":
+                segs = amg_utils.mask_to_rle(segs)
+        anns = []
+        for k in range(len(keep)):
+            ann = {
+                "segmentation": None if segs is None else segs[k],
+                "area": int(area[k]),
+                "bbox": amg_utils.box_xyxy_to_xywh(boxes[k]).tolist(),
+                "predicted_iou": float(iou[k]),
+                "stability_score": float(stab[k]),
+                "crop_box": amg_utils.box_xyxy_to_xywh(list(crop_box)),
+            }
+            if pts is not None:
+                ann["point_coords"] = [pts[k].tolist()]
+            anns.append(ann)
+        return anns
+
+    def get_state(self) -> Dict[str, Any]:
+        if not self.is_initialized:
+            raise RuntimeError("The state has not been computed yet. Call initialize first.")
+        return {"crop_list": self.crop_list, "crop_boxes": self.crop_boxes, "original_size": self.original_size}
+
+    def set_state(self, state: Dict[str, Any]) -> None:
+        self._crop_list = state["crop_list"]
+        self._crop_boxes = state["crop_boxes"]
+        self._original_size = state["original_size"]
+        self._is_initialized = True
+
+    def clear_state(self):
+        self._crop_list = None
+        self._crop_boxes = None
+        self._original_size = None
+        self._is_initialized = False
+
+
+class AutomaticMaskGenerator(AMGBase):
+    """instance_segmentation.py:288-530.  Same constructor / initialize / generate signatures."""
+
+    def __init__(self, predictor, points_per_side: Optional[int] = 32, points_per_batch: Optional[int] = None,
+                 crop_n_layers: int = 0, crop_overlap_ratio: float = 512 / 1500,
+                 crop_n_points_downscale_factor: int = 1, point_grids: Optional[List[np.ndarray]] = None,
+                 stability_score_offset: float = 1.0):
+        super().__init__()
+        if points_per_side is not None:
+            self.point_grids = amg_utils.build_all_layer_point_grids(points_per_side, crop_n_layers,
+                                                                     crop_n_points_downscale_factor)
+        elif point_grids is not None:
+            self.point_grids = point_grids
+        else:
+            raise ValueError("Can't have both points_per_side and point_grid be None or not None.")
+        if crop_n_layers != 0:
+            raise NotImplementedError("crop_n_layers > 0 is not implemented on the B200 path (default is 0)")
+        self._predictor = predictor
+        self._points_per_side = points_per_side
+        # the whole grid fits one decoder launch sequence; the engine chunks internally by its max_prompts
+        self._points_per_batch = 1024 if points_per_batch is None else points_per_batch
+        self._crop_n_layers = crop_n_layers
+        self._crop_overlap_ratio = crop_overlap_ratio
+        self._crop_n_points_downscale_factor = crop_n_points_downscale_factor
+        self._stability_score_offset = stability_score_offset
+
+    def _process_batch(self, points, im_size, crop_box, original_size):
+        """instance_segmentation.py:356-369 + _to_mask_data :229-255, fused on the device."""
+        pred = self._predictor
+        transformed = pred.transform.apply_coords(points, im_size)
+        in_points = torch.as_tensor(transformed, dtype=torch.float, device=pred.device)
+        in_labels = torch.ones(in_points.shape[0], dtype=torch.float, device=pred.device)
+        low, iou = pred.decode_low_res(in_points[:, None, :], in_labels[:, None], None, multimask_output=True)
+        P, M = low.shape[:2]
+        low = low.view(P * M, 256, 256)
+        boxes, stab, area = mask_stats(low, pred.input_size, pred.original_size, pred.model.mask_threshold,
+                                       self._stability_score_offset)
+        data = amg_utils.MaskData(low_res=low, iou_preds=iou.reshape(-1), stability_score=stab, boxes=boxes, area=area)
+        data["points"] = torch.as_tensor(points.repeat(M, axis=0), dtype=torch.float)
+        return data
+
+    def _process_crop(self, image_size, crop_box, crop_layer_idx, pbar_init=None, pbar_update=None):
+        x0, y0, x1, y1 = crop_box
+        cropped_im_size = (min(y1, image_size[0]) - y0, min(x1, image_size[1]) - x0)
+        points_scale = np.array(cropped_im_size)[None, ::-1]
+        points_for_image = self.point_grids[crop_layer_idx] * points_scale
+        data = amg_utils.MaskData()
+        n_batches = len(points_for_image) // self._points_per_batch + int(len(points_for_image) % self._points_per_batch != 0)
+        if pbar_init is not None:
+            pbar_init(n_batches, "Predict masks for point grid prompts")
+        for (points,) in amg_utils.batch_iterator(self._points_per_batch, points_for_image):
+            data.cat(self._process_batch(points, cropped_im_size, crop_box, self.original_size))
+            if pbar_update is not None:
+                pbar_update(1)
+        return data
+
+    @torch.no_grad()
+    def initialize(self, image: np.ndarray, image_embeddings: Optional[util.ImageEmbeddings] = None,
+                   i: Optional[int] = None, verbose: bool = False, pbar_init: Optional[Callable] = None,
+                   pbar_update: Optional[Callable] = None) -> None:
+        original_size = image.shape[:2]
+        self._original_size = original_size
+        crop_boxes, layer_idxs = amg_utils.generate_crop_boxes(original_size, self._crop_n_layers,
+                                                               self._crop_overlap_ratio)
+        if image_embeddings is None:
+            image_embeddings = util.precompute_image_embeddings(self._predictor, image, to_numpy=False)
+        util.set_precomputed(self._predictor, image_embeddings, i=i)
+        _, pbar_init, pbar_update, pbar_close = util.handle_pbar(verbose, pbar_init, pbar_update)
+        crop_list = []
+        for crop_box, layer_idx in zip(crop_boxes, layer_idxs):
+            crop_list.append(self._process_crop(original_size, crop_box, layer_idx, pbar_init, pbar_update))
+        pbar_close()
+        self._geoms = [dict(inp=tuple(self._predictor.input_size), orig=tuple(self._predictor.original_size))
+                       for _ in crop_boxes]
+        self._is_initialized = True
+        self._crop_list = crop_list
+        self._crop_boxes = crop_boxes
+
+    @torch.no_grad()
+    def generate(self, pred_iou_thresh: float = 0.88, stability_score_thresh: float = 0.95, box_nms_thresh: float = 0.7,
+                 crop_nms_thresh: float = 0.7, min_mask_region_area: int = 0,
+                 output_mode: str = "instance_segmentation", with_background: bool = True):
+        if not self.is_initialized:
+            raise RuntimeError("AutomaticMaskGenerator has not been initialized. Call initialize first.")
+        if min_mask_region_area > 0:
+            raise NotImplementedError("min_mask_region_area > 0 (cv2 hole/island removal) is not on the B200 path yet")
+        if output_mode not in ("instance_segmentation", "binary_mask", "rle", "coco_rle"):
+            raise ValueError(f"Invalid output mode {output_mode}.")
+        if output_mode == "coco_rle":
+            raise NotImplementedError("coco_rle needs pycocotools")
+        geoms = getattr(self, "_geoms", None)
+        results, painted = [], None
+        for ci, (data, crop_box) in enumerate(zip(self.crop_list, self.crop_boxes)):
+            geom = geoms[ci] if geoms else dict(inp=tuple(self._predictor.input_size),
+                                                orig=(crop_box[3] - crop_box[1], crop_box[2] - crop_box[0]))
+            keep = self._filter_nms(data, crop_box, self.original_size, pred_iou_thresh, stability_score_thresh,
+                                    box_nms_thresh)
+            if output_mode == "instance_segmentation":
+                painted = self._paint(data, keep, crop_box, geom, painted)
+            else:
+                results += self._records(data, keep, crop_box, output_mode, geom)
+        if output_mode != "instance_segmentation":
+            return results
+        seg = painted.cpu().numpy() if painted is not None else np.zeros(self.original_size, dtype="uint32")
+        return util._finish_segmentation(seg, min_object_size=0, label_masks=True, with_background=with_background)
+
+    @torch.no_grad()
+    def generate_device(self, pred_iou_thresh: float = 0.88, stability_score_thresh: float = 0.95,
+                        box_nms_thresh: float = 0.7, **_):
+        """generate() up to the painted (pre connected-components) label image, left on the device: int32 (H, W) tensor.
+        Used by bench.py's device-resident throughput number; generate() = this + D2H + util._finish_segmentation."""
+        if not self.is_initialized:
+            raise RuntimeError("AutomaticMaskGenerator has not been initialized. Call initialize first.")
+        painted = None
+        for ci, (data, crop_box) in enumerate(zip(self.crop_list, self.crop_boxes)):
+            keep = self._filter_nms(data, crop_box, self.original_size, pred_iou_thresh, stability_score_thresh,
+                                    box_nms_thresh)
+            painted = self._paint(data, keep, crop_box, self._geoms[ci], painted)
+        return painted
+
+    def _paint(self, data, keep, crop_box, geom, label):
+        """mask_data_to_segmentation(..., merge_exclusively=False) painting (util.py:1799-1829): descending area, later
+        (smaller) masks overwrite.  Stable order like Python's sorted(reverse=True)."""
+        H, W = self.original_size
+        dev = data["low_res"].device
+        if label is None:
+            label = torch.zeros(H, W, dtype=torch.int32, device=dev)
+        if len(keep) == 0:
+            return label
+        area = data["area"][keep]
+        order = torch.argsort(area, descending=True, stable=True)
+        sel = keep[order].to(torch.int32).contiguous()
+        seg_ids = torch.arange(1, len(sel) + 1, dtype=torch.int32, device=dev)
+        x0, y0 = int(crop_box[0]), int(crop_box[1])
+        view = label[y0:, x0:]
+        _lib.check(_lib.lib().msam_paint(_lib.ptr(data["low_res"]), _lib.ptr(sel), _lib.ptr(data["boxes"]), _lib.ptr(seg_ids),
+                                         len(sel), geom["inp"][0], geom["inp"][1], geom["orig"][0], geom["orig"][1], 0.0, 0,
+                                         ctypes.c_void_p(view.data_ptr()), W, _lib.cur_stream()))
+        return label
+
+
+def get_instance_segmentation_generator(predictor, is_tiled: bool, decoder=None, segmentation_mode: Optional[str] = None,
+                                        **kwargs):
+    """instance_segmentation.py:1631: only the AMG mode exists on this path (AIS/APG need the UNETR decoder, 8f-2)."""
+    if decoder is not None or segmentation_mode not in (None, "amg"):
+        raise NotImplementedError("only segmentation_mode='amg' is available on the B200 path")
+    if is_tiled:
+        raise NotImplementedError("TiledAutomaticMaskGenerator is not implemented yet")
+    return AutomaticMaskGenerator(predictor, **kwargs)

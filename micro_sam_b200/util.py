@@ -1,0 +1,401 @@
+"""micro_sam.util's hot-path functions with their reference signatures, on the B200 core.
+
+Mirrors (reference file:line): get_sam_model util.py:318-476, _to_image :618-651, _compute_embeddings_batched
+:654-681, tiled / 3-D drivers :765-1041, precompute_image_embeddings :1133-1212, set_precomputed :1215-1258,
+mask_data_to_segmentation :1773-1848.
+Out of scope: the zarr on-disk container (`save_path`), pooch downloads.  Embeddings are returned in
+memory with the same dict layout; tiled embeddings use an in-memory group with the same keys/attrs as the zarr one.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import warnings
+from typing import Any, Callable, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._amg_utils import Blocking
+from .sam import ARCH, B200Sam, B200SamPredictor, validate_model_type
+
+ImageEmbeddings = Dict[str, Any]
+
+
+# ------------------------------------------------------------------------------------------------ model loading
+def get_device(device: Optional[Union[str, torch.device]] = None) -> torch.device:
+    """util.py:204-246 restricted to what this core can run on: a CUDA (sm_100a) device."""
+    if device is None or str(device) == "auto":
+        device = "cuda"
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"micro_sam_b200 only runs on CUDA sm_100a devices, not {device!r} (no CPU fallback).")
+    if not torch.cuda.is_available():
+        raise RuntimeError("PyTorch CUDA backend is not available.")
+    return dev
+
+
+def _load_checkpoint(checkpoint_path):
+    """util.py:273-290: torch_em checkpoints carry {"model_state": {"sam.<key>": ...}, "decoder_state": ...}."""
+    state = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+    if "model_state" in state:
+        model_state = state["model_state"]
+        model_state = {k[len("module."):] if k.startswith("module.") else k: v for k, v in model_state.items()}
+        model_state = {k[len("sam."):] if k.startswith("sam.") else k: v for k, v in model_state.items()}
+    else:
+        model_state = state
+    return state, model_state
+
+
+def get_sam_model(model_type: str = "vit_b", device: Optional[Union[str, torch.device]] = None,
+                  checkpoint_path: Optional[Union[str, os.PathLike]] = None, return_sam: bool = False,
+                  return_state: bool = False, state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                  max_batch: int = 16, max_prompts: int = 256, **unsupported):
+    """util.get_sam_model (util.py:318).  Weights come from `checkpoint_path` (upstream SAM or micro-sam/torch_em
+    checkpoint layouts) or from an in-memory upstream-keyed `state_dict`.  There is no download (no network)."""
+    for k in ("peft_kwargs", "decoder_path"):
+        if unsupported.get(k) is not None:
+            raise NotImplementedError(f"get_sam_model({k}=...) is outside the B200 hot path (SURVEY.md 8f)")
+    device = get_device(device)
+    state = None
+    if state_dict is None:
+        if checkpoint_path is None:
+            raise RuntimeError("No weights: pass checkpoint_path=... or state_dict=... (model download needs network).")
+        state, state_dict = _load_checkpoint(checkpoint_path)
+    abbrev = model_type[:5]
+    detected = validate_model_type(state_dict)
+    if detected in ARCH and detected != abbrev and abbrev in ("vit_b", "vit_l", "vit_h"):
+        raise RuntimeError(f"model_type {model_type!r} does not match the checkpoint ({detected!r})")
+    if detected == "vit_t":
+        raise NotImplementedError("vit_t (MobileSAM / TinyViT) has no B200 kernels yet (SURVEY.md 8f-4)")
+    sam = B200Sam(detected, state_dict, device=device, max_batch=max_batch, max_prompts=max_prompts)
+    predictor = B200SamPredictor(sam)
+    predictor.model_type = model_type
+    predictor._hash = None
+    predictor.model_name = model_type if checkpoint_path is None else os.path.basename(str(checkpoint_path))
+    predictor.checkpoint_path = checkpoint_path
+    ret = (predictor,)
+    if return_sam:
+        ret = ret + (sam,)
+    if return_state:
+        ret = ret + (state,)
+    return ret[0] if len(ret) == 1 else ret
+
+
+# ------------------------------------------------------------------------------------------------ input pipeline
+def _to_image(image):
+    """util.py:618-651: any grayscale / 2-ch / RGB input -> per-channel min-max normalised uint8 HxWx3."""
+    input_ = image
+    ndim = input_.ndim
+    n_channels = 1 if ndim == 2 else input_.shape[-1]
+    if ndim == 2:
+        input_ = np.concatenate([input_[..., None]] * 3, axis=-1)
+    elif ndim == 3 and n_channels == 1:
+        input_ = np.concatenate([input_] * 3, axis=-1)
+    elif ndim == 3 and n_channels == 2:
+        zero_channel = np.zeros(input_.shape[:2] + (1,), dtype=input_.dtype)
+        input_ = np.concatenate([input_, zero_channel], axis=-1)
+    elif input_.ndim == 3 and n_channels == 3:
+        pass
+    elif input_.ndim == 3 and n_channels > 3:
+        warnings.warn(f"You provided an input with {n_channels} channels. Only the first three will be used.")
+        input_ = input_[..., :3]
+    else:
+        raise ValueError(
+            f"Invalid input dimensionality {ndim}. Expect either a 2D input (=grayscale image) "
+            "or a 3D input (= image with channels)."
+        )
+    assert input_.ndim == 3 and input_.shape[-1] == 3
+    input_ = input_.astype("float32")
+    input_ -= input_.min(axis=(0, 1))[None, None]
+    input_ /= (input_.max(axis=(0, 1))[None, None] + 1e-7)
+    input_ = (input_ * 255).astype("uint8")
+    return np.array(input_)
+
+
+@torch.no_grad()
+def _compute_embeddings_batched(predictor, batched_images):
+    """util.py:654-681: resize each image, then ONE encoder call for the batch (preprocess is fused in the kernel when
+    all resized images share a shape, which is always the case for tiles of one tiling)."""
+    predictor.reset_image()
+    resized, original_sizes, input_sizes = [], [], []
+    for image in batched_images:
+        t = predictor.transform.apply_image(image)
+        original_sizes.append(image.shape[:2])
+        input_sizes.append(tuple(t.shape[:2]))
+        resized.append(t)
+    sam = predictor.model
+    if len(set(input_sizes)) == 1:
+        batch = torch.from_numpy(np.stack(resized))
+        if batch.numel() > 0:
+            batch = batch.pin_memory() if torch.cuda.is_available() else batch
+        features = sam.encode_u8(batch.to(sam.device, non_blocking=True))
+    else:  # ragged border tiles: normalise + pad on the device, one fp32 batch
+        tensors = [sam.preprocess(torch.from_numpy(t).to(sam.device).permute(2, 0, 1)[None]) for t in resized]
+        features = sam.image_encoder(torch.cat(tensors))
+    predictor.original_size = original_sizes[-1]
+    predictor.input_size = input_sizes[-1]
+    predictor.features = features[-1:]  # NB: the reference leaves features[-1] (3-D); kept 4-D for the decoder
+    predictor.is_image_set = True
+    return features, original_sizes, input_sizes
+
+
+class _MemDataset:
+    """Stand-in for a zarr array with `.attrs` (util.py:720-729)."""
+
+    def __init__(self, data, attrs=None):
+        self.data = data
+        self.attrs = dict(attrs or {})
+
+    @property
+    def ndim(self):
+        return self.data.ndim
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    def __getitem__(self, idx):
+        return self.data[idx]
+
+    def __setitem__(self, idx, val):
+        self.data[idx] = val
+
+
+class _MemGroup(dict):
+    """Stand-in for a zarr group: datasets by name + attrs."""
+
+    def __init__(self):
+        super().__init__()
+        self.attrs = {}
+
+
+def handle_pbar(verbose, pbar_init, pbar_update):
+    """util.py:1098-1130 without tqdm dependency on the hot path."""
+    if verbose and pbar_init is None:
+        from tqdm import tqdm
+        pbar = tqdm()
+
+        def pbar_init(total, description):  # noqa: F811
+            pbar.total = total
+            pbar.set_description(description)
+
+        def pbar_update(update):  # noqa: F811
+            pbar.update(update)
+
+        def pbar_close():
+            pbar.close()
+    elif pbar_init is not None and pbar_update is not None:
+        pbar = None
+
+        def pbar_close():
+            pass
+    else:
+        pbar = None
+
+        def pbar_init(total, description):  # noqa: F811
+            pass
+
+        def pbar_update(update):  # noqa: F811
+            pass
+
+        def pbar_close():
+            pass
+    return pbar, pbar_init, pbar_update, pbar_close
+
+
+def _get_tiles_in_mask(mask, tiling, halo, z=None):
+    out = []
+    for tile_id in range(tiling.number_of_blocks):
+        tile = tiling.get_block_with_halo(tile_id, list(halo))
+        outer = tuple(slice(b, e) for b, e in zip(tile.outer_block.begin, tile.outer_block.end))
+        if z is not None:
+            outer = (z,) + outer
+        if np.asarray(mask[outer]).astype(bool).sum() != 0:
+            out.append(tile_id)
+    return out
+
+
+def _compute_tiled_features(predictor, input_, is3d, tile_shape, halo, pbar_init, pbar_update, batch_size, mask, to_numpy,
+                            rank: int = 0, world_size: int = 1):
+    """util.py:765-899 (_compute_tiled_features_2d/_3d + _BatchProvider): (z, tile) pairs in row-major order, batches of
+    `batch_size`, each tile normalised on its own (_to_image) -- tiled embeddings are NOT crops of a global embedding.
+    rank/world_size: static block partition of that order for multi-GPU sharding -- each rank fills only
+    its own (z, tile) entries; no collective."""
+    plane_shape = input_.shape[1:3] if is3d else input_.shape[:2]
+    tiling = Blocking([0, 0], plane_shape, tile_shape)
+    features = _MemGroup()
+    features.attrs["shape"] = tuple(plane_shape)
+    features.attrs["tile_shape"] = tuple(tile_shape)
+    features.attrs["halo"] = tuple(halo)
+    n_slices = input_.shape[0] if is3d else 1
+    work = []
+    tiles_in_mask = {}
+    for z in range(n_slices):
+        ids = range(tiling.number_of_blocks) if mask is None else _get_tiles_in_mask(mask, tiling, halo, z if is3d else None)
+        tiles_in_mask[str(z)] = list(ids)
+        work += [(z, t) for t in ids]
+    lo, hi = (len(work) * rank) // world_size, (len(work) * (rank + 1)) // world_size
+    my_work = work[lo:hi]
+    pbar_init(len(my_work), "Compute Image Embeddings tiled")
+    for b0 in range(0, len(my_work), batch_size):
+        chunk = my_work[b0:b0 + batch_size]
+        images = []
+        for z, tile_id in chunk:
+            tile = tiling.get_block_with_halo(tile_id, list(halo))
+            outer = tuple(slice(b, e) for b, e in zip(tile.outer_block.begin, tile.outer_block.end))
+            images.append(_to_image(input_[(z,) + outer] if is3d else input_[outer]))
+        emb, original_sizes, input_sizes = _compute_embeddings_batched(predictor, images)
+        emb_host = emb.cpu().numpy() if to_numpy else emb
+        for k, (z, tile_id) in enumerate(chunk):
+            name = str(tile_id)
+            if is3d:
+                if name not in features:
+                    shape = (n_slices, 1) + tuple(emb.shape[1:])
+                    data = np.zeros(shape, dtype="float32") if to_numpy else torch.zeros(shape, device=emb.device)
+                    features[name] = _MemDataset(data, {"original_size": original_sizes[k], "input_size": input_sizes[k]})
+                features[name][z] = emb_host[k][None]
+            else:
+                features[name] = _MemDataset(emb_host[k][None], {"original_size": original_sizes[k],
+                                                                   "input_size": input_sizes[k]})
+        pbar_update(len(chunk))
+    if mask is not None:
+        features.attrs["tiles_in_mask"] = tiles_in_mask if is3d else tiles_in_mask["0"]
+    return features
+
+
+def precompute_image_embeddings(predictor, input_: np.ndarray, save_path=None, lazy_loading: bool = False,
+                                ndim: Optional[int] = None, tile_shape: Optional[Tuple[int, int]] = None,
+                                halo: Optional[Tuple[int, int]] = None, verbose: bool = False, batch_size: int = 1,
+                                mask=None, pbar_init: Optional[Callable] = None, pbar_update: Optional[Callable] = None,
+                                to_numpy: bool = True, rank: int = 0, world_size: int = 1) -> ImageEmbeddings:
+    """util.precompute_image_embeddings (util.py:1133).  `to_numpy=False` keeps the embeddings on the device (skips the
+    reference's D2H, util.py:917); rank/world_size shard tiled work across processes."""
+    if save_path is not None:
+        raise NotImplementedError("zarr embedding containers (save_path=...) are outside the B200 hot path (8f-3)")
+    ndim = input_.ndim if ndim is None else ndim
+    _, pbar_init, pbar_update, pbar_close = handle_pbar(verbose, pbar_init, pbar_update)
+    if tile_shape is not None and halo is None:
+        raise ValueError("To compute tiled embeddings the parameters tile_shape and halo have to be passed.")
+    if ndim == 2 and tile_shape is None:
+        pbar_init(1, "Compute Image Embeddings 2D")
+        predictor.reset_image()
+        predictor.set_image(_to_image(input_))
+        feats = predictor.get_image_embedding()
+        feats = feats.cpu().numpy() if to_numpy else feats
+        pbar_update(1)
+        emb = {"features": feats, "input_size": predictor.input_size, "original_size": predictor.original_size}
+    elif ndim == 3 and tile_shape is None:
+        n = input_.shape[0]
+        pbar_init(n, "Compute Image Embeddings 3D")
+        outs = []
+        for z0 in range(0, n, batch_size):
+            images = [_to_image(input_[z]) for z in range(z0, min(z0 + batch_size, n))]
+            e, original_sizes, input_sizes = _compute_embeddings_batched(predictor, images)
+            outs.append(e[:, None])
+            pbar_update(len(images))
+        feats = torch.cat(outs)  # (Z,1,256,64,64) (util.py:968-970)
+        feats = feats.cpu().numpy() if to_numpy else feats
+        emb = {"features": feats, "input_size": input_sizes[-1], "original_size": original_sizes[-1]}
+    elif ndim in (2, 3):
+        feats = _compute_tiled_features(predictor, input_, ndim == 3, tuple(tile_shape), tuple(halo), pbar_init, pbar_update,
+                                        batch_size, mask, to_numpy, rank, world_size)
+        emb = {"features": feats, "input_size": None, "original_size": None}
+    else:
+        raise ValueError(f"Invalid dimesionality {input_.ndim}, expect 2 or 3 dim data.")
+    pbar_close()
+    return emb
+
+
+def set_precomputed(predictor, image_embeddings: ImageEmbeddings, i: Optional[int] = None, tile_id: Optional[int] = None):
+    """util.py:1215-1258."""
+    if tile_id is not None:
+        tile_features = image_embeddings["features"][str(tile_id)]
+        return set_precomputed(predictor, {"features": tile_features, "input_size": tile_features.attrs["input_size"],
+                                           "original_size": tile_features.attrs["original_size"]}, i=i)
+    device = predictor.device
+    features = image_embeddings["features"]
+    assert features.ndim in (4, 5), f"{features.ndim}"
+    if features.ndim == 5 and i is None:
+        raise ValueError("The data is 3D so an index i is needed.")
+    elif features.ndim == 4 and i is not None:
+        raise ValueError("The data is 2D so an index is not needed.")
+    f = features[:] if i is None else features[i]
+    predictor.features = f.to(device) if torch.is_tensor(f) else torch.from_numpy(np.asarray(f)).to(device)
+    predictor.original_size = tuple(image_embeddings["original_size"])
+    predictor.input_size = tuple(image_embeddings["input_size"])
+    predictor.is_image_set = True
+    return predictor
+
+
+# ------------------------------------------------------------------------------------------------ label image assembly
+def _label_connected(seg: np.ndarray) -> np.ndarray:
+    """Connected components of a label image (what elf.parallel.label does at util.py:1831-1834): 4-connectivity,
+    components of equal non-zero label, ids in raster order of first pixel."""
+    from scipy import ndimage
+    h, w = seg.shape
+    # edges exist only between equal labels: label the foreground with horizontal/vertical links masked out where the
+    # neighbour differs, by labelling a 2x up-sampled "pixels + links" grid.
+    big = np.zeros((2 * h - 1, 2 * w - 1), dtype=bool)
+    fg = seg != 0
+    big[::2, ::2] = fg
+    big[::2, 1::2] = fg[:, :-1] & (seg[:, :-1] == seg[:, 1:])
+    big[1::2, ::2] = fg[:-1, :] & (seg[:-1, :] == seg[1:, :])
+    lab, _ = ndimage.label(big)  # default 4-connectivity; raster-order ids
+    lab = lab[::2, ::2]
+    ids = np.unique(lab)
+    ids = ids[ids != 0]
+    lut = np.zeros(int(lab.max()) + 1, dtype=np.uint32)
+    lut[ids] = np.arange(1, len(ids) + 1, dtype=np.uint32)
+    return lut[lab]
+
+
+def _finish_segmentation(segmentation: np.ndarray, min_object_size: int, label_masks: bool, with_background: bool):
+    """util.py:1831-1848: CC-label, drop small objects (and the largest one if with_background), relabel."""
+    if label_masks:
+        segmentation = _label_connected(segmentation)
+    seg_ids, sizes = np.unique(segmentation, return_counts=True)
+    filter_ids = seg_ids[sizes < min_object_size]
+    if with_background:
+        filter_ids = np.concatenate([filter_ids, [seg_ids[np.argmax(sizes)]]])
+    if len(filter_ids):
+        segmentation = segmentation.copy()
+        segmentation[np.isin(segmentation, filter_ids)] = 0
+    ids = np.unique(segmentation)
+    ids = ids[ids != 0]
+    lut = np.zeros(int(segmentation.max()) + 1, dtype=np.uint32)
+    lut[ids] = np.arange(1, len(ids) + 1, dtype=np.uint32)
+    return lut[segmentation]
+
+
+def mask_data_to_segmentation(masks: List[Dict[str, Any]], shape: Optional[Tuple[int, int]] = None,
+                              min_object_size: int = 0, max_object_size: Optional[int] = None, label_masks: bool = True,
+                              with_background: bool = False, merge_exclusively: bool = True) -> np.ndarray:
+    """util.mask_data_to_segmentation (util.py:1773-1848) for host-side binary-mask records (API parity; the AMG /
+    batched-inference fast path paints on the device instead, see instance_segmentation.py)."""
+    masks = sorted(masks, key=(lambda x: x["area"]), reverse=True)
+    if shape is None:
+        shape = next(iter(masks))["segmentation"].shape
+    segmentation = np.zeros(shape, dtype="uint32")
+    seg_id = 1
+    for mask_data in masks:
+        area = mask_data["area"]
+        if (area < min_object_size) or (max_object_size is not None and area > max_object_size):
+            continue
+        this_mask = mask_data["segmentation"]
+        this_mask = this_mask.cpu().numpy() if torch.is_tensor(this_mask) else np.asarray(this_mask)
+        this_seg_id = mask_data.get("seg_id", seg_id)
+        if "global_bbox" in mask_data:
+            bb = mask_data["bbox"]
+            bb = np.s_[bb[1]:bb[1] + bb[3], bb[0]:bb[0] + bb[2]]
+            gbb = mask_data["global_bbox"]
+            gbb = np.s_[gbb[1]:gbb[1] + gbb[3], gbb[0]:gbb[0] + gbb[2]]
+            this_mask = np.logical_and(this_mask[bb], segmentation[gbb] == 0) if merge_exclusively else this_mask[bb]
+            segmentation[gbb][this_mask] = this_seg_id
+        else:
+            if merge_exclusively:
+                this_mask = np.logical_and(this_mask, segmentation == 0)
+            segmentation[this_mask] = this_seg_id
+        seg_id = this_seg_id + 1
+    return _finish_segmentation(segmentation, min_object_size, label_masks, with_background)

@@ -301,7 +301,8 @@ def sec_post():
         boxes, stab, area = bsam.mask_stats(low.to(DEV), inp, orig, 0.0, 1.0)
         full = torch.empty(12, orig[0], orig[1], device=DEV)
         binm = torch.empty(12, orig[0], orig[1], device=DEV, dtype=torch.uint8)
-        _lib.check(L.msam_upsample_masks(_lib.ptr(low.to(DEV).contiguous()), None, 12, inp[0], inp[1], orig[0], orig[1], 0.0,
+        dlow = low.to(DEV).contiguous()
+        _lib.check(L.msam_upsample_masks(_lib.ptr(dlow), None, 12, inp[0], inp[1], orig[0], orig[1], 0.0,
                                          _lib.ptr(full), _lib.ptr(binm), _lib.cur_stream()))
         torch.cuda.synchronize()
         report(f"postprocess_masks {inp}->{orig}", full.cpu(), ref_full, 1e-5)
@@ -336,8 +337,9 @@ def sec_nms():
         nk = torch.zeros(1, dtype=torch.int32, device=DEV)
         import ctypes
         crop = (ctypes.c_int32 * 4)(0, 0, 1024, 1024)
+        dboxes, dscores, dstab = boxes.to(DEV), scores.to(DEV), stab.to(DEV)
         for use_f in (0, 1):
-            _lib.check(L.msam_amg_filter_nms(_lib.ptr(boxes.to(DEV)), _lib.ptr(scores.to(DEV)), _lib.ptr(stab.to(DEV)), n, use_f,
+            _lib.check(L.msam_amg_filter_nms(_lib.ptr(dboxes), _lib.ptr(dscores), _lib.ptr(dstab), n, use_f,
                                              0.5, 0.9, 0.7, crop, crop, _lib.ptr(keep), _lib.ptr(nk), _lib.cur_stream()))
             torch.cuda.synchronize()
             got = keep[: int(nk.item())].cpu().long()

@@ -1,0 +1,144 @@
+"""`-m gpu` parity tests: the CUDA path (through the C ABI / the reference-facing Python API) against the oracle.
+
+Tolerances (the reference states none -- its inference is fp32, ours uses bf16 MMA operands with fp32
+accumulation / residual stream / softmax):  encoder rel-L2 <= 2e-2; low-res logits rel-L2 <= 3e-2; iou_pred abs <= 2e-2;
+integer stages (boxes, area, stability counts, NMS keep set, painting) bit-exact GIVEN the same low-res logits.
+"""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _diag():
+    spec = importlib.util.spec_from_file_location("gpu_diag", os.path.join(HERE, "gpu_diag.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("section", ["gemm", "ln", "attn", "encoder", "decoder", "post", "nms"])
+def test_ops(section):
+    d = _diag()
+    d.SECTIONS[section]()
+    assert d.RESULTS and all(d.RESULTS), f"{section}: {sum(d.RESULTS)}/{len(d.RESULTS)} checks ok"
+
+
+def _partition_equal(a, b):
+    """label images equal up to a relabelling."""
+    if a.shape != b.shape or (a == 0).sum() != (b == 0).sum() or not np.array_equal(a == 0, b == 0):
+        return False
+    pairs = np.unique(np.stack([a.ravel(), b.ravel()], 1), axis=0)
+    return len(pairs) == len(np.unique(a)) == len(np.unique(b))
+
+
+@pytest.fixture(scope="module")
+def models():
+    from oracle import sam_ref
+    from micro_sam_b200 import util
+    sd = sam_ref.seeded_state_dict("vit_test", seed=1)
+    osam = sam_ref.build_sam("vit_test")
+    osam.load_state_dict(sd)
+    pred = util.get_sam_model("vit_test", state_dict=sd, max_batch=4, max_prompts=64)
+    return sam_ref.SamPredictor(osam), pred
+
+
+def test_to_image_and_embeddings(models):
+    from oracle import amg_ref
+    from micro_sam_b200 import util
+    from micro_sam_b200.sample_data import lm_tile
+    opred, pred = models
+    img = lm_tile((512, 512), 40, seed=0)
+    assert np.array_equal(util._to_image(img), amg_ref.to_image(img))
+    ref = amg_ref.precompute_image_embeddings_2d(opred, img)
+    got = util.precompute_image_embeddings(pred, img)
+    assert got["features"].shape == (1, 256, 64, 64) and got["input_size"] == (1024, 1024) and got["original_size"] == (512, 512)
+    rel = np.linalg.norm(got["features"] - ref["features"]) / np.linalg.norm(ref["features"])
+    assert rel < 2e-2, rel
+    # tiled: 4 tiles for 512^2 / tile 256 / halo 16 (test/test_util.py:179-208), each tile normalised on its own
+    tiled = util.precompute_image_embeddings(pred, img, tile_shape=(256, 256), halo=(16, 16), batch_size=3)
+    feats = tiled["features"]
+    assert sorted(feats.keys()) == ["0", "1", "2", "3"] and feats.attrs["tile_shape"] == (256, 256)
+    tile1 = amg_ref.precompute_image_embeddings_2d(opred, img[0:272, 240:512])
+    rel = np.linalg.norm(feats["1"][:] - tile1["features"]) / np.linalg.norm(tile1["features"])
+    assert feats["1"].attrs["original_size"] == (272, 272) and rel < 2e-2, rel
+    # 3d
+    vol = np.stack([img, img[::-1]])
+    e3 = util.precompute_image_embeddings(pred, vol, batch_size=2)
+    assert e3["features"].shape == (2, 1, 256, 64, 64)
+    assert np.allclose(e3["features"][0], got["features"], atol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(512, 512), (300, 500)])
+def test_amg_against_oracle(models, shape):
+    """End to end AMG.  (1) float stages within tolerance of the oracle; (2) every integer stage bit-exact when the
+    oracle is fed the SAME low-res logits the GPU produced."""
+    from oracle import amg_ref
+    from micro_sam_b200 import instance_segmentation as iseg
+    from micro_sam_b200.sample_data import lm_tile
+    opred, pred = models
+    img = lm_tile(shape, 30, seed=3)
+    amg = iseg.AutomaticMaskGenerator(pred, points_per_side=6)
+    amg.initialize(img)
+    d = amg.crop_list[0]
+    oamg = amg_ref.AutomaticMaskGenerator(opred, points_per_side=6, points_per_batch=12)
+    oamg.initialize(img)
+    od = oamg._crop_list[0]
+    # (1) float stages
+    assert np.abs(d["iou_preds"].cpu().numpy() - od["iou_preds"].numpy()).max() < 2e-2
+    # (2) integer stages from identical logits: patch the oracle predictor to return the GPU low-res logits
+    low = d["low_res"].cpu().view(-1, 3, 256, 256)
+    iou = d["iou_preds"].cpu().view(-1, 3)
+    state = {"i": 0}
+
+    def fake_predict_torch(point_coords, point_labels, boxes=None, mask_input=None, multimask_output=True,
+                           return_logits=False):
+        n = point_coords.shape[0]
+        s = state["i"]
+        state["i"] += n
+        masks = opred.model.postprocess_masks(low[s:s + n], opred.input_size, opred.original_size)
+        return masks, iou[s:s + n], low[s:s + n]
+
+    orig = opred.predict_torch
+    opred.predict_torch = fake_predict_torch
+    try:
+        oamg2 = amg_ref.AutomaticMaskGenerator(opred, points_per_side=6, points_per_batch=12)
+        oamg2.initialize(img)
+    finally:
+        opred.predict_torch = orig
+    od2 = oamg2._crop_list[0]
+    assert np.array_equal(d["boxes"].cpu().numpy(), od2["boxes"].numpy())
+    assert np.array_equal(d["stability_score"].cpu().numpy(), od2["stability_score"].numpy(), equal_nan=True)
+    assert np.array_equal(d["area"].cpu().numpy(), np.array([amg_ref.area_from_rle(r) for r in od2["rles"]]))
+    for kw in (dict(pred_iou_thresh=0.0, stability_score_thresh=0.0), dict(pred_iou_thresh=0.2, stability_score_thresh=0.6),
+               dict(pred_iou_thresh=0.3, stability_score_thresh=0.8, box_nms_thresh=0.3)):
+        recs = amg.generate(output_mode="binary_mask", **kw)
+        orecs = oamg2.generate(output_mode="binary_mask", **kw)
+        assert len(recs) == len(orecs), (kw, len(recs), len(orecs))
+        for a, b in zip(recs, orecs):
+            assert a["bbox"] == b["bbox"] and a["area"] == b["area"] and np.array_equal(a["segmentation"], b["segmentation"])
+            assert a["point_coords"] == b["point_coords"]
+        rles = amg.generate(output_mode="rle", **kw)
+        orles = oamg2.generate(output_mode="rle", **kw)
+        assert [r["segmentation"] for r in rles] == [r["segmentation"] for r in orles]
+        seg = amg.generate(output_mode="instance_segmentation", **kw)
+        oseg = oamg2.generate(output_mode="instance_segmentation", **kw)
+        assert _partition_equal(seg, oseg), kw
+        assert np.array_equal(seg, amg.generate(output_mode="instance_segmentation", **kw))  # deterministic
+
+
+def test_errors(models):
+    _, pred = models
+    from micro_sam_b200 import util
+    pred.reset_image()
+    with pytest.raises(RuntimeError):
+        pred.get_image_embedding()
+    with pytest.raises(RuntimeError):
+        pred.predict_torch(torch.zeros(1, 1, 2), torch.ones(1, 1))
+    with pytest.raises(RuntimeError):
+        util.get_sam_model("vit_b", device="cpu", state_dict={})
