@@ -135,6 +135,8 @@ def compute_rle(mask_fortran_flat: np.ndarray) -> List[int]:
 def mask_to_rle(masks: np.ndarray) -> List[Dict[str, Any]]:
     """(b,h,w) bool -> uncompressed column-major RLE dicts (_vendored.py:114-152)."""
     b, h, w = masks.shape
+    if b == 0:
+        return []
     flat = np.ascontiguousarray(masks.transpose(0, 2, 1)).reshape(b, -1)
     return [{"size": [h, w], "counts": compute_rle(m)} for m in flat]
 

@@ -50,13 +50,17 @@ struct DecoderState {
   float* src = nullptr;               // [4096,256] image embedding + no_mask_embed (fp32, residual of layer 0)
   __nv_bfloat16 *src_bf = nullptr, *src_pe_bf = nullptr;
   __nv_bfloat16 *k0 = nullptr, *v0 = nullptr, *q0 = nullptr;  // hoisted layer-0 projections [4096,128]
+  // fused image-side projections of layer 1 ([k_t2i | v_t2i | q_i2t], N=384) and of the final attention ([k | v], N=256).
+  // (keys + pe) W^T = keys W^T + pe W^T: the prompt-independent second term is precomputed ([4096, N] fp32, zero for the
+  // v columns) and added through the GEMM's row-modulus residual, so `keys + pe` is never materialised.
+  __nv_bfloat16 *kvq1_w = nullptr, *kvf_w = nullptr;
+  float *kvq1_b = nullptr, *kvf_b = nullptr, *kvq1_res = nullptr, *kvf_res = nullptr;
   // per-chunk workspace (P = max_prompts)
   float *tok0 = nullptr, *queries = nullptr, *tok_f32 = nullptr;
   __nv_bfloat16 *tok0_bf = nullptr, *q_bf = nullptr, *qpe_bf = nullptr, *t_qkv = nullptr, *t_att = nullptr, *t_mlp = nullptr;
   __nv_bfloat16 *t_q128 = nullptr, *t_k128 = nullptr, *t_v128 = nullptr, *t_att128 = nullptr;
-  __nv_bfloat16 *keys = nullptr, *keys_pe = nullptr, *img_a = nullptr, *img_b = nullptr, *img_att = nullptr;
-  float* img_f32 = nullptr;           // [P*4096, 256] fp32 scratch (out_proj result before norm4 / conv-transpose 1)
-  __nv_bfloat16 *up1 = nullptr, *up2 = nullptr;
+  __nv_bfloat16 *keys = nullptr, *img_kvq = nullptr, *img_att = nullptr;
+  __nv_bfloat16* up1 = nullptr;       // [P*4096*4, 64] after conv-transpose 1 + LN2d + GELU
   __nv_bfloat16 *h1 = nullptr, *h2 = nullptr;
   float *hyper_in = nullptr, *iou_out = nullptr;
 };
@@ -203,14 +207,14 @@ __global__ void token_self_attn_kernel(const __nv_bfloat16* __restrict__ q, int 
 // online softmax per (token, lane), combined across lanes at the end.  Tokens handled in groups of 8.
 __global__ void __launch_bounds__(256)
 t2i_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
-                const __nv_bfloat16* __restrict__ v, long kv_stride_rows, int T, int NI,
+                const __nv_bfloat16* __restrict__ v, int ld, long kv_stride_rows, int T, int NI,
                 __nv_bfloat16* __restrict__ out) {
   const int p = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __shared__ float sq[TMAX][DI];
   for (int i = threadIdx.x; i < T * DI; i += 256) sq[i / DI][i % DI] = __bfloat162float(q[(long)p * T * DI + i]) * 0.25f;
   __syncthreads();
-  const __nv_bfloat16* kp = k + (long)p * kv_stride_rows * DI + h * 16;
-  const __nv_bfloat16* vp = v + (long)p * kv_stride_rows * DI + h * 16;
+  const __nv_bfloat16* kp = k + (long)p * kv_stride_rows * ld + h * 16;
+  const __nv_bfloat16* vp = v + (long)p * kv_stride_rows * ld + h * 16;
   for (int t0 = 0; t0 < T; t0 += 8) {
     const int nt = (T - t0 < 8) ? (T - t0) : 8;
     float m[8], l[8], acc[8][16];
@@ -221,8 +225,8 @@ t2i_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
       for (int d = 0; d < 16; ++d) acc[t][d] = 0.f;
     }
     for (int n = lane; n < NI; n += 32) {
-      const uint4 ka = *reinterpret_cast<const uint4*>(kp + (long)n * DI), kb = *reinterpret_cast<const uint4*>(kp + (long)n * DI + 8);
-      const uint4 va = *reinterpret_cast<const uint4*>(vp + (long)n * DI), vb = *reinterpret_cast<const uint4*>(vp + (long)n * DI + 8);
+      const uint4 ka = *reinterpret_cast<const uint4*>(kp + (long)n * ld), kb = *reinterpret_cast<const uint4*>(kp + (long)n * ld + 8);
+      const uint4 va = *reinterpret_cast<const uint4*>(vp + (long)n * ld), vb = *reinterpret_cast<const uint4*>(vp + (long)n * ld + 8);
       const uint32_t kw[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
       const uint32_t vw[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
       float kf[16], vf[16];
@@ -273,7 +277,7 @@ t2i_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
 // image -> token attention core.  q_img [*,128] (q_stride_rows = 0 when shared), k_tok / v_tok [P*T,128].
 // grid = (NI/32, P), block = 256: thread = (image token n = blockIdx.x*32 + tid/8, head = tid%8).
 __global__ void __launch_bounds__(256)
-i2t_attn_kernel(const __nv_bfloat16* __restrict__ qimg, long q_stride_rows, const __nv_bfloat16* __restrict__ ktok,
+i2t_attn_kernel(const __nv_bfloat16* __restrict__ qimg, int ldq, long q_stride_rows, const __nv_bfloat16* __restrict__ ktok,
                 const __nv_bfloat16* __restrict__ vtok, int T, int NI, __nv_bfloat16* __restrict__ out) {
   const int p = blockIdx.y;
   __shared__ float sk[TMAX][NHEAD][17], sv[TMAX][NHEAD][17];
@@ -284,7 +288,7 @@ i2t_attn_kernel(const __nv_bfloat16* __restrict__ qimg, long q_stride_rows, cons
   }
   __syncthreads();
   const int h = threadIdx.x & 7, n = blockIdx.x * 32 + (threadIdx.x >> 3);
-  const __nv_bfloat16* qp = qimg + ((long)p * q_stride_rows + n) * DI + h * 16;
+  const __nv_bfloat16* qp = qimg + ((long)p * q_stride_rows + n) * ldq + h * 16;
   const uint4 qa = *reinterpret_cast<const uint4*>(qp), qb = *reinterpret_cast<const uint4*>(qp + 8);
   const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
   float qf[16];
@@ -323,33 +327,6 @@ i2t_attn_kernel(const __nv_bfloat16* __restrict__ qimg, long q_stride_rows, cons
   __nv_bfloat16* dst = out + ((long)p * NI + n) * DI + h * 16;
   *reinterpret_cast<uint4*>(dst) = o0;
   *reinterpret_cast<uint4*>(dst + 8) = o1;
-}
-
-// masks[p, mi, Y, X] = sum_ch hyper_in[p, m0+mi, ch] * up2[p, tok(y,x), sub(dy,dx), subsub(ey,ex), ch]
-// with Y = 4y + 2dy + ey, X = 4x + 2dx + ex.  up2 row = (p*4096 + tok)*4 + sub, 128 cols = subsub*32 + ch.
-// grid = (256 /*Y*/, P), block = 256 /*X*/.
-__global__ void __launch_bounds__(256)
-mask_product_kernel(const __nv_bfloat16* __restrict__ up2, const float* __restrict__ hyper_in, int m0, int nm,
-                    float* __restrict__ masks) {
-  const int p = blockIdx.y, Y = blockIdx.x, X = threadIdx.x;
-  __shared__ float sh[4][32];
-  if (threadIdx.x < nm * 32) sh[threadIdx.x / 32][threadIdx.x % 32] = hyper_in[((long)p * 4 + m0 + threadIdx.x / 32) * 32 + threadIdx.x % 32];
-  __syncthreads();
-  const int y = Y >> 2, dy = (Y >> 1) & 1, ey = Y & 1, x = X >> 2, dx = (X >> 1) & 1, ex = X & 1;
-  const __nv_bfloat16* src = up2 + (((long)p * 4096 + y * 64 + x) * 4 + dy * 2 + dx) * 128 + (ey * 2 + ex) * 32;
-  float u[32];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint4 w = *reinterpret_cast<const uint4*>(src + 8 * i);
-    u[8 * i] = bf_lo(w.x); u[8 * i + 1] = bf_hi(w.x); u[8 * i + 2] = bf_lo(w.y); u[8 * i + 3] = bf_hi(w.y);
-    u[8 * i + 4] = bf_lo(w.z); u[8 * i + 5] = bf_hi(w.z); u[8 * i + 6] = bf_lo(w.w); u[8 * i + 7] = bf_hi(w.w);
-  }
-  for (int mi = 0; mi < nm; ++mi) {
-    float a = 0.f;
-#pragma unroll
-    for (int c = 0; c < 32; ++c) a += sh[mi][c] * u[c];
-    masks[(((long)p * nm + mi) * 256 + Y) * 256 + X] = a;
-  }
 }
 
 __global__ void gather_iou_kernel(const float* __restrict__ iou32, int P, int m0, int nm, float* __restrict__ out) {
@@ -486,6 +463,38 @@ int Engine::finalize_decoder() {
   CHK(d.pos = (float*)dalloc((size_t)NI * DC * 4));
   dense_pe_kernel<<<(NI * 128 + 255) / 256, 256>>>(d.gauss, g, d.pos);
   LAUNCH_CHECK("dense_pe");
+  {
+    // fused projection weights and their positional-encoding terms
+    auto cat_w = [&](std::initializer_list<std::pair<std::string, int>> parts, __nv_bfloat16** w, float** b) -> int {
+      std::vector<float> W, B;
+      for (auto& pr : parts) {
+        const auto *hw = host(pr.first + ".weight", {DI, DC}), *hb = host(pr.first + ".bias", {DI});
+        if (!hw || !hb) return -1;
+        W.insert(W.end(), hw->begin(), hw->end());
+        B.insert(B.end(), hb->begin(), hb->end());
+      }
+      *w = upload_bf16(W.data(), W.size());
+      *b = upload_f32(B.data(), B.size());
+      return (*w && *b) ? 0 : -1;
+    };
+    const std::string l1 = md + "transformer.layers.1.", fa = md + "transformer.final_attn_token_to_image.";
+    if (cat_w({{l1 + "cross_attn_token_to_image.k_proj", 0}, {l1 + "cross_attn_token_to_image.v_proj", 0},
+               {l1 + "cross_attn_image_to_token.q_proj", 0}}, &d.kvq1_w, &d.kvq1_b)) return -1;
+    if (cat_w({{fa + "k_proj", 0}, {fa + "v_proj", 0}}, &d.kvf_w, &d.kvf_b)) return -1;
+    __nv_bfloat16* pos_bf = (__nv_bfloat16*)dalloc((size_t)NI * DC * 2);
+    CHK(pos_bf);
+    if (launch_cast_bf16(d.pos, (long)NI * DC, pos_bf, 0)) return -1;
+    CHK(d.kvq1_res = (float*)dalloc((size_t)NI * 3 * DI * 4, true));
+    CHK(d.kvf_res = (float*)dalloc((size_t)NI * 2 * DI * 4, true));
+    auto pe_proj = [&](const __nv_bfloat16* w, float* out, int ldc) {
+      GemmArgs a;
+      a.A = pos_bf; a.W = w; a.M = NI; a.N = DI; a.K = DC; a.lda = DC; a.ldw = DC; a.out = out; a.ldc = ldc; a.out_fp32 = 1;
+      return launch_gemm(a, num_sms, 0);
+    };
+    if (pe_proj(d.layers[1].t2i.k, d.kvq1_res, 3 * DI)) return -1;
+    if (pe_proj(d.layers[1].i2t.q, d.kvq1_res + 2 * DI, 3 * DI)) return -1;
+    if (pe_proj(d.final_t2i.k, d.kvf_res, 2 * DI)) return -1;
+  }
   CHK(d.src = (float*)dalloc((size_t)NI * DC * 4));
   CHK(d.src_bf = (__nv_bfloat16*)dalloc((size_t)NI * DC * 2));
   CHK(d.src_pe_bf = (__nv_bfloat16*)dalloc((size_t)NI * DC * 2));
@@ -508,13 +517,9 @@ int Engine::finalize_decoder() {
   CHK(d.t_v128 = (__nv_bfloat16*)dalloc(PT * DI * 2));
   CHK(d.t_att128 = (__nv_bfloat16*)dalloc(PT * DI * 2));
   CHK(d.keys = (__nv_bfloat16*)dalloc(PN * DC * 2));
-  CHK(d.keys_pe = (__nv_bfloat16*)dalloc(PN * DC * 2));
-  CHK(d.img_a = (__nv_bfloat16*)dalloc(PN * DI * 2));
-  CHK(d.img_b = (__nv_bfloat16*)dalloc(PN * DI * 2));
+  CHK(d.img_kvq = (__nv_bfloat16*)dalloc(PN * 3 * DI * 2));
   CHK(d.img_att = (__nv_bfloat16*)dalloc(PN * DI * 2));
-  CHK(d.img_f32 = (float*)dalloc(PN * DC * 4));
   CHK(d.up1 = (__nv_bfloat16*)dalloc(PN * 4 * 64 * 2));
-  CHK(d.up2 = (__nv_bfloat16*)dalloc(PN * 4 * 128 * 2));
   CHK(d.h1 = (__nv_bfloat16*)dalloc(P * DC * 2));
   CHK(d.h2 = (__nv_bfloat16*)dalloc(P * DC * 2));
   CHK(d.hyper_in = (float*)dalloc(P * 4 * 32 * 4));
@@ -525,10 +530,12 @@ int Engine::finalize_decoder() {
 // ================================================================================================ forward
 static int gemm(Engine& E, cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int M, int N, int K,
                 const float* bias, void* out, int ldc, int out_fp32, int act = 0, const void* residual = nullptr,
-                int res_rows = 0, int res_bf16 = 0) {
+                int res_rows = 0, int res_bf16 = 0, int epi = 0, const float* ln_g = nullptr, const float* ln_b = nullptr,
+                float ln_eps = 1e-5f) {
   GemmArgs a;
   a.A = A; a.W = W; a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldw = K; a.bias = bias; a.out = out; a.ldc = ldc;
   a.out_fp32 = out_fp32; a.act = act; a.residual = residual; a.res_rows = res_rows; a.res_bf16 = res_bf16;
+  a.epi = epi; a.ln_gamma = ln_g; a.ln_beta = ln_b; a.ln_eps = ln_eps;
   return launch_gemm(a, E.num_sms, st);
 }
 static int ln(cudaStream_t st, const float* x, int rows, int D, const float* g, const float* b, float eps,
@@ -568,9 +575,11 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
                                                           d.point_emb, d.not_a_point, d.out_tokens, d.tok0, d.tok0_bf);
   LAUNCH_CHECK("prompt_tokens");
 
-  const __nv_bfloat16 *keys = nullptr, *keys_pe = nullptr;  // per-prompt image tokens (null = shared src of layer 0)
   for (int l = 0; l < 2; ++l) {
     const DecLayer& L = d.layers[l];
+    if (l == 1) {  // all image-side projections of layer 1 in one pass over the per-prompt keys: [k_t2i | v_t2i | q_i2t]
+      if (gemm(E, st, d.keys, DC, d.kvq1_w, PN, 3 * DI, DC, d.kvq1_b, d.img_kvq, 3 * DI, 0, 0, d.kvq1_res, NI)) return -1;
+    }
     // ---- (1) token self attention
     if (l == 0) {
       if (gemm(E, st, d.tok0_bf, DC, L.self_attn.qkv, PT, 3 * DC, DC, L.self_attn.qkvb, d.t_qkv, 3 * DC, 0)) return -1;
@@ -591,11 +600,9 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
     // ---- (2) token -> image cross attention
     if (gemm(E, st, d.qpe_bf, DC, L.t2i.q, PT, DI, DC, L.t2i.qb, d.t_q128, DI, 0)) return -1;
     if (l == 0) {
-      t2i_attn_kernel<<<P, 256, 0, st>>>(d.t_q128, d.k0, d.v0, 0, T, NI, d.t_att128);
+      t2i_attn_kernel<<<P, 256, 0, st>>>(d.t_q128, d.k0, d.v0, DI, 0, T, NI, d.t_att128);
     } else {
-      if (gemm(E, st, keys_pe, DC, L.t2i.k, PN, DI, DC, L.t2i.kb, d.img_a, DI, 0)) return -1;
-      if (gemm(E, st, keys, DC, L.t2i.v, PN, DI, DC, L.t2i.vb, d.img_b, DI, 0)) return -1;
-      t2i_attn_kernel<<<P, 256, 0, st>>>(d.t_q128, d.img_a, d.img_b, NI, T, NI, d.t_att128);
+      t2i_attn_kernel<<<P, 256, 0, st>>>(d.t_q128, d.img_kvq, d.img_kvq + DI, 3 * DI, NI, T, NI, d.t_att128);
     }
     LAUNCH_CHECK("t2i_attn");
     if (gemm(E, st, d.t_att128, DI, L.t2i.o, PT, DC, DI, L.t2i.ob, d.tok_f32, DC, 1, 0, d.queries, PT)) return -1;
@@ -608,28 +615,25 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
     if (gemm(E, st, d.qpe_bf, DC, L.i2t.k, PT, DI, DC, L.i2t.kb, d.t_k128, DI, 0)) return -1;
     if (gemm(E, st, d.q_bf, DC, L.i2t.v, PT, DI, DC, L.i2t.vb, d.t_v128, DI, 0)) return -1;
     if (l == 0) {
-      i2t_attn_kernel<<<dim3(NI / 32, P), 256, 0, st>>>(d.q0, 0, d.t_k128, d.t_v128, T, NI, d.img_att);
+      i2t_attn_kernel<<<dim3(NI / 32, P), 256, 0, st>>>(d.q0, DI, 0, d.t_k128, d.t_v128, T, NI, d.img_att);
     } else {
-      if (gemm(E, st, keys_pe, DC, L.i2t.q, PN, DI, DC, L.i2t.qb, d.img_a, DI, 0)) return -1;
-      i2t_attn_kernel<<<dim3(NI / 32, P), 256, 0, st>>>(d.img_a, NI, d.t_k128, d.t_v128, T, NI, d.img_att);
+      i2t_attn_kernel<<<dim3(NI / 32, P), 256, 0, st>>>(d.img_kvq + 2 * DI, 3 * DI, NI, d.t_k128, d.t_v128, T, NI, d.img_att);
     }
     LAUNCH_CHECK("i2t_attn");
+    // keys = norm4(keys + out_proj(attn)): LayerNorm fused into the GEMM epilogue (in place for layer 1: every thread
+    // reads the residual of exactly the row segment it later overwrites)
     if (l == 0) {
-      if (gemm(E, st, d.img_att, DI, L.i2t.o, PN, DC, DI, L.i2t.ob, d.img_f32, DC, 1, 0, d.src, NI)) return -1;
+      if (gemm(E, st, d.img_att, DI, L.i2t.o, PN, DC, DI, L.i2t.ob, d.keys, DC, 0, 0, d.src, NI, 0, 1, L.n4g, L.n4b, 1e-5f)) return -1;
     } else {
-      if (gemm(E, st, d.img_att, DI, L.i2t.o, PN, DC, DI, L.i2t.ob, d.img_f32, DC, 1, 0, keys, PN, 1)) return -1;
+      if (gemm(E, st, d.img_att, DI, L.i2t.o, PN, DC, DI, L.i2t.ob, d.keys, DC, 0, 0, d.keys, PN, 1, 1, L.n4g, L.n4b, 1e-5f)) return -1;
     }
-    if (ln(st, d.img_f32, PN, DC, L.n4g, L.n4b, 1e-5f, d.keys, nullptr, d.pos, NI, d.keys_pe)) return -1;
-    keys = d.keys;
-    keys_pe = d.keys_pe;
   }
   // ---- final token -> image attention
   {
     const AttnW& A = d.final_t2i;
     if (gemm(E, st, d.qpe_bf, DC, A.q, PT, DI, DC, A.qb, d.t_q128, DI, 0)) return -1;
-    if (gemm(E, st, keys_pe, DC, A.k, PN, DI, DC, A.kb, d.img_a, DI, 0)) return -1;
-    if (gemm(E, st, keys, DC, A.v, PN, DI, DC, A.vb, d.img_b, DI, 0)) return -1;
-    t2i_attn_kernel<<<P, 256, 0, st>>>(d.t_q128, d.img_a, d.img_b, NI, T, NI, d.t_att128);
+    if (gemm(E, st, d.keys, DC, d.kvf_w, PN, 2 * DI, DC, d.kvf_b, d.img_kvq, 2 * DI, 0, 0, d.kvf_res, NI)) return -1;
+    t2i_attn_kernel<<<P, 256, 0, st>>>(d.t_q128, d.img_kvq, d.img_kvq + DI, 2 * DI, NI, T, NI, d.t_att128);
     LAUNCH_CHECK("t2i_attn");
     if (gemm(E, st, d.t_att128, DI, A.o, PT, DC, DI, A.ob, d.tok_f32, DC, 1, 0, d.queries, PT)) return -1;
     if (ln(st, d.tok_f32, PT, DC, d.nfg, d.nfb, 1e-5f, d.q_bf)) return -1;
@@ -648,12 +652,16 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
     }
   }
   // ---- output upscaling: convT(256->64) -> LN2d(64) -> GELU -> convT(64->32) -> GELU, then the hyper product
-  if (gemm(E, st, keys, DC, d.ct1, PN, 256, DC, d.ct1b, d.img_f32, 256, 1)) return -1;
-  if (ln(st, d.img_f32, PN * 4, 64, d.upln_g, d.upln_b, 1e-6f, d.up1, nullptr, nullptr, 1, nullptr, /*gelu*/ 1)) return -1;
-  if (gemm(E, st, d.up1, 64, d.ct2, PN * 4, 128, 64, d.ct2b, d.up2, 128, 0, 1)) return -1;
+  // convT1 + LayerNorm2d(64) + GELU in one GEMM; convT2 + GELU + hyper-network product in the next: neither the fp32
+  // conv output nor the 32-channel up-scaled embedding ever reaches HBM.
   const int m0 = multimask ? 1 : 0, nm = multimask ? 3 : 1;
-  mask_product_kernel<<<dim3(256, P), 256, 0, st>>>(d.up2, d.hyper_in, m0, nm, low_res);
-  LAUNCH_CHECK("mask_product");
+  if (gemm(E, st, d.keys, DC, d.ct1, PN, 256, DC, d.ct1b, d.up1, 256, 0, 0, nullptr, 0, 0, 2, d.upln_g, d.upln_b, 1e-6f)) return -1;
+  {
+    GemmArgs a;
+    a.A = d.up1; a.W = d.ct2; a.M = PN * 4; a.N = 128; a.K = 64; a.lda = 64; a.ldw = 64; a.bias = d.ct2b; a.act = 1;
+    a.epi = 3; a.hyper = d.hyper_in; a.hyper_m0 = m0; a.hyper_nm = nm; a.out = low_res; a.out_fp32 = 1;
+    if (launch_gemm(a, E.num_sms, st)) return -1;
+  }
   gather_iou_kernel<<<(P * nm + 127) / 128, 128, 0, st>>>(d.iou_out, P, m0, nm, iou);
   LAUNCH_CHECK("gather_iou");
   return 0;

@@ -409,8 +409,11 @@ int msam_decode(msam_handle* h, const float* points, const float* labels, int n_
 }
 int msam_mask_stats(const float* low_res, int n_masks, int in_h, int in_w, int orig_h, int orig_w, float mask_threshold,
                     float stability_offset, int32_t* boxes_xyxy, float* stability, int32_t* area, void* stream) {
-  return post_mask_stats(low_res, n_masks, in_h, in_w, orig_h, orig_w, mask_threshold, stability_offset, boxes_xyxy,
-                         stability, area, (cudaStream_t)stream);
+  // a negative stability_offset selects the generic (any-geometry) kernel with |offset| (used by the parity tests to
+  // cross-check the 4x fast path)
+  const bool generic = stability_offset < 0.f;
+  return post_mask_stats(low_res, n_masks, in_h, in_w, orig_h, orig_w, mask_threshold, fabsf(stability_offset), boxes_xyxy,
+                         stability, area, (cudaStream_t)stream, generic);
 }
 int msam_upsample_masks(const float* low_res, const int32_t* sel, int n_sel, int in_h, int in_w, int orig_h, int orig_w,
                         float mask_threshold, float* logits, uint8_t* binary, void* stream) {

@@ -68,7 +68,7 @@ struct Engine {
 
 // postprocess.cu
 int post_mask_stats(const float* low_res, int n, int in_h, int in_w, int out_h, int out_w, float thr, float off,
-                    int32_t* boxes, float* stability, int32_t* area, cudaStream_t st);
+                    int32_t* boxes, float* stability, int32_t* area, cudaStream_t st, bool force_generic = false);
 int post_upsample(const float* low_res, const int32_t* sel, int n_sel, int in_h, int in_w, int out_h, int out_w, float thr,
                   float* logits, uint8_t* bin, cudaStream_t st);
 int post_paint(const float* low_res, const int32_t* sel, const int32_t* boxes, const int32_t* seg_ids, int n_sel, int in_h,

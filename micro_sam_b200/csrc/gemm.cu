@@ -24,7 +24,7 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*LN exchange*/;
   static constexpr int TMEM_COLS = 2 * BN;  // power of two >= 32 for BN in {64,128,256}
 };
 
@@ -37,6 +37,11 @@ struct GemmParams {
   int ldc;
   int out_fp32;
   int act;                // 0 none, 1 GELU(erf), 2 ReLU
+  const float* ln_gamma;  // fused LayerNorm epilogues
+  const float* ln_beta;
+  float ln_eps;
+  const float* hyper;     // EPI_HYPER: [P, 4, 32] hyper-network outputs
+  int hyper_m0, hyper_nm;
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -45,7 +50,9 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-template <int BN>
+enum { EPI_PLAIN = 0, EPI_LN256 = 1, EPI_LN64_GELU = 2, EPI_HYPER = 3 };
+
+template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -56,6 +63,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* exch = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);  // [2][256] float2 (EPI_LN256)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -135,11 +143,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue: TMEM -> regs -> global
+    // ------------------------------------------------------------ epilogue: TMEM -> regs -> (fused op) -> global
     const int ew = warp - 4;         // 0..7
     const int quad = warp & 3;       // TMEM lane quadrant this warp may access
     const int half = ew >> 2;        // column half of the tile
-    constexpr int COLS_PER_WARP = BN / 2;
+    constexpr int CPW = BN / 2;      // columns per warp
+    constexpr int NCH = CPW / 32;    // 32-column chunks per warp
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
@@ -156,70 +165,167 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.res_bf16) res_row_bf = reinterpret_cast<const __nv_bfloat16*>(p.residual) + off;
         else res_row = reinterpret_cast<const float*>(p.residual) + off;
       }
-#pragma unroll 1
-      for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
-        const int col0 = n_blk * BN + half * COLS_PER_WARP + c * 32;
+      // accumulator chunk c (+ bias, activation, residual) -> f[0..32)
+      auto load_chunk = [&](int c, float* f, int col0) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + half * COLS_PER_WARP + c * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + half * CPW + c * 32), v);
         tmem_ld_wait();
-        if (c == COLS_PER_WARP / 32 - 1) {
+        if (c == NCH - 1) {
           // all TMEM reads of this accumulator stage by this warp are complete -> hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
-        if (row_ok && col0 < p.N) {
-          float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) {
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (!(row_ok && col0 < p.N)) return;
+        if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-            }
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+            f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
           }
-          if (p.act) {
+        }
+        if (p.act) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+        }
+        if (res_row) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 r = *reinterpret_cast<const float4*>(res_row + col0 + j);
+            f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
           }
-          if (res_row) {
+        } else if (res_row_bf) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 r = *reinterpret_cast<const float4*>(res_row + col0 + j);
-              f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
-            }
-          } else if (res_row_bf) {
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 r = *reinterpret_cast<const uint4*>(res_row_bf + col0 + j);
+            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 r = *reinterpret_cast<const uint4*>(res_row_bf + col0 + j);
-              const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                f[j + 2 * q] += __uint_as_float(w[q] << 16);
-                f[j + 2 * q + 1] += __uint_as_float(w[q] & 0xffff0000u);
-              }
-            }
-          }
-          if (p.out_fp32) {
-            float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldc + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldc + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u;
-              u.x = pack_bf16(f[j], f[j + 1]);
-              u.y = pack_bf16(f[j + 2], f[j + 3]);
-              u.z = pack_bf16(f[j + 4], f[j + 5]);
-              u.w = pack_bf16(f[j + 6], f[j + 7]);
-              *reinterpret_cast<uint4*>(o + j) = u;
+            for (int q = 0; q < 4; ++q) {
+              f[j + 2 * q] += __uint_as_float(w[q] << 16);
+              f[j + 2 * q + 1] += __uint_as_float(w[q] & 0xffff0000u);
             }
           }
         }
-        __syncwarp();  // reconverge before the next warp-collective tcgen05.ld
+      };
+      auto store_bf16 = [&](const float* f, int col0) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldc + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 u;
+          u.x = pack_bf16(f[j], f[j + 1]);
+          u.y = pack_bf16(f[j + 2], f[j + 3]);
+          u.z = pack_bf16(f[j + 4], f[j + 5]);
+          u.w = pack_bf16(f[j + 6], f[j + 7]);
+          *reinterpret_cast<uint4*>(o + j) = u;
+        }
+      };
+
+      if constexpr (EPI == EPI_PLAIN) {
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          const int col0 = n_blk * BN + half * CPW + c * 32;
+          float f[32];
+          load_chunk(c, f, col0);
+          if (row_ok && col0 < p.N) {
+            if (p.out_fp32) {
+              float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldc + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              store_bf16(f, col0);
+            }
+          }
+          __syncwarp();  // reconverge before the next warp-collective tcgen05.ld
+        }
+      } else {
+        // fused row epilogues: the whole half-row (CPW columns) of this thread lives in registers
+        float f[CPW];
+        const int colbase = n_blk * BN + half * CPW;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          load_chunk(c, f + c * 32, colbase + c * 32);
+          __syncwarp();
+        }
+        if constexpr (EPI == EPI_LN256) {
+          // LayerNorm over the full 256-wide row (BN == N == 256): exact two-pass statistics per half, combined
+          // across the two column halves with Chan's formula through shared memory.
+          float mean_h = 0.f;
+#pragma unroll
+          for (int j = 0; j < CPW; ++j) mean_h += f[j];
+          mean_h *= (1.0f / CPW);
+          float m2_h = 0.f;
+#pragma unroll
+          for (int j = 0; j < CPW; ++j) { const float d = f[j] - mean_h; m2_h += d * d; }
+          float2* ex = reinterpret_cast<float2*>(exch) + (it & 1) * 256;
+          ex[half * 128 + quad * 32 + lane] = make_float2(mean_h, m2_h);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const float2 o2 = ex[(half ^ 1) * 128 + quad * 32 + lane];
+          const float mean = 0.5f * (mean_h + o2.x);
+          const float dm = mean_h - o2.x;
+          const float var = (m2_h + o2.y + dm * dm * (0.5f * CPW)) * (1.0f / (2 * CPW));
+          const float rstd = rsqrtf(var + p.ln_eps);
+          if (row_ok) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + colbase + c * 32 + j));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.ln_beta + colbase + c * 32 + j));
+                float* x = f + c * 32 + j;
+                x[0] = (x[0] - mean) * rstd * g.x + b.x; x[1] = (x[1] - mean) * rstd * g.y + b.y;
+                x[2] = (x[2] - mean) * rstd * g.z + b.z; x[3] = (x[3] - mean) * rstd * g.w + b.w;
+              }
+              store_bf16(f + c * 32, colbase + c * 32);
+            }
+          }
+        } else if constexpr (EPI == EPI_LN64_GELU) {
+          // LayerNorm2d over 64-channel groups (conv-transpose sub-pixels) + exact GELU; groups never straddle threads
+          if (row_ok) {
+#pragma unroll
+            for (int g0 = 0; g0 < CPW; g0 += 64) {
+              float mean = 0.f;
+#pragma unroll
+              for (int j = 0; j < 64; ++j) mean += f[g0 + j];
+              mean *= (1.0f / 64);
+              float m2 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 64; ++j) { const float d = f[g0 + j] - mean; m2 += d * d; }
+              const float rstd = rsqrtf(m2 * (1.0f / 64) + p.ln_eps);
+#pragma unroll
+              for (int j = 0; j < 64; ++j) {
+                const float y = (f[g0 + j] - mean) * rstd * __ldg(p.ln_gamma + j) + __ldg(p.ln_beta + j);
+                f[g0 + j] = 0.5f * y * (1.0f + erff(y * 0.70710678118654752440f));
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) store_bf16(f + c * 32, colbase + c * 32);
+          }
+        } else if constexpr (EPI == EPI_HYPER) {
+          // second conv-transpose (BN == N == 128: 4 sub-sub-pixels x 32 channels, bias + GELU already applied) fused
+          // with the hyper-network product: masks[p, mi, Y, X] = sum_ch hyper[p, m0+mi, ch] * up[.., ss*32 + ch].
+          // GEMM row = (prompt p, token (y,x), sub-pixel (dy,dx)); this thread holds sub-sub-pixels ey = half, ex = 0,1.
+          if (row_ok) {
+            const int sub = row & 3, tok = (row >> 2) & 4095, pp = row >> 14;
+            const int y = tok >> 6, x = tok & 63, dy = sub >> 1, dx = sub & 1;
+            const int Y = 4 * y + 2 * dy + half, X = 4 * x + 2 * dx;
+            for (int mi = 0; mi < p.hyper_nm; ++mi) {
+              const float* hw = p.hyper + ((size_t)pp * 4 + p.hyper_m0 + mi) * 32;
+              float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+              for (int c = 0; c < 32; c += 4) {
+                const float4 h4 = __ldg(reinterpret_cast<const float4*>(hw + c));
+                a0 += h4.x * f[c] + h4.y * f[c + 1] + h4.z * f[c + 2] + h4.w * f[c + 3];
+                a1 += h4.x * f[32 + c] + h4.y * f[33 + c] + h4.z * f[34 + c] + h4.w * f[35 + c];
+              }
+              float* o = reinterpret_cast<float*>(p.out) + (((size_t)pp * p.hyper_nm + mi) * 256 + Y) * 256 + X;
+              *reinterpret_cast<float2*>(o) = make_float2(a0, a1);
+            }
+          }
+        }
+        __syncwarp();
       }
     }
   }
@@ -232,12 +338,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN>
+template <int BN, int EPI>
 static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e =
+        cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -255,10 +362,12 @@ static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   p.ldc = a.ldc > 0 ? a.ldc : a.N;
   p.out_fp32 = a.out_fp32;
   p.act = a.act;
+  p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;
+  p.hyper = a.hyper; p.hyper_m0 = a.hyper_m0; p.hyper_nm = a.hyper_nm;
   const int tiles = ((a.M + GEMM_BM - 1) / GEMM_BM) * ((a.N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
   prof_begin(stream, PROF_GEMM, 2.0 * a.M * a.N * a.K);
-  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm_bf16_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm launch failed: %s", cudaGetErrorString(e));
@@ -271,11 +380,20 @@ int launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   if (a.N % 32 != 0) return set_error("gemm: N=%d must be a multiple of 32", a.N);
   if (a.K % 8 != 0 || a.lda % 8 != 0 || a.ldw % 8 != 0)
     return set_error("gemm: K/lda/ldw must be multiples of 8 (16-byte TMA strides)");
+  if (a.epi == EPI_LN256 || a.epi == EPI_LN64_GELU) {
+    if (a.N != 256 || a.out_fp32 || !a.ln_gamma || !a.ln_beta) return set_error("gemm: fused LN needs N=256, bf16 out, gamma/beta");
+    return a.epi == EPI_LN256 ? launch_gemm_bn<256, EPI_LN256>(a, num_sms, stream)
+                              : launch_gemm_bn<256, EPI_LN64_GELU>(a, num_sms, stream);
+  }
+  if (a.epi == EPI_HYPER) {
+    if (a.N != 128 || !a.hyper || a.hyper_nm < 1 || a.hyper_nm > 4) return set_error("gemm: fused hyper product needs N=128");
+    return launch_gemm_bn<128, EPI_HYPER>(a, num_sms, stream);
+  }
   // BN=256 keeps the tensor pipe at its 1-CTA rate with the fewest smem bytes per flop; fall back to 128 / 64 when N is
   // not a multiple (or is small), to avoid wasted columns.
-  if (a.N % 256 == 0) return launch_gemm_bn<256>(a, num_sms, stream);
-  if (a.N % 128 == 0) return launch_gemm_bn<128>(a, num_sms, stream);
-  return launch_gemm_bn<64>(a, num_sms, stream);
+  if (a.N % 256 == 0) return launch_gemm_bn<256, EPI_PLAIN>(a, num_sms, stream);
+  if (a.N % 128 == 0) return launch_gemm_bn<128, EPI_PLAIN>(a, num_sms, stream);
+  return launch_gemm_bn<64, EPI_PLAIN>(a, num_sms, stream);
 }
 
 }  // namespace msam

@@ -103,6 +103,88 @@ mask_stats_kernel(const float* __restrict__ low_res, PostGeom g, float thr, floa
   }
 }
 
+// Fast path of mask_stats for the common geometry input_size == original_size == (img, img) (1024^2 tiles, 4x
+// up-sampling): thread j owns the 4 output columns 4j..4j+3, whose taps are low-res columns j-1, j, j+1; rows are walked
+// in order and the two low-res rows are re-read only when the row pair changes (every 4 output rows).  Same
+// interp_axis / bilerp arithmetic as the generic path (bit-identical results), ~10x fewer instructions per pixel.
+// grid = n_masks, block = 512 (two row halves x 256 low-res columns).
+__global__ void __launch_bounds__(512)
+mask_stats_x4_kernel(const float* __restrict__ low_res, PostGeom g, float thr, float off, int32_t* __restrict__ boxes,
+                     float* __restrict__ stability, int32_t* __restrict__ area) {
+  const long mi = blockIdx.x;
+  const float* lr = low_res + mi * 65536;
+  const int j = threadIdx.x & 255, part = threadIdx.x >> 8;
+  Interp ix[4];
+  int k0[4], k1[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    ix[r] = interp_axis(4 * j + r, g.s1, 256);
+    k0[r] = ix[r].i0 - j + 1;  // which of the cached columns (j-1, j, j+1) is tap 0 / tap 1
+    k1[r] = ix[r].i1 - j + 1;
+  }
+  const int cm = max(j - 1, 0), cp = min(j + 1, 255);
+  int hi = 0, lo = 0, ar = 0, x0 = 1 << 30, y0 = 1 << 30, x1 = -1, y1 = -1;
+  const float t_hi = thr + off, t_lo = thr - off;
+  int ci0 = -1, ci1 = -1;
+  float a0[4], a1[4], b0[4], b1[4];
+  for (int y = part * 512; y < part * 512 + 512; ++y) {
+    const Interp iy = interp_axis(y, g.s1, 256);
+    if (iy.i0 != ci0 || iy.i1 != ci1) {  // block-uniform
+      ci0 = iy.i0; ci1 = iy.i1;
+      const float* r0 = lr + ci0 * 256;
+      const float* r1 = lr + ci1 * 256;
+      const float A[3] = {__ldg(r0 + cm), __ldg(r0 + j), __ldg(r0 + cp)};
+      const float B[3] = {__ldg(r1 + cm), __ldg(r1 + j), __ldg(r1 + cp)};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        a0[r] = k0[r] == 0 ? A[0] : (k0[r] == 1 ? A[1] : A[2]);
+        a1[r] = k1[r] == 0 ? A[0] : (k1[r] == 1 ? A[1] : A[2]);
+        b0[r] = k0[r] == 0 ? B[0] : (k0[r] == 1 ? B[1] : B[2]);
+        b1[r] = k1[r] == 0 ? B[0] : (k1[r] == 1 ? B[1] : B[2]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float v = bilerp(a0[r], a1[r], b0[r], b1[r], iy, ix[r]);
+      hi += v > t_hi;
+      lo += v > t_lo;
+      if (v > thr) {
+        ++ar;
+        const int x = 4 * j + r;
+        x0 = min(x0, x); x1 = max(x1, x); y0 = min(y0, y); y1 = max(y1, y);
+      }
+    }
+  }
+  __shared__ int red[7][16];
+  int vals[7] = {hi, lo, ar, x0, y0, x1, y1};
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    int v = vals[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int w = __shfl_xor_sync(0xffffffffu, v, o);
+      v = (k < 3) ? v + w : ((k == 3 || k == 4) ? min(v, w) : max(v, w));
+    }
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int r[7];
+    for (int k = 0; k < 7; ++k) {
+      int v = red[k][0];
+      for (int w = 1; w < 16; ++w) v = (k < 3) ? v + red[k][w] : ((k == 3 || k == 4) ? min(v, red[k][w]) : max(v, red[k][w]));
+      r[k] = v;
+    }
+    stability[mi] = (float)r[0] / (float)r[1];
+    area[mi] = r[2];
+    const bool empty = r[2] == 0;
+    boxes[mi * 4 + 0] = empty ? 0 : r[3];
+    boxes[mi * 4 + 1] = empty ? 0 : r[4];
+    boxes[mi * 4 + 2] = empty ? 0 : r[5];
+    boxes[mi * 4 + 3] = empty ? 0 : r[6];
+  }
+}
+
 // Materialise selected masks: logits (fp32) and/or thresholded (uint8 0/1), each [n_sel, out_h, out_w].
 __global__ void upsample_kernel(const float* __restrict__ low_res, const int32_t* __restrict__ sel, PostGeom g,
                                 float thr, float* __restrict__ logits, uint8_t* __restrict__ bin) {
@@ -270,11 +352,15 @@ static int make_geom(int in_h, int in_w, int out_h, int out_w, PostGeom* g) {
 }
 
 int post_mask_stats(const float* low_res, int n, int in_h, int in_w, int out_h, int out_w, float thr, float off,
-                    int32_t* boxes, float* stability, int32_t* area, cudaStream_t st) {
+                    int32_t* boxes, float* stability, int32_t* area, cudaStream_t st, bool force_generic) {
   PostGeom g;
   if (make_geom(in_h, in_w, out_h, out_w, &g)) return -1;
   if (n <= 0) return 0;
-  mask_stats_kernel<<<n, 256, 0, st>>>(low_res, g, thr, off, boxes, stability, area);
+  if (g.identity2 && in_h == 1024 && in_w == 1024 && !force_generic) {
+    mask_stats_x4_kernel<<<n, 512, 0, st>>>(low_res, g, thr, off, boxes, stability, area);
+  } else {
+    mask_stats_kernel<<<n, 256, 0, st>>>(low_res, g, thr, off, boxes, stability, area);
+  }
   LAUNCH_CHECK("mask_stats");
   return 0;
 }

@@ -299,6 +299,11 @@ def sec_post():
     for (inp, orig) in (((1024, 1024), (1024, 1024)), ((1024, 683), (768, 512)), ((640, 1024), (500, 800))):
         ref_full = osam.postprocess_masks(low[:, None], inp, orig)[:, 0]
         boxes, stab, area = bsam.mask_stats(low.to(DEV), inp, orig, 0.0, 1.0)
+        if inp == (1024, 1024) and orig == (1024, 1024):  # 4x fast path vs the generic kernel (negative offset selects it)
+            b2, s2, a2 = bsam.mask_stats(low.to(DEV), inp, orig, 0.0, -1.0)
+            same = bool((b2 == boxes).all()) and bool((a2 == area).all()) and bool(torch.equal(s2.nan_to_num(-1), stab.nan_to_num(-1)))
+            RESULTS.append(same)
+            print(f"[{'OK ' if same else 'BAD'}] mask_stats 4x fast path == generic path", flush=True)
         full = torch.empty(12, orig[0], orig[1], device=DEV)
         binm = torch.empty(12, orig[0], orig[1], device=DEV, dtype=torch.uint8)
         dlow = low.to(DEV).contiguous()
