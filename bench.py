@@ -292,7 +292,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="vit_b")
-    ap.add_argument("--max-prompts", type=int, default=256)
+    ap.add_argument("--max-prompts", type=int, default=1024)
     ap.add_argument("--pred-iou-thresh", type=float, default=0.88)
     ap.add_argument("--stability-score-thresh", type=float, default=0.95)
     ap.add_argument("--no-vith", action="store_true")

@@ -202,15 +202,17 @@ __global__ void token_self_attn_kernel(const __nv_bfloat16* __restrict__ q, int 
   }
 }
 
-// token -> image attention core.  q [P*T,128] (bf16, projected), k/v [*,128] image-side (kv_stride = 0 rows when shared
-// by all prompts, else 4096 rows per prompt).  One CTA per prompt, warp = head (16 dims), lane = slice of image tokens,
-// online softmax per (token, lane), combined across lanes at the end.  Tokens handled in groups of 8.
+// token -> image attention core.  q [P*T,128] (bf16, projected), k/v [*, ld] image-side (kv_stride_rows = 0 when shared
+// by all prompts, else 4096 rows per prompt).  One CTA per prompt, warp = head (16 dims), lane = slice of image tokens;
+// per-(token, lane) online softmax with lazy rescaling (the running max rarely moves after the first keys), the next
+// key/value rows are prefetched into registers while the current ones are consumed; lanes are combined at the end.
+// Tokens are handled in groups of 8 (AMG / box prompts have T = 7).
 __global__ void __launch_bounds__(256)
 t2i_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                 const __nv_bfloat16* __restrict__ v, int ld, long kv_stride_rows, int T, int NI,
                 __nv_bfloat16* __restrict__ out) {
   const int p = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ float sq[TMAX][DI];
+  __shared__ __align__(16) float sq[TMAX][DI];
   for (int i = threadIdx.x; i < T * DI; i += 256) sq[i / DI][i % DI] = __bfloat162float(q[(long)p * T * DI + i]) * 0.25f;
   __syncthreads();
   const __nv_bfloat16* kp = k + (long)p * kv_stride_rows * ld + h * 16;
@@ -220,15 +222,20 @@ t2i_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     float m[8], l[8], acc[8][16];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-      m[t] = -INFINITY; l[t] = 0.f;
+      m[t] = -1e30f; l[t] = 0.f;
 #pragma unroll
       for (int d = 0; d < 16; ++d) acc[t][d] = 0.f;
     }
+    uint4 ka = *reinterpret_cast<const uint4*>(kp + (long)lane * ld), kb = *reinterpret_cast<const uint4*>(kp + (long)lane * ld + 8);
+    uint4 va = *reinterpret_cast<const uint4*>(vp + (long)lane * ld), vb = *reinterpret_cast<const uint4*>(vp + (long)lane * ld + 8);
     for (int n = lane; n < NI; n += 32) {
-      const uint4 ka = *reinterpret_cast<const uint4*>(kp + (long)n * ld), kb = *reinterpret_cast<const uint4*>(kp + (long)n * ld + 8);
-      const uint4 va = *reinterpret_cast<const uint4*>(vp + (long)n * ld), vb = *reinterpret_cast<const uint4*>(vp + (long)n * ld + 8);
       const uint32_t kw[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
       const uint32_t vw[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+      if (n + 32 < NI) {  // prefetch the next rows of this lane
+        const long nn = (long)(n + 32) * ld;
+        ka = *reinterpret_cast<const uint4*>(kp + nn); kb = *reinterpret_cast<const uint4*>(kp + nn + 8);
+        va = *reinterpret_cast<const uint4*>(vp + nn); vb = *reinterpret_cast<const uint4*>(vp + nn + 8);
+      }
       float kf[16], vf[16];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -237,17 +244,24 @@ t2i_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
       }
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
-        if (t < nt) {
-          float s = 0.f;
+        if (t >= nt) break;
+        float s = 0.f;
 #pragma unroll
-          for (int d = 0; d < 16; ++d) s += sq[t0 + t][h * 16 + d] * kf[d];
-          const float mn = fmaxf(m[t], s);
-          const float corr = __expf(m[t] - mn), pj = __expf(s - mn);
-          m[t] = mn;
-          l[t] = l[t] * corr + pj;
-#pragma unroll
-          for (int d = 0; d < 16; ++d) acc[t][d] = acc[t][d] * corr + pj * vf[d];
+        for (int d = 0; d < 16; d += 4) {
+          const float4 qq = *reinterpret_cast<const float4*>(&sq[t0 + t][h * 16 + d]);  // warp-uniform -> broadcast
+          s += qq.x * kf[d] + qq.y * kf[d + 1] + qq.z * kf[d + 2] + qq.w * kf[d + 3];
         }
+        if (s > m[t]) {  // lazy rescale
+          const float corr = __expf(m[t] - s);
+          m[t] = s;
+          l[t] *= corr;
+#pragma unroll
+          for (int d = 0; d < 16; ++d) acc[t][d] *= corr;
+        }
+        const float pj = __expf(s - m[t]);
+        l[t] += pj;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) acc[t][d] += pj * vf[d];
       }
     }
     // combine the 32 lanes
@@ -257,7 +271,7 @@ t2i_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
         float mm = m[t];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
-        const float sc = (m[t] == -INFINITY) ? 0.f : __expf(m[t] - mm);
+        const float sc = __expf(m[t] - mm);
         float ll = l[t] * sc;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
@@ -274,59 +288,76 @@ t2i_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
   }
 }
 
-// image -> token attention core.  q_img [*,128] (q_stride_rows = 0 when shared), k_tok / v_tok [P*T,128].
-// grid = (NI/32, P), block = 256: thread = (image token n = blockIdx.x*32 + tid/8, head = tid%8).
+// image -> token attention core.  q_img [*, ldq] (q_stride_rows = 0 when shared), k_tok / v_tok [P*T,128].
+// grid = (NI/64, P), block = 256: thread = (head = tid%8, two image tokens n0 = blockIdx.x*64 + tid/8 and n0 + 32);
+// token keys/values live in shared memory as 16-byte vectors (LDS.128, conflict-free with the 20-float pitch).
 __global__ void __launch_bounds__(256)
 i2t_attn_kernel(const __nv_bfloat16* __restrict__ qimg, int ldq, long q_stride_rows, const __nv_bfloat16* __restrict__ ktok,
                 const __nv_bfloat16* __restrict__ vtok, int T, int NI, __nv_bfloat16* __restrict__ out) {
   const int p = blockIdx.y;
-  __shared__ float sk[TMAX][NHEAD][17], sv[TMAX][NHEAD][17];
+  __shared__ __align__(16) float sk[TMAX][NHEAD][20], sv[TMAX][NHEAD][20];
   for (int i = threadIdx.x; i < T * DI; i += 256) {
     const int t = i / DI, c = i % DI;
-    sk[t][c / 16][c % 16] = __bfloat162float(ktok[((long)p * T + t) * DI + c]);
+    sk[t][c / 16][c % 16] = __bfloat162float(ktok[((long)p * T + t) * DI + c]) * 0.25f;
     sv[t][c / 16][c % 16] = __bfloat162float(vtok[((long)p * T + t) * DI + c]);
   }
   __syncthreads();
-  const int h = threadIdx.x & 7, n = blockIdx.x * 32 + (threadIdx.x >> 3);
-  const __nv_bfloat16* qp = qimg + ((long)p * q_stride_rows + n) * ldq + h * 16;
-  const uint4 qa = *reinterpret_cast<const uint4*>(qp), qb = *reinterpret_cast<const uint4*>(qp + 8);
-  const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-  float qf[16];
+  const int h = threadIdx.x & 7;
+  float qf[2][16];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { qf[2 * i] = bf_lo(qw[i]) * 0.25f; qf[2 * i + 1] = bf_hi(qw[i]) * 0.25f; }
-  float s[TMAX], m = -INFINITY;
+  for (int r = 0; r < 2; ++r) {
+    const int n = blockIdx.x * 64 + (threadIdx.x >> 3) + 32 * r;
+    const __nv_bfloat16* qp = qimg + ((long)p * q_stride_rows + n) * ldq + h * 16;
+    const uint4 qa = *reinterpret_cast<const uint4*>(qp), qb = *reinterpret_cast<const uint4*>(qp + 8);
+    const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { qf[r][2 * i] = bf_lo(qw[i]); qf[r][2 * i + 1] = bf_hi(qw[i]); }
+  }
+  float s[2][TMAX], m[2] = {-1e30f, -1e30f};
 #pragma unroll
   for (int t = 0; t < TMAX; ++t) {
-    s[t] = -INFINITY;
+    s[0][t] = s[1][t] = -1e30f;
     if (t < T) {
-      float a = 0.f;
+      float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-      for (int d = 0; d < 16; ++d) a += qf[d] * sk[t][h][d];
-      s[t] = a;
-      m = fmaxf(m, a);
+      for (int d = 0; d < 16; d += 4) {
+        const float4 kk = *reinterpret_cast<const float4*>(&sk[t][h][d]);
+        a0 += qf[0][d] * kk.x + qf[0][d + 1] * kk.y + qf[0][d + 2] * kk.z + qf[0][d + 3] * kk.w;
+        a1 += qf[1][d] * kk.x + qf[1][d + 1] * kk.y + qf[1][d + 2] * kk.z + qf[1][d + 3] * kk.w;
+      }
+      s[0][t] = a0; s[1][t] = a1;
+      m[0] = fmaxf(m[0], a0); m[1] = fmaxf(m[1], a1);
     }
   }
-  float l = 0.f, o[16];
+  float l[2] = {0.f, 0.f}, o[2][16];
 #pragma unroll
-  for (int d = 0; d < 16; ++d) o[d] = 0.f;
+  for (int d = 0; d < 16; ++d) o[0][d] = o[1][d] = 0.f;
 #pragma unroll
   for (int t = 0; t < TMAX; ++t) {
     if (t < T) {
-      const float pj = __expf(s[t] - m);
-      l += pj;
+      const float p0 = __expf(s[0][t] - m[0]), p1 = __expf(s[1][t] - m[1]);
+      l[0] += p0; l[1] += p1;
 #pragma unroll
-      for (int d = 0; d < 16; ++d) o[d] += pj * sv[t][h][d];
+      for (int d = 0; d < 16; d += 4) {
+        const float4 vv = *reinterpret_cast<const float4*>(&sv[t][h][d]);
+        o[0][d] += p0 * vv.x; o[0][d + 1] += p0 * vv.y; o[0][d + 2] += p0 * vv.z; o[0][d + 3] += p0 * vv.w;
+        o[1][d] += p1 * vv.x; o[1][d + 1] += p1 * vv.y; o[1][d + 2] += p1 * vv.z; o[1][d + 3] += p1 * vv.w;
+      }
     }
   }
-  const float inv = 1.f / l;
-  uint4 o0, o1;
-  o0.x = pk2(o[0] * inv, o[1] * inv); o0.y = pk2(o[2] * inv, o[3] * inv);
-  o0.z = pk2(o[4] * inv, o[5] * inv); o0.w = pk2(o[6] * inv, o[7] * inv);
-  o1.x = pk2(o[8] * inv, o[9] * inv); o1.y = pk2(o[10] * inv, o[11] * inv);
-  o1.z = pk2(o[12] * inv, o[13] * inv); o1.w = pk2(o[14] * inv, o[15] * inv);
-  __nv_bfloat16* dst = out + ((long)p * NI + n) * DI + h * 16;
-  *reinterpret_cast<uint4*>(dst) = o0;
-  *reinterpret_cast<uint4*>(dst + 8) = o1;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const float inv = 1.f / l[r];
+    const int n = blockIdx.x * 64 + (threadIdx.x >> 3) + 32 * r;
+    uint4 o0, o1;
+    o0.x = pk2(o[r][0] * inv, o[r][1] * inv); o0.y = pk2(o[r][2] * inv, o[r][3] * inv);
+    o0.z = pk2(o[r][4] * inv, o[r][5] * inv); o0.w = pk2(o[r][6] * inv, o[r][7] * inv);
+    o1.x = pk2(o[r][8] * inv, o[r][9] * inv); o1.y = pk2(o[r][10] * inv, o[r][11] * inv);
+    o1.z = pk2(o[r][12] * inv, o[r][13] * inv); o1.w = pk2(o[r][14] * inv, o[r][15] * inv);
+    __nv_bfloat16* dst = out + ((long)p * NI + n) * DI + h * 16;
+    *reinterpret_cast<uint4*>(dst) = o0;
+    *reinterpret_cast<uint4*>(dst + 8) = o1;
+  }
 }
 
 __global__ void gather_iou_kernel(const float* __restrict__ iou32, int P, int m0, int nm, float* __restrict__ out) {
@@ -615,15 +646,15 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
     if (gemm(E, st, d.qpe_bf, DC, L.i2t.k, PT, DI, DC, L.i2t.kb, d.t_k128, DI, 0)) return -1;
     if (gemm(E, st, d.q_bf, DC, L.i2t.v, PT, DI, DC, L.i2t.vb, d.t_v128, DI, 0)) return -1;
     if (l == 0) {
-      i2t_attn_kernel<<<dim3(NI / 32, P), 256, 0, st>>>(d.q0, DI, 0, d.t_k128, d.t_v128, T, NI, d.img_att);
+      i2t_attn_kernel<<<dim3(NI / 64, P), 256, 0, st>>>(d.q0, DI, 0, d.t_k128, d.t_v128, T, NI, d.img_att);
     } else {
-      i2t_attn_kernel<<<dim3(NI / 32, P), 256, 0, st>>>(d.img_kvq + 2 * DI, 3 * DI, NI, d.t_k128, d.t_v128, T, NI, d.img_att);
+      i2t_attn_kernel<<<dim3(NI / 64, P), 256, 0, st>>>(d.img_kvq + 2 * DI, 3 * DI, NI, d.t_k128, d.t_v128, T, NI, d.img_att);
     }
     LAUNCH_CHECK("i2t_attn");
     // keys = norm4(keys + out_proj(attn)): LayerNorm fused into the GEMM epilogue (in place for layer 1: every thread
     // reads the residual of exactly the row segment it later overwrites)
     if (l == 0) {
-      if (gemm(E, st, d.img_att, DI, L.i2t.o, PN, DC, DI, L.i2t.ob, d.keys, DC, 0, 0, d.src, NI, 0, 1, L.n4g, L.n4b, 1e-5f)) return -1;
+      if (gemm(E, st, d.img_att, DI, L.i2t.o, PN, DC, DI, L.i2t.ob, d.keys, DC, 0, 0, d.src_bf, NI, 1, 1, L.n4g, L.n4b, 1e-5f)) return -1;
     } else {
       if (gemm(E, st, d.img_att, DI, L.i2t.o, PN, DC, DI, L.i2t.ob, d.keys, DC, 0, 0, d.keys, PN, 1, 1, L.n4g, L.n4b, 1e-5f)) return -1;
     }

@@ -123,10 +123,11 @@ mask_stats_x4_kernel(const float* __restrict__ low_res, PostGeom g, float thr, f
     k1[r] = ix[r].i1 - j + 1;
   }
   const int cm = max(j - 1, 0), cp = min(j + 1, 255);
-  int hi = 0, lo = 0, ar = 0, x0 = 1 << 30, y0 = 1 << 30, x1 = -1, y1 = -1;
+  int hi = 0, lo = 0, ar = 0, y0 = 1 << 30, y1 = -1;
+  bool colany[4] = {false, false, false, false};
   const float t_hi = thr + off, t_lo = thr - off;
   int ci0 = -1, ci1 = -1;
-  float a0[4], a1[4], b0[4], b1[4];
+  float hA[4], hB[4];  // horizontally interpolated values of the two cached low-res rows (the inner terms of bilerp)
   for (int y = part * 512; y < part * 512 + 512; ++y) {
     const Interp iy = interp_axis(y, g.s1, 256);
     if (iy.i0 != ci0 || iy.i1 != ci1) {  // block-uniform
@@ -137,24 +138,31 @@ mask_stats_x4_kernel(const float* __restrict__ low_res, PostGeom g, float thr, f
       const float B[3] = {__ldg(r1 + cm), __ldg(r1 + j), __ldg(r1 + cp)};
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        a0[r] = k0[r] == 0 ? A[0] : (k0[r] == 1 ? A[1] : A[2]);
-        a1[r] = k1[r] == 0 ? A[0] : (k1[r] == 1 ? A[1] : A[2]);
-        b0[r] = k0[r] == 0 ? B[0] : (k0[r] == 1 ? B[1] : B[2]);
-        b1[r] = k1[r] == 0 ? B[0] : (k1[r] == 1 ? B[1] : B[2]);
+        const float a0 = k0[r] == 0 ? A[0] : (k0[r] == 1 ? A[1] : A[2]);
+        const float a1 = k1[r] == 0 ? A[0] : (k1[r] == 1 ? A[1] : A[2]);
+        const float b0 = k0[r] == 0 ? B[0] : (k0[r] == 1 ? B[1] : B[2]);
+        const float b1 = k1[r] == 0 ? B[0] : (k1[r] == 1 ? B[1] : B[2]);
+        hA[r] = ix[r].l0 * a0 + ix[r].l1 * a1;
+        hB[r] = ix[r].l0 * b0 + ix[r].l1 * b1;
       }
     }
+    bool rowany = false;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const float v = bilerp(a0[r], a1[r], b0[r], b1[r], iy, ix[r]);
+      const float v = iy.l0 * hA[r] + iy.l1 * hB[r];
+      const bool pos = v > thr;
       hi += v > t_hi;
       lo += v > t_lo;
-      if (v > thr) {
-        ++ar;
-        const int x = 4 * j + r;
-        x0 = min(x0, x); x1 = max(x1, x); y0 = min(y0, y); y1 = max(y1, y);
-      }
+      ar += pos;
+      colany[r] |= pos;
+      rowany |= pos;
     }
+    if (rowany) { y0 = min(y0, y); y1 = max(y1, y); }
   }
+  int x0 = 1 << 30, x1 = -1;
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    if (colany[r]) { x0 = min(x0, 4 * j + r); x1 = max(x1, 4 * j + r); }
   __shared__ int red[7][16];
   int vals[7] = {hi, lo, ar, x0, y0, x1, y1};
 #pragma unroll

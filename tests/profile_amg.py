@@ -13,7 +13,7 @@ from oracle import sam_ref  # noqa: E402  (seeded weights only)
 model = sys.argv[1] if len(sys.argv) > 1 else "vit_b"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 sd = sam_ref.seeded_state_dict(model, seed=0)
-pred = util.get_sam_model(model, state_dict=sd, max_batch=4, max_prompts=256)
+pred = util.get_sam_model(model, state_dict=sd, max_batch=4, max_prompts=1024)
 amg = iseg.AutomaticMaskGenerator(pred, points_per_side=32)
 tiles = np.stack([lm_tile((1024, 1024), 150, seed=i) for i in range(n + 1)])
 for t in range(n + 1):
