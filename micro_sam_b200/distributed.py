@@ -1,0 +1,48 @@
+"""Tile-level data parallelism: units (tiles / (z, tile) pairs / images) are independent, so ranks take
+static contiguous shards and no data-path collective is needed.  The only exchange micro-sam's algorithms ever need is
+for stitched results: per-rank *instance tables* (box, score, area, tile id ...) are all-gathered so that cross-tile NMS /
+painting (instance_segmentation.py:511-521, util.py:1750-1770) sees every instance, and per-slice id offsets
+(multi_dimensional_segmentation.py:401-414) need an exclusive scan of per-slice max ids."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_units: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous block partition [lo, hi) of n_units; sizes differ by at most one; covers every unit exactly once."""
+    if not (0 <= rank < world_size):
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    return (n_units * rank) // world_size, (n_units * (rank + 1)) // world_size
+
+
+def all_gather_tables(table: torch.Tensor, group=None) -> Tuple[torch.Tensor, List[int]]:
+    """All-gather row-tables of different lengths ([n_r, C] per rank, same C/dtype) -> ([sum n_r, C], counts).
+    One all_gather of the counts, one all_gather of tables padded to the maximum count (NCCL over NVLink on GPU, gloo on
+    CPU).  Without an initialised process group this is the identity."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return table, [int(table.shape[0])]
+    world = dist.get_world_size(group)
+    n = torch.tensor([table.shape[0]], dtype=torch.int64, device=table.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    mx = max(counts) if counts else 0
+    padded = torch.zeros((mx,) + tuple(table.shape[1:]), dtype=table.dtype, device=table.device)
+    padded[: table.shape[0]] = table
+    parts = [torch.zeros_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0), counts
+
+
+def exclusive_id_offsets(local_max_ids: torch.Tensor, group=None) -> torch.Tensor:
+    """Per-unit id offsets for slice-wise segmentation: exclusive scan over ALL units (in rank order) of their max ids.
+    `local_max_ids` [n_r] int64 -> offsets [n_r] for this rank's units."""
+    allv, counts = all_gather_tables(local_max_ids.reshape(-1, 1).to(torch.int64), group)
+    allv = allv.reshape(-1)
+    scan = torch.cumsum(allv, 0) - allv
+    rank = dist.get_rank(group) if (dist.is_available() and dist.is_initialized()) else 0
+    lo = sum(counts[:rank])
+    return scan[lo: lo + local_max_ids.numel()]

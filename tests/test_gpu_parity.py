@@ -142,3 +142,47 @@ def test_errors(models):
         pred.predict_torch(torch.zeros(1, 1, 2), torch.ones(1, 1))
     with pytest.raises(RuntimeError):
         util.get_sam_model("vit_b", device="cpu", state_dict={})
+
+
+def test_batched_inference_against_oracle(models):
+    """inference.batched_inference (boxes, cfg4 recipe): float stages within tolerance, integer stages bit-exact given the
+    GPU's own low-res logits."""
+    from oracle import amg_ref
+    from micro_sam_b200 import inference
+    from micro_sam_b200.sample_data import lm_tile, random_boxes
+    opred, pred = models
+    img = lm_tile((512, 512), 30, seed=5)
+    boxes = random_boxes(20, (512, 512), seed=1)
+    recs = inference.batched_inference(pred, img, batch_size=8, boxes=boxes, return_instance_segmentation=False)
+    orecs = amg_ref.batched_inference(opred, img, batch_size=8, boxes=boxes, return_instance_segmentation=False)
+    assert len(recs) == len(orecs) == 20
+    iou_g = np.array([r["predicted_iou"] for r in recs]); iou_o = np.array([r["predicted_iou"] for r in orecs])
+    assert np.abs(iou_g - iou_o).max() < 2e-2
+    agree = np.mean([(r["segmentation"].cpu().numpy() == o["segmentation"].numpy()).mean() for r, o in zip(recs, orecs)])
+    assert agree > 0.98, agree
+    # integer stages: feed the oracle the GPU low-res logits
+    low = torch.stack([r["logits"] for r in recs]).cpu()          # (20,1,256,256)
+    iou = torch.tensor(iou_g, dtype=torch.float32)[:, None]
+    state = {"i": 0}
+
+    def fake(point_coords, point_labels, boxes=None, mask_input=None, multimask_output=True, return_logits=False):
+        n = boxes.shape[0]
+        s = state["i"]; state["i"] += n
+        return opred.model.postprocess_masks(low[s:s + n], opred.input_size, opred.original_size), iou[s:s + n], low[s:s + n]
+
+    orig = opred.predict_torch
+    opred.predict_torch = fake
+    try:
+        orecs2 = amg_ref.batched_inference(opred, img, batch_size=8, boxes=boxes, return_instance_segmentation=False)
+        state["i"] = 0
+        oseg = amg_ref.batched_inference(opred, img, batch_size=8, boxes=boxes, return_instance_segmentation=True)
+    finally:
+        opred.predict_torch = orig
+    for r, o in zip(recs, orecs2):
+        assert r["bbox"] == o["bbox"] and r["area"] == int(o["area"]) and r["seg_id"] == o["seg_id"]
+        assert np.array_equal(r["segmentation"].cpu().numpy(), o["segmentation"].numpy())
+        assert r["stability_score"] == o["stability_score"] or (np.isnan(r["stability_score"]) and np.isnan(o["stability_score"]))
+    seg = inference.batched_inference(pred, img, batch_size=8, boxes=boxes)
+    assert _partition_equal(seg, oseg)
+    with pytest.raises(ValueError):
+        inference.batched_inference(pred, img, batch_size=8)

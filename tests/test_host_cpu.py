@@ -1,0 +1,151 @@
+"""CPU-only tests (`-m "not gpu"`): host logic against the oracle / golden vectors, C-ABI surface, loud failure without
+a GPU, and the world_size-2 gloo path of the multi-GPU helpers."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_abi_exports_every_declared_symbol():
+    from micro_sam_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "msam_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(msam_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 15, names
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    L.msam_last_error.restype = ctypes.c_char_p
+    assert isinstance(L.msam_last_error(), bytes)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_fails_loudly_without_gpu():
+    from micro_sam_b200 import _lib, util
+    h = ctypes.c_void_p()
+    cfg = _lib.MsamConfig(768, 12, 12, (ctypes.c_int32 * 8)(2, 5, 8, 11, -1, -1, -1, -1), 14, 1024, 16, 256, 1, 64)
+    assert _lib.lib().msam_create(ctypes.byref(cfg), 0, ctypes.byref(h)) != 0
+    assert b"no CUDA device" in _lib.lib().msam_last_error()
+    with pytest.raises(RuntimeError):
+        util.get_sam_model("vit_b", state_dict={"x": torch.zeros(1)})
+    with pytest.raises(RuntimeError):
+        util.get_sam_model("vit_b", device="cpu", state_dict={"x": torch.zeros(1)})
+
+
+def _unpack(packed, shape):
+    n, h, w = shape
+    return np.unpackbits(packed, axis=-1)[..., :w].astype(bool).reshape(n, h, w)
+
+
+def test_host_helpers_match_reference_golden():
+    from micro_sam_b200 import _amg_utils as A, util
+    z = np.load(os.path.join(G, "util.npz"))
+    for k in ("gray_f32", "gray_u16", "one_ch", "two_ch", "rgb_u8", "const"):
+        assert np.array_equal(util._to_image(z[f"in_{k}"]), z[f"out_{k}"]), k
+    with pytest.raises(ValueError):
+        util._to_image(np.zeros((2, 2, 2, 2)))
+    v = np.load(os.path.join(G, "vendored.npz"))
+    for tag in "abc":
+        m = _unpack(v[f"masks_{tag}"], v[f"shape_{tag}"])
+        rles = A.mask_to_rle(m)
+        assert np.array_equal(np.concatenate([np.asarray(r["counts"]) for r in rles]), v[f"rle_counts_{tag}"])
+        for r, mm in zip(rles, m):
+            assert np.array_equal(A.rle_to_mask(r), mm) and A.area_from_rle(r) == mm.sum()
+    assert A.mask_to_rle(np.zeros((0, 4, 4), bool)) == []
+
+
+def test_blocking_matches_reference_expectations():
+    """test/test_util.py:179-208: 512^2 image, tile 256, halo 16 -> 4 tiles, row-major ids, halo clipped to the image."""
+    from micro_sam_b200._amg_utils import Blocking
+    b = Blocking([0, 0], [512, 512], [256, 256])
+    assert b.number_of_blocks == 4 and b.blocks_per_axis == [2, 2]
+    t = b.get_block_with_halo(1, [16, 16])
+    assert (t.inner_block.begin, t.inner_block.end) == ([0, 256], [256, 512])
+    assert (t.outer_block.begin, t.outer_block.end) == ([0, 240], [272, 512])
+    assert t.inner_block_local.begin == [0, 16] and t.outerBlock is t.outer_block
+    assert b.coordinates_to_block_id([300, 10]) == 2 and b.block_grid_position(3) == [1, 1]
+    r = Blocking([0, 0], [500, 700], [256, 256])  # ragged border tiles
+    assert r.number_of_blocks == 6 and r.get_block(5).shape == [244, 188]
+
+
+def test_segmentation_assembly_matches_oracle():
+    from oracle import amg_ref
+    from micro_sam_b200 import util
+    rng = np.random.default_rng(0)
+    yy, xx = np.mgrid[:96, :128]
+    recs = []
+    for k in range(14):
+        cy, cx, r = rng.integers(0, 96), rng.integers(0, 128), rng.integers(4, 25)
+        m = (yy - cy) ** 2 + (xx - cx) ** 2 < r * r
+        if k % 5 == 0:  # disconnected mask -> connected components must split it
+            m |= (yy - (cy + 40) % 96) ** 2 + (xx - (cx + 50) % 128) ** 2 < 9
+        recs.append({"segmentation": m, "area": int(m.sum())})
+    for kw in (dict(), dict(merge_exclusively=False), dict(with_background=True), dict(min_object_size=30),
+               dict(merge_exclusively=False, with_background=True, min_object_size=10)):
+        a = util.mask_data_to_segmentation(recs, **kw)
+        b = amg_ref.mask_data_to_segmentation(recs, **kw)
+        assert a.dtype == np.uint32 and np.array_equal(a == 0, b == 0)
+        pairs = np.unique(np.stack([a.ravel(), b.ravel()], 1), axis=0)
+        assert len(pairs) == len(np.unique(a)) == len(np.unique(b)), kw  # equal up to relabelling
+        assert a.max() == len(np.unique(a)) - 1                           # consecutive ids
+
+
+def test_maskdata_and_point_grid():
+    from micro_sam_b200 import _amg_utils as A
+    from oracle import amg_ref
+    assert np.array_equal(A.build_point_grid(32), amg_ref.build_point_grid(32))
+    assert A.generate_crop_boxes((300, 500), 1, 512 / 1500) == amg_ref.generate_crop_boxes((300, 500), 1, 512 / 1500)
+    d = A.MaskData(a=torch.arange(6), b=list("abcdef"), c=np.arange(6) * 2)
+    d.filter(torch.tensor([True, False, True, True, False, False]))
+    assert d["a"].tolist() == [0, 2, 3] and d["b"] == ["a", "c", "d"] and d["c"].tolist() == [0, 4, 6]
+    d.cat(A.MaskData(a=torch.tensor([9]), b=["z"], c=np.array([1])))
+    d.filter(torch.tensor([3, 0]))
+    assert d["a"].tolist() == [9, 0] and d["b"] == ["z", "a"]
+    assert [len(x[0]) for x in A.batch_iterator(4, list(range(10)))] == [4, 4, 2]
+
+
+def _dist_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    from micro_sam_b200 import distributed as D
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        lo, hi = D.shard_range(11, rank, world)
+        table = torch.arange(lo, hi, dtype=torch.float32)[:, None] * torch.ones(1, 3)
+        table[:, 1] = rank
+        full, counts = D.all_gather_tables(table)
+        offs = D.exclusive_id_offsets(torch.arange(lo, hi) + 1)
+        ret[rank] = (lo, hi, full.tolist(), counts, offs.tolist())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_sharding_and_instance_table_gather():
+    import socket
+    import torch.multiprocessing as mp
+    from micro_sam_b200 import distributed as D
+    for n in (0, 1, 7, 256):
+        cov = []
+        for r in range(4):
+            lo, hi = D.shard_range(n, r, 4)
+            cov += list(range(lo, hi))
+            assert hi - lo in (n // 4, n // 4 + 1)
+        assert cov == list(range(n))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_dist_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert set(ret.keys()) == {0, 1}
+    (lo0, hi0, full0, counts0, offs0), (lo1, hi1, full1, counts1, offs1) = ret[0], ret[1]
+    assert (lo0, hi0, lo1, hi1) == (0, 5, 5, 11) and counts0 == counts1 == [5, 6]
+    assert full0 == full1 and [row[0] for row in full0] == list(map(float, range(11)))
+    assert [row[1] for row in full0] == [0.0] * 5 + [1.0] * 6
+    scan = np.cumsum(np.arange(1, 12)) - np.arange(1, 12)
+    assert offs0 == scan[:5].tolist() and offs1 == scan[5:].tolist()
+    # without a process group the helpers are the identity
+    t = torch.ones(3, 2)
+    assert D.all_gather_tables(t)[1] == [3]
