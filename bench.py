@@ -83,13 +83,31 @@ def make_tiles(seed0=0):
     return np.stack([lm_tile((TILE, TILE), 150, seed=seed0 + i) for i in range(N_TILES)])
 
 
+def best_cpu_threads():
+    """All host threads are allowed, but PyTorch's CPU GEMMs peak below the logical-core count on SMT hosts: pick the
+    thread count that runs an encoder-sized matmul fastest (candidates: all, 1/2, 1/4 of the logical cores)."""
+    n = os.cpu_count() or 1
+    a, b = torch.randn(4096, 768), torch.randn(768, 3072)
+    best, best_t = n, None
+    for c in sorted({n, max(1, n // 2), max(1, n // 4)}, reverse=True):
+        torch.set_num_threads(c)
+        a @ b
+        t0 = time.perf_counter()
+        for _ in range(3):
+            a @ b
+        t = time.perf_counter() - t0
+        if best_t is None or t < best_t:
+            best, best_t = c, t
+    return best
+
+
 # ---------------------------------------------------------------------------------------------------- reference arm
 def cpu_baseline(model_type="vit_b", n_point_batches=2, threads=None):
     """The reference algorithm's CPU path (oracle port of segment_anything + micro-sam's AMG) on the host cores, on a
     BOUNDED sample of the same workload: 1 tile embedding + `n_point_batches` x 64 grid points through predict_torch /
     _to_mask_data, + generate; scaled to the 16-batch (1024 point) grid."""
     from oracle import amg_ref, sam_ref
-    threads = threads or os.cpu_count()
+    threads = threads or best_cpu_threads()
     torch.set_num_threads(threads)
     sam = sam_ref.build_seeded_sam(model_type, seed=0)
     pred = sam_ref.SamPredictor(sam)
