@@ -287,7 +287,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(N_TILES * TILE * TILE * 3 + N_TILES * GRID * GRID * 12),
                 "d2h_bytes_per_step": int(N_TILES * TILE * TILE * 4)},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,
-        "survivors_last_tile": getattr(amg, "_last_n_keep", None),
+        "survivors_last_tile": int(amg._n_keep_dev.item()) if hasattr(amg, "_n_keep_dev") else None,
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args.model, 1)

@@ -89,6 +89,22 @@ int msam_amg_filter_nms(const int32_t* boxes_xyxy, const float* iou_preds, const
                         float pred_iou_thresh, float stability_thresh, float box_nms_thresh, const int32_t* crop_box_host,
                         const int32_t* orig_box_host, int32_t* keep, int32_t* n_keep, void* stream);
 
+/* util._to_image (util.py:618-651): H x W x C raw image (device; dtype 0 u8, 1 u16, 2 f32, 3 i16, 4 f64; C = 1..)
+ * -> H x W x 3 uint8 with per-channel min-max normalisation in the reference's exact float32 arithmetic.
+ * scratch6: 6 x uint32 device scratch. */
+int msam_to_image(const void* src, int dtype, int h, int w, int c, uint8_t* out_hwc3, uint32_t* scratch6, void* stream);
+/* AMG painting (mask_data_to_segmentation(..., merge_exclusively=False), util.py:1799-1829) of the masks sel[0..*n_sel)
+ * (n_sel read on the device: chain it to msam_amg_filter_nms without a host sync); per pixel the covering mask with the
+ * smallest area wins (later position on ties); label = position + 1, int32 [orig_h, ld_label]. */
+int msam_paint_min_area(const float* low_res, const int32_t* sel, const int32_t* n_sel, const int32_t* boxes_xyxy,
+                        const int32_t* area, int in_h, int in_w, int orig_h, int orig_w, float mask_threshold,
+                        int32_t* label, int ld_label, void* stream);
+/* util.mask_data_to_segmentation tail (util.py:1831-1848): connected components of equal labels (4-connectivity), drop
+ * components smaller than min_object_size and (with_background) the largest segment, relabel consecutively in raster
+ * order.  workspace: int32 [4*h*w + 4096 + 8]. */
+int msam_finish_segmentation(const int32_t* painted, int h, int w, int min_object_size, int with_background, uint32_t* out,
+                             int32_t* workspace, void* stream);
+
 /* ---- single-op entry points (unit tests / profiling; the same kernels the calls above are built from) ---- */
 /* out[M,N] = act(A[M,K] @ W[N,K]^T + bias) + residual[row % res_rows];  A, W bf16; bias/residual fp32 or NULL;
  * out bf16 (out_fp32=0) or fp32; act: 0 none, 1 GELU(erf), 2 ReLU. */

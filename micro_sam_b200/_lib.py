@@ -52,6 +52,10 @@ def lib() -> ctypes.CDLL:
                                  c_void_p, c_int, c_void_p]
         L.msam_amg_filter_nms.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float,
                                           POINTER(c_int32), POINTER(c_int32), c_void_p, c_void_p, c_void_p]
+        L.msam_to_image.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+        L.msam_paint_min_area.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                          c_float, c_void_p, c_int, c_void_p]
+        L.msam_finish_segmentation.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
         L.msam_profile.argtypes = [c_int]
         L.msam_profile_summary.argtypes = [POINTER(ctypes.c_double)]
         _lib = L

@@ -432,6 +432,20 @@ int msam_amg_filter_nms(const int32_t* boxes_xyxy, const float* iou_preds, const
                          box_nms_thresh, crop_box_host, orig_box_host, keep, n_keep, (cudaStream_t)stream);
 }
 
+int msam_to_image(const void* src, int dtype, int h, int w, int c, uint8_t* out_hwc3, uint32_t* scratch6, void* stream) {
+  return post_to_image(src, dtype, h, w, c, out_hwc3, scratch6, (cudaStream_t)stream);
+}
+int msam_paint_min_area(const float* low_res, const int32_t* sel, const int32_t* n_sel, const int32_t* boxes_xyxy,
+                        const int32_t* area, int in_h, int in_w, int orig_h, int orig_w, float mask_threshold,
+                        int32_t* label, int ld_label, void* stream) {
+  return post_paint_min_area(low_res, sel, n_sel, boxes_xyxy, area, in_h, in_w, orig_h, orig_w, mask_threshold, label,
+                             ld_label, (cudaStream_t)stream);
+}
+int msam_finish_segmentation(const int32_t* painted, int h, int w, int min_object_size, int with_background, uint32_t* out,
+                             int32_t* workspace, void* stream) {
+  return post_finish_segmentation(painted, h, w, min_object_size, with_background, out, workspace, (cudaStream_t)stream);
+}
+
 static int sm_count() {
   static int n = 0;
   if (!n) {

@@ -73,6 +73,12 @@ int post_upsample(const float* low_res, const int32_t* sel, int n_sel, int in_h,
                   float* logits, uint8_t* bin, cudaStream_t st);
 int post_paint(const float* low_res, const int32_t* sel, const int32_t* boxes, const int32_t* seg_ids, int n_sel, int in_h,
                int in_w, int out_h, int out_w, float thr, int exclusive, uint32_t* label, int ld_label, cudaStream_t st);
+int post_to_image(const void* src, int dtype, int h, int w, int c, uint8_t* out, uint32_t* scratch6, cudaStream_t st);
+int post_paint_min_area(const float* low_res, const int32_t* sel, const int32_t* n_sel, const int32_t* boxes,
+                        const int32_t* area, int in_h, int in_w, int out_h, int out_w, float thr, int32_t* label,
+                        int ld_label, cudaStream_t st);
+int post_finish_segmentation(const int32_t* seg, int h, int w, int min_size, int with_background, uint32_t* out,
+                             int32_t* ws, cudaStream_t st);
 int post_filter_nms(const int32_t* boxes, const float* scores, const float* stab, int n, int use_filters, float iou_thresh,
                     float stab_thresh, float nms_thresh, const int32_t* crop_box, const int32_t* orig_box, int32_t* keep,
                     int32_t* n_keep, cudaStream_t st);

@@ -433,3 +433,269 @@ int post_filter_nms(const int32_t* boxes, const float* scores, const float* stab
 }
 
 }  // namespace msam
+
+// =================================================================================================================
+// util._to_image (util.py:618-651) on the device: per-channel min-max normalisation to uint8 with the reference's exact
+// float32 arithmetic:  y = x - min;  y = y / (max(y) + 1e-7f);  u8 = trunc(y * 255).   (max(x - min) == fl(max - min)
+// because float subtraction/rounding is monotonic.)  Input: H x W x C (C = 1, 2, 3; C > 3 uses the first three),
+// dtype 0 = u8, 1 = u16, 2 = f32, 3 = i16, 4 = f64.  Output H x W x 3 uint8 (gray replicated, 2 channels + zero).
+namespace msam {
+
+__device__ __forceinline__ float load_as_f32(const void* p, int dtype, long i) {
+  switch (dtype) {
+    case 0: return (float)reinterpret_cast<const uint8_t*>(p)[i];
+    case 1: return (float)reinterpret_cast<const uint16_t*>(p)[i];
+    case 2: return reinterpret_cast<const float*>(p)[i];
+    case 3: return (float)reinterpret_cast<const int16_t*>(p)[i];
+    default: return (float)reinterpret_cast<const double*>(p)[i];
+  }
+}
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// mm[2*c] = min (ordered-uint encoding), mm[2*c+1] = max
+__global__ void to_image_minmax_kernel(const void* __restrict__ src, int dtype, long npix, int C, int cuse,
+                                       uint32_t* __restrict__ mm) {
+  uint32_t mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long)gridDim.x * blockDim.x) {
+    for (int c = 0; c < cuse; ++c) {
+      const uint32_t o = f2ord(load_as_f32(src, dtype, i * C + c));
+      mn[c] = min(mn[c], o);
+      mx[c] = max(mx[c], o);
+    }
+  }
+  for (int c = 0; c < cuse; ++c) {
+    uint32_t a = mn[c], b = mx[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a = min(a, __shfl_xor_sync(0xffffffffu, a, o));
+      b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&mm[2 * c], a);
+      atomicMax(&mm[2 * c + 1], b);
+    }
+  }
+}
+
+__global__ void to_image_apply_kernel(const void* __restrict__ src, int dtype, long npix, int C, int cuse,
+                                      const uint32_t* __restrict__ mm, uint8_t* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  uint8_t px[3] = {0, 0, 0};
+  for (int c = 0; c < cuse; ++c) {
+    const float mn = ord2f(mm[2 * c]), mx = ord2f(mm[2 * c + 1]);
+    const float den = __fadd_rn(__fsub_rn(mx, mn), 1e-7f);
+    const float y = __fsub_rn(load_as_f32(src, dtype, i * C + c), mn);
+    px[c] = (uint8_t)(int)__fmul_rn(__fdiv_rn(y, den), 255.0f);
+  }
+  if (cuse == 1) px[1] = px[2] = px[0];
+  out[3 * i] = px[0]; out[3 * i + 1] = px[1]; out[3 * i + 2] = px[2];
+}
+
+int post_to_image(const void* src, int dtype, int h, int w, int c, uint8_t* out, uint32_t* scratch6, cudaStream_t st) {
+  if (dtype < 0 || dtype > 4 || c < 1 || h <= 0 || w <= 0) return set_error("to_image: bad arguments");
+  const int cuse = c > 3 ? 3 : c;
+  const long npix = (long)h * w;
+  static const uint32_t init[6] = {0xffffffffu, 0u, 0xffffffffu, 0u, 0xffffffffu, 0u};
+  cudaMemcpyAsync(scratch6, init, sizeof(init), cudaMemcpyHostToDevice, st);
+  int blocks = (int)((npix + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  to_image_minmax_kernel<<<blocks, 256, 0, st>>>(src, dtype, npix, c, cuse, scratch6);
+  LAUNCH_CHECK("to_image_minmax");
+  to_image_apply_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(src, dtype, npix, c, cuse, scratch6, out);
+  LAUNCH_CHECK("to_image_apply");
+  return 0;
+}
+
+// =================================================================================================================
+// AMG painting without a host round trip: n_sel is read from device memory (the NMS kernel's n_keep) and the
+// "descending area, later overwrites" order of mask_data_to_segmentation(merge_exclusively=False) is evaluated per pixel
+// as: the covering mask with the smallest (area, -position) wins.  Ids are position + 1 (any unique id works: the
+// connected-component pass re-assigns ids in raster order afterwards).
+__global__ void paint_min_area_kernel(const float* __restrict__ low_res, const int32_t* __restrict__ sel,
+                                      const int32_t* __restrict__ n_sel_ptr, const int32_t* __restrict__ boxes,
+                                      const int32_t* __restrict__ area, PostGeom g, float thr, int32_t* __restrict__ label,
+                                      int ld_label) {
+  const int n_sel = *n_sel_ptr;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= g.out_w) return;
+  int best_pos = -1, best_area = 0x7fffffff;
+  for (int k = 0; k < n_sel; ++k) {
+    const int mi = sel[k];
+    const int4 b = *reinterpret_cast<const int4*>(boxes + 4L * mi);
+    if (x < b.x || x > b.z || y < b.y || y > b.w) continue;
+    const int a = area[mi];
+    if (a > best_area) continue;  // a later mask only wins with area <= the current winner
+    const float v = full_res(low_res + (long)mi * g.lr * g.lr, g, y, x);
+    if (v > thr) { best_area = a; best_pos = k; }
+  }
+  label[(long)y * ld_label + x] = best_pos + 1;
+}
+
+int post_paint_min_area(const float* low_res, const int32_t* sel, const int32_t* n_sel, const int32_t* boxes,
+                        const int32_t* area, int in_h, int in_w, int out_h, int out_w, float thr, int32_t* label,
+                        int ld_label, cudaStream_t st) {
+  PostGeom g;
+  if (make_geom(in_h, in_w, out_h, out_w, &g)) return -1;
+  paint_min_area_kernel<<<dim3((out_w + 255) / 256, out_h), 256, 0, st>>>(low_res, sel, n_sel, boxes, area, g, thr, label,
+                                                                        ld_label);
+  LAUNCH_CHECK("paint_min_area");
+  return 0;
+}
+
+// =================================================================================================================
+// util.mask_data_to_segmentation tail (util.py:1831-1848) on the device: connected components of equal non-zero labels
+// (4-connectivity; union-find with atomicMin roots, so a component's root is its first pixel in raster order), size
+// filter, optional removal of the largest segment (`with_background`; the unlabelled area counts as segment 0 exactly
+// like np.unique), consecutive relabelling in raster order of the roots.
+__device__ __forceinline__ int uf_find(int* parent, int i) {
+  int p = parent[i];
+  while (p != i) { i = p; p = parent[i]; }
+  return i;
+}
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a > b) { const int t = a; a = b; b = t; }
+    const int old = atomicMin(&parent[b], a);
+    if (old == b) return;
+    b = old;
+  }
+}
+__global__ void cc_init_kernel(const int32_t* __restrict__ seg, int n, int* __restrict__ parent, int* __restrict__ size) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { parent[i] = seg[i] != 0 ? i : -1; size[i] = 0; }
+}
+__global__ void cc_merge_kernel(const int32_t* __restrict__ seg, int h, int w, int* __restrict__ parent) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h * w) return;
+  const int s = seg[i];
+  if (s == 0) return;
+  const int x = i % w, y = i / w;
+  if (x + 1 < w && seg[i + 1] == s) uf_union(parent, i, i + 1);
+  if (y + 1 < h && seg[i + w] == s) uf_union(parent, i, i + w);
+}
+__global__ void cc_flatten_count_kernel(int n, int* __restrict__ parent, int* __restrict__ size, int* __restrict__ bg_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int bg = 0;
+  if (i < n) {
+    if (parent[i] >= 0) {
+      const int r = uf_find(parent, i);
+      parent[i] = r;
+      atomicAdd(&size[r], 1);
+    } else {
+      bg = 1;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, bg);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(bg_count, __popc(m));
+}
+// largest component: packed (size << 32 | ~root) maximum -> largest size, smallest root on ties (np.argmax order)
+__global__ void cc_largest_kernel(int n, const int* __restrict__ parent, const int* __restrict__ size,
+                                  unsigned long long* __restrict__ best) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long v = 0;
+  if (i < n && parent[i] == i) v = ((unsigned long long)(unsigned)size[i] << 32) | (unsigned)(~(unsigned)i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = v > w ? v : w;
+  }
+  if ((threadIdx.x & 31) == 0 && v) atomicMax(best, v);
+}
+// flag[i] = 1 for kept roots; then block-wise inclusive scan in three kernels
+__global__ void cc_flag_kernel(int n, const int* __restrict__ parent, const int* __restrict__ size, int min_size,
+                               int with_background, const unsigned long long* __restrict__ best,
+                               const int* __restrict__ bg_count, int* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int f = 0;
+  if (parent[i] == i) {
+    f = size[i] >= min_size;
+    if (with_background && *best) {
+      const int bsize = (int)(*best >> 32), broot = (int)(~(unsigned)(*best & 0xffffffffu));
+      // np.unique lists id 0 (unlabelled) first: it is the argmax when its count >= the largest component
+      if (*bg_count < bsize && i == broot) f = 0;
+    }
+  }
+  flag[i] = f;
+}
+__global__ void scan_block_kernel(const int* __restrict__ in, int n, int* __restrict__ out, int* __restrict__ block_sums) {
+  __shared__ int s[1024];
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  int v = i < n ? in[i] : 0;
+  s[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+    __syncthreads();
+    s[threadIdx.x] += t;
+    __syncthreads();
+  }
+  if (i < n) out[i] = s[threadIdx.x];
+  if (threadIdx.x == 1023) block_sums[blockIdx.x] = s[1023];
+}
+__global__ void scan_sums_kernel(int* __restrict__ block_sums, int nb) {  // single block, nb <= 4096
+  __shared__ int s[4096];
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) s[i] = block_sums[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < nb; ++i) { const int t = s[i]; s[i] = acc; acc += t; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) block_sums[i] = s[i];
+}
+__global__ void cc_relabel_kernel(int n, const int* __restrict__ parent, const int* __restrict__ flag,
+                                  const int* __restrict__ scan, const int* __restrict__ block_offs,
+                                  uint32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = parent[i];
+  uint32_t v = 0;
+  if (r >= 0 && flag[r]) v = (uint32_t)(scan[r] + block_offs[r >> 10]);
+  out[i] = v;
+}
+
+int post_finish_segmentation(const int32_t* seg, int h, int w, int min_size, int with_background, uint32_t* out,
+                             int32_t* ws /* 4*h*w + 4096 + 8 ints */, cudaStream_t st) {
+  const int n = h * w;
+  const int nb = (n + 1023) / 1024;
+  if (nb > 4096) return set_error("finish_segmentation: image too large (%d x %d)", h, w);
+  int* parent = ws;
+  int* size = ws + n;
+  int* flag = ws + 2 * n;
+  int* scan = ws + 3 * n;
+  int* bsums = ws + 4 * (size_t)n;
+  int* bg = bsums + 4096;
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(bg + 2);
+  cudaMemsetAsync(bg, 0, 6 * sizeof(int), st);
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  cc_init_kernel<<<blocks, 256, 0, st>>>(seg, n, parent, size);
+  LAUNCH_CHECK("cc_init");
+  cc_merge_kernel<<<blocks, 256, 0, st>>>(seg, h, w, parent);
+  LAUNCH_CHECK("cc_merge");
+  cc_flatten_count_kernel<<<blocks, 256, 0, st>>>(n, parent, size, bg);
+  LAUNCH_CHECK("cc_flatten");
+  cc_largest_kernel<<<blocks, 256, 0, st>>>(n, parent, size, best);
+  LAUNCH_CHECK("cc_largest");
+  cc_flag_kernel<<<blocks, 256, 0, st>>>(n, parent, size, min_size, with_background, best, bg, flag);
+  LAUNCH_CHECK("cc_flag");
+  scan_block_kernel<<<nb, 1024, 0, st>>>(flag, n, scan, bsums);
+  LAUNCH_CHECK("scan_block");
+  scan_sums_kernel<<<1, 1024, 0, st>>>(bsums, nb);
+  LAUNCH_CHECK("scan_sums");
+  cc_relabel_kernel<<<blocks, 256, 0, st>>>(n, parent, flag, scan, bsums, out);
+  LAUNCH_CHECK("cc_relabel");
+  return 0;
+}
+
+}  // namespace msam

@@ -51,7 +51,8 @@ class AMGBase(ABC):
         return self._original_size
 
     # ---- device-side equivalents of _postprocess_batch (instance_segmentation.py:99-144)
-    def _filter_nms(self, data, crop_box, original_size, pred_iou_thresh, stability_score_thresh, box_nms_thresh):
+    def _filter_nms(self, data, crop_box, original_size, pred_iou_thresh, stability_score_thresh, box_nms_thresh,
+                    sync: bool = True):
         orig_h, orig_w = original_size
         n = int(data["iou_preds"].shape[0])
         dev = data["iou_preds"].device
@@ -63,6 +64,9 @@ class AMGBase(ABC):
             _lib.ptr(data["boxes"]), _lib.ptr(data["iou_preds"]), _lib.ptr(data["stability_score"]), n, 1,
             float(pred_iou_thresh), float(stability_score_thresh), float(box_nms_thresh), crop, orig, _lib.ptr(keep),
             _lib.ptr(n_keep), _lib.cur_stream()))
+        self._n_keep_dev = n_keep
+        if not sync:
+            return keep
         self._last_n_keep = int(n_keep.item())
         return keep[: self._last_n_keep].long()
 
@@ -208,6 +212,10 @@ class AutomaticMaskGenerator(AMGBase):
         if output_mode == "coco_rle":
             raise NotImplementedError("coco_rle needs pycocotools")
         geoms = getattr(self, "_geoms", None)
+        if output_mode == "instance_segmentation" and len(self.crop_list) == 1 and geoms and \
+                tuple(self.crop_boxes[0]) == (0, 0, self.original_size[1], self.original_size[0]):
+            out = self.generate_device(pred_iou_thresh, stability_score_thresh, box_nms_thresh, with_background)
+            return out.cpu().numpy().view(np.uint32)
         results, painted = [], None
         for ci, (data, crop_box) in enumerate(zip(self.crop_list, self.crop_boxes)):
             geom = geoms[ci] if geoms else dict(inp=tuple(self._predictor.input_size),
@@ -225,17 +233,34 @@ class AutomaticMaskGenerator(AMGBase):
 
     @torch.no_grad()
     def generate_device(self, pred_iou_thresh: float = 0.88, stability_score_thresh: float = 0.95,
-                        box_nms_thresh: float = 0.7, **_):
-        """generate() up to the painted (pre connected-components) label image, left on the device: int32 (H, W) tensor.
-        Used by bench.py's device-resident throughput number; generate() = this + D2H + util._finish_segmentation."""
+                        box_nms_thresh: float = 0.7, with_background: bool = True, finish: bool = True, **_):
+        """generate(output_mode="instance_segmentation") entirely on the device and without any host synchronisation:
+        filter+NMS -> per-pixel min-area painting (n_keep read on the device) -> connected components / background
+        removal / consecutive relabel (msam_finish_segmentation).  Returns a uint32-valued int32 (H, W) device tensor."""
         if not self.is_initialized:
             raise RuntimeError("AutomaticMaskGenerator has not been initialized. Call initialize first.")
-        painted = None
-        for ci, (data, crop_box) in enumerate(zip(self.crop_list, self.crop_boxes)):
-            keep = self._filter_nms(data, crop_box, self.original_size, pred_iou_thresh, stability_score_thresh,
-                                    box_nms_thresh)
-            painted = self._paint(data, keep, crop_box, self._geoms[ci], painted)
-        return painted
+        if len(self.crop_list) != 1:
+            raise NotImplementedError("device-side generate supports a single crop")
+        data, crop_box, geom = self.crop_list[0], self.crop_boxes[0], self._geoms[0]
+        H, W = self.original_size
+        dev = data["low_res"].device
+        keep = self._filter_nms(data, crop_box, self.original_size, pred_iou_thresh, stability_score_thresh,
+                                box_nms_thresh, sync=False)
+        bufs = getattr(self, "_dev_bufs", None)
+        if bufs is None or bufs[0].shape != (H, W) or bufs[0].device != dev:
+            bufs = (torch.empty(H, W, dtype=torch.int32, device=dev), torch.empty(H, W, dtype=torch.int32, device=dev),
+                    torch.empty(4 * H * W + 4096 + 8, dtype=torch.int32, device=dev))
+            self._dev_bufs = bufs
+        painted, out, ws = bufs
+        L = _lib.lib()
+        _lib.check(L.msam_paint_min_area(_lib.ptr(data["low_res"]), _lib.ptr(keep), _lib.ptr(self._n_keep_dev),
+                                         _lib.ptr(data["boxes"]), _lib.ptr(data["area"]), geom["inp"][0], geom["inp"][1],
+                                         geom["orig"][0], geom["orig"][1], 0.0, _lib.ptr(painted), W, _lib.cur_stream()))
+        if not finish:
+            return painted
+        _lib.check(L.msam_finish_segmentation(_lib.ptr(painted), H, W, 0, int(with_background), _lib.ptr(out), _lib.ptr(ws),
+                                              _lib.cur_stream()))
+        return out
 
     def _paint(self, data, keep, crop_box, geom, label):
         """mask_data_to_segmentation(..., merge_exclusively=False) painting (util.py:1799-1829): descending area, later

@@ -114,6 +114,58 @@ def _to_image(image):
     return np.array(input_)
 
 
+_DTYPE_CODES = {np.dtype("uint8"): 0, np.dtype("uint16"): 1, np.dtype("float32"): 2, np.dtype("int16"): 3,
+                np.dtype("float64"): 4}
+
+
+def _to_image_device(image, device) -> torch.Tensor:
+    """`_to_image` on the GPU (msam_to_image): raw host (numpy) or device (torch) image -> uint8 (H, W, 3) device tensor,
+    bit-identical to the host function for the supported dtypes (u8/u16/i16/f32/f64, 1-3+ channels)."""
+    if isinstance(image, torch.Tensor):
+        t = image.to(device).contiguous()
+        np_dtype = np.dtype(str(t.dtype).replace("torch.", ""))
+    else:
+        arr = np.ascontiguousarray(image)
+        np_dtype = arr.dtype
+        if np_dtype not in _DTYPE_CODES:
+            return torch.from_numpy(_to_image(arr)).to(device)
+        if np_dtype == np.dtype("uint16"):  # torch has no full uint16 support: ship the bytes
+            t = torch.from_numpy(arr.view(np.int16)).to(device, non_blocking=True)
+        else:
+            t = torch.from_numpy(arr).to(device, non_blocking=True)
+    if np_dtype not in _DTYPE_CODES or t.ndim not in (2, 3):
+        raise ValueError(f"Invalid input for _to_image: shape {tuple(t.shape)}, dtype {np_dtype}")
+    h, w = t.shape[:2]
+    c = 1 if t.ndim == 2 else t.shape[2]
+    out = torch.empty(h, w, 3, dtype=torch.uint8, device=device)
+    scratch = torch.empty(6, dtype=torch.int32, device=device)
+    _lib.check(_lib.lib().msam_to_image(_lib.ptr(t), _DTYPE_CODES[np_dtype], h, w, c, _lib.ptr(out), _lib.ptr(scratch),
+                                        _lib.cur_stream()))
+    return out
+
+
+@torch.no_grad()
+def _compute_embeddings_batched_raw(predictor, raw_images):
+    """_to_image + _compute_embeddings_batched for raw images that need no resize (longest side == model input size):
+    normalisation runs on the device, so the host only ships the raw bytes."""
+    sam = predictor.model
+    predictor.reset_image()
+    u8 = torch.stack([_to_image_device(im, sam.device) for im in raw_images])
+    features = sam.encode_u8(u8)
+    sizes = [tuple(im.shape[:2]) for im in raw_images]
+    predictor.original_size = sizes[-1]
+    predictor.input_size = sizes[-1]
+    predictor.features = features[-1:]
+    predictor.is_image_set = True
+    return features, sizes, sizes
+
+
+def _needs_no_resize(predictor, image) -> bool:
+    h, w = image.shape[:2]
+    return max(h, w) == predictor.transform.target_length and (image.ndim == 2 or image.shape[2] >= 1) \
+        and np.dtype(image.dtype) in _DTYPE_CODES
+
+
 @torch.no_grad()
 def _compute_embeddings_batched(predictor, batched_images):
     """util.py:654-681: resize each image, then ONE encoder call for the batch (preprocess is fused in the kernel when
@@ -280,8 +332,11 @@ def precompute_image_embeddings(predictor, input_: np.ndarray, save_path=None, l
         raise ValueError("To compute tiled embeddings the parameters tile_shape and halo have to be passed.")
     if ndim == 2 and tile_shape is None:
         pbar_init(1, "Compute Image Embeddings 2D")
-        predictor.reset_image()
-        predictor.set_image(_to_image(input_))
+        if _needs_no_resize(predictor, input_):
+            _compute_embeddings_batched_raw(predictor, [input_])
+        else:
+            predictor.reset_image()
+            predictor.set_image(_to_image(input_))
         feats = predictor.get_image_embedding()
         feats = feats.cpu().numpy() if to_numpy else feats
         pbar_update(1)
@@ -291,8 +346,12 @@ def precompute_image_embeddings(predictor, input_: np.ndarray, save_path=None, l
         pbar_init(n, "Compute Image Embeddings 3D")
         outs = []
         for z0 in range(0, n, batch_size):
-            images = [_to_image(input_[z]) for z in range(z0, min(z0 + batch_size, n))]
-            e, original_sizes, input_sizes = _compute_embeddings_batched(predictor, images)
+            raw = [input_[z] for z in range(z0, min(z0 + batch_size, n))]
+            if all(_needs_no_resize(predictor, im) for im in raw):
+                e, original_sizes, input_sizes = _compute_embeddings_batched_raw(predictor, raw)
+            else:
+                e, original_sizes, input_sizes = _compute_embeddings_batched(predictor, [_to_image(im) for im in raw])
+            images = raw
             outs.append(e[:, None])
             pbar_update(len(images))
         feats = torch.cat(outs)  # (Z,1,256,64,64) (util.py:968-970)

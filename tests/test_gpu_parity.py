@@ -186,3 +186,40 @@ def test_batched_inference_against_oracle(models):
     assert _partition_equal(seg, oseg)
     with pytest.raises(ValueError):
         inference.batched_inference(pred, img, batch_size=8)
+
+
+def test_device_to_image_and_finish_segmentation_bit_exact(models):
+    """a1 / a20 on the device: msam_to_image == util._to_image (== oracle) bit for bit; msam_finish_segmentation ==
+    util._finish_segmentation (ids included) and == the oracle up to relabelling."""
+    from oracle import amg_ref
+    from micro_sam_b200 import _lib, util
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(0, 60000, (333, 517)).astype("uint16"), rng.normal(5, 3, (256, 300)).astype("float32"),
+            rng.integers(0, 255, (100, 120, 3)).astype("uint8"), rng.random((64, 80, 2)), np.full((32, 32), 3, "int16"),
+            rng.normal(0, 1e-3, (50, 60, 1)).astype("float32")]
+    for im in imgs:
+        got = util._to_image_device(im, "cuda").cpu().numpy()
+        assert np.array_equal(got, amg_ref.to_image(im)), (im.dtype, im.shape)
+    # finish_segmentation
+    yy, xx = np.mgrid[:200, :260]
+    seg = np.zeros((200, 260), np.int32)
+    for k in range(40):
+        cy, cx, r = rng.integers(0, 200), rng.integers(0, 260), rng.integers(3, 30)
+        seg[(yy - cy) ** 2 + (xx - cx) ** 2 < r * r] = k + 1
+    seg[50:60, :] = 7   # a label split into several components by overpainting, and one touching itself diagonally only
+    seg[100, 100] = 99; seg[101, 101] = 99
+    L = _lib.lib()
+    for (mn, wb) in ((0, 0), (0, 1), (25, 0), (40, 1)):
+        d = torch.from_numpy(seg).cuda()
+        out = torch.empty(200, 260, dtype=torch.int32, device="cuda")
+        ws = torch.empty(4 * 200 * 260 + 4096 + 8, dtype=torch.int32, device="cuda")
+        _lib.check(L.msam_finish_segmentation(_lib.ptr(d), 200, 260, mn, wb, _lib.ptr(out), _lib.ptr(ws), _lib.cur_stream()))
+        got = out.cpu().numpy().view(np.uint32)
+        ref = util._finish_segmentation(seg.astype(np.uint32), mn, True, bool(wb))
+        assert np.array_equal(got, ref), (mn, wb)
+    full = np.ones((64, 64), np.int32)   # no background pixel at all: the single component is the largest segment
+    d = torch.from_numpy(full).cuda()
+    out = torch.empty(64, 64, dtype=torch.int32, device="cuda")
+    ws = torch.empty(4 * 64 * 64 + 4096 + 8, dtype=torch.int32, device="cuda")
+    _lib.check(L.msam_finish_segmentation(_lib.ptr(d), 64, 64, 0, 1, _lib.ptr(out), _lib.ptr(ws), _lib.cur_stream()))
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), util._finish_segmentation(full.astype(np.uint32), 0, True, True))
