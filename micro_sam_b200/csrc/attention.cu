@@ -396,6 +396,266 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ C
   }
 }
 
+
+// =================================================================================================================
+// Windowed attention (14x14 windows, 196 keys incl. pad tokens): one CTA per (128-query tile, head, window).
+// All 196 keys fit one N=208 MMA tile, so S = Q K^T is computed ONCE and kept in TMEM for both softmax passes
+// (max, then exp), P (128 x 208, bf16) goes to shared memory over the dead Q/K tiles and O = P V accumulates over
+// the dead S columns: 256 TMEM columns and < 113 KB shared memory for head_dim 64 -> two CTAs per SM overlap each
+// other's serial phases.  Warp roles as in attn_kernel.
+constexpr int WIN_NK = 208;                      // keys padded to a multiple of 16
+constexpr int WIN_KBOX = WIN_NK * 128;           // bytes of one 64-column K/V box (208 rows)
+
+template <int D>
+struct WinCfg {
+  static constexpr int NB = (D + 63) / 64;
+  static constexpr int KSTEPS = D / 16;
+  static constexpr int Q_BYTES = NB * ATT_BOX_BYTES;
+  static constexpr int K_BYTES = NB * WIN_KBOX;
+  static constexpr int P_BYTES = 4 * ATT_BOX_BYTES;              // 4 blocks of 64 keys (last one 16 keys used)
+  static constexpr int R0_BYTES = (Q_BYTES + K_BYTES) > P_BYTES ? (Q_BYTES + K_BYTES) : P_BYTES;  // Q|K aliased by P
+  static constexpr int OFF_V = R0_BYTES;
+  static constexpr int OFF_RT = OFF_V + K_BYTES;
+  static constexpr int RT_BOX = 64 * 128;
+  static constexpr int OFF_BAR = OFF_RT + NB * RT_BOX;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+};
+
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS, (D == 64) ? 2 : 1)
+attn_window_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                   const __grid_constant__ CUtensorMap tmRT, const AttParams p) {
+  using C = WinCfg<D>;
+  constexpr int S = 14, G = 196;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + C::Q_BYTES;
+  uint8_t* sP = smem;  // aliases Q|K once S has been computed
+  uint8_t* sV = smem + C::OFF_V;
+  uint8_t* sRT = smem + C::OFF_RT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t *ld_full = bars, *v_full = bars + 1, *t_full = bars + 2, *t_done = bars + 3, *s_full = bars + 4,
+           *p_full = bars + 5, *o_full = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, head = blockIdx.y, group = blockIdx.z;
+
+  if (warp == 4 && lane == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmKV);
+    prefetch_tmap(&tmRT);
+    mbar_init(ld_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(t_full, 1);
+    mbar_init(t_done, 128);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int row0 = group * G;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const int qcol = head * D, kcol = p.d_model + head * D, vcol = 2 * p.d_model + head * D;
+      mbar_expect_tx(ld_full, C::Q_BYTES + C::K_BYTES + C::NB * C::RT_BOX);
+      for (int b = 0; b < C::NB; ++b) {
+        tma_load_2d(sQ + b * ATT_BOX_BYTES, &tmQ, ld_full, qcol + b * 64, row0 + qt * 128);
+        tma_load_2d(sK + b * WIN_KBOX, &tmKV, ld_full, kcol + b * 64, row0);
+        tma_load_2d(sRT + b * C::RT_BOX, &tmRT, ld_full, b * 64, 0);
+      }
+      mbar_expect_tx(v_full, C::K_BYTES);
+      for (int b = 0; b < C::NB; ++b) tma_load_2d(sV + b * WIN_KBOX, &tmKV, v_full, vcol + b * 64, row0);
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idescT = make_idesc_bf16(128, 64);
+      constexpr uint32_t idescS = make_idesc_bf16(128, WIN_NK);
+      constexpr uint32_t idescO = make_idesc_bf16(128, D, 1);
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), aRT = smem_u32(sRT);
+      auto kdesc = [](uint32_t base, uint32_t box_bytes, int ks) {
+        return make_desc_sw128(base + (uint32_t)(ks >> 2) * box_bytes + (uint32_t)(ks & 3) * 32u, 0, 1024);
+      };
+      mbar_wait(ld_full, 0, 40);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < C::KSTEPS; ++ks)
+        umma_bf16(tmem, kdesc(aQ, ATT_BOX_BYTES, ks), kdesc(aRT, C::RT_BOX, ks), idescT, ks > 0);
+      umma_commit(t_full);
+      mbar_wait(t_done, 0, 41);  // T (columns [0,64)) is in registers: S may overwrite it
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < C::KSTEPS; ++ks)
+        umma_bf16(tmem, kdesc(aQ, ATT_BOX_BYTES, ks), kdesc(aK, WIN_KBOX, ks), idescS, ks > 0);
+      umma_commit(s_full);
+      mbar_wait(p_full, 0, 42);  // P written (over Q|K) and S fully consumed
+      mbar_wait(v_full, 0, 43);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < WIN_NK / 16; ++ks) {
+        const uint64_t da = make_desc_sw128(aP + (uint32_t)(ks >> 2) * ATT_BOX_BYTES + (uint32_t)(ks & 3) * 32u, 0, 1024);
+        const uint64_t db = make_desc_sw128(aV + (uint32_t)ks * 2048u, WIN_KBOX, 1024);
+        umma_bf16(tmem, da, db, idescO, ks > 0);   // O over the dead S columns [0, D)
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    const int r = threadIdx.x;
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const int qi = qt * 128 + r;
+    constexpr float LOG2E = 1.4426950408889634f;
+    float yh[S], yw[S];
+    mbar_wait(t_full, 0, 50);
+    tc_fence_after();
+    {
+      int qh = qi / S;
+      const int qw = qi % S;
+      if (qh > S - 1) qh = S - 1;
+      float x[32];
+      uint32_t v[32];
+      tmem_ld32(tlane + 0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
+      lane_shift<32, 4>(x, qh);
+#pragma unroll
+      for (int kh = 0; kh < S; ++kh) yh[kh] = x[S - 1 - kh] * LOG2E;
+      tmem_ld32(tlane + 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
+      lane_shift<32, 4>(x, qw);
+#pragma unroll
+      for (int kw = 0; kw < S; ++kw) yw[kw] = x[S - 1 - kw] * LOG2E;
+    }
+    tc_fence_before();
+    mbar_arrive(t_done);
+
+    const float sl2 = p.scale_log2;
+    mbar_wait(s_full, 0, 51);
+    tc_fence_after();
+    // pass A: row max over the 196 valid keys (S stays in TMEM)
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+      uint32_t v[32];
+      if (c < 6) tmem_ld32(tlane + c * 32, v);
+      else { uint32_t w[16]; tmem_ld16(tlane + 192, w);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = w[i]; }
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int key = c * 32 + i;
+        if (key < G) m = fmaxf(m, fmaf(__uint_as_float(v[i]), sl2, yh[key / S] + yw[key % S]));
+      }
+    }
+    // pass B: p = exp2(s - m) -> bf16 P tile (K-major SW128 blocks of 64 keys) over the dead Q|K buffers
+    float l = 0.f;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+      uint32_t v[32];
+      if (c < 6) tmem_ld32(tlane + c * 32, v);
+      else { uint32_t w[16]; tmem_ld16(tlane + 192, w);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = w[i]; }
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const int key = c * 32 + i;
+        float p0 = 0.f, p1 = 0.f;
+        if (key < G) p0 = ex2f(fmaf(__uint_as_float(v[i]), sl2, yh[key / S] + yw[key % S]) - m);
+        if (key + 1 < G) p1 = ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, yh[(key + 1) / S] + yw[(key + 1) % S]) - m);
+        l += p0 + p1;
+        pk[i >> 1] = pack_bf16(p0, p1);
+      }
+      uint8_t* prow = sP + (c >> 1) * ATT_BOX_BYTES + r * 128;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (c == 6 && q >= 2) break;  // keys 208.. do not exist
+        const int ch = (c & 1) * 4 + q;
+        *reinterpret_cast<uint4*>(prow + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    mbar_arrive(p_full);
+
+    mbar_wait(o_full, 0, 52);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    long out_row = -1;
+    {
+      const int wpr = (p.grid + S - 1) / S;
+      const int b = group / (wpr * wpr), wy = (group / wpr) % wpr, wx = group % wpr;
+      const int y = wy * S + qi / S, x = wx * S + qi % S;
+      if (qi < G && y < p.grid && x < p.grid) out_row = (long)b * p.grid * p.grid + y * p.grid + x;
+    }
+    __nv_bfloat16* orow = p.out + (out_row < 0 ? 0 : out_row) * p.d_model + head * D;
+#pragma unroll
+    for (int c = 0; c < D / 16; ++c) {
+      uint32_t v[16];
+      tmem_ld16(tlane + c * 16, v);
+      tmem_ld_wait();
+      if (out_row >= 0) {
+        uint4 u0, u1;
+        u0.x = pack_bf16(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+        u0.y = pack_bf16(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+        u0.z = pack_bf16(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+        u0.w = pack_bf16(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+        u1.x = pack_bf16(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
+        u1.y = pack_bf16(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
+        u1.z = pack_bf16(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
+        u1.w = pack_bf16(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
+        *reinterpret_cast<uint4*>(orow + c * 16) = u0;
+        *reinterpret_cast<uint4*>(orow + c * 16 + 8) = u1;
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+template <int D>
+static int launch_attn_window(const AttnArgs& a, cudaStream_t stream) {
+  using C = WinCfg<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_window_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int d_model = a.heads * D, S = 14;
+  const int wpr = (a.grid + S - 1) / S;
+  const int groups = a.batch * wpr * wpr;
+  const long rows = (long)groups * 196;
+  CUtensorMap tmQ, tmKV, tmRT;
+  if (make_tmap_bf16_2d(&tmQ, a.qkv, rows, 3 * d_model, 3 * d_model, 128)) return -1;
+  if (make_tmap_bf16_2d(&tmKV, a.qkv, rows, 3 * d_model, 3 * d_model, WIN_NK)) return -1;
+  if (make_tmap_bf16_2d(&tmRT, a.rel_table, 64, C::NB * 64, C::NB * 64, 64)) return -1;
+  AttParams p;
+  p.out = a.out; p.d_model = d_model; p.grid = a.grid; p.scale_log2 = a.scale * 1.4426950408889634f;
+  prof_begin(stream, PROF_ATTN, (double)groups * a.heads * (4.0 * 196 * 196 * D + 4.0 * 196 * S * D));
+  attn_window_kernel<D><<<dim3(2, a.heads, groups), ATT_THREADS, C::SMEM_BYTES, stream>>>(tmQ, tmKV, tmRT, p);
+  prof_end(stream);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("window attention launch failed: %s", cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
 template <int D, int S>
 static int launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
   using C = AttCfg<D, S>;
@@ -434,8 +694,8 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     if (a.head_dim == 64) return launch_attn_t<64, 64>(a, stream);
     if (a.head_dim == 80) return launch_attn_t<80, 64>(a, stream);
   } else if (a.window == 14) {
-    if (a.head_dim == 64) return launch_attn_t<64, 14>(a, stream);
-    if (a.head_dim == 80) return launch_attn_t<80, 14>(a, stream);
+    if (a.head_dim == 64) return launch_attn_window<64>(a, stream);
+    if (a.head_dim == 80) return launch_attn_window<80>(a, stream);
   }
   return set_error("attention: unsupported head_dim=%d window=%d", a.head_dim, a.window);
 }
