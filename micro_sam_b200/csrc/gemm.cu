@@ -15,7 +15,6 @@
 #include "kernels.h"
 #include "ptx.cuh"
 #include "tensormap.h"
-#include <cstdlib>
 
 namespace msam {
 
@@ -81,10 +80,7 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& r, float* f) {
   }
 }
 
-// MC = true: clusters of 2 CTAs work on two M-adjacent tiles of the same N block; each CTA TMA-loads half of the weight
-// tile and multicasts it to both, which halves the L2 -> SM weight traffic (the 1-CTA 128x256 tile is L2-bandwidth
-// bound on B200: 48 KB per 128x256x64 MMA block per SM ~ 19 TB/s at tensor peak vs ~12 TB/s of L2).
-template <int BN, int EPI, bool MC>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -105,12 +101,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int m_blocks = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int n_blocks = (p.N + BN - 1) / BN;
   const int k_blocks = (p.K + GEMM_BK - 1) / GEMM_BK;
-  // tile schedule: `sched_id` walks (m-pair, n) for MC (this CTA takes m = 2*pair + cluster rank), (m, n) otherwise
-  const uint32_t crank = MC ? cluster_ctarank() : 0;
-  const int sched_rows = MC ? (m_blocks + 1) / 2 : m_blocks;
-  const int num_tiles = sched_rows * n_blocks;
-  const int sched_first = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int sched_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_tiles = m_blocks * n_blocks;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -119,7 +110,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], MC ? 2 : 1);  // MC: released by the MMA warps of both CTAs of the cluster
+      mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -137,7 +128,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC) cluster_sync_all();  // barrier inits visible cluster-wide before any remote complete_tx / arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -146,18 +136,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = sched_first; tile < num_tiles; tile += sched_step) {
-        const int m_blk = (tile / n_blocks) * (MC ? 2 : 1) + (int)crank, n_blk = tile % n_blocks;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
-          if constexpr (MC) {  // my half of the weight tile -> both CTAs (tmB box = BN/2 rows)
-            tma_load_2d_mc(sb + crank * (Cfg::B_BYTES / 2), &tmB, &full_bar[stage], kb * GEMM_BK,
-                           n_blk * BN + (int)crank * (BN / 2), (uint16_t)0x3);
-          } else
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -170,7 +156,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = sched_first; tile < num_tiles; tile += sched_step, ++it) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1, 2);  // epilogue drained this accumulator stage
@@ -188,8 +174,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // +32 B per K=16 step inside the 128-B swizzle atom -> +2 on the encoded (>>4) start address
             umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           }
-          if constexpr (MC) umma_commit_mc(&empty_bar[stage], (uint16_t)0x3);  // release the stage in both CTAs
-          else umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs have read it
+          umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs have read it
           if (kb == k_blocks - 1) umma_commit(&tfull_bar[as]);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -200,8 +185,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quad = warp & 3;           // TMEM lane quadrant this warp may access
     const int grp = (warp - 4) >> 2;     // column group of the tile
     int it = 0;
-    for (int tile = sched_first; tile < num_tiles; tile += sched_step, ++it) {
-      const int m_blk = (tile / n_blocks) * (MC ? 2 : 1) + (int)crank, n_blk = tile % n_blocks;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int row = m_blk * GEMM_BM + quad * 32 + lane;
@@ -406,26 +391,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <int BN, int EPI, bool MC = false>
+template <int BN, int EPI>
 static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
-        cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   CUtensorMap tmA, tmB;
   if (make_tmap_bf16_2d(&tmA, a.A, a.M, a.K, a.lda, GEMM_BM)) return -1;
-  if (make_tmap_bf16_2d(&tmB, a.W, a.N, a.K, a.ldw, MC ? BN / 2 : BN)) return -1;
+  if (make_tmap_bf16_2d(&tmB, a.W, a.N, a.K, a.ldw, BN)) return -1;
   GemmParams p;
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.bias = a.bias;
@@ -439,28 +423,10 @@ static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   p.act = a.act;
   p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;
   p.hyper = a.hyper; p.hyper_m0 = a.hyper_m0; p.hyper_nm = a.hyper_nm;
-  const int m_blocks = (a.M + GEMM_BM - 1) / GEMM_BM, n_blocks = (a.N + BN - 1) / BN;
+  const int tiles = ((a.M + GEMM_BM - 1) / GEMM_BM) * ((a.N + BN - 1) / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
   prof_begin(stream, PROF_GEMM, 2.0 * a.M * a.N * a.K);
-  if constexpr (MC) {
-    const int pairs = ((m_blocks + 1) / 2) * n_blocks;
-    const int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(Cfg::THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, EPI, true>, tmA, tmB, p);
-    if (le != cudaSuccess) return set_error("gemm cluster launch failed: %s", cudaGetErrorString(le));
-  } else {
-    const int tiles = m_blocks * n_blocks;
-    const int grid = tiles < num_sms ? tiles : num_sms;
-    gemm_bf16_kernel<BN, EPI, false><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
-  }
+  gemm_bf16_kernel<BN, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm launch failed: %s", cudaGetErrorString(e));
@@ -487,12 +453,7 @@ int launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   }
   // BN=256 keeps the tensor pipe at its 1-CTA rate with the fewest smem bytes per flop; fall back to 128 / 64 when N is
   // not a multiple (or is small), to avoid wasted columns.
-  if (a.N % 256 == 0) {
-    // weight multicast pays when the K loop dominates (encoder GEMMs); short-K decoder GEMMs are epilogue/HBM bound
-    static const bool mc_off = getenv("MSAM_NO_MULTICAST") != nullptr;
-    if (!mc_off && a.K >= 512 && a.M >= 2 * GEMM_BM * 8) return launch_gemm_bn<256, EPI_PLAIN, true>(a, num_sms, stream);
-    return launch_gemm_bn<256, EPI_PLAIN>(a, num_sms, stream);
-  }
+  if (a.N % 256 == 0) return launch_gemm_bn<256, EPI_PLAIN>(a, num_sms, stream);
   if (a.N % 128 == 0) return launch_gemm_bn<128, EPI_PLAIN>(a, num_sms, stream);
   return launch_gemm_bn<64, EPI_PLAIN>(a, num_sms, stream);
 }
