@@ -15,6 +15,7 @@
 #include "kernels.h"
 #include "ptx.cuh"
 #include "tensormap.h"
+#include <cstdlib>
 
 namespace msam {
 
@@ -23,18 +24,25 @@ constexpr int GEMM_BK = 64;
 
 enum { EPI_PLAIN = 0, EPI_LN256 = 1, EPI_LN64_GELU = 2, EPI_HYPER = 3 };
 
-template <int BN>
+// MT = 2: the CTA computes a 256 x BN tile as two M=128 MMAs per K step that share the weight tile in shared memory.
+// The 1-CTA 128x256 tile pulls 48 KB per 128x256x64 MMA block; at the measured chip-wide L2 throughput (~6300 B/clk,
+// 42.6 B/clk/SM) that caps the tensor pipe at ~45 % -- exactly what the MT = 1 kernel reached (1.0 PFLOP/s; a 2-CTA
+// cluster with TMA weight multicast did not move it).  MT = 2 needs 32 KB per block-equivalent (cap ~68 %), at the
+// price of a single (not double-buffered) accumulator stage.
+template <int BN, int MT = 1>
 struct GemmCfg {
   static constexpr int NG = (BN >= 128) ? 4 : 2;        // epilogue column groups
   static constexpr int CPW = BN / NG;                   // columns per epilogue thread (64 / 32 / 32)
   static constexpr int THREADS = 128 + NG * 128;        // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, epilogue
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int STAGES = (MT == 2) ? 3 : ((BN == 256) ? 4 : 6);
+  static constexpr int A_BYTES = MT * GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OFF_BAR = STAGES * STAGE_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024 /*align slack*/;   // + 11 KB static (exch, rowp)
-  static constexpr int TMEM_COLS = 2 * BN;              // power of two >= 32 for BN in {64,128,256}
+  static constexpr int TMEM_COLS = 2 * BN;              // 2 accumulator stages (MT=1) or 2 row halves (MT=2)
+  static constexpr int ACC_STAGES = (MT == 2) ? 1 : 2;
+  static_assert(MT == 1 || BN == 256, "MT = 2 is only instantiated for BN = 256");
 };
 
 struct GemmParams {
@@ -80,10 +88,11 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& r, float* f) {
   }
 }
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
+template <int BN, int EPI, int MT>
+__global__ void __launch_bounds__(GemmCfg<BN, MT>::THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, MT>;
+  constexpr int TILE_M = MT * GEMM_BM;
   constexpr int NG = Cfg::NG, CPW = Cfg::CPW, NCH = CPW / 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -98,7 +107,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_blocks = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int m_blocks = (p.M + TILE_M - 1) / TILE_M;
   const int n_blocks = (p.N + BN - 1) / BN;
   const int k_blocks = (p.K + GEMM_BK - 1) / GEMM_BK;
   const int num_tiles = m_blocks * n_blocks;
@@ -143,7 +152,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * TILE_M);  // one box of TILE_M rows
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -157,8 +166,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
+        const int as = (Cfg::ACC_STAGES == 2) ? (it & 1) : 0;
+        const uint32_t aphase = (Cfg::ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(&tempty_bar[as], aphase ^ 1, 2);  // epilogue drained this accumulator stage
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
@@ -173,6 +182,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // +32 B per K=16 step inside the 128-B swizzle atom -> +2 on the encoded (>>4) start address
             umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            if constexpr (MT == 2)  // rows 128..255 of the tile: A box + 16 KB (encoded +1024), accumulator columns + BN
+              umma_bf16(tmem_d + BN, da + (uint64_t)(1024 + 2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs have read it
           if (kb == k_blocks - 1) umma_commit(&tfull_bar[as]);
@@ -187,12 +198,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      const int row = m_blk * GEMM_BM + quad * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int as = (Cfg::ACC_STAGES == 2) ? (it & 1) : 0;
+      const uint32_t aphase = (Cfg::ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
       const int colbase = n_blk * BN + grp * CPW;
-      const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + grp * CPW);
+#pragma unroll 1
+      for (int mh = 0; mh < MT; ++mh) {
+      const int row = m_blk * TILE_M + mh * GEMM_BM + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((MT == 2 ? mh : as) * BN + grp * CPW);
+      const bool last_half = (mh == MT - 1);
 
       if constexpr (EPI == EPI_PLAIN) {
         const bool active = row_ok && colbase < p.N;  // N % 32 == 0 and CPW % 32 == 0: whole chunks are in or out
@@ -211,8 +225,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int b = 0; b < CPW * 2; b += 128) prefetch_l1(reinterpret_cast<const char*>(res_b) + b);
         }
-        mbar_wait(&tfull_bar[as], aphase, 4);
-        tc_fence_after();
+        if (mh == 0) {
+          mbar_wait(&tfull_bar[as], aphase, 4);
+          tc_fence_after();
+        }
 #pragma unroll 1
         for (int c = 0; c < NCH; ++c) {
           const int col0 = colbase + c * 32;
@@ -220,7 +236,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t v[32];
           tmem_ld32(tcol + c * 32, v);
           tmem_ld_wait();
-          if (c == NCH - 1) {  // this warp's reads of the accumulator stage are complete -> hand it back to the MMA warp
+          if (c == NCH - 1 && last_half) {  // this warp's reads of the accumulator are complete -> back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -386,6 +402,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         __syncwarp();
       }
+      }  // mh
     }
   }
 
@@ -397,18 +414,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int MT = 1>
 static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, MT>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
-        cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   CUtensorMap tmA, tmB;
-  if (make_tmap_bf16_2d(&tmA, a.A, a.M, a.K, a.lda, GEMM_BM)) return -1;
+  if (make_tmap_bf16_2d(&tmA, a.A, a.M, a.K, a.lda, MT * GEMM_BM)) return -1;
   if (make_tmap_bf16_2d(&tmB, a.W, a.N, a.K, a.ldw, BN)) return -1;
   GemmParams p;
   p.M = a.M; p.N = a.N; p.K = a.K;
@@ -423,10 +440,10 @@ static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   p.act = a.act;
   p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;
   p.hyper = a.hyper; p.hyper_m0 = a.hyper_m0; p.hyper_nm = a.hyper_nm;
-  const int tiles = ((a.M + GEMM_BM - 1) / GEMM_BM) * ((a.N + BN - 1) / BN);
+  const int tiles = ((a.M + MT * GEMM_BM - 1) / (MT * GEMM_BM)) * ((a.N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
   prof_begin(stream, PROF_GEMM, 2.0 * a.M * a.N * a.K);
-  gemm_bf16_kernel<BN, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm_bf16_kernel<BN, EPI, MT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm launch failed: %s", cudaGetErrorString(e));
@@ -453,7 +470,13 @@ int launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   }
   // BN=256 keeps the tensor pipe at its 1-CTA rate with the fewest smem bytes per flop; fall back to 128 / 64 when N is
   // not a multiple (or is small), to avoid wasted columns.
-  if (a.N % 256 == 0) return launch_gemm_bn<256, EPI_PLAIN>(a, num_sms, stream);
+  if (a.N % 256 == 0) {
+    // long-K GEMMs with enough 256-row tiles to fill the machine: 256x256 tiles (weight tile shared by two MMAs)
+    static const bool mt2_off = getenv("MSAM_GEMM_MT1") != nullptr;
+    const long tiles256 = (long)((a.M + 255) / 256) * (a.N / 256);
+    if (!mt2_off && a.K >= 512 && tiles256 >= 2L * num_sms) return launch_gemm_bn<256, EPI_PLAIN, 2>(a, num_sms, stream);
+    return launch_gemm_bn<256, EPI_PLAIN>(a, num_sms, stream);
+  }
   if (a.N % 128 == 0) return launch_gemm_bn<128, EPI_PLAIN>(a, num_sms, stream);
   return launch_gemm_bn<64, EPI_PLAIN>(a, num_sms, stream);
 }
