@@ -53,16 +53,23 @@ PFN_encodeTiled get_encode_tiled() {
 }
 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  return make_tmap_2d(out, gptr, 2, rows, cols, ld, box_rows);
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
-  if ((reinterpret_cast<uintptr_t>(gptr) & 15) != 0 || (ld * 2) % 16 != 0)
+  if (elem_bytes != 2 && elem_bytes != 4) return set_error("tensor map: unsupported element size %d", elem_bytes);
+  if ((reinterpret_cast<uintptr_t>(gptr) & 15) != 0 || (ld * elem_bytes) % 16 != 0)
     return set_error("tensor map: base/stride must be 16-byte aligned (ptr=%p ld=%llu)", gptr, (unsigned long long)ld);
   if (box_rows > 256) return set_error("tensor map: box_rows=%u > 256", box_rows);
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t strides[1] = {ld * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, estr,
+  CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(gptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)

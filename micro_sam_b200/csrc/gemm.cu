@@ -1,11 +1,12 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] * W[N,K]^T)
 //   * operands: TMA (SWIZZLE_128B boxes of 64 K-elements) -> shared memory ring (mbarrier full/empty)
 //   * math:     tcgen05.mma cta_group::1 kind::f16, M=128 x N=BN x K=16, fp32 accumulators in TMEM (2 stages)
-//   * epilogue: NG column groups x 4 warps (warp%4 = TMEM lane quadrant), tcgen05.ld 32x32b -> registers ->
-//               bias / GELU(erf) / ReLU / residual (fp32 or bf16, row modulus) -> bf16 or fp32, or one of the fused
-//               row epilogues: LayerNorm over N=256 (EPI_LN256), LayerNorm over 64-column groups + GELU (EPI_LN64_GELU),
-//               GELU + hyper-network mask product (EPI_HYPER).  Residual / bias loads are issued BEFORE the wait on the
-//               accumulator barrier so their latency hides behind the MMA of the same tile.
+//   * epilogue: BN/64 column groups x 4 warps (warp%4 = TMEM lane quadrant); tcgen05.ld 32x32b -> registers ->
+//               bias / GELU(erf) / ReLU / residual (fp32 or bf16, row modulus), or a fused row epilogue
+//               (LayerNorm over N=256, LayerNorm over 64-column groups + GELU, GELU + hyper-network mask product) ->
+//               128-byte rows in a swizzled shared-memory staging tile -> TMA store (cp.async.bulk.tensor, coalesced,
+//               asynchronous: the row-per-thread global stores of the first version saturated the LSU queue --
+//               ncu: stall lg_throttle 8.9, tensor pipe 51 %, profiles/r1_ncu_gemm_plain_v1.txt).
 // One CTA per SM; tiles are distributed round-robin, N-block fastest so that the CTAs that run concurrently share the
 // same A row-block through L2.
 //
@@ -15,34 +16,28 @@
 #include "kernels.h"
 #include "ptx.cuh"
 #include "tensormap.h"
-#include <cstdlib>
 
 namespace msam {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
+constexpr int CPW = 64;              // accumulator columns per epilogue thread
+constexpr int STG_BYTES = 128 * 128; // staging tile of one column group: 128 rows x 128 B
 
 enum { EPI_PLAIN = 0, EPI_LN256 = 1, EPI_LN64_GELU = 2, EPI_HYPER = 3 };
 
-// MT = 2: the CTA computes a 256 x BN tile as two M=128 MMAs per K step that share the weight tile in shared memory.
-// The 1-CTA 128x256 tile pulls 48 KB per 128x256x64 MMA block; at the measured chip-wide L2 throughput (~6300 B/clk,
-// 42.6 B/clk/SM) that caps the tensor pipe at ~45 % -- exactly what the MT = 1 kernel reached (1.0 PFLOP/s; a 2-CTA
-// cluster with TMA weight multicast did not move it).  MT = 2 needs 32 KB per block-equivalent (cap ~68 %), at the
-// price of a single (not double-buffered) accumulator stage.
-template <int BN, int MT = 1>
+template <int BN>
 struct GemmCfg {
-  static constexpr int NG = (BN >= 128) ? 4 : 2;        // epilogue column groups
-  static constexpr int CPW = BN / NG;                   // columns per epilogue thread (64 / 32 / 32)
+  static constexpr int NG = BN / 64;                    // epilogue column groups (4 / 2 / 1)
   static constexpr int THREADS = 128 + NG * 128;        // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, epilogue
-  static constexpr int STAGES = (MT == 2) ? 3 : ((BN == 256) ? 4 : 6);
-  static constexpr int A_BYTES = MT * GEMM_BM * GEMM_BK * 2;
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int OFF_BAR = STAGES * STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 3 : ((BN == 128) ? 5 : 6);
+  static constexpr int OFF_STG = STAGES * STAGE_BYTES;  // NG staging tiles
+  static constexpr int OFF_BAR = OFF_STG + NG * STG_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024 /*align slack*/;   // + 11 KB static (exch, rowp)
-  static constexpr int TMEM_COLS = 2 * BN;              // 2 accumulator stages (MT=1) or 2 row halves (MT=2)
-  static constexpr int ACC_STAGES = (MT == 2) ? 1 : 2;
-  static_assert(MT == 1 || BN == 256, "MT = 2 is only instantiated for BN = 256");
+  static constexpr int TMEM_COLS = 2 * BN;              // power of two >= 32 for BN in {64,128,256}
 };
 
 struct GemmParams {
@@ -50,14 +45,13 @@ struct GemmParams {
   const float* bias;      // [N] or null
   const void* residual;   // fp32 (or bf16 if res_bf16) [res_rows, ldr] or null; row index = row % res_rows
   int res_rows, ldr, res_bf16;
-  void* out;              // bf16 or fp32 [M, ldc]
-  int ldc;
   int out_fp32;
   int act;                // 0 none, 1 GELU(erf), 2 ReLU
   const float* ln_gamma;  // fused LayerNorm epilogues
   const float* ln_beta;
   float ln_eps;
   const float* hyper;     // EPI_HYPER: [P, 4, 32] hyper-network outputs
+  float* hyper_out;       // EPI_HYPER: low-res masks [P, hyper_nm, 256, 256]
   int hyper_m0, hyper_nm;
 };
 
@@ -87,13 +81,17 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& r, float* f) {
     f[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
   }
 }
+// 16-byte chunk `ch` (0..7) of row `r` in a 128-B-row staging tile with the TMA SWIZZLE_128B pattern
+__device__ __forceinline__ void stg_write(uint8_t* stg, int r, int ch, const uint4& v) {
+  *reinterpret_cast<uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4)) = v;
+}
 
-template <int BN, int EPI, int MT>
-__global__ void __launch_bounds__(GemmCfg<BN, MT>::THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BN, MT>;
-  constexpr int TILE_M = MT * GEMM_BM;
-  constexpr int NG = Cfg::NG, CPW = Cfg::CPW, NCH = CPW / 32;
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int NG = Cfg::NG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
@@ -107,7 +105,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_blocks = (p.M + TILE_M - 1) / TILE_M;
+  const int m_blocks = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int n_blocks = (p.N + BN - 1) / BN;
   const int k_blocks = (p.K + GEMM_BK - 1) / GEMM_BK;
   const int num_tiles = m_blocks * n_blocks;
@@ -115,6 +113,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if constexpr (EPI != EPI_HYPER) prefetch_tmap(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
@@ -152,7 +151,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * TILE_M);  // one box of TILE_M rows
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -166,8 +165,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int as = (Cfg::ACC_STAGES == 2) ? (it & 1) : 0;
-        const uint32_t aphase = (Cfg::ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1, 2);  // epilogue drained this accumulator stage
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
@@ -182,8 +181,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // +32 B per K=16 step inside the 128-B swizzle atom -> +2 on the encoded (>>4) start address
             umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-            if constexpr (MT == 2)  // rows 128..255 of the tile: A box + 16 KB (encoded +1024), accumulator columns + BN
-              umma_bf16(tmem_d + BN, da + (uint64_t)(1024 + 2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs have read it
           if (kb == k_blocks - 1) umma_commit(&tfull_bar[as]);
@@ -192,59 +189,65 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue: TMEM -> regs -> (fused op) -> global
+    // ------------------------------------------------------------ epilogue: TMEM -> regs -> staging smem -> TMA store
     const int quad = warp & 3;           // TMEM lane quadrant this warp may access
-    const int grp = (warp - 4) >> 2;     // column group of the tile
+    const int grp = (warp - 4) >> 2;     // 64-column group of the tile
+    const int r = quad * 32 + lane;      // row inside the tile
+    uint8_t* stg = smem + Cfg::OFF_STG + grp * STG_BYTES;
+    const bool issuer = (quad == 0 && lane == 0);
+    const int bar_id = 2 + grp;          // named barrier of this column group (128 threads)
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
-      const int as = (Cfg::ACC_STAGES == 2) ? (it & 1) : 0;
-      const uint32_t aphase = (Cfg::ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
-      const int colbase = n_blk * BN + grp * CPW;
-#pragma unroll 1
-      for (int mh = 0; mh < MT; ++mh) {
-      const int row = m_blk * TILE_M + mh * GEMM_BM + quad * 32 + lane;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int row = m_blk * GEMM_BM + r;
       const bool row_ok = row < p.M;
-      const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((MT == 2 ? mh : as) * BN + grp * CPW);
-      const bool last_half = (mh == MT - 1);
+      const int colbase = n_blk * BN + grp * CPW;
+      const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + grp * CPW);
+      auto release_acc = [&]() {  // this warp's reads of the accumulator stage are complete -> hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      };
+      // staging protocol: (a) the previous TMA store has finished reading the tile, (b) every row is written and visible
+      // to the async proxy, then one thread issues the store of the [128 x 128 B] box (rows / columns beyond M / N are clipped)
+      auto stg_acquire = [&]() {
+        if (issuer) tma_store_wait_read();
+        named_bar_sync(bar_id, 128);
+      };
+      auto stg_publish = [&](int col) {
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (issuer) {
+          tma_store_2d(&tmC, stg, col, m_blk * GEMM_BM);
+          tma_store_commit();
+        }
+      };
 
       if constexpr (EPI == EPI_PLAIN) {
-        const bool active = row_ok && colbase < p.N;  // N % 32 == 0 and CPW % 32 == 0: whole chunks are in or out
+        const bool has_res = p.residual != nullptr && row_ok;
         const float* res_f = nullptr;
         const __nv_bfloat16* res_b = nullptr;
-        if (p.residual && active) {
+        if (has_res) {
           const size_t off = (size_t)(row % p.res_rows) * p.ldr + colbase;
           if (p.res_bf16) res_b = reinterpret_cast<const __nv_bfloat16*>(p.residual) + off;
           else res_f = reinterpret_cast<const float*>(p.residual) + off;
         }
-        // pull this thread's residual row segment towards L1 while the MMA of the tile is still running
-        if (res_f) {
-#pragma unroll
-          for (int b = 0; b < CPW * 4; b += 128) prefetch_l1(reinterpret_cast<const char*>(res_f) + b);
-        } else if (res_b) {
-#pragma unroll
-          for (int b = 0; b < CPW * 2; b += 128) prefetch_l1(reinterpret_cast<const char*>(res_b) + b);
-        }
-        if (mh == 0) {
-          mbar_wait(&tfull_bar[as], aphase, 4);
-          tc_fence_after();
-        }
+        mbar_wait(&tfull_bar[as], aphase, 4);
+        tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < NCH; ++c) {
+        for (int c = 0; c < 2; ++c) {  // two 32-column chunks
           const int col0 = colbase + c * 32;
-          const bool on = active && col0 < p.N;
+          const bool on = col0 < p.N;  // N % 32 == 0: a chunk is entirely inside or outside
           uint32_t v[32];
           tmem_ld32(tcol + c * 32, v);
           tmem_ld_wait();
-          if (c == NCH - 1 && last_half) {  // this warp's reads of the accumulator are complete -> back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
-          }
-          if (on) {
-            float f[32];
+          if (c == 1) release_acc();
+          float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (on) {
             if (p.bias) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -259,8 +262,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (res_f) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                const float4 r = *reinterpret_cast<const float4*>(res_f + c * 32 + j);
-                f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
+                const float4 rr = *reinterpret_cast<const float4*>(res_f + c * 32 + j);
+                f[j] += rr.x; f[j + 1] += rr.y; f[j + 2] += rr.z; f[j + 3] += rr.w;
               }
             } else if (res_b) {
 #pragma unroll
@@ -271,23 +274,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int q = 0; q < 8; ++q) f[j + q] += r8[q];
               }
             }
-            if (p.out_fp32) {
-              float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldc + col0;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldc + col0;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8)
-                *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
-                                                              pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
-            }
           }
-          __syncwarp();  // reconverge before the next warp-collective tcgen05.ld
+          if (p.out_fp32) {  // 32 fp32 columns fill the 128-B staging row: one store per chunk
+            if (!on) continue;  // uniform across the column group (depends on col0 only)
+            stg_acquire();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              stg_write(stg, r, q, make_uint4(__float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]),
+                                              __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3])));
+            stg_publish(col0);
+          } else {           // 64 bf16 columns per staging row: one store per tile
+            if (c == 0) stg_acquire();
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              stg_write(stg, r, c * 4 + q, make_uint4(pack_bf16(f[8 * q], f[8 * q + 1]), pack_bf16(f[8 * q + 2], f[8 * q + 3]),
+                                                      pack_bf16(f[8 * q + 4], f[8 * q + 5]), pack_bf16(f[8 * q + 6], f[8 * q + 7])));
+            if (c == 1) stg_publish(colbase);
+          }
         }
       } else {
-        // ---- fused row epilogues (N == BN): this thread's CPW columns of the row live in registers
+        // ---- fused row epilogues (N == BN): this thread's 64 columns of the row live in registers
         float f[CPW];
         // residual (bf16 only in these modes): pulled towards L1 before the accumulator is ready, read after it
         const bool has_res = (EPI == EPI_LN256) && p.residual != nullptr && row_ok;
@@ -299,16 +305,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tfull_bar[as], aphase, 4);
         tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t v[32];
           tmem_ld32(tcol + c * 32, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[c * 32 + j] = __uint_as_float(v[j]) + rowp[grp * CPW + c * 32 + j];
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        release_acc();
 
         if constexpr (EPI == EPI_LN256) {
           if (has_res) {
@@ -331,79 +335,75 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < CPW; ++j) { const float d = f[j] - mean_g; q4[j & 3] = fmaf(d, d, q4[j & 3]); }
           const float m2_g = (q4[0] + q4[1]) + (q4[2] + q4[3]);
           float2* ex = exch + (it & 1) * (NG * 128);
-          ex[grp * 128 + quad * 32 + lane] = make_float2(mean_g, m2_g);
-          asm volatile("bar.sync 1, %0;" ::"n"(NG * 128) : "memory");
+          ex[grp * 128 + r] = make_float2(mean_g, m2_g);
+          named_bar_sync(1, NG * 128);
           float mean = 0.f;
           float2 st[NG];
 #pragma unroll
-          for (int g = 0; g < NG; ++g) { st[g] = ex[g * 128 + quad * 32 + lane]; mean += st[g].x; }
+          for (int g = 0; g < NG; ++g) { st[g] = ex[g * 128 + r]; mean += st[g].x; }
           mean *= (1.0f / NG);
           float m2 = 0.f;
 #pragma unroll
           for (int g = 0; g < NG; ++g) { const float d = st[g].x - mean; m2 += st[g].y + d * d * CPW; }
           const float rstd = rsqrtf(m2 * (1.0f / (NG * CPW)) + p.ln_eps);
-          if (row_ok) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldc + colbase;
+          stg_acquire();
 #pragma unroll
-            for (int j = 0; j < CPW; j += 8) {
-              float y[8];
+          for (int j = 0; j < CPW; j += 8) {
+            float y[8];
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
-                y[q] = (f[j + q] - mean) * rstd * rowp[256 + grp * CPW + j + q] + rowp[512 + grp * CPW + j + q];
-              *reinterpret_cast<uint4*>(o + j) =
-                  make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
-            }
+            for (int q = 0; q < 8; ++q)
+              y[q] = (f[j + q] - mean) * rstd * rowp[256 + grp * CPW + j + q] + rowp[512 + grp * CPW + j + q];
+            stg_write(stg, r, j >> 3, make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]),
+                                                  pack_bf16(y[6], y[7])));
           }
+          stg_publish(colbase);
         } else if constexpr (EPI == EPI_LN64_GELU) {
-          // LayerNorm2d over one 64-channel group (= one conv-transpose sub-pixel) + exact GELU; CPW == 64
-          static_assert(EPI != EPI_LN64_GELU || CPW == 64, "one group per thread");
-          if (row_ok) {
-            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+          // LayerNorm2d over one 64-channel group (= one conv-transpose sub-pixel) + GELU
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < CPW; ++j) s4[j & 3] += f[j];
-            const float mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / CPW);
-            float q4[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int j = 0; j < CPW; ++j) s4[j & 3] += f[j];
+          const float mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / CPW);
+          float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < CPW; ++j) { const float d = f[j] - mean; q4[j & 3] = fmaf(d, d, q4[j & 3]); }
-            const float m2 = (q4[0] + q4[1]) + (q4[2] + q4[3]);
-            const float rstd = rsqrtf(m2 * (1.0f / CPW) + p.ln_eps);
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldc + colbase;
+          for (int j = 0; j < CPW; ++j) { const float d = f[j] - mean; q4[j & 3] = fmaf(d, d, q4[j & 3]); }
+          const float rstd = rsqrtf(((q4[0] + q4[1]) + (q4[2] + q4[3])) * (1.0f / CPW) + p.ln_eps);
+          stg_acquire();
 #pragma unroll
-            for (int j = 0; j < CPW; j += 8) {
-              float y[8];
+          for (int j = 0; j < CPW; j += 8) {
+            float y[8];
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
-                y[q] = gelu_fast((f[j + q] - mean) * rstd * rowp[256 + j + q] + rowp[512 + j + q]);
-              *reinterpret_cast<uint4*>(o + j) =
-                  make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
-            }
+            for (int q = 0; q < 8; ++q)
+              y[q] = gelu_fast((f[j + q] - mean) * rstd * rowp[256 + j + q] + rowp[512 + j + q]);
+            stg_write(stg, r, j >> 3, make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]),
+                                                  pack_bf16(y[6], y[7])));
           }
+          stg_publish(colbase);
         } else if constexpr (EPI == EPI_HYPER) {
           // second conv-transpose (N = 128 = 4 sub-sub-pixels x 32 channels; bias added above) + GELU + hyper product:
-          // masks[p, mi, Y, X] = sum_ch hyper[p, m0+mi, ch] * gelu(up[row, ss*32 + ch]); CPW == 32: thread = one (row, ss).
-          // GEMM row = (prompt p, token (y,x), sub-pixel (dy,dx)); ss = grp = ey*2 + ex.
-          static_assert(EPI != EPI_HYPER || CPW == 32, "one sub-sub-pixel per thread");
+          // masks[p, mi, Y, X] = sum_ch hyper[p, m0+mi, ch] * gelu(up[row, ss*32 + ch]).  GEMM row = (prompt p, token
+          // (y,x), sub-pixel (dy,dx)); this thread holds sub-sub-pixels ey = grp, ex = 0,1 -> two adjacent pixels.
           if (row_ok) {
 #pragma unroll
             for (int j = 0; j < CPW; ++j) f[j] = gelu_fast(f[j]);
             const int sub = row & 3, tok = (row >> 2) & 4095, pp = row >> 14;
-            const int Y = 4 * (tok >> 6) + 2 * (sub >> 1) + (grp >> 1), X = 4 * (tok & 63) + 2 * (sub & 1) + (grp & 1);
+            const int Y = 4 * (tok >> 6) + 2 * (sub >> 1) + grp, X = 4 * (tok & 63) + 2 * (sub & 1);
             for (int mi = 0; mi < p.hyper_nm; ++mi) {
               const float* hw = p.hyper + ((size_t)pp * 4 + p.hyper_m0 + mi) * 32;
-              float a = 0.f;
+              float a0 = 0.f, a1 = 0.f;
 #pragma unroll
               for (int c = 0; c < 32; c += 4) {
                 const float4 h4 = __ldg(reinterpret_cast<const float4*>(hw + c));
-                a += h4.x * f[c] + h4.y * f[c + 1] + h4.z * f[c + 2] + h4.w * f[c + 3];
+                a0 += h4.x * f[c] + h4.y * f[c + 1] + h4.z * f[c + 2] + h4.w * f[c + 3];
+                a1 += h4.x * f[32 + c] + h4.y * f[33 + c] + h4.z * f[34 + c] + h4.w * f[35 + c];
               }
-              reinterpret_cast<float*>(p.out)[(((size_t)pp * p.hyper_nm + mi) * 256 + Y) * 256 + X] = a;
+              *reinterpret_cast<float2*>(p.hyper_out + (((size_t)pp * p.hyper_nm + mi) * 256 + Y) * 256 + X) = make_float2(a0, a1);
             }
           }
         }
-        __syncwarp();
       }
-      }  // mh
+      __syncwarp();
     }
+    if (issuer) tma_store_wait_all();  // all bulk stores of this thread have completed before the CTA exits
   }
 
   tc_fence_before();
@@ -414,19 +414,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, int EPI, int MT = 1>
+template <int BN, int EPI>
 static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, MT>;
+  using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
-        cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  CUtensorMap tmA, tmB;
-  if (make_tmap_bf16_2d(&tmA, a.A, a.M, a.K, a.lda, MT * GEMM_BM)) return -1;
+  const int ldc = a.ldc > 0 ? a.ldc : a.N;
+  CUtensorMap tmA, tmB, tmC;
+  if (make_tmap_bf16_2d(&tmA, a.A, a.M, a.K, a.lda, GEMM_BM)) return -1;
   if (make_tmap_bf16_2d(&tmB, a.W, a.N, a.K, a.ldw, BN)) return -1;
+  if (EPI == EPI_HYPER) tmC = tmA;  // unused
+  else if (make_tmap_2d(&tmC, a.out, a.out_fp32 ? 4 : 2, a.M, a.N, ldc, GEMM_BM)) return -1;
   GemmParams p;
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.bias = a.bias;
@@ -434,16 +437,14 @@ static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   p.res_bf16 = a.res_bf16;
   p.res_rows = a.res_rows > 0 ? a.res_rows : a.M;
   p.ldr = a.ldr > 0 ? a.ldr : a.N;
-  p.out = a.out;
-  p.ldc = a.ldc > 0 ? a.ldc : a.N;
   p.out_fp32 = a.out_fp32;
   p.act = a.act;
   p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;
-  p.hyper = a.hyper; p.hyper_m0 = a.hyper_m0; p.hyper_nm = a.hyper_nm;
-  const int tiles = ((a.M + MT * GEMM_BM - 1) / (MT * GEMM_BM)) * ((a.N + BN - 1) / BN);
+  p.hyper = a.hyper; p.hyper_m0 = a.hyper_m0; p.hyper_nm = a.hyper_nm; p.hyper_out = reinterpret_cast<float*>(a.out);
+  const int tiles = ((a.M + GEMM_BM - 1) / GEMM_BM) * ((a.N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
   prof_begin(stream, PROF_GEMM, 2.0 * a.M * a.N * a.K);
-  gemm_bf16_kernel<BN, EPI, MT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm_bf16_kernel<BN, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm launch failed: %s", cudaGetErrorString(e));
@@ -470,13 +471,7 @@ int launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   }
   // BN=256 keeps the tensor pipe at its 1-CTA rate with the fewest smem bytes per flop; fall back to 128 / 64 when N is
   // not a multiple (or is small), to avoid wasted columns.
-  if (a.N % 256 == 0) {
-    // long-K GEMMs with enough 256-row tiles to fill the machine: 256x256 tiles (weight tile shared by two MMAs)
-    static const bool mt2_off = getenv("MSAM_GEMM_MT1") != nullptr;
-    const long tiles256 = (long)((a.M + 255) / 256) * (a.N / 256);
-    if (!mt2_off && a.K >= 512 && tiles256 >= 2L * num_sms) return launch_gemm_bn<256, EPI_PLAIN, 2>(a, num_sms, stream);
-    return launch_gemm_bn<256, EPI_PLAIN>(a, num_sms, stream);
-  }
+  if (a.N % 256 == 0) return launch_gemm_bn<256, EPI_PLAIN>(a, num_sms, stream);
   if (a.N % 128 == 0) return launch_gemm_bn<128, EPI_PLAIN>(a, num_sms, stream);
   return launch_gemm_bn<64, EPI_PLAIN>(a, num_sms, stream);
 }
