@@ -35,8 +35,9 @@ const char* msam_last_error(void);
 int64_t msam_launch_count(void);
 
 /* bench instrumentation: when enabled, CUDA events are recorded on the launching stream around every GEMM / attention
- * launch; msam_profile_summary synchronises and returns {ms, algorithmic flops, launches} per category
- * (0 = tcgen05 GEMM, 1 = encoder attention) in out[6]. */
+ * launch; msam_profile_summary synchronises and returns {ms, algorithmic work, launches} per category in out[9]:
+ * 0 = long-K tcgen05 GEMMs (work = FLOPs), 1 = encoder attention (FLOPs), 2 = short-K GEMMs with fused epilogues
+ * (HBM-bound, work = algorithmic bytes). */
 int msam_profile(int enable);
 int msam_profile_summary(double* out);
 

@@ -443,7 +443,13 @@ static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   p.hyper = a.hyper; p.hyper_m0 = a.hyper_m0; p.hyper_nm = a.hyper_nm; p.hyper_out = reinterpret_cast<float*>(a.out);
   const int tiles = ((a.M + GEMM_BM - 1) / GEMM_BM) * ((a.N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  prof_begin(stream, PROF_GEMM, 2.0 * a.M * a.N * a.K);
+  if (a.K >= 512) {
+    prof_begin(stream, PROF_GEMM, 2.0 * a.M * a.N * a.K);
+  } else {  // HBM-bound: algorithmic bytes
+    const double out_b = EPI == EPI_HYPER ? (double)a.M * a.hyper_nm * 16.0 : (double)a.M * a.N * (a.out_fp32 ? 4 : 2);
+    const double res_b = a.residual ? (double)(a.res_rows > 0 ? a.res_rows : a.M) * a.N * (a.res_bf16 ? 2 : 4) : 0.0;
+    prof_begin(stream, PROF_GEMM_HBM, (double)a.M * a.K * 2 + (double)a.N * a.K * 2 + out_b + res_b);
+  }
   gemm_bf16_kernel<BN, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();

@@ -10,7 +10,9 @@ int set_error(const char* fmt, ...);  // records msam_last_error(); returns -1
 void count_launch();                  // per-thread launch counter (msam_launch_count)
 
 // Optional per-kernel timing (bench.py roofline): CUDA events recorded on the launching stream around a launch.
-enum ProfCat { PROF_GEMM = 0, PROF_ATTN = 1, PROF_NCAT = 2 };
+// GEMM launches are split by what bounds them: long-K (encoder) GEMMs -> tensor pipe, work = FLOPs; short-K (decoder)
+// GEMMs with fused epilogues -> HBM, work = algorithmic bytes (A + W + residual + output).
+enum ProfCat { PROF_GEMM = 0, PROF_ATTN = 1, PROF_GEMM_HBM = 2, PROF_NCAT = 3 };
 void prof_begin(cudaStream_t st, int cat, double work);  // work = algorithmic FLOPs (or bytes) of the launch
 void prof_end(cudaStream_t st);
 
