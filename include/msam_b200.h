@@ -106,6 +106,15 @@ int msam_paint_min_area(const float* low_res, const int32_t* sel, const int32_t*
 int msam_finish_segmentation(const int32_t* painted, int h, int w, int min_object_size, int with_background, uint32_t* out,
                              int32_t* workspace, void* stream);
 
+/* Multi-crop / tiled AMG painting (instance_segmentation.py:499-529 + util.py:1799-1829): each crop paints its
+ * surviving masks sel[0..n_sel) (global list positions global_pos[k]) into a uint64 canvas [H, ld_canvas] initialised to
+ * all-ones with atomicMin((area << 32) | ~pos): smallest area wins, later position on ties.  msam_canvas_to_label turns
+ * the canvas into int32 ids (position + 1, 0 = empty). */
+int msam_paint_canvas(const float* low_res, const int32_t* sel, const int32_t* global_pos, int n_sel,
+                      const int32_t* boxes_xyxy, const int32_t* area, int in_h, int in_w, int crop_h, int crop_w,
+                      float mask_threshold, int off_x, int off_y, uint64_t* canvas, int ld_canvas, void* stream);
+int msam_canvas_to_label(const uint64_t* canvas, int64_t n, int32_t* label, void* stream);
+
 /* ---- single-op entry points (unit tests / profiling; the same kernels the calls above are built from) ---- */
 /* out[M,N] = act(A[M,K] @ W[N,K]^T + bias) + residual[row % res_rows];  A, W bf16; bias/residual fp32 or NULL;
  * out bf16 (out_fp32=0) or fp32; act: 0 none, 1 GELU(erf), 2 ReLU. */

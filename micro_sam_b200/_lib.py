@@ -56,6 +56,9 @@ def lib() -> ctypes.CDLL:
         L.msam_paint_min_area.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                           c_float, c_void_p, c_int, c_void_p]
         L.msam_finish_segmentation.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+        L.msam_paint_canvas.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                        c_float, c_int, c_int, c_void_p, c_int, c_void_p]
+        L.msam_canvas_to_label.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
         L.msam_profile.argtypes = [c_int]
         L.msam_profile_summary.argtypes = [POINTER(ctypes.c_double)]
         _lib = L

@@ -453,6 +453,16 @@ int msam_finish_segmentation(const int32_t* painted, int h, int w, int min_objec
   return post_finish_segmentation(painted, h, w, min_object_size, with_background, out, workspace, (cudaStream_t)stream);
 }
 
+int msam_paint_canvas(const float* low_res, const int32_t* sel, const int32_t* global_pos, int n_sel,
+                      const int32_t* boxes_xyxy, const int32_t* area, int in_h, int in_w, int crop_h, int crop_w,
+                      float mask_threshold, int off_x, int off_y, uint64_t* canvas, int ld_canvas, void* stream) {
+  return post_paint_canvas(low_res, sel, global_pos, n_sel, boxes_xyxy, area, in_h, in_w, crop_h, crop_w, mask_threshold,
+                           off_x, off_y, reinterpret_cast<unsigned long long*>(canvas), ld_canvas, (cudaStream_t)stream);
+}
+int msam_canvas_to_label(const uint64_t* canvas, int64_t n, int32_t* label, void* stream) {
+  return post_canvas_to_label(reinterpret_cast<const unsigned long long*>(canvas), (long)n, label, (cudaStream_t)stream);
+}
+
 static int sm_count() {
   static int n = 0;
   if (!n) {

@@ -699,3 +699,56 @@ int post_finish_segmentation(const int32_t* seg, int h, int w, int min_size, int
 }
 
 }  // namespace msam
+
+// =================================================================================================================
+// Multi-crop / tiled AMG painting (AutomaticMaskGenerator.generate with several crops, instance_segmentation.py:499-529):
+// every crop paints its surviving masks into one global canvas with a packed 64-bit atomicMin
+//   key = (area << 32) | (0xFFFFFFFF - global position)   ->  smallest area wins, later position on ties,
+// which is the "descending area, later overwrites" order of mask_data_to_segmentation(merge_exclusively=False)
+// evaluated per pixel.  canvas_to_label turns the winners into ids (position + 1).
+namespace msam {
+
+__global__ void paint_canvas_kernel(const float* __restrict__ low_res, const int32_t* __restrict__ sel,
+                                    const int32_t* __restrict__ gpos, int n_sel, const int32_t* __restrict__ boxes,
+                                    const int32_t* __restrict__ area, PostGeom g, float thr, int off_x, int off_y,
+                                    unsigned long long* __restrict__ canvas, int ld_canvas) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= g.out_w) return;
+  unsigned long long best = ~0ull;
+  for (int k = 0; k < n_sel; ++k) {
+    const int mi = sel[k];
+    const int4 b = *reinterpret_cast<const int4*>(boxes + 4L * mi);
+    if (x < b.x || x > b.z || y < b.y || y > b.w) continue;
+    const unsigned long long key = ((unsigned long long)(unsigned)area[mi] << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)gpos[k]);
+    if (key >= best) continue;
+    if (full_res(low_res + (long)mi * g.lr * g.lr, g, y, x) > thr) best = key;
+  }
+  if (best != ~0ull) atomicMin(&canvas[(long)(off_y + y) * ld_canvas + off_x + x], best);
+}
+
+__global__ void canvas_to_label_kernel(const unsigned long long* __restrict__ canvas, long n, int32_t* __restrict__ label) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long v = canvas[i];
+  label[i] = v == ~0ull ? 0 : (int32_t)(0xFFFFFFFFu - (unsigned)(v & 0xFFFFFFFFull)) + 1;
+}
+
+int post_paint_canvas(const float* low_res, const int32_t* sel, const int32_t* gpos, int n_sel, const int32_t* boxes,
+                      const int32_t* area, int in_h, int in_w, int out_h, int out_w, float thr, int off_x, int off_y,
+                      unsigned long long* canvas, int ld_canvas, cudaStream_t st) {
+  PostGeom g;
+  if (make_geom(in_h, in_w, out_h, out_w, &g)) return -1;
+  if (n_sel <= 0) return 0;
+  paint_canvas_kernel<<<dim3((out_w + 255) / 256, out_h), 256, 0, st>>>(low_res, sel, gpos, n_sel, boxes, area, g, thr, off_x,
+                                                                        off_y, canvas, ld_canvas);
+  LAUNCH_CHECK("paint_canvas");
+  return 0;
+}
+
+int post_canvas_to_label(const unsigned long long* canvas, long n, int32_t* label, cudaStream_t st) {
+  canvas_to_label_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(canvas, n, label);
+  LAUNCH_CHECK("canvas_to_label");
+  return 0;
+}
+
+}  // namespace msam

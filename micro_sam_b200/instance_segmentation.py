@@ -216,20 +216,79 @@ class AutomaticMaskGenerator(AMGBase):
                 tuple(self.crop_boxes[0]) == (0, 0, self.original_size[1], self.original_size[0]):
             out = self.generate_device(pred_iou_thresh, stability_score_thresh, box_nms_thresh, with_background)
             return out.cpu().numpy().view(np.uint32)
-        results, painted = [], None
+        return self._generate_multi(pred_iou_thresh, stability_score_thresh, box_nms_thresh, crop_nms_thresh, output_mode,
+                                    with_background, geoms)
+
+    def _generate_multi(self, pred_iou_thresh, stability_score_thresh, box_nms_thresh, crop_nms_thresh, output_mode,
+                        with_background, geoms):
+        """generate() for any number of crops / tiles (instance_segmentation.py:499-529): per-crop filters + NMS, then the
+        cross-crop NMS that prefers masks from smaller crops, then records or painting."""
+        H, W = self.original_size
+        dev = self._predictor.device
+        keeps, gboxes, crop_id = [], [], []
         for ci, (data, crop_box) in enumerate(zip(self.crop_list, self.crop_boxes)):
-            geom = geoms[ci] if geoms else dict(inp=tuple(self._predictor.input_size),
-                                                orig=(crop_box[3] - crop_box[1], crop_box[2] - crop_box[0]))
             keep = self._filter_nms(data, crop_box, self.original_size, pred_iou_thresh, stability_score_thresh,
                                     box_nms_thresh)
-            if output_mode == "instance_segmentation":
-                painted = self._paint(data, keep, crop_box, geom, painted)
-            else:
-                results += self._records(data, keep, crop_box, output_mode, geom)
+            keeps.append(keep)
+            off = torch.tensor([crop_box[0], crop_box[1], crop_box[0], crop_box[1]], dtype=torch.int32, device=dev)
+            gboxes.append(data["boxes"][keep] + off)
+            crop_id.append(torch.full((len(keep),), ci, dtype=torch.int64, device=dev))
+        gboxes = torch.cat(gboxes).contiguous() if gboxes else torch.zeros(0, 4, dtype=torch.int32, device=dev)
+        crop_id = torch.cat(crop_id) if crop_id else torch.zeros(0, dtype=torch.int64, device=dev)
+        local = torch.cat(keeps) if keeps else torch.zeros(0, dtype=torch.int64, device=dev)
+        n = int(gboxes.shape[0])
+        order = torch.arange(n, device=dev)
+        if len(self.crop_boxes) > 1 and n > 0:
+            cb = torch.tensor(self.crop_boxes, dtype=torch.float32, device=dev)
+            scores = (1.0 / ((cb[:, 2] - cb[:, 0]) * (cb[:, 3] - cb[:, 1])))[crop_id].contiguous()
+            keep2 = torch.empty(n, dtype=torch.int32, device=dev)
+            n2 = torch.zeros(1, dtype=torch.int32, device=dev)
+            zero4 = (ctypes.c_int32 * 4)(0, 0, 0, 0)
+            _lib.check(_lib.lib().msam_amg_filter_nms(_lib.ptr(gboxes), _lib.ptr(scores), _lib.ptr(scores), n, 0, 0.0, 0.0,
+                                                      float(crop_nms_thresh), zero4, zero4, _lib.ptr(keep2), _lib.ptr(n2),
+                                                      _lib.cur_stream()))
+            order = keep2[: int(n2.item())].long()
+        crop_id, local, gboxes = crop_id[order], local[order], gboxes[order]
+        n = len(order)
         if output_mode != "instance_segmentation":
-            return results
-        seg = painted.cpu().numpy() if painted is not None else np.zeros(self.original_size, dtype="uint32")
-        return util._finish_segmentation(seg, min_object_size=0, label_masks=True, with_background=with_background)
+            out = [None] * n
+            for ci, (data, crop_box) in enumerate(zip(self.crop_list, self.crop_boxes)):
+                pos = (crop_id == ci).nonzero()[:, 0]
+                if len(pos) == 0:
+                    continue
+                recs = self._records(data, local[pos], crop_box, output_mode, geoms[ci])
+                x0, y0, x1, y1 = crop_box
+                for k, r in zip(pos.tolist(), recs):
+                    if output_mode == "binary_mask" and (x1 - x0, y1 - y0) != (W, H):  # uncrop_masks
+                        full = np.zeros((H, W), dtype=bool)
+                        full[y0:y1, x0:x1] = r["segmentation"]
+                        r["segmentation"] = full
+                    elif output_mode == "rle" and (x1 - x0, y1 - y0) != (W, H):
+                        full = np.zeros((H, W), dtype=bool)
+                        full[y0:y1, x0:x1] = amg_utils.rle_to_mask(r["segmentation"])
+                        r["segmentation"] = amg_utils.mask_to_rle(full[None])[0]
+                    out[k] = r
+            return out
+        canvas = torch.full((H, W), -1, dtype=torch.int64, device=dev)
+        L = _lib.lib()
+        for ci, (data, crop_box) in enumerate(zip(self.crop_list, self.crop_boxes)):
+            pos = (crop_id == ci).nonzero()[:, 0]
+            if len(pos) == 0:
+                continue
+            sel = local[pos].to(torch.int32).contiguous()
+            gpos = pos.to(torch.int32).contiguous()
+            g = geoms[ci]
+            _lib.check(L.msam_paint_canvas(_lib.ptr(data["low_res"]), _lib.ptr(sel), _lib.ptr(gpos), len(sel),
+                                           _lib.ptr(data["boxes"]), _lib.ptr(data["area"]), g["inp"][0], g["inp"][1],
+                                           g["orig"][0], g["orig"][1], 0.0, int(crop_box[0]), int(crop_box[1]),
+                                           _lib.ptr(canvas), W, _lib.cur_stream()))
+        label = torch.empty(H, W, dtype=torch.int32, device=dev)
+        out = torch.empty(H, W, dtype=torch.int32, device=dev)
+        ws = torch.empty(4 * H * W + 4096 + 8, dtype=torch.int32, device=dev)
+        _lib.check(L.msam_canvas_to_label(_lib.ptr(canvas), H * W, _lib.ptr(label), _lib.cur_stream()))
+        _lib.check(L.msam_finish_segmentation(_lib.ptr(label), H, W, 0, int(with_background), _lib.ptr(out), _lib.ptr(ws),
+                                              _lib.cur_stream()))
+        return out.cpu().numpy().view(np.uint32)
 
     @torch.no_grad()
     def generate_device(self, pred_iou_thresh: float = 0.88, stability_score_thresh: float = 0.95,
@@ -262,25 +321,59 @@ class AutomaticMaskGenerator(AMGBase):
                                               _lib.cur_stream()))
         return out
 
-    def _paint(self, data, keep, crop_box, geom, label):
-        """mask_data_to_segmentation(..., merge_exclusively=False) painting (util.py:1799-1829): descending area, later
-        (smaller) masks overwrite.  Stable order like Python's sorted(reverse=True)."""
-        H, W = self.original_size
-        dev = data["low_res"].device
-        if label is None:
-            label = torch.zeros(H, W, dtype=torch.int32, device=dev)
-        if len(keep) == 0:
-            return label
-        area = data["area"][keep]
-        order = torch.argsort(area, descending=True, stable=True)
-        sel = keep[order].to(torch.int32).contiguous()
-        seg_ids = torch.arange(1, len(sel) + 1, dtype=torch.int32, device=dev)
-        x0, y0 = int(crop_box[0]), int(crop_box[1])
-        view = label[y0:, x0:]
-        _lib.check(_lib.lib().msam_paint(_lib.ptr(data["low_res"]), _lib.ptr(sel), _lib.ptr(data["boxes"]), _lib.ptr(seg_ids),
-                                         len(sel), geom["inp"][0], geom["inp"][1], geom["orig"][0], geom["orig"][1], 0.0, 0,
-                                         ctypes.c_void_p(view.data_ptr()), W, _lib.cur_stream()))
-        return label
+
+
+class TiledAutomaticMaskGenerator(AutomaticMaskGenerator):
+    """instance_segmentation.py:564-680: AMG over tiled embeddings; every (outer) tile acts as a crop, `generate` is the
+    inherited multi-crop path (per-tile filters + NMS, cross-tile NMS, global painting)."""
+
+    def __init__(self, predictor, points_per_side: Optional[int] = 32, points_per_batch: Optional[int] = None,
+                 point_grids: Optional[List[np.ndarray]] = None, stability_score_offset: float = 1.0) -> None:
+        super().__init__(predictor=predictor, points_per_side=points_per_side, points_per_batch=points_per_batch,
+                         point_grids=point_grids, stability_score_offset=stability_score_offset)
+
+    @torch.no_grad()
+    def initialize(self, image: np.ndarray, image_embeddings: Optional[util.ImageEmbeddings] = None,
+                   i: Optional[int] = None, tile_shape=None, halo=None, verbose: bool = False,
+                   pbar_init: Optional[Callable] = None, pbar_update: Optional[Callable] = None, batch_size: int = 1,
+                   mask=None) -> None:
+        original_size = image.shape[:2]
+        self._original_size = original_size
+        if image_embeddings is None:
+            if tile_shape is None or halo is None:
+                raise ValueError("To compute tiled embeddings the parameters tile_shape and halo have to be passed.")
+            image_embeddings = util.precompute_image_embeddings(self._predictor, image, tile_shape=tile_shape, halo=halo,
+                                                                verbose=verbose, batch_size=batch_size, mask=mask,
+                                                                to_numpy=False)
+        feats = image_embeddings["features"]
+        tile_shape_, halo_ = tuple(feats.attrs["tile_shape"]), tuple(feats.attrs["halo"])
+        if tile_shape is not None and tuple(tile_shape) != tile_shape_:
+            raise ValueError(f"Inconsistent tile_shape parameter {tile_shape} with precomputed embeedings: {tile_shape_}.")
+        if halo is not None and tuple(halo) != halo_:
+            raise ValueError(f"Inconsistent halo parameter {halo} with precomputed embeedings: {halo_}.")
+        tile_shape, halo = tile_shape_, halo_
+        tiles_in_mask = feats.attrs.get("tiles_in_mask", None)
+        if tiles_in_mask is not None and i is not None:
+            tiles_in_mask = tiles_in_mask[str(i)]
+        tiling = amg_utils.Blocking([0, 0], original_size, tile_shape)
+        tile_ids = range(tiling.number_of_blocks) if tiles_in_mask is None else tiles_in_mask
+        tiles = [tiling.get_block_with_halo(t, list(halo)).outer_block for t in tile_ids]
+        crop_boxes = [[t.begin[1], t.begin[0], t.end[1], t.end[0]] for t in tiles]
+        _, pbar_init, pbar_update, pbar_close = util.handle_pbar(verbose, pbar_init, pbar_update)
+        pbar_init(len(crop_boxes), "Compute masks for tile")
+        mask_data, geoms = [], []
+        for idx, tile_id in enumerate(tile_ids):
+            f = feats[str(tile_id)]
+            util.set_precomputed(self._predictor, {"features": f, "input_size": f.attrs["input_size"],
+                                                   "original_size": f.attrs["original_size"]}, i)
+            mask_data.append(self._process_crop(original_size, crop_boxes[idx], 0))
+            geoms.append(dict(inp=tuple(self._predictor.input_size), orig=tuple(self._predictor.original_size)))
+            pbar_update(1)
+        pbar_close()
+        self._geoms = geoms
+        self._is_initialized = True
+        self._crop_list = mask_data
+        self._crop_boxes = crop_boxes
 
 
 def get_instance_segmentation_generator(predictor, is_tiled: bool, decoder=None, segmentation_mode: Optional[str] = None,
@@ -288,6 +381,4 @@ def get_instance_segmentation_generator(predictor, is_tiled: bool, decoder=None,
     """instance_segmentation.py:1631: only the AMG mode exists on this path (AIS/APG need the UNETR decoder, 8f-2)."""
     if decoder is not None or segmentation_mode not in (None, "amg"):
         raise NotImplementedError("only segmentation_mode='amg' is available on the B200 path")
-    if is_tiled:
-        raise NotImplementedError("TiledAutomaticMaskGenerator is not implemented yet")
-    return AutomaticMaskGenerator(predictor, **kwargs)
+    return (TiledAutomaticMaskGenerator if is_tiled else AutomaticMaskGenerator)(predictor, **kwargs)

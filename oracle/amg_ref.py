@@ -473,6 +473,11 @@ class AutomaticMaskGenerator:
         for data_, crop_box in zip(self._crop_list, self._crop_boxes):
             data.cat(self._postprocess_batch(deepcopy(data_), crop_box, self._original_size, pred_iou_thresh,
                                              stability_score_thresh, box_nms_thresh))
+        if len(self._crop_boxes) > 1 and len(data["crop_boxes"]) > 0:  # prefer masks from smaller crops (:511-521)
+            scores = 1 / box_area(data["crop_boxes"])
+            keep_by_nms = batched_nms(data["boxes"].float(), scores, torch.zeros_like(data["boxes"][:, 0]),
+                                      iou_threshold=crop_nms_thresh)
+            data.filter(keep_by_nms)
         data.to_numpy()
         if output_mode in ("binary_mask", "instance_segmentation"):
             segs = [rle_to_mask(rle) for rle in data["rles"]]
@@ -594,3 +599,72 @@ def batched_mask_nms(masks, boxes, scores, nms_thresh: float, intersection_over_
             break
         sorted_indices = sorted_indices[1:][mat[i, sorted_indices[1:]] <= nms_thresh]
     return torch.tensor(keep)
+
+
+# ------------------------------------------------------------------------------------------------ tiling
+class Blocking:
+    """bioimage_cpp.utils.Blocking (nifty semantics): row-major block ids, halo clipped to the ROI."""
+
+    class _B:
+        def __init__(self, begin, end):
+            self.begin, self.end = list(begin), list(end)
+            self.shape = [e - b for b, e in zip(begin, end)]
+
+    def __init__(self, roi_begin, roi_end, block_shape):
+        self.rb, self.re, self.bs = list(roi_begin), list(roi_end), list(block_shape)
+        self.blocks_per_axis = [-(-(e - b) // s) for b, e, s in zip(self.rb, self.re, self.bs)]
+        self.number_of_blocks = int(np.prod(self.blocks_per_axis))
+
+    def get_block_with_halo(self, block_id, halo):
+        pos = np.unravel_index(block_id, self.blocks_per_axis)
+        ib = [b + p * s for b, p, s in zip(self.rb, pos, self.bs)]
+        ie = [min(x + s, e) for x, s, e in zip(ib, self.bs, self.re)]
+        ob = [max(x - h, b) for x, h, b in zip(ib, halo, self.rb)]
+        oe = [min(x + h, e) for x, h, e in zip(ie, halo, self.re)]
+
+        class R:
+            pass
+        r = R()
+        r.inner_block, r.outer_block = Blocking._B(ib, ie), Blocking._B(ob, oe)
+        r.inner_block_local = Blocking._B([a - b for a, b in zip(ib, ob)], [a - b for a, b in zip(ie, ob)])
+        return r
+
+
+def precompute_tiled_embeddings_2d(predictor, image, tile_shape, halo):
+    """util.py:765-803 (_compute_tiled_features_2d): every outer tile is normalised on its own (_to_image)."""
+    tiling = Blocking([0, 0], image.shape[:2], tile_shape)
+    feats = {}
+    for tile_id in range(tiling.number_of_blocks):
+        t = tiling.get_block_with_halo(tile_id, list(halo)).outer_block
+        tile = image[t.begin[0]:t.end[0], t.begin[1]:t.end[1]]
+        feats[str(tile_id)] = precompute_image_embeddings_2d(predictor, tile)
+    return {"features": feats, "tile_shape": tuple(tile_shape), "halo": tuple(halo)}
+
+
+class TiledAutomaticMaskGenerator(AutomaticMaskGenerator):
+    """instance_segmentation.py:564-680."""
+
+    @torch.no_grad()
+    def initialize(self, image, image_embeddings=None, tile_shape=None, halo=None):
+        original_size = image.shape[:2]
+        self._original_size = original_size
+        if image_embeddings is None:
+            image_embeddings = precompute_tiled_embeddings_2d(self._predictor, image, tile_shape, halo)
+        tile_shape, halo = image_embeddings["tile_shape"], image_embeddings["halo"]
+        tiling = Blocking([0, 0], original_size, tile_shape)
+        tiles = [tiling.get_block_with_halo(t, list(halo)).outer_block for t in range(tiling.number_of_blocks)]
+        crop_boxes = [[t.begin[1], t.begin[0], t.end[1], t.end[0]] for t in tiles]
+        image = to_image(image)
+        mask_data = []
+        for tile_id, crop_box in enumerate(crop_boxes):
+            set_precomputed(self._predictor, image_embeddings["features"][str(tile_id)])
+            x0, y0, x1, y1 = crop_box
+            cropped_im_size = image[y0:y1, x0:x1, :].shape[:2]
+            points_for_image = self.point_grids[0] * np.array(cropped_im_size)[None, ::-1]
+            data = MaskData()
+            for (points,) in batch_iterator(self._points_per_batch, points_for_image):
+                data.cat(self._process_batch(points, cropped_im_size, crop_box, original_size))
+            mask_data.append(data)
+        self._is_initialized = True
+        self._crop_list = mask_data
+        self._crop_boxes = crop_boxes

@@ -223,3 +223,51 @@ def test_device_to_image_and_finish_segmentation_bit_exact(models):
     ws = torch.empty(4 * 64 * 64 + 4096 + 8, dtype=torch.int32, device="cuda")
     _lib.check(L.msam_finish_segmentation(_lib.ptr(d), 64, 64, 0, 1, _lib.ptr(out), _lib.ptr(ws), _lib.cur_stream()))
     assert np.array_equal(out.cpu().numpy().view(np.uint32), util._finish_segmentation(full.astype(np.uint32), 0, True, True))
+
+
+def test_tiled_amg_against_oracle(models):
+    """TiledAutomaticMaskGenerator (a13): tiles as crops, per-tile filters + NMS, cross-tile NMS, global painting.
+    Integer stages bit-exact given the GPU's low-res logits; tiled embeddings within tolerance."""
+    from oracle import amg_ref
+    from micro_sam_b200 import instance_segmentation as iseg
+    from micro_sam_b200.sample_data import lm_tile
+    opred, pred = models
+    img = lm_tile((300, 420), 30, seed=7)
+    tile_shape, halo = (160, 224), (24, 24)
+    amg = iseg.TiledAutomaticMaskGenerator(pred, points_per_side=4)
+    amg.initialize(img, tile_shape=tile_shape, halo=halo, batch_size=2)
+    assert len(amg.crop_list) == 4 and amg.crop_boxes[3] == [200, 136, 420, 300]
+    lows = [d["low_res"].cpu().view(-1, 3, 256, 256) for d in amg.crop_list]
+    ious = [d["iou_preds"].cpu().view(-1, 3) for d in amg.crop_list]
+    calls = {"i": 0}
+
+    def fake(point_coords, point_labels, boxes=None, mask_input=None, multimask_output=True, return_logits=False):
+        t = calls["i"]
+        calls["i"] += 1
+        return opred.model.postprocess_masks(lows[t], opred.input_size, opred.original_size), ious[t], lows[t]
+
+    oamg_f = amg_ref.TiledAutomaticMaskGenerator(opred, points_per_side=4, points_per_batch=16)
+    oamg_f.initialize(img, tile_shape=tile_shape, halo=halo)       # float path: embeddings + decoder on the oracle
+    for d, od in zip(amg.crop_list, oamg_f._crop_list):
+        assert np.abs(d["iou_preds"].cpu().numpy() - od["iou_preds"].numpy()).max() < 2e-2
+    orig = opred.predict_torch
+    opred.predict_torch = fake
+    try:
+        oamg = amg_ref.TiledAutomaticMaskGenerator(opred, points_per_side=4, points_per_batch=16)
+        oamg.initialize(img, tile_shape=tile_shape, halo=halo)
+    finally:
+        opred.predict_torch = orig
+    for d, od in zip(amg.crop_list, oamg._crop_list):
+        assert np.array_equal(d["boxes"].cpu().numpy(), od["boxes"].numpy())
+        assert np.array_equal(d["stability_score"].cpu().numpy(), od["stability_score"].numpy(), equal_nan=True)
+    for kw in (dict(pred_iou_thresh=0.0, stability_score_thresh=0.0), dict(pred_iou_thresh=0.1, stability_score_thresh=0.6),
+               dict(pred_iou_thresh=0.0, stability_score_thresh=0.5, crop_nms_thresh=0.2)):
+        recs = amg.generate(output_mode="binary_mask", **kw)
+        orecs = oamg.generate(output_mode="binary_mask", **kw)
+        assert len(recs) == len(orecs), (kw, len(recs), len(orecs))
+        for a, b in zip(recs, orecs):
+            assert a["bbox"] == b["bbox"] and a["area"] == b["area"] and a["crop_box"] == b["crop_box"]
+            assert np.array_equal(a["segmentation"], b["segmentation"])
+        seg = amg.generate(output_mode="instance_segmentation", **kw)
+        oseg = oamg.generate(output_mode="instance_segmentation", **kw)
+        assert seg.shape == (300, 420) and _partition_equal(seg, oseg), kw
