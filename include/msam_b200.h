@@ -115,6 +115,13 @@ int msam_paint_canvas(const float* low_res, const int32_t* sel, const int32_t* g
                       float mask_threshold, int off_x, int off_y, uint64_t* canvas, int ld_canvas, void* stream);
 int msam_canvas_to_label(const uint64_t* canvas, int64_t n, int32_t* label, void* stream);
 
+/* util._batched_mask_nms (util.py:1647-1676) with _calculate_ious_/_iomin_between_pred_masks (:1601-1644): masks uint8
+ * [n,h,w]; boxes fp32 xyxy [n,4]; scores fp32 [n].  Workspaces: bits_ws uint32 [n*ceil(h*w/32)], areas int32 [n] (out:
+ * popcount areas), matrix_ws fp32 [n*n] (out: the overlap matrix).  keep int32 [n] in greedy order, n_keep int32 [1]. */
+int msam_mask_nms(const uint8_t* masks, int n, int h, int w, const float* boxes_xyxy, const float* scores, float nms_thresh,
+                  int intersection_over_min, uint32_t* bits_ws, int32_t* areas, float* matrix_ws, int32_t* keep,
+                  int32_t* n_keep, void* stream);
+
 /* ---- single-op entry points (unit tests / profiling; the same kernels the calls above are built from) ---- */
 /* out[M,N] = act(A[M,K] @ W[N,K]^T + bias) + residual[row % res_rows];  A, W bf16; bias/residual fp32 or NULL;
  * out bf16 (out_fp32=0) or fp32; act: 0 none, 1 GELU(erf), 2 ReLU. */

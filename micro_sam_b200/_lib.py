@@ -59,6 +59,8 @@ def lib() -> ctypes.CDLL:
         L.msam_paint_canvas.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                         c_float, c_int, c_int, c_void_p, c_int, c_void_p]
         L.msam_canvas_to_label.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
+        L.msam_mask_nms.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p]
         L.msam_profile.argtypes = [c_int]
         L.msam_profile_summary.argtypes = [POINTER(ctypes.c_double)]
         _lib = L

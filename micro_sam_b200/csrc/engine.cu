@@ -463,6 +463,13 @@ int msam_canvas_to_label(const uint64_t* canvas, int64_t n, int32_t* label, void
   return post_canvas_to_label(reinterpret_cast<const unsigned long long*>(canvas), (long)n, label, (cudaStream_t)stream);
 }
 
+int msam_mask_nms(const uint8_t* masks, int n, int h, int w, const float* boxes_xyxy, const float* scores, float nms_thresh,
+                  int intersection_over_min, uint32_t* bits_ws, int32_t* areas, float* matrix_ws, int32_t* keep,
+                  int32_t* n_keep, void* stream) {
+  return post_mask_nms(masks, n, h, w, boxes_xyxy, scores, nms_thresh, intersection_over_min, bits_ws, areas, matrix_ws,
+                       keep, n_keep, (cudaStream_t)stream);
+}
+
 static int sm_count() {
   static int n = 0;
   if (!n) {

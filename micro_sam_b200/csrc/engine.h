@@ -79,6 +79,9 @@ int post_paint_min_area(const float* low_res, const int32_t* sel, const int32_t*
                         int ld_label, cudaStream_t st);
 int post_finish_segmentation(const int32_t* seg, int h, int w, int min_size, int with_background, uint32_t* out,
                              int32_t* ws, cudaStream_t st);
+int post_mask_nms(const uint8_t* masks, int n, int h, int w, const float* boxes_xyxy, const float* scores, float thresh,
+                  int iomin, uint32_t* bits_ws, int32_t* areas, float* matrix_ws, int32_t* keep, int32_t* n_keep,
+                  cudaStream_t st);
 int post_paint_canvas(const float* low_res, const int32_t* sel, const int32_t* gpos, int n_sel, const int32_t* boxes,
                       const int32_t* area, int in_h, int in_w, int out_h, int out_w, float thr, int off_x, int off_y,
                       unsigned long long* canvas, int ld_canvas, cudaStream_t st);

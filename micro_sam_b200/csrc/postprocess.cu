@@ -752,3 +752,128 @@ int post_canvas_to_label(const unsigned long long* canvas, long n, int32_t* labe
 }
 
 }  // namespace msam
+
+// =================================================================================================================
+// Mask NMS (util._batched_mask_nms / _calculate_ious_between_pred_masks / _calculate_iomin_between_pred_masks,
+// util.py:1589-1676) on bit-packed masks: integer popcount intersections (exact), the reference's float32 ratios, box
+// pre-filter, greedy suppression that keeps `iou <= thresh`.
+namespace msam {
+
+// uint8 masks [n, npix] -> bit-packed [n, words] (npix padded with zeros to 32*words) + areas
+__global__ void pack_bits_kernel(const uint8_t* __restrict__ masks, int n, long npix, int words, uint32_t* __restrict__ bits,
+                                 int32_t* __restrict__ areas) {
+  const int mi = blockIdx.y;
+  int cnt = 0;
+  for (int wd = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wd < words; wd += gridDim.x * (blockDim.x >> 5)) {
+    const long px = (long)wd * 32 + (threadIdx.x & 31);
+    const bool on = px < npix && masks[(long)mi * npix + px] != 0;
+    const uint32_t w = __ballot_sync(0xffffffffu, on);
+    if ((threadIdx.x & 31) == 0) {
+      bits[(long)mi * words + wd] = w;
+      cnt += __popc(w);
+    }
+  }
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&areas[mi], cnt);
+}
+
+// one warp per (i, j > i) pair with overlapping boxes: m[i][j] = m[j][i] = ratio
+__global__ void mask_overlap_kernel(const uint32_t* __restrict__ bits, const int32_t* __restrict__ areas,
+                                    const float* __restrict__ boxes /*xyxy*/, int n, int words, int iomin,
+                                    float* __restrict__ m) {
+  const long pair = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pair >= (long)n * n) return;
+  const int i = pair / n, j = pair % n, lane = threadIdx.x & 31;
+  if (j <= i) {
+    if (j == i && lane == 0) m[(long)i * n + i] = 1.0f;
+    return;
+  }
+  const float w = fmaxf(fminf(boxes[4 * i + 2], boxes[4 * j + 2]) - fmaxf(boxes[4 * i], boxes[4 * j]), 0.f);
+  const float h = fmaxf(fminf(boxes[4 * i + 3], boxes[4 * j + 3]) - fmaxf(boxes[4 * i + 1], boxes[4 * j + 1]), 0.f);
+  float v = 0.f;
+  if (w * h > 0.f) {  // warp-uniform
+    int inter = 0;
+    const uint32_t* a = bits + (long)i * words;
+    const uint32_t* b = bits + (long)j * words;
+    for (int k = lane; k < words; k += 32) inter += __popc(a[k] & b[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) inter += __shfl_xor_sync(0xffffffffu, inter, o);
+    if (iomin) v = (float)inter / ((float)min(areas[i], areas[j]) + 1e-6f);
+    else v = (float)inter / (float)(areas[i] + areas[j] - inter);
+  }
+  if (lane == 0) { m[(long)i * n + j] = v; m[(long)j * n + i] = v; }
+}
+
+// greedy NMS over a precomputed symmetric overlap matrix: descending score (index ascending on ties), keep <= thresh
+__global__ void __launch_bounds__(1024)
+matrix_nms_kernel(const float* __restrict__ m, const float* __restrict__ scores, int n, float thresh,
+                  int32_t* __restrict__ keep, int32_t* __restrict__ n_keep) {
+  extern __shared__ unsigned long long skey[];
+  __shared__ int s_cnt;
+  int npow2 = 1;
+  while (npow2 < n) npow2 <<= 1;
+  uint8_t* alive = reinterpret_cast<uint8_t*>(skey + npow2);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < npow2; i += nt)
+    skey[i] = i < n ? (((unsigned long long)orderable(scores[i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i)) : 0ull;
+  __syncthreads();
+  for (int k = 2; k <= npow2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < npow2; i += nt) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = skey[i], b = skey[ixj];
+          if (((i & k) == 0) ? (a < b) : (a > b)) { skey[i] = b; skey[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = tid; i < n; i += nt) alive[i] = 1;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  int cur = 0;
+  while (true) {
+    while (cur < n && !alive[cur]) ++cur;
+    if (cur >= n) break;
+    const int ci = (int)(0xFFFFFFFFu - (uint32_t)(skey[cur] & 0xFFFFFFFFull));
+    if (tid == 0) keep[s_cnt++] = ci;
+    __syncthreads();
+    for (int j = cur + 1 + tid; j < n; j += nt) {
+      if (!alive[j]) continue;
+      const int cj = (int)(0xFFFFFFFFu - (uint32_t)(skey[j] & 0xFFFFFFFFull));
+      if (m[(long)ci * n + cj] > thresh) alive[j] = 0;
+    }
+    ++cur;
+    __syncthreads();
+  }
+  if (tid == 0) *n_keep = s_cnt;
+}
+
+int post_mask_nms(const uint8_t* masks, int n, int h, int w, const float* boxes_xyxy, const float* scores, float thresh,
+                  int iomin, uint32_t* bits_ws, int32_t* areas, float* matrix_ws, int32_t* keep, int32_t* n_keep,
+                  cudaStream_t st) {
+  if (n <= 0) {
+    cudaMemsetAsync(n_keep, 0, 4, st);
+    return 0;
+  }
+  if (n > NMS_MAX) return set_error("mask_nms: n=%d exceeds %d", n, NMS_MAX);
+  const long npix = (long)h * w;
+  const int words = (int)((npix + 31) / 32);
+  cudaMemsetAsync(areas, 0, (size_t)n * 4, st);
+  pack_bits_kernel<<<dim3(64, n), 256, 0, st>>>(masks, n, npix, words, bits_ws, areas);
+  LAUNCH_CHECK("pack_bits");
+  const long pairs = (long)n * n;
+  mask_overlap_kernel<<<(unsigned)((pairs + 7) / 8), 256, 0, st>>>(bits_ws, areas, boxes_xyxy, n, words, iomin, matrix_ws);
+  LAUNCH_CHECK("mask_overlap");
+  int npow2 = 1;
+  while (npow2 < n) npow2 <<= 1;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(matrix_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr = true;
+  }
+  matrix_nms_kernel<<<1, 1024, (size_t)npow2 * 8 + n + 16, st>>>(matrix_ws, scores, n, thresh, keep, n_keep);
+  LAUNCH_CHECK("matrix_nms");
+  return 0;
+}
+
+}  // namespace msam

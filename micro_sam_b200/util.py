@@ -458,3 +458,75 @@ def mask_data_to_segmentation(masks: List[Dict[str, Any]], shape: Optional[Tuple
             segmentation[this_mask] = this_seg_id
         seg_id = this_seg_id + 1
     return _finish_segmentation(segmentation, min_object_size, label_masks, with_background)
+
+
+# ------------------------------------------------------------------------------------------------ mask NMS
+def _xywh_to_xyxy(boxes):
+    boxes = boxes.clone() if isinstance(boxes, torch.Tensor) else torch.tensor(np.asarray(boxes))
+    boxes = boxes.to(torch.float32)
+    boxes[:, 2] += boxes[:, 0]
+    boxes[:, 3] += boxes[:, 1]
+    return boxes
+
+
+def batched_mask_nms(masks: torch.Tensor, boxes_xyxy: torch.Tensor, scores: torch.Tensor, nms_thresh: float,
+                     intersection_over_min: bool = False, return_matrix: bool = False):
+    """util._batched_mask_nms (util.py:1647-1676) on the device (the reference forces this to the CPU, :1648-1656):
+    bit-packed popcount intersections, the same float32 ratios, greedy `keep iou <= thresh`."""
+    dev = torch.device("cuda") if not masks.is_cuda else masks.device
+    m = masks.to(dev).to(torch.uint8).contiguous()
+    n, h, w = m.shape
+    bx = boxes_xyxy.to(dev, torch.float32).contiguous()
+    sc = scores.to(dev, torch.float32).contiguous()
+    words = (h * w + 31) // 32
+    bits = torch.empty(max(n, 1) * words, dtype=torch.int32, device=dev)
+    areas = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    mat = torch.empty(max(n * n, 1), dtype=torch.float32, device=dev)
+    keep = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    nk = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().msam_mask_nms(_lib.ptr(m), n, h, w, _lib.ptr(bx), _lib.ptr(sc), float(nms_thresh),
+                                        int(intersection_over_min), _lib.ptr(bits), _lib.ptr(areas), _lib.ptr(mat),
+                                        _lib.ptr(keep), _lib.ptr(nk), _lib.cur_stream()))
+    out = keep[: int(nk.item())].long()
+    return (out, mat.view(n, n)) if return_matrix else out
+
+
+def apply_nms(predictions: List[Dict[str, Any]], min_size: int, shape: Optional[Tuple[int, int]] = None,
+              perform_box_nms: bool = False, nms_thresh: float = 0.9, max_size: Optional[int] = None,
+              intersection_over_min: bool = False) -> np.ndarray:
+    """util.apply_nms (util.py:1851-1957) for non-tiled predictions (records with full-size `segmentation` masks)."""
+    if len(predictions) and "global_bbox" in predictions[0]:
+        raise NotImplementedError("apply_nms on tiled predictions (global_bbox) is not on the B200 path yet")
+    if shape is None:
+        shape = tuple(predictions[0]["segmentation"].shape)
+    dev = torch.device("cuda")
+    masks = torch.stack([torch.as_tensor(p["segmentation"]).to(dev) for p in predictions]).to(torch.uint8)
+    iou = torch.tensor([p["predicted_iou"] for p in predictions], dtype=torch.float32)
+    stab = torch.tensor([p["stability_score"] for p in predictions], dtype=torch.float32)
+    boxes = torch.tensor(np.array([p["bbox"] for p in predictions]))
+    area = masks.flatten(1).sum(1).cpu()
+    idx = torch.arange(len(predictions))
+    if min_size > 0:
+        idx = idx[area[idx] > min_size]
+    if max_size is not None:
+        idx = idx[area[idx] < max_size]
+    if len(idx) == 0:
+        return np.zeros(shape, dtype="uint32")
+    scores = (iou * stab)[idx]
+    bxyxy = _xywh_to_xyxy(boxes[idx])
+    if perform_box_nms:
+        assert not intersection_over_min
+        keep = torch.empty(len(idx), dtype=torch.int32, device=dev)
+        nk = torch.zeros(1, dtype=torch.int32, device=dev)
+        import ctypes
+        z = (ctypes.c_int32 * 4)(0, 0, 0, 0)
+        bi = bxyxy.to(dev, torch.int32).contiguous()
+        sd = scores.to(dev).contiguous()
+        _lib.check(_lib.lib().msam_amg_filter_nms(_lib.ptr(bi), _lib.ptr(sd), _lib.ptr(sd), len(idx), 0, 0.0, 0.0,
+                                                  float(nms_thresh), z, z, _lib.ptr(keep), _lib.ptr(nk), _lib.cur_stream()))
+        keep = keep[: int(nk.item())].long().cpu()
+    else:
+        keep = batched_mask_nms(masks[idx.to(dev)], bxyxy, scores, nms_thresh, intersection_over_min).cpu()
+    sel = idx[keep]
+    mask_data = [{"segmentation": masks[k].bool(), "area": int(area[k]), "bbox": boxes[k]} for k in sel.tolist()]
+    return mask_data_to_segmentation(mask_data, shape=shape, min_object_size=min_size)
