@@ -271,3 +271,27 @@ def test_tiled_amg_against_oracle(models):
         seg = amg.generate(output_mode="instance_segmentation", **kw)
         oseg = oamg.generate(output_mode="instance_segmentation", **kw)
         assert seg.shape == (300, 420) and _partition_equal(seg, oseg), kw
+
+
+def test_mask_nms_bit_exact_vs_reference_golden():
+    """a19: device mask NMS == the reference's own `_batched_mask_nms` outputs (golden, IoU and IoMin) incl. the IoU matrix."""
+    from micro_sam_b200 import util
+    z = np.load(os.path.join(HERE, "golden", "util.npz"))
+    m = torch.from_numpy(np.unpackbits(z["nms_masks"], axis=-1)[..., :64].astype(bool).reshape(24, 64, 64))
+    boxes, scores = torch.from_numpy(z["nms_boxes"]).float(), torch.from_numpy(z["nms_scores"])
+    keep, mat = util.batched_mask_nms(m, boxes, scores, 0.3, False, return_matrix=True)
+    assert np.array_equal(mat.cpu().numpy(), z["nms_iou_matrix"])
+    for thr in (0.3, 0.9):
+        assert util.batched_mask_nms(m, boxes, scores, thr, False).tolist() == z[f"nms_keep_iou_{thr}"].tolist()
+        assert util.batched_mask_nms(m, boxes, scores, thr, True).tolist() == z[f"nms_keep_iomin_{thr}"].tolist()
+    # apply_nms end to end against the oracle restatement
+    from oracle import amg_ref
+    recs = [{"segmentation": m[k], "bbox": [int(boxes[k][0]), int(boxes[k][1]), int(boxes[k][2] - boxes[k][0]), int(boxes[k][3] - boxes[k][1])],
+             "predicted_iou": float(scores[k]), "stability_score": 1.0} for k in range(24)]
+    seg = util.apply_nms(recs, min_size=5, nms_thresh=0.3)
+    area = m.flatten(1).sum(1)
+    idx = torch.arange(24)[area > 5]
+    keep = amg_ref.batched_mask_nms(m[idx], boxes[idx], scores[idx], 0.3, False)
+    oseg = amg_ref.mask_data_to_segmentation([{"segmentation": m[k].numpy(), "area": int(area[k])} for k in idx[keep].tolist()],
+                                             shape=(64, 64), min_object_size=5)
+    assert _partition_equal(seg, oseg)
