@@ -26,14 +26,19 @@ constexpr int STG_BYTES = 128 * 128; // staging tile of one column group: 128 ro
 
 enum { EPI_PLAIN = 0, EPI_LN256 = 1, EPI_LN64_GELU = 2, EPI_HYPER = 3 };
 
-template <int BN>
+// SK ("short K", K <= 256, BN = 128 only): the per-tile main loop is 1-4 K blocks, the epilogue chain (accumulator wait,
+// residual / parameter loads, row statistics, staging, TMA store) is latency bound and all epilogue warps of a CTA stall
+// together -> two shallow CTAs per SM (2 pipeline stages, 256 TMEM columns each) overlap each other's stalls.
+template <int BN, bool SK = false>
 struct GemmCfg {
   static constexpr int NG = BN / 64;                    // epilogue column groups (4 / 2 / 1)
   static constexpr int THREADS = 128 + NG * 128;        // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, epilogue
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 3 : ((BN == 128) ? 5 : 6);
+  static constexpr int STAGES = SK ? 2 : ((BN == 256) ? 3 : ((BN == 128) ? 5 : 6));
+  static constexpr int MIN_CTAS = SK ? 2 : 1;
+  static_assert(!SK || BN == 128, "short-K variant is instantiated for BN = 128");
   static constexpr int OFF_STG = STAGES * STAGE_BYTES;  // NG staging tiles
   static constexpr int OFF_BAR = OFF_STG + NG * STG_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024 /*align slack*/;   // + 11 KB static (exch, rowp)
@@ -86,11 +91,11 @@ __device__ __forceinline__ void stg_write(uint8_t* stg, int r, int ch, const uin
   *reinterpret_cast<uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4)) = v;
 }
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
+template <int BN, int EPI, bool SK>
+__global__ void __launch_bounds__(GemmCfg<BN, SK>::THREADS, GemmCfg<BN, SK>::MIN_CTAS)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, SK>;
   constexpr int NG = Cfg::NG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -127,8 +132,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-  if constexpr (EPI != EPI_PLAIN) {  // N == BN: per-column parameters are tile-invariant -> shared memory
-    for (int i = threadIdx.x; i < BN; i += Cfg::THREADS) {
+  if constexpr (EPI != EPI_PLAIN) {  // N <= 256: per-column parameters -> shared memory (indexed by global column)
+    for (int i = threadIdx.x; i < p.N && i < 256; i += Cfg::THREADS) {
       rowp[i] = p.bias ? p.bias[i] : 0.f;
       if constexpr (EPI == EPI_LN256) { rowp[256 + i] = p.ln_gamma[i]; rowp[512 + i] = p.ln_beta[i]; }
       if constexpr (EPI == EPI_LN64_GELU) { rowp[256 + i] = p.ln_gamma[i & 63]; rowp[512 + i] = p.ln_beta[i & 63]; }
@@ -310,7 +315,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tmem_ld32(tcol + c * 32, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[c * 32 + j] = __uint_as_float(v[j]) + rowp[grp * CPW + c * 32 + j];
+          for (int j = 0; j < 32; ++j) f[c * 32 + j] = __uint_as_float(v[j]) + rowp[colbase + c * 32 + j];
         }
         release_acc();
 
@@ -352,7 +357,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float y[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              y[q] = (f[j + q] - mean) * rstd * rowp[256 + grp * CPW + j + q] + rowp[512 + grp * CPW + j + q];
+              y[q] = (f[j + q] - mean) * rstd * rowp[256 + colbase + j + q] + rowp[512 + colbase + j + q];
             stg_write(stg, r, j >> 3, make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]),
                                                   pack_bf16(y[6], y[7])));
           }
@@ -414,13 +419,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool SK = false>
 static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, SK>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
-        cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -442,7 +447,8 @@ static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;
   p.hyper = a.hyper; p.hyper_m0 = a.hyper_m0; p.hyper_nm = a.hyper_nm; p.hyper_out = reinterpret_cast<float*>(a.out);
   const int tiles = ((a.M + GEMM_BM - 1) / GEMM_BM) * ((a.N + BN - 1) / BN);
-  const int grid = tiles < num_sms ? tiles : num_sms;
+  const int max_ctas = num_sms * Cfg::MIN_CTAS;
+  const int grid = tiles < max_ctas ? tiles : max_ctas;
   if (a.K >= 512) {
     prof_begin(stream, PROF_GEMM, 2.0 * a.M * a.N * a.K);
   } else {  // HBM-bound: algorithmic bytes
@@ -450,7 +456,7 @@ static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     const double res_b = a.residual ? (double)(a.res_rows > 0 ? a.res_rows : a.M) * a.N * (a.res_bf16 ? 2 : 4) : 0.0;
     prof_begin(stream, PROF_GEMM_HBM, (double)a.M * a.K * 2 + (double)a.N * a.K * 2 + out_b + res_b);
   }
-  gemm_bf16_kernel<BN, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+  gemm_bf16_kernel<BN, EPI, SK><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm launch failed: %s", cudaGetErrorString(e));
@@ -467,16 +473,21 @@ int launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     if (a.N != 256 || a.out_fp32 || !a.ln_gamma || !a.ln_beta || a.act)
       return set_error("gemm: fused LN needs N=256, bf16 out, gamma/beta, no act");
     if (a.residual && !a.res_bf16) return set_error("gemm: fused LN takes a bf16 residual");
-    return a.epi == EPI_LN256 ? launch_gemm_bn<256, EPI_LN256>(a, num_sms, stream)
-                              : launch_gemm_bn<256, EPI_LN64_GELU>(a, num_sms, stream);
+    if (a.epi == EPI_LN256) return launch_gemm_bn<256, EPI_LN256>(a, num_sms, stream);
+    // the 64-column LayerNorm groups are independent: run as two 128-wide N blocks, two CTAs per SM
+    if (a.K <= 256) return launch_gemm_bn<128, EPI_LN64_GELU, true>(a, num_sms, stream);
+    return launch_gemm_bn<256, EPI_LN64_GELU>(a, num_sms, stream);
   }
   if (a.epi == EPI_HYPER) {
     if (a.N != 128 || !a.hyper || a.hyper_nm < 1 || a.hyper_nm > 4 || a.residual)
       return set_error("gemm: fused hyper product needs N=128");
+    if (a.K <= 256) return launch_gemm_bn<128, EPI_HYPER, true>(a, num_sms, stream);
     return launch_gemm_bn<128, EPI_HYPER>(a, num_sms, stream);
   }
   // BN=256 keeps the tensor pipe at its 1-CTA rate with the fewest smem bytes per flop; fall back to 128 / 64 when N is
   // not a multiple (or is small), to avoid wasted columns.
+  const bool short_k = a.K <= 256 && (long)a.M * a.N >= (1L << 24);  // big streaming decoder GEMMs
+  if (a.N % 128 == 0 && short_k) return launch_gemm_bn<128, EPI_PLAIN, true>(a, num_sms, stream);
   if (a.N % 256 == 0) return launch_gemm_bn<256, EPI_PLAIN>(a, num_sms, stream);
   if (a.N % 128 == 0) return launch_gemm_bn<128, EPI_PLAIN>(a, num_sms, stream);
   return launch_gemm_bn<64, EPI_PLAIN>(a, num_sms, stream);
