@@ -26,9 +26,9 @@ constexpr int STG_BYTES = 128 * 128; // staging tile of one column group: 128 ro
 
 enum { EPI_PLAIN = 0, EPI_LN256 = 1, EPI_LN64_GELU = 2, EPI_HYPER = 3 };
 
-// SK ("short K", K <= 256, BN = 128 only): the per-tile main loop is 1-4 K blocks, the epilogue chain (accumulator wait,
-// residual / parameter loads, row statistics, staging, TMA store) is latency bound and all epilogue warps of a CTA stall
-// together -> two shallow CTAs per SM (2 pipeline stages, 256 TMEM columns each) overlap each other's stalls.
+// SK = two shallow CTAs per SM (2 pipeline stages, BN = 128) for short-K GEMMs.  Measured SLOWER than one deep CTA on
+// every decoder GEMM (profiles/r1_launches_amg_vit_b_1tile_sk.txt: hyper 3.4 -> 5.3 ms, kvq 1.8 -> 2.1 ms, LN64 1.7 -> 2.4 ms;
+// register cap 85/thread -> spills, A re-read per N block), so no launch path selects it; kept for the record only.
 template <int BN, bool SK = false>
 struct GemmCfg {
   static constexpr int NG = BN / 64;                    // epilogue column groups (4 / 2 / 1)
@@ -474,20 +474,15 @@ int launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream) {
       return set_error("gemm: fused LN needs N=256, bf16 out, gamma/beta, no act");
     if (a.residual && !a.res_bf16) return set_error("gemm: fused LN takes a bf16 residual");
     if (a.epi == EPI_LN256) return launch_gemm_bn<256, EPI_LN256>(a, num_sms, stream);
-    // the 64-column LayerNorm groups are independent: run as two 128-wide N blocks, two CTAs per SM
-    if (a.K <= 256) return launch_gemm_bn<128, EPI_LN64_GELU, true>(a, num_sms, stream);
     return launch_gemm_bn<256, EPI_LN64_GELU>(a, num_sms, stream);
   }
   if (a.epi == EPI_HYPER) {
     if (a.N != 128 || !a.hyper || a.hyper_nm < 1 || a.hyper_nm > 4 || a.residual)
       return set_error("gemm: fused hyper product needs N=128");
-    if (a.K <= 256) return launch_gemm_bn<128, EPI_HYPER, true>(a, num_sms, stream);
     return launch_gemm_bn<128, EPI_HYPER>(a, num_sms, stream);
   }
   // BN=256 keeps the tensor pipe at its 1-CTA rate with the fewest smem bytes per flop; fall back to 128 / 64 when N is
   // not a multiple (or is small), to avoid wasted columns.
-  const bool short_k = a.K <= 256 && (long)a.M * a.N >= (1L << 24);  // big streaming decoder GEMMs
-  if (a.N % 128 == 0 && short_k) return launch_gemm_bn<128, EPI_PLAIN, true>(a, num_sms, stream);
   if (a.N % 256 == 0) return launch_gemm_bn<256, EPI_PLAIN>(a, num_sms, stream);
   if (a.N % 128 == 0) return launch_gemm_bn<128, EPI_PLAIN>(a, num_sms, stream);
   return launch_gemm_bn<64, EPI_PLAIN>(a, num_sms, stream);
