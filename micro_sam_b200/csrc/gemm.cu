@@ -21,7 +21,6 @@ namespace msam {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int CPW = 64;              // accumulator columns per epilogue thread
 constexpr int STG_BYTES = 128 * 128; // staging tile of one column group: 128 rows x 128 B
 
 enum { EPI_PLAIN = 0, EPI_LN256 = 1, EPI_LN64_GELU = 2, EPI_HYPER = 3 };
@@ -29,9 +28,10 @@ enum { EPI_PLAIN = 0, EPI_LN256 = 1, EPI_LN64_GELU = 2, EPI_HYPER = 3 };
 // SK = two shallow CTAs per SM (2 pipeline stages, BN = 128) for short-K GEMMs.  Measured SLOWER than one deep CTA on
 // every decoder GEMM (profiles/r1_launches_amg_vit_b_1tile_sk.txt: hyper 3.4 -> 5.3 ms, kvq 1.8 -> 2.1 ms, LN64 1.7 -> 2.4 ms;
 // register cap 85/thread -> spills, A re-read per N block), so no launch path selects it; kept for the record only.
-template <int BN, bool SK = false>
+template <int BN, bool SK = false, int CPW_ = 64>
 struct GemmCfg {
-  static constexpr int NG = BN / 64;                    // epilogue column groups (4 / 2 / 1)
+  static constexpr int CPW = CPW_;                      // accumulator columns per epilogue thread
+  static constexpr int NG = BN / CPW;                   // epilogue column groups
   static constexpr int THREADS = 128 + NG * 128;        // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, epilogue
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
@@ -39,8 +39,8 @@ struct GemmCfg {
   static constexpr int STAGES = SK ? 2 : ((BN == 256) ? 3 : ((BN == 128) ? 5 : 6));
   static constexpr int MIN_CTAS = SK ? 2 : 1;
   static_assert(!SK || BN == 128, "short-K variant is instantiated for BN = 128");
-  static constexpr int OFF_STG = STAGES * STAGE_BYTES;  // NG staging tiles
-  static constexpr int OFF_BAR = OFF_STG + NG * STG_BYTES;
+  static constexpr int OFF_STG = STAGES * STAGE_BYTES;  // one staging tile per column group (none for the hyper epilogue)
+  static constexpr int OFF_BAR = OFF_STG + (CPW == 64 ? NG : 0) * STG_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024 /*align slack*/;   // + 11 KB static (exch, rowp)
   static constexpr int TMEM_COLS = 2 * BN;              // power of two >= 32 for BN in {64,128,256}
 };
@@ -91,12 +91,15 @@ __device__ __forceinline__ void stg_write(uint8_t* stg, int r, int ch, const uin
   *reinterpret_cast<uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4)) = v;
 }
 
+// the hyper-product epilogue is ALU bound (GELU + 3 dot products per element): 32 columns per thread -> 16 epilogue warps
+template <int EPI> struct EpiCols { static constexpr int value = (EPI == 3) ? 32 : 64; };
+
 template <int BN, int EPI, bool SK>
-__global__ void __launch_bounds__(GemmCfg<BN, SK>::THREADS, GemmCfg<BN, SK>::MIN_CTAS)
+__global__ void __launch_bounds__(GemmCfg<BN, SK, EpiCols<EPI>::value>::THREADS, GemmCfg<BN, SK, EpiCols<EPI>::value>::MIN_CTAS)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-  using Cfg = GemmCfg<BN, SK>;
-  constexpr int NG = Cfg::NG;
+  using Cfg = GemmCfg<BN, SK, EpiCols<EPI>::value>;
+  constexpr int NG = Cfg::NG, CPW = Cfg::CPW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
@@ -310,7 +313,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tfull_bar[as], aphase, 4);
         tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < CPW / 32; ++c) {
           uint32_t v[32];
           tmem_ld32(tcol + c * 32, v);
           tmem_ld_wait();
@@ -386,22 +389,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         } else if constexpr (EPI == EPI_HYPER) {
           // second conv-transpose (N = 128 = 4 sub-sub-pixels x 32 channels; bias added above) + GELU + hyper product:
           // masks[p, mi, Y, X] = sum_ch hyper[p, m0+mi, ch] * gelu(up[row, ss*32 + ch]).  GEMM row = (prompt p, token
-          // (y,x), sub-pixel (dy,dx)); this thread holds sub-sub-pixels ey = grp, ex = 0,1 -> two adjacent pixels.
+          // (y,x), sub-pixel (dy,dx)); this thread holds sub-sub-pixel ss = grp = ey*2 + ex (CPW == 32).
+          static_assert(EPI != EPI_HYPER || CPW == 32, "one sub-sub-pixel per thread");
           if (row_ok) {
 #pragma unroll
             for (int j = 0; j < CPW; ++j) f[j] = gelu_fast(f[j]);
             const int sub = row & 3, tok = (row >> 2) & 4095, pp = row >> 14;
-            const int Y = 4 * (tok >> 6) + 2 * (sub >> 1) + grp, X = 4 * (tok & 63) + 2 * (sub & 1);
+            const int Y = 4 * (tok >> 6) + 2 * (sub >> 1) + (grp >> 1), X = 4 * (tok & 63) + 2 * (sub & 1) + (grp & 1);
             for (int mi = 0; mi < p.hyper_nm; ++mi) {
               const float* hw = p.hyper + ((size_t)pp * 4 + p.hyper_m0 + mi) * 32;
               float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-              for (int c = 0; c < 32; c += 4) {
-                const float4 h4 = __ldg(reinterpret_cast<const float4*>(hw + c));
+              for (int c = 0; c < 32; c += 8) {
+                const float4 h4 = __ldg(reinterpret_cast<const float4*>(hw + c)), g4 = __ldg(reinterpret_cast<const float4*>(hw + c + 4));
                 a0 += h4.x * f[c] + h4.y * f[c + 1] + h4.z * f[c + 2] + h4.w * f[c + 3];
-                a1 += h4.x * f[32 + c] + h4.y * f[33 + c] + h4.z * f[34 + c] + h4.w * f[35 + c];
+                a1 += g4.x * f[c + 4] + g4.y * f[c + 5] + g4.z * f[c + 6] + g4.w * f[c + 7];
               }
-              *reinterpret_cast<float2*>(p.hyper_out + (((size_t)pp * p.hyper_nm + mi) * 256 + Y) * 256 + X) = make_float2(a0, a1);
+              p.hyper_out[(((size_t)pp * p.hyper_nm + mi) * 256 + Y) * 256 + X] = a0 + a1;
             }
           }
         }
@@ -421,7 +425,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int BN, int EPI, bool SK = false>
 static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, SK>;
+  using Cfg = GemmCfg<BN, SK, EpiCols<EPI>::value>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
