@@ -24,6 +24,7 @@ struct AttnW {  // one SamAttention: q,k,v [inner, 256], out [256, inner]
 };
 struct DecLayer {
   AttnW self_attn, t2i, i2t;
+  __nv_bfloat16* i2t_qT = nullptr;  // image->token q_proj weight transposed [256, 128] (operand of the Mq GEMM, i2t_fused.cu)
   float *n1g, *n1b, *n2g, *n2b, *n3g, *n3b, *n4g, *n4b;
   __nv_bfloat16 *mlp1, *mlp2;
   float *mlp1b, *mlp2b;
@@ -37,6 +38,7 @@ struct DecoderState {
   // prompt encoder
   float *gauss = nullptr, *point_emb = nullptr /*[4,256]*/, *not_a_point = nullptr, *no_mask = nullptr;
   float* pos = nullptr;  // dense PE, token-major [4096, 256]
+  __nv_bfloat16* pos_bf = nullptr;
   // mask decoder
   float* out_tokens = nullptr;  // [5, 256] = iou_token ; mask_tokens
   DecLayer layers[2];
@@ -60,6 +62,8 @@ struct DecoderState {
   __nv_bfloat16 *tok0_bf = nullptr, *q_bf = nullptr, *qpe_bf = nullptr, *t_qkv = nullptr, *t_att = nullptr, *t_mlp = nullptr;
   __nv_bfloat16 *t_q128 = nullptr, *t_k128 = nullptr, *t_v128 = nullptr, *t_att128 = nullptr;
   __nv_bfloat16 *keys = nullptr, *img_kvq = nullptr, *img_att = nullptr;
+  __nv_bfloat16 *kexp = nullptr, *vexp = nullptr, *mq = nullptr, *vt = nullptr;  // fused i2t operands (i2t_fused.cu)
+  float* sbias = nullptr;
   __nv_bfloat16* up1 = nullptr;       // [P*4096*4, 64] after conv-transpose 1 + LN2d + GELU
   __nv_bfloat16 *h1 = nullptr, *h2 = nullptr;
   float *hyper_in = nullptr, *iou_out = nullptr;
@@ -456,6 +460,14 @@ int Engine::finalize_decoder() {
     CHK(L.n4g = up_f32(p + "norm4.weight", {DC})); CHK(L.n4b = up_f32(p + "norm4.bias", {DC}));
     CHK(L.mlp1 = up_bf16(p + "mlp.lin1.weight", {2048, DC})); CHK(L.mlp1b = up_f32(p + "mlp.lin1.bias", {2048}));
     CHK(L.mlp2 = up_bf16(p + "mlp.lin2.weight", {DC, 2048})); CHK(L.mlp2b = up_f32(p + "mlp.lin2.bias", {DC}));
+    {
+      const auto* wq = host(p + "cross_attn_image_to_token.q_proj.weight", {DI, DC});
+      CHK(wq);
+      std::vector<float> wt((size_t)DC * DI);
+      for (int o = 0; o < DI; ++o)
+        for (int c = 0; c < DC; ++c) wt[(size_t)c * DI + o] = (*wq)[(size_t)o * DC + c];
+      CHK(L.i2t_qT = upload_bf16(wt.data(), wt.size()));
+    }
   }
   if (load_attn(*this, md + "transformer.final_attn_token_to_image.", DI, d.final_t2i, false)) return -1;
   CHK(d.nfg = up_f32(md + "transformer.norm_final_attn.weight", {DC}));
@@ -512,7 +524,7 @@ int Engine::finalize_decoder() {
     if (cat_w({{l1 + "cross_attn_token_to_image.k_proj", 0}, {l1 + "cross_attn_token_to_image.v_proj", 0},
                {l1 + "cross_attn_image_to_token.q_proj", 0}}, &d.kvq1_w, &d.kvq1_b)) return -1;
     if (cat_w({{fa + "k_proj", 0}, {fa + "v_proj", 0}}, &d.kvf_w, &d.kvf_b)) return -1;
-    __nv_bfloat16* pos_bf = (__nv_bfloat16*)dalloc((size_t)NI * DC * 2);
+    __nv_bfloat16* pos_bf = d.pos_bf = (__nv_bfloat16*)dalloc((size_t)NI * DC * 2);
     CHK(pos_bf);
     if (launch_cast_bf16(d.pos, (long)NI * DC, pos_bf, 0)) return -1;
     CHK(d.kvq1_res = (float*)dalloc((size_t)NI * 3 * DI * 4, true));
@@ -551,6 +563,11 @@ int Engine::finalize_decoder() {
   CHK(d.img_kvq = (__nv_bfloat16*)dalloc(PN * 3 * DI * 2));
   CHK(d.img_att = (__nv_bfloat16*)dalloc(PN * DI * 2));
   CHK(d.up1 = (__nv_bfloat16*)dalloc(PN * 4 * 64 * 2));
+  CHK(d.kexp = (__nv_bfloat16*)dalloc(P * 64 * DI * 2));
+  CHK(d.vexp = (__nv_bfloat16*)dalloc(P * 64 * DI * 2));
+  CHK(d.mq = (__nv_bfloat16*)dalloc(P * 64 * DC * 2));
+  CHK(d.vt = (__nv_bfloat16*)dalloc(P * 64 * DC * 2));
+  CHK(d.sbias = (float*)dalloc(P * 64 * 4));
   CHK(d.h1 = (__nv_bfloat16*)dalloc(P * DC * 2));
   CHK(d.h2 = (__nv_bfloat16*)dalloc(P * DC * 2));
   CHK(d.hyper_in = (float*)dalloc(P * 4 * 32 * 4));
@@ -562,11 +579,11 @@ int Engine::finalize_decoder() {
 static int gemm(Engine& E, cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int M, int N, int K,
                 const float* bias, void* out, int ldc, int out_fp32, int act = 0, const void* residual = nullptr,
                 int res_rows = 0, int res_bf16 = 0, int epi = 0, const float* ln_g = nullptr, const float* ln_b = nullptr,
-                float ln_eps = 1e-5f) {
+                float ln_eps = 1e-5f, int ldr = 0) {
   GemmArgs a;
   a.A = A; a.W = W; a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldw = K; a.bias = bias; a.out = out; a.ldc = ldc;
   a.out_fp32 = out_fp32; a.act = act; a.residual = residual; a.res_rows = res_rows; a.res_bf16 = res_bf16;
-  a.epi = epi; a.ln_gamma = ln_g; a.ln_beta = ln_b; a.ln_eps = ln_eps;
+  a.epi = epi; a.ln_gamma = ln_g; a.ln_beta = ln_b; a.ln_eps = ln_eps; a.ldr = ldr;
   return launch_gemm(a, E.num_sms, st);
 }
 static int ln(cudaStream_t st, const float* x, int rows, int D, const float* g, const float* b, float eps,
@@ -608,8 +625,13 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
 
   for (int l = 0; l < 2; ++l) {
     const DecLayer& L = d.layers[l];
-    if (l == 1) {  // all image-side projections of layer 1 in one pass over the per-prompt keys: [k_t2i | v_t2i | q_i2t]
-      if (gemm(E, st, d.keys, DC, d.kvq1_w, PN, 3 * DI, DC, d.kvq1_b, d.img_kvq, 3 * DI, 0, 0, d.kvq1_res, NI)) return -1;
+    // image-side projections of layer 1 in one pass over the per-prompt keys: [k_t2i | v_t2i (| q_i2t when the
+    // image->token block is not fused)]
+    const bool fused_i2t = T <= 8;
+    const int ld1 = fused_i2t ? 2 * DI : 3 * DI;
+    if (l == 1) {
+      if (gemm(E, st, d.keys, DC, d.kvq1_w, PN, ld1, DC, d.kvq1_b, d.img_kvq, ld1, 0, 0, d.kvq1_res, NI, 0, 0, nullptr,
+               nullptr, 1e-5f, 3 * DI)) return -1;
     }
     // ---- (1) token self attention
     if (l == 0) {
@@ -633,7 +655,7 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
     if (l == 0) {
       t2i_attn_kernel<<<P, 256, 0, st>>>(d.t_q128, d.k0, d.v0, DI, 0, T, NI, d.t_att128);
     } else {
-      t2i_attn_kernel<<<P, 256, 0, st>>>(d.t_q128, d.img_kvq, d.img_kvq + DI, 3 * DI, NI, T, NI, d.t_att128);
+      t2i_attn_kernel<<<P, 256, 0, st>>>(d.t_q128, d.img_kvq, d.img_kvq + DI, ld1, NI, T, NI, d.t_att128);
     }
     LAUNCH_CHECK("t2i_attn");
     if (gemm(E, st, d.t_att128, DI, L.t2i.o, PT, DC, DI, L.t2i.ob, d.tok_f32, DC, 1, 0, d.queries, PT)) return -1;
@@ -645,18 +667,33 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
     // ---- (4) image -> token cross attention (updates all image tokens of every prompt)
     if (gemm(E, st, d.qpe_bf, DC, L.i2t.k, PT, DI, DC, L.i2t.kb, d.t_k128, DI, 0)) return -1;
     if (gemm(E, st, d.q_bf, DC, L.i2t.v, PT, DI, DC, L.i2t.vb, d.t_v128, DI, 0)) return -1;
-    if (l == 0) {
-      i2t_attn_kernel<<<dim3(NI / 64, P), 256, 0, st>>>(d.q0, DI, 0, d.t_k128, d.t_v128, T, NI, d.img_att);
+    if (fused_i2t) {
+      // keys = norm4(keys + out_proj(attn)) in one pass over the image tokens (i2t_fused.cu)
+      if (launch_i2t_prep(d.t_k128, d.t_v128, L.i2t.qb, P, T, d.kexp, d.vexp, d.sbias, st)) return -1;
+      if (gemm(E, st, d.kexp, DI, L.i2t_qT, P * 64, DC, DI, nullptr, d.mq, DC, 0)) return -1;
+      if (gemm(E, st, L.i2t.o, DI, d.vexp, DC, P * 64, DI, nullptr, d.vt, P * 64, 0)) return -1;
+      I2tFusedArgs fa;
+      fa.P = P; fa.T = T; fa.mode = l;
+      fa.a0 = l == 0 ? d.src_pe_bf : d.keys;
+      fa.a1 = l == 0 ? d.src_bf : d.pos_bf;
+      fa.mq = d.mq; fa.vt = d.vt; fa.sbias = d.sbias;
+      fa.bias = L.i2t.ob; fa.gamma = L.n4g; fa.beta = L.n4b; fa.eps = 1e-5f;
+      fa.out = d.keys;
+      if (launch_i2t_fused(fa, E.num_sms, st)) return -1;
     } else {
-      i2t_attn_kernel<<<dim3(NI / 64, P), 256, 0, st>>>(d.img_kvq + 2 * DI, 3 * DI, NI, d.t_k128, d.t_v128, T, NI, d.img_att);
-    }
-    LAUNCH_CHECK("i2t_attn");
-    // keys = norm4(keys + out_proj(attn)): LayerNorm fused into the GEMM epilogue (in place for layer 1: every thread
-    // reads the residual of exactly the row segment it later overwrites)
-    if (l == 0) {
-      if (gemm(E, st, d.img_att, DI, L.i2t.o, PN, DC, DI, L.i2t.ob, d.keys, DC, 0, 0, d.src_bf, NI, 1, 1, L.n4g, L.n4b, 1e-5f)) return -1;
-    } else {
-      if (gemm(E, st, d.img_att, DI, L.i2t.o, PN, DC, DI, L.i2t.ob, d.keys, DC, 0, 0, d.keys, PN, 1, 1, L.n4g, L.n4b, 1e-5f)) return -1;
+      if (l == 0) {
+        i2t_attn_kernel<<<dim3(NI / 64, P), 256, 0, st>>>(d.q0, DI, 0, d.t_k128, d.t_v128, T, NI, d.img_att);
+      } else {
+        i2t_attn_kernel<<<dim3(NI / 64, P), 256, 0, st>>>(d.img_kvq + 2 * DI, 3 * DI, NI, d.t_k128, d.t_v128, T, NI, d.img_att);
+      }
+      LAUNCH_CHECK("i2t_attn");
+      // LayerNorm fused into the out-projection GEMM epilogue (in place for layer 1: every thread reads the residual of
+      // exactly the row segment it later overwrites)
+      if (l == 0) {
+        if (gemm(E, st, d.img_att, DI, L.i2t.o, PN, DC, DI, L.i2t.ob, d.keys, DC, 0, 0, d.src_bf, NI, 1, 1, L.n4g, L.n4b, 1e-5f)) return -1;
+      } else {
+        if (gemm(E, st, d.img_att, DI, L.i2t.o, PN, DC, DI, L.i2t.ob, d.keys, DC, 0, 0, d.keys, PN, 1, 1, L.n4g, L.n4b, 1e-5f)) return -1;
+      }
     }
   }
   // ---- final token -> image attention

@@ -39,6 +39,26 @@ struct GemmArgs {
 };
 int launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream);
 
+// ---- i2t_fused.cu : fused image -> token cross-attention block (q projection + attention + out projection + residual +
+// LayerNorm in one pass over the per-prompt image tokens); T <= 8 prompt tokens
+struct I2tFusedArgs {
+  int P = 0, T = 0;
+  int mode = 0;                       // 0: layer 0 (a0 = src + pe, a1 = src, shared by all prompts); 1: a0 = keys [P*4096,256], a1 = pe
+  const __nv_bfloat16* a0 = nullptr;
+  const __nv_bfloat16* a1 = nullptr;
+  const __nv_bfloat16* mq = nullptr;  // [P*64, 256]
+  const __nv_bfloat16* vt = nullptr;  // [256, P*64]
+  const float* sbias = nullptr;       // [P*64]
+  const float* bias = nullptr;        // out-proj bias [256]
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  float eps = 1e-5f;
+  __nv_bfloat16* out = nullptr;       // keys [P*4096, 256] (may alias a0)
+};
+int launch_i2t_fused(const I2tFusedArgs& a, int num_sms, cudaStream_t stream);
+int launch_i2t_prep(const __nv_bfloat16* ktok, const __nv_bfloat16* vtok, const float* bq, int P, int T,
+                    __nv_bfloat16* kexp, __nv_bfloat16* vexp, float* sbias, cudaStream_t stream);
+
 // ---- attention.cu : ViT encoder attention with decomposed relative-position bias
 struct AttnArgs {
   const __nv_bfloat16* qkv = nullptr;  // [groups*G, 3*D] rows = tokens (window-partitioned incl. pad tokens, or global)
