@@ -21,6 +21,7 @@ constexpr int TMAX = 16;    // max tokens per prompt (5 output tokens + sparse p
 struct AttnW {  // one SamAttention: q,k,v [inner, 256], out [256, inner]
   __nv_bfloat16 *q = nullptr, *k = nullptr, *v = nullptr, *o = nullptr, *qk = nullptr, *qkv = nullptr;
   float *qb = nullptr, *kb = nullptr, *vb = nullptr, *ob = nullptr, *qkb = nullptr, *qkvb = nullptr;
+  __nv_bfloat16 *kT = nullptr, *vT = nullptr;  // cross attention: k_proj / v_proj weights transposed [256, inner] (t2i_fused.cu)
 };
 struct DecLayer {
   AttnW self_attn, t2i, i2t;
@@ -64,6 +65,8 @@ struct DecoderState {
   __nv_bfloat16 *keys = nullptr, *img_kvq = nullptr, *img_att = nullptr;
   __nv_bfloat16 *kexp = nullptr, *vexp = nullptr, *mq = nullptr, *vt = nullptr;  // fused i2t operands (i2t_fused.cu)
   float* sbias = nullptr;
+  __nv_bfloat16 *qexp = nullptr, *qp = nullptr;  // fused t2i operands (t2i_fused.cu)
+  float* un = nullptr;
   __nv_bfloat16* up1 = nullptr;       // [P*4096*4, 64] after conv-transpose 1 + LN2d + GELU
   __nv_bfloat16 *h1 = nullptr, *h2 = nullptr;
   float *hyper_in = nullptr, *iou_out = nullptr;
@@ -387,6 +390,16 @@ static int load_attn(Engine& E, const std::string& p, int inner, AttnW& w, bool 
   CHK(w.kb = E.up_f32(p + "k_proj.bias", {inner}));
   CHK(w.vb = E.up_f32(p + "v_proj.bias", {inner}));
   CHK(w.ob = E.up_f32(p + "out_proj.bias", {DC}));
+  if (inner == DI) {
+    for (int which = 0; which < 2; ++which) {
+      const auto* hw = E.host(p + (which ? "v_proj.weight" : "k_proj.weight"), {inner, DC});
+      CHK(hw);
+      std::vector<float> wt((size_t)DC * inner);
+      for (int o = 0; o < inner; ++o)
+        for (int c = 0; c < DC; ++c) wt[(size_t)c * inner + o] = (*hw)[(size_t)o * DC + c];
+      CHK((which ? w.vT : w.kT) = E.upload_bf16(wt.data(), wt.size()));
+    }
+  }
   if (fuse_qkv) {  // [q;k;v] and [q;k] stacked along the output dim for single-GEMM projections
     const auto *hq = E.host(p + "q_proj.weight", {inner, DC}), *hk = E.host(p + "k_proj.weight", {inner, DC}),
                *hv = E.host(p + "v_proj.weight", {inner, DC});
@@ -568,6 +581,9 @@ int Engine::finalize_decoder() {
   CHK(d.mq = (__nv_bfloat16*)dalloc(P * 64 * DC * 2));
   CHK(d.vt = (__nv_bfloat16*)dalloc(P * 64 * DC * 2));
   CHK(d.sbias = (float*)dalloc(P * 64 * 4));
+  CHK(d.qexp = (__nv_bfloat16*)dalloc(P * 128 * DI * 2));
+  CHK(d.qp = (__nv_bfloat16*)dalloc(P * 128 * DC * 2));
+  CHK(d.un = (float*)dalloc(P * 128 * DC * 4));
   CHK(d.h1 = (__nv_bfloat16*)dalloc(P * DC * 2));
   CHK(d.h2 = (__nv_bfloat16*)dalloc(P * DC * 2));
   CHK(d.hyper_in = (float*)dalloc(P * 4 * 32 * 4));
@@ -602,8 +618,6 @@ int Engine::set_image_embedding(const float* feat, cudaStream_t st) {
   set_image_kernel<<<dim3(NI / 32, DC / 32), dim3(32, 8), 0, st>>>(feat, d.no_mask, d.pos, NI, d.src, d.src_bf, d.src_pe_bf);
   LAUNCH_CHECK("set_image");
   const DecLayer& L0 = d.layers[0];
-  if (gemm(*this, st, d.src_pe_bf, DC, L0.t2i.k, NI, DI, DC, L0.t2i.kb, d.k0, DI, 0)) return -1;
-  if (gemm(*this, st, d.src_bf, DC, L0.t2i.v, NI, DI, DC, L0.t2i.vb, d.v0, DI, 0)) return -1;
   if (gemm(*this, st, d.src_pe_bf, DC, L0.i2t.q, NI, DI, DC, L0.i2t.qb, d.q0, DI, 0)) return -1;
   d.image_set = true;
   return 0;
@@ -623,15 +637,27 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
                                                           d.point_emb, d.not_a_point, d.out_tokens, d.tok0, d.tok0_bf);
   LAUNCH_CHECK("prompt_tokens");
 
+  // token -> image attention core: t_q128 -> t_att128 (t2i_fused.cu)
+  auto t2i = [&](const AttnW& A, int mode) -> int {
+    const int paired = (mode == 0 && T <= 8) ? 1 : 0;
+    const int n_items = paired ? (P + 1) / 2 : P;
+    if (launch_t2i_prep(d.t_q128, P, T, paired, n_items, d.qexp, st)) return -1;
+    if (gemm(E, st, d.qexp, DI, A.kT, n_items * 128, DC, DI, nullptr, d.qp, DC, 0)) return -1;
+    T2iFusedArgs ta;
+    ta.n_items = n_items; ta.mode = mode;
+    ta.x = mode ? d.keys : d.src_bf;
+    ta.xs = mode ? d.pos_bf : d.src_pe_bf;
+    ta.qp = d.qp; ta.out = d.un;
+    if (launch_t2i_fused(ta, E.num_sms, st)) return -1;
+    return launch_t2i_head_proj(d.un, A.vT, A.vb, P, T, paired, d.t_att128, st);
+  };
+
   for (int l = 0; l < 2; ++l) {
     const DecLayer& L = d.layers[l];
-    // image-side projections of layer 1 in one pass over the per-prompt keys: [k_t2i | v_t2i (| q_i2t when the
-    // image->token block is not fused)]
     const bool fused_i2t = T <= 8;
-    const int ld1 = fused_i2t ? 2 * DI : 3 * DI;
-    if (l == 1) {
-      if (gemm(E, st, d.keys, DC, d.kvq1_w, PN, ld1, DC, d.kvq1_b, d.img_kvq, ld1, 0, 0, d.kvq1_res, NI, 0, 0, nullptr,
-               nullptr, 1e-5f, 3 * DI)) return -1;
+    if (l == 1 && !fused_i2t) {  // q of the (unfused) image -> token attention: (keys + pe) Wq^T, pe term through the residual
+      if (gemm(E, st, d.keys, DC, d.kvq1_w + (size_t)2 * DI * DC, PN, DI, DC, d.kvq1_b + 2 * DI, d.img_kvq, DI, 0, 0,
+               d.kvq1_res + 2 * DI, NI, 0, 0, nullptr, nullptr, 1e-5f, 3 * DI)) return -1;
     }
     // ---- (1) token self attention
     if (l == 0) {
@@ -652,12 +678,7 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
     if (ln(st, d.tok_f32, PT, DC, L.n1g, L.n1b, 1e-5f, d.q_bf, d.queries, d.tok0, PT, d.qpe_bf)) return -1;
     // ---- (2) token -> image cross attention
     if (gemm(E, st, d.qpe_bf, DC, L.t2i.q, PT, DI, DC, L.t2i.qb, d.t_q128, DI, 0)) return -1;
-    if (l == 0) {
-      t2i_attn_kernel<<<P, 256, 0, st>>>(d.t_q128, d.k0, d.v0, DI, 0, T, NI, d.t_att128);
-    } else {
-      t2i_attn_kernel<<<P, 256, 0, st>>>(d.t_q128, d.img_kvq, d.img_kvq + DI, ld1, NI, T, NI, d.t_att128);
-    }
-    LAUNCH_CHECK("t2i_attn");
+    if (t2i(L.t2i, l)) return -1;
     if (gemm(E, st, d.t_att128, DI, L.t2i.o, PT, DC, DI, L.t2i.ob, d.tok_f32, DC, 1, 0, d.queries, PT)) return -1;
     if (ln(st, d.tok_f32, PT, DC, L.n2g, L.n2b, 1e-5f, d.q_bf, d.queries)) return -1;
     // ---- (3) MLP (ReLU)
@@ -684,7 +705,7 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
       if (l == 0) {
         i2t_attn_kernel<<<dim3(NI / 64, P), 256, 0, st>>>(d.q0, DI, 0, d.t_k128, d.t_v128, T, NI, d.img_att);
       } else {
-        i2t_attn_kernel<<<dim3(NI / 64, P), 256, 0, st>>>(d.img_kvq + 2 * DI, 3 * DI, NI, d.t_k128, d.t_v128, T, NI, d.img_att);
+        i2t_attn_kernel<<<dim3(NI / 64, P), 256, 0, st>>>(d.img_kvq, DI, NI, d.t_k128, d.t_v128, T, NI, d.img_att);
       }
       LAUNCH_CHECK("i2t_attn");
       // LayerNorm fused into the out-projection GEMM epilogue (in place for layer 1: every thread reads the residual of
@@ -700,9 +721,7 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
   {
     const AttnW& A = d.final_t2i;
     if (gemm(E, st, d.qpe_bf, DC, A.q, PT, DI, DC, A.qb, d.t_q128, DI, 0)) return -1;
-    if (gemm(E, st, d.keys, DC, d.kvf_w, PN, 2 * DI, DC, d.kvf_b, d.img_kvq, 2 * DI, 0, 0, d.kvf_res, NI)) return -1;
-    t2i_attn_kernel<<<P, 256, 0, st>>>(d.t_q128, d.img_kvq, d.img_kvq + DI, 2 * DI, NI, T, NI, d.t_att128);
-    LAUNCH_CHECK("t2i_attn");
+    if (t2i(A, 1)) return -1;
     if (gemm(E, st, d.t_att128, DI, A.o, PT, DC, DI, A.ob, d.tok_f32, DC, 1, 0, d.queries, PT)) return -1;
     if (ln(st, d.tok_f32, PT, DC, d.nfg, d.nfb, 1e-5f, d.q_bf)) return -1;
   }

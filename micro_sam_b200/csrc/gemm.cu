@@ -93,7 +93,7 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& r, float* f) {
 }
 // 16-byte chunk `ch` (0..7) of row `r` in a 128-B-row staging tile with the TMA SWIZZLE_128B pattern
 __device__ __forceinline__ void stg_write(uint8_t* stg, int r, int ch, const uint4& v) {
-  *reinterpret_cast<uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4)) = v;
+  st_shared_v4(smem_u32(stg) + r * 128 + ((ch ^ (r & 7)) << 4), v);
 }
 
 // the hyper-product epilogue is ALU bound (GELU + 3 dot products per element): 32 columns per thread -> 16 epilogue warps
@@ -171,8 +171,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (whole warp in uniform control flow, one
+    // elected lane issues)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -190,13 +191,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t sb = sa + Cfg::A_BYTES;
           const uint64_t da = make_desc_sw128(sa, 0, 1024);
           const uint64_t db = make_desc_sw128(sb, 0, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // +32 B per K=16 step inside the 128-B swizzle atom -> +2 on the encoded (>>4) start address
-            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              // +32 B per K=16 step inside the 128-B swizzle atom -> +2 on the encoded (>>4) start address
+              umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            }
+            umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs have read it
+            if (kb == k_blocks - 1) umma_commit(&tfull_bar[as]);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs have read it
-          if (kb == k_blocks - 1) umma_commit(&tfull_bar[as]);
+          __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }

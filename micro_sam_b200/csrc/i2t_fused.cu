@@ -65,7 +65,9 @@ i2t_fused_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* p_full = s_full + 1;
   uint64_t* o_full = p_full + 1;
   uint64_t* o_empty = o_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+  uint64_t* stg_full = o_empty + 1;   // [2] staging tile written (4 warps)
+  uint64_t* stg_free = stg_full + 2;  // [2] TMA store has read the tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_free + 2);
   __shared__ __align__(16) float2 exch[4 * 128];
   __shared__ __align__(16) float rowp[768];  // out-proj bias | gamma | beta
 
@@ -80,6 +82,7 @@ i2t_fused_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(mv_full, 1); mbar_init(mv_empty, 1); mbar_init(s_full, 1); mbar_init(p_full, 16);
     mbar_init(o_full, 1); mbar_init(o_empty, 16);
+    for (int i = 0; i < 2; ++i) { mbar_init(&stg_full[i], 4); mbar_init(&stg_free[i], 1); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -92,7 +95,7 @@ i2t_fused_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int w = (n & 7) >> 1;
       if (w == 0) v.x = one; else if (w == 1) v.y = one; else if (w == 2) v.z = one; else v.w = one;
     }
-    *reinterpret_cast<uint4*>(smem + OFF_I + n * 128 + ((c ^ (n & 7)) << 4)) = v;
+    st_shared_v4(smem_u32(smem + OFF_I) + n * 128 + ((c ^ (n & 7)) << 4), v);
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -127,8 +130,8 @@ i2t_fused_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (warp-uniform control flow, elected lane issues)
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 64);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 256);
       const uint64_t di = make_desc_sw128(smem_u32(smem + OFF_I), 0, 1024);
@@ -140,51 +143,71 @@ i2t_fused_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int pp = item / TILES;
         if (pp != cur_p) {
           mbar_wait(mv_full, nload & 1, 12);
-          tc_fence_after();
           cur_p = pp; ++nload;
         }
         for (int j = 0; j < 4; ++j) {
           mbar_wait(&full_bar[stage], phase, 13);
+          if (j == 0 && it > 0) mbar_wait(o_empty, (it - 1) & 1, 14);  // the row warps have pulled the previous O out of TMEM
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t d0 = make_desc_sw128(sa, 0, 1024), d1 = make_desc_sw128(sa + SUB, 0, 1024);
           const uint64_t dm = make_desc_sw128(smem_u32(smem + OFF_M + j * 8192), 0, 1024);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TM_S, d0 + 2 * k, dm + 2 * k, idesc_s, (j | k) != 0);
-          if (p.mode) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TM_S, d1 + 2 * k, dm + 2 * k, idesc_s, 1);
-          }
-          if (j == 0 && it > 0) {  // the row warps have pulled the previous O out of TMEM
-            mbar_wait(o_empty, (it - 1) & 1, 14);
-            tc_fence_after();
-          }
           const uint64_t dr = p.mode ? d0 : d1;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TM_O + 64 * j, dr + 2 * k, di + 2 * k, idesc_s, k != 0);
-          umma_commit(&empty_bar[stage]);
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TM_S, d0 + 2 * k, dm + 2 * k, idesc_s, (j | k) != 0);
+            if (p.mode) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TM_S, d1 + 2 * k, dm + 2 * k, idesc_s, 1);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TM_O + 64 * j, dr + 2 * k, di + 2 * k, idesc_s, k != 0);
+            umma_commit(&empty_bar[stage]);
+            if (j == 3) umma_commit(s_full);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(s_full);
         mbar_wait(p_full, it & 1, 15);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TM_O, dp + 2 * k, dv + 2 * k, idesc_o, 1);
-        umma_commit(o_full);
-        if (item + 1 == it_end || (item + 1) / TILES != pp) umma_commit(mv_empty);
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TM_O, dp + 2 * k, dv + 2 * k, idesc_o, 1);
+          umma_commit(o_full);
+          if (item + 1 == it_end || (item + 1) / TILES != pp) umma_commit(mv_empty);
+        }
+        __syncwarp();
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    // ------------------------------------------------------------ store warps: warp 2 -> staging tile 0, warp 3 -> tile 1.
+    // Each tile is used twice per item: column group sb (use 2*it), then column group sb + 2 (use 2*it + 1).
+    if (lane == 0) {
+      const int sb = warp - 2;
+      const uint8_t* stg = smem + OFF_STG + sb * 16384;
+      uint32_t n = 0;
+      for (int item = it_begin; item < it_end; ++item) {
+        const int orow = (item / TILES) * 4096 + (item % TILES) * 128;
+        for (int round = 0; round < 2; ++round, ++n) {
+          mbar_wait(&stg_full[sb], n & 1, 18);
+          tma_store_2d(&tmOut, stg, 64 * (sb + 2 * round), orow);
+          tma_store_commit();
+          tma_store_wait_read();
+          mbar_arrive(&stg_free[sb]);
+        }
+      }
+      tma_store_wait_all();
+    }
+  } else {
     // ------------------------------------------------------------ row warps: softmax, then LayerNorm epilogue
     const int quad = warp & 3, grp = (warp - 4) >> 2, r = quad * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int sb = grp & 1;                                  // staging tile shared by groups sb and sb + 2
-    uint8_t* stg = smem + OFF_STG + sb * 16384;
-    const bool issuer = (grp < 2 && quad == 0 && lane == 0);
+    const uint32_t stg = smem_u32(smem + OFF_STG + sb * 16384);
     const int T = p.T;
     int it = 0;
     for (int item = it_begin; item < it_end; ++item, ++it) {
-      const int pp = item / TILES, rt = item % TILES;
+      const int pp = item / TILES;
       // ---- softmax over the T prompt tokens for heads 2*grp, 2*grp + 1
       float cb[16];
       {
@@ -215,7 +238,7 @@ i2t_fused_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const float inv = __fdividef(1.0f, l);
           const uint4 pk = make_uint4(pack_bf16(s[0] * inv, s[1] * inv), pack_bf16(s[2] * inv, s[3] * inv),
                                       pack_bf16(s[4] * inv, s[5] * inv), pack_bf16(s[6] * inv, s[7] * inv));
-          *reinterpret_cast<uint4*>(smem + OFF_P + r * 128 + (((2 * grp + hh) ^ (r & 7)) << 4)) = pk;
+          st_shared_v4(smem_u32(smem + OFF_P) + r * 128 + (((2 * grp + hh) ^ (r & 7)) << 4), pk);
         }
       }
       fence_proxy_async_smem();
@@ -260,37 +283,23 @@ i2t_fused_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       for (int g = 0; g < 4; ++g) { const float d = st[g].x - mean; m2 += st[g].y + d * d * 64.f; }
       const float rstd = rsqrtf(m2 * (1.0f / 256) + p.eps);
 
-      auto write_rows = [&]() {
+      // staging tile sb: use n = 2*it (+1 for column groups 2, 3); free once the store of use n-1 has read it
+      const uint32_t n = 2 * it + (grp >> 1);
+      if (grp >= 2) mbar_wait(&stg_free[sb], n & 1, 19);  // (use n-2 first: a parity wait only resolves one phase back)
+      mbar_wait(&stg_free[sb], (n & 1) ^ 1, 19);
 #pragma unroll
-        for (int j = 0; j < 64; j += 8) {
-          float y[8];
+      for (int j = 0; j < 64; j += 8) {
+        float y[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            y[q] = (f[j + q] - mean) * rstd * rowp[256 + 64 * grp + j + q] + rowp[512 + 64 * grp + j + q];
-          *reinterpret_cast<uint4*>(stg + r * 128 + (((j >> 3) ^ (r & 7)) << 4)) =
-              make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
-        }
-        fence_proxy_async_smem();
-      };
-      const int orow = pp * 4096 + rt * 128;
-      if (issuer) tma_store_wait_read();
-      named_bar_sync(2 + sb, 256);  // staging tile free
-      if (grp < 2) write_rows();
-      named_bar_sync(2 + sb, 256);
-      if (issuer) {
-        tma_store_2d(&tmOut, stg, 64 * grp, orow);
-        tma_store_commit();
-        tma_store_wait_read();
+        for (int q = 0; q < 8; ++q)
+          y[q] = (f[j + q] - mean) * rstd * rowp[256 + 64 * grp + j + q] + rowp[512 + 64 * grp + j + q];
+        st_shared_v4(stg + r * 128 + (((j >> 3) ^ (r & 7)) << 4),
+                     make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7])));
       }
-      named_bar_sync(2 + sb, 256);  // free again -> column groups 2, 3
-      if (grp >= 2) write_rows();
-      named_bar_sync(2 + sb, 256);
-      if (issuer) {
-        tma_store_2d(&tmOut, stg, 64 * (grp + 2), orow);
-        tma_store_commit();
-      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&stg_full[sb]);
     }
-    if (issuer) tma_store_wait_all();
   }
 
   tc_fence_before();

@@ -59,6 +59,21 @@ int launch_i2t_fused(const I2tFusedArgs& a, int num_sms, cudaStream_t stream);
 int launch_i2t_prep(const __nv_bfloat16* ktok, const __nv_bfloat16* vtok, const float* bq, int P, int T,
                     __nv_bfloat16* kexp, __nv_bfloat16* vexp, float* sbias, cudaStream_t stream);
 
+// ---- t2i_fused.cu : fused token -> image cross-attention (k / v projections folded into the query / output side; the image
+// tokens are read once and used as both K and V)
+struct T2iFusedArgs {
+  int n_items = 0;                    // work items of 128 Q' rows (one prompt, or two prompts when paired)
+  int mode = 0;                       // 1: x = keys [n_items*4096, 256], xs = pe;  0: x = src (shared), xs = src + pe
+  const __nv_bfloat16* x = nullptr;
+  const __nv_bfloat16* xs = nullptr;
+  const __nv_bfloat16* qp = nullptr;  // Q' [n_items*128, 256]
+  float* out = nullptr;               // [n_items*128, 256]
+};
+int launch_t2i_fused(const T2iFusedArgs& a, int num_sms, cudaStream_t stream);
+int launch_t2i_prep(const __nv_bfloat16* q, int P, int T, int paired, int n_items, __nv_bfloat16* qexp, cudaStream_t stream);
+int launch_t2i_head_proj(const float* U, const __nv_bfloat16* WvT, const float* bv, int P, int T, int paired,
+                         __nv_bfloat16* out, cudaStream_t stream);
+
 // ---- attention.cu : ViT encoder attention with decomposed relative-position bias
 struct AttnArgs {
   const __nv_bfloat16* qkv = nullptr;  // [groups*G, 3*D] rows = tokens (window-partitioned incl. pad tokens, or global)

@@ -114,6 +114,38 @@ def sec_gemm():
     print(f"[perf] cublas same shape: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
 
 
+def sec_gemmperf():
+    """Event-timed throughput of the encoder GEMM shapes (batch of 4 tiles), next to cuBLAS for the bare product."""
+    L = _lib.lib()
+    for model, D in (("vit_b", 768), ("vit_h", 1280)):
+        shapes = [("qkv (windowed rows)", 19600, 3 * D, D, 0, 0, False), ("proj +res f32", 16384, D, D, 0, 16384, True),
+                  ("fc1 +gelu", 16384, 4 * D, D, 1, 0, False), ("fc2 +res f32", 16384, D, 4 * D, 0, 16384, True)]
+        for name, M, N, K, act, rr, f32 in shapes:
+            A = torch.randn(M, K, device=DEV).bfloat16()
+            W = (torch.randn(N, K, device=DEV) / math.sqrt(K)).bfloat16()
+            bias = torch.randn(N, device=DEV)
+            res = torch.randn(rr, N, device=DEV) if rr else None
+            out = torch.empty(M, N, device=DEV, dtype=torch.float32 if f32 else torch.bfloat16)
+
+            def run():
+                L.msam_op_gemm(_lib.ptr(A), _lib.ptr(W), M, N, K, _lib.ptr(bias), _lib.ptr(res), rr, _lib.ptr(out), int(f32),
+                               act, _lib.cur_stream())
+            ms = _time(run)
+            ms_cb = _time(lambda: A @ W.t())
+            print(f"[perf] {model} {name} M={M} N={N} K={K}: {ms*1e3:.1f} us {2*M*N*K/ms/1e9:.0f} TF/s | cublas bare "
+                  f"{ms_cb*1e3:.1f} us {2*M*N*K/ms_cb/1e9:.0f} TF/s", flush=True)
+
+
+def _time(fn, n=10):
+    fn(); fn()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(n):
+        fn()
+    t1.record(); torch.cuda.synchronize()
+    return t0.elapsed_time(t1) / n
+
+
 def sec_ln():
     L = _lib.lib()
     for D in (768, 1280, 256, 160):
@@ -360,7 +392,7 @@ def sec_nms():
             print(f"[{'OK ' if ok else 'BAD'}] filter_nms n={n} filters={use_f}: kept {len(got)} (ref {len(ref)})", flush=True)
 
 
-SECTIONS = {"gemm": sec_gemm, "ln": sec_ln, "attn": sec_attn, "encoder": sec_encoder, "decoder": sec_decoder,
+SECTIONS = {"gemm": sec_gemm, "gemmperf": sec_gemmperf, "ln": sec_ln, "attn": sec_attn, "encoder": sec_encoder, "decoder": sec_decoder,
             "post": sec_post, "nms": sec_nms}
 
 if __name__ == "__main__":
