@@ -32,7 +32,7 @@ constexpr int OFF_I = OFF_P + 16384;           // identity [64 x 64]
 constexpr int OFF_STG = OFF_I + 8192;          // 2 output staging tiles [128 x 64]
 constexpr int OFF_BAR = OFF_STG + 2 * 16384;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-constexpr int THREADS = 128 + 512;
+constexpr int THREADS = 128 + 128 + 512;  // 4 control warps, 4 softmax warps, 16 LayerNorm warps
 constexpr uint32_t TM_O = 0, TM_S = 256, TMEM_COLS = 512;
 constexpr int TILES = 32;                      // 4096 image tokens / 128 rows
 }  // namespace i2t
@@ -67,7 +67,8 @@ i2t_fused_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* o_empty = o_full + 1;
   uint64_t* stg_full = o_empty + 1;   // [2] staging tile written (4 warps)
   uint64_t* stg_free = stg_full + 2;  // [2] TMA store has read the tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_free + 2);
+  uint64_t* ln_done = stg_free + 2;   // every LayerNorm warp has read the statistics exchange of the item
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_done + 1);
   __shared__ __align__(16) float2 exch[4 * 128];
   __shared__ __align__(16) float rowp[768];  // out-proj bias | gamma | beta
 
@@ -80,8 +81,8 @@ i2t_fused_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(mv_full, 1); mbar_init(mv_empty, 1); mbar_init(s_full, 1); mbar_init(p_full, 16);
-    mbar_init(o_full, 1); mbar_init(o_empty, 16);
+    mbar_init(mv_full, 1); mbar_init(mv_empty, 1); mbar_init(s_full, 1); mbar_init(p_full, 4);
+    mbar_init(o_full, 1); mbar_init(o_empty, 16); mbar_init(ln_done, 16);
     for (int i = 0; i < 2; ++i) { mbar_init(&stg_full[i], 4); mbar_init(&stg_free[i], 1); }
     fence_barrier_init();
   }
@@ -198,90 +199,94 @@ i2t_fused_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       tma_store_wait_all();
     }
-  } else {
-    // ------------------------------------------------------------ row warps: softmax, then LayerNorm epilogue
-    const int quad = warp & 3, grp = (warp - 4) >> 2, r = quad * 32 + lane;
+  } else if (warp < 8) {
+    // ------------------------------------------------------------ softmax warps: thread = image token (row), 8 heads x T tokens
+    const int quad = warp & 3, r = quad * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const int sb = grp & 1;                                  // staging tile shared by groups sb and sb + 2
-    const uint32_t stg = smem_u32(smem + OFF_STG + sb * 16384);
+    const uint32_t prow = smem_u32(smem + OFF_P) + r * 128;
     const int T = p.T;
     int it = 0;
     for (int item = it_begin; item < it_end; ++item, ++it) {
-      const int pp = item / TILES;
-      // ---- softmax over the T prompt tokens for heads 2*grp, 2*grp + 1
-      float cb[16];
-      {
-        const float4* c4 = reinterpret_cast<const float4*>(p.sbias + (size_t)pp * 64 + 16 * grp);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 c = __ldg(c4 + q);
-          cb[4 * q] = c.x; cb[4 * q + 1] = c.y; cb[4 * q + 2] = c.z; cb[4 * q + 3] = c.w;
-        }
-      }
+      const float4* c4 = reinterpret_cast<const float4*>(p.sbias + (size_t)(item / TILES) * 64);
       mbar_wait(s_full, it & 1, 16);
       tc_fence_after();
-      {
-        uint32_t v[16];
-        tmem_ld16(tlane + TM_S + 16 * grp, v);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(tlane + TM_S + 32 * half, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          float s[8], m = -1e30f;
+        for (int hh = 0; hh < 4; ++hh) {
+          const float4 ca = __ldg(c4 + (half * 4 + hh) * 2), cb = __ldg(c4 + (half * 4 + hh) * 2 + 1);
+          const float c[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+          float sc[8], m = -1e30f;
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
-            s[t] = (t < T) ? (__uint_as_float(v[hh * 8 + t]) + cb[hh * 8 + t]) * 1.4426950408889634f : -1e30f;
-            m = fmaxf(m, s[t]);
+            sc[t] = (t < T) ? (__uint_as_float(v[hh * 8 + t]) + c[t]) * 1.4426950408889634f : -1e30f;
+            m = fmaxf(m, sc[t]);
           }
           float l = 0.f;
 #pragma unroll
-          for (int t = 0; t < 8; ++t) { s[t] = ex2_approx(s[t] - m); l += s[t]; }
+          for (int t = 0; t < 8; ++t) { sc[t] = ex2_approx(sc[t] - m); l += sc[t]; }
           const float inv = __fdividef(1.0f, l);
-          const uint4 pk = make_uint4(pack_bf16(s[0] * inv, s[1] * inv), pack_bf16(s[2] * inv, s[3] * inv),
-                                      pack_bf16(s[4] * inv, s[5] * inv), pack_bf16(s[6] * inv, s[7] * inv));
-          st_shared_v4(smem_u32(smem + OFF_P) + r * 128 + (((2 * grp + hh) ^ (r & 7)) << 4), pk);
+          st_shared_v4(prow + (((half * 4 + hh) ^ (r & 7)) << 4),
+                       make_uint4(pack_bf16(sc[0] * inv, sc[1] * inv), pack_bf16(sc[2] * inv, sc[3] * inv),
+                                  pack_bf16(sc[4] * inv, sc[5] * inv), pack_bf16(sc[6] * inv, sc[7] * inv)));
         }
       }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-
-      // ---- O = residual + P V' (+ bias) -> LayerNorm over the 256 channels
+    }
+  } else {
+    // ------------------------------------------------------------ LayerNorm warps: O = residual + P V' (+ bias) -> LN(256)
+    const int quad = warp & 3, grp = (warp - 8) >> 2, r = quad * 32 + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int sb = grp & 1;                                  // staging tile shared by groups sb and sb + 2
+    const uint32_t stg = smem_u32(smem + OFF_STG + sb * 16384);
+    int it = 0;
+    for (int item = it_begin; item < it_end; ++item, ++it) {
       float f[64];
       mbar_wait(o_full, it & 1, 17);
       tc_fence_after();
+      float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
         tmem_ld32(tlane + TM_O + 64 * grp + 32 * c, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[c * 32 + j] = __uint_as_float(v[j]) + rowp[64 * grp + c * 32 + j];
+        for (int j = 0; j < 32; ++j) {
+          const float x = __uint_as_float(v[j]) + rowp[64 * grp + c * 32 + j];
+          f[c * 32 + j] = x;
+          s4[j & 3] += x;
+          q4[j & 3] = fmaf(x, x, q4[j & 3]);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
-
-      float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int j = 0; j < 64; ++j) s4[j & 3] += f[j];
-      const float mean_g = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / 64);
-      float q4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int j = 0; j < 64; ++j) { const float d = f[j] - mean_g; q4[j & 3] = fmaf(d, d, q4[j & 3]); }
-      // single exchange buffer: a warp can only get here for the next item after every warp has arrived on p_full, i.e.
-      // after every warp has finished reading this item's statistics
-      exch[grp * 128 + r] = make_float2(mean_g, (q4[0] + q4[1]) + (q4[2] + q4[3]));
+      // group statistics in one pass (fp32 sums of 64 O(1) values: the cancellation error is ~1e-5 of the variance),
+      // combined across the four column groups with Chan's formula
+      const float sum_g = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      const float mean_g = sum_g * (1.0f / 64);
+      const float m2_g = fmaxf(((q4[0] + q4[1]) + (q4[2] + q4[3])) - sum_g * mean_g, 0.f);
+      if (it > 0) mbar_wait(ln_done, (it - 1) & 1, 20);  // every warp has read the previous item's statistics
+      exch[grp * 128 + r] = make_float2(mean_g, m2_g);
       named_bar_sync(1, 512);
       float mean = 0.f;
       float2 st[4];
 #pragma unroll
       for (int g = 0; g < 4; ++g) { st[g] = exch[g * 128 + r]; mean += st[g].x; }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ln_done);
       mean *= 0.25f;
       float m2 = 0.f;
 #pragma unroll
       for (int g = 0; g < 4; ++g) { const float d = st[g].x - mean; m2 += st[g].y + d * d * 64.f; }
       const float rstd = rsqrtf(m2 * (1.0f / 256) + p.eps);
+      const float shift = -mean * rstd;
 
       // staging tile sb: use n = 2*it (+1 for column groups 2, 3); free once the store of use n-1 has read it
       const uint32_t n = 2 * it + (grp >> 1);
@@ -292,7 +297,7 @@ i2t_fused_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         float y[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-          y[q] = (f[j + q] - mean) * rstd * rowp[256 + 64 * grp + j + q] + rowp[512 + 64 * grp + j + q];
+          y[q] = fmaf(fmaf(f[j + q], rstd, shift), rowp[256 + 64 * grp + j + q], rowp[512 + 64 * grp + j + q]);
         st_shared_v4(stg + r * 128 + (((j >> 3) ^ (r & 7)) << 4),
                      make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7])));
       }
