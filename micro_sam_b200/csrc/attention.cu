@@ -691,8 +691,7 @@ static int launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
 int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   if (a.grid != 64) return set_error("attention: token grid %d unsupported (kernel is specialised for 64x64)", a.grid);
   if (a.window == 0) {
-    if (a.head_dim == 64) return launch_attn_t<64, 64>(a, stream);
-    if (a.head_dim == 80) return launch_attn_t<80, 64>(a, stream);
+    return launch_attention_global(a, stream);
   } else if (a.window == 14) {
     if (a.head_dim == 64) return launch_attn_window<64>(a, stream);
     if (a.head_dim == 80) return launch_attn_window<80>(a, stream);

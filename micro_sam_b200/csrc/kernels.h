@@ -87,6 +87,7 @@ struct AttnArgs {
   float scale = 0.f;
 };
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
+int launch_attention_global(const AttnArgs& a, cudaStream_t stream);  // attention_global.cu (window == 0)
 
 // ---- elementwise.cu
 int launch_patchify(const uint8_t* u8, const float* f32, int B, int h, int w, int img, const float* mean,
