@@ -65,9 +65,14 @@ int msam_set_image_embedding(msam_handle* h, const float* feat_256x64x64, void* 
  * prompt_encoder(points=(coords,labels)|None, boxes|None, masks=None) -> mask_decoder(multimask_output).
  * points [P,n_points,2] / labels [P,n_points] (fp32; -1 pad, 0 neg, 1 pos) in the 1024-frame (already
  * ResizeLongestSide.apply_coords'ed), boxes [P,4] xyxy; either may be NULL, not both.
- * Outputs: low_res [P,M,256,256] fp32, iou [P,M] fp32, M = 3 (multimask) or 1.  mask_input is not supported. */
+ * Outputs: low_res [P,M,256,256] fp32, iou [P,M] fp32, M = 3 (multimask) or 1. */
 int msam_decode(msam_handle* h, const float* points, const float* labels, int n_points, const float* boxes, int P,
                 int multimask, float* low_res, float* iou, void* stream);
+/* Same with mask prompts (predict_torch(mask_input=...), prompt_based_segmentation.py:289-493; PromptEncoder._embed_masks):
+ * mask_input [P,1,256,256] fp32 low-res logits of a previous prediction, or NULL.  With a mask prompt the dense prompt
+ * embedding differs per prompt, so the layer-0 image-side work is no longer shared between prompts. */
+int msam_decode_ex(msam_handle* h, const float* points, const float* labels, int n_points, const float* boxes,
+                   const float* mask_input, int P, int multimask, float* low_res, float* iou, void* stream);
 
 /* Sam.postprocess_masks + calculate_stability_score + threshold + batched_mask_to_box + area, fused, never
  * materialising the upsampled logits (instance_segmentation.py:229-255; inference.py:137-151; _vendored.py:33-85).

@@ -44,6 +44,8 @@ def lib() -> ctypes.CDLL:
         L.msam_op_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]
         L.msam_set_image_embedding.argtypes = [c_void_p, c_void_p, c_void_p]
         L.msam_decode.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
+        L.msam_decode_ex.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                     c_void_p]
         L.msam_mask_stats.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p,
                                       c_void_p, c_void_p]
         L.msam_upsample_masks.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,

@@ -52,12 +52,14 @@ struct DecoderState {
   bool image_set = false;
   float* src = nullptr;               // [4096,256] image embedding + no_mask_embed (fp32, residual of layer 0)
   __nv_bfloat16 *src_bf = nullptr, *src_pe_bf = nullptr;
-  __nv_bfloat16 *k0 = nullptr, *v0 = nullptr, *q0 = nullptr;  // hoisted layer-0 projections [4096,128]
-  // fused image-side projections of layer 1 ([k_t2i | v_t2i | q_i2t], N=384) and of the final attention ([k | v], N=256).
-  // (keys + pe) W^T = keys W^T + pe W^T: the prompt-independent second term is precomputed ([4096, N] fp32, zero for the
-  // v columns) and added through the GEMM's row-modulus residual, so `keys + pe` is never materialised.
-  __nv_bfloat16 *kvq1_w = nullptr, *kvf_w = nullptr;
-  float *kvq1_b = nullptr, *kvf_b = nullptr, *kvq1_res = nullptr, *kvf_res = nullptr;
+  float* emb = nullptr;               // [4096,256] image embedding without no_mask_embed (mask prompts add their own dense term)
+  __nv_bfloat16* q0 = nullptr;        // hoisted layer-0 image->token q projection [4096,128] (unfused path, T > 8)
+  // (keys + pe) Wq^T = keys Wq^T + pe Wq^T for the unfused image->token path (T > 8): the prompt-independent second term is
+  // precomputed per layer ([4096, 128] fp32) and added through the GEMM's row-modulus residual.
+  float* q_res[2] = {nullptr, nullptr};
+  // PromptEncoder.mask_downscaling (mask prompts): conv 1->4 k2s2, LN2d, GELU, conv 4->16 k2s2, LN2d, GELU, conv 16->256 k1
+  float *md_w1 = nullptr, *md_b1 = nullptr, *md_g1 = nullptr, *md_be1 = nullptr, *md_w2 = nullptr, *md_b2 = nullptr,
+        *md_g2 = nullptr, *md_be2 = nullptr, *md_w3 = nullptr, *md_b3 = nullptr;
   // per-chunk workspace (P = max_prompts)
   float *tok0 = nullptr, *queries = nullptr, *tok_f32 = nullptr;
   __nv_bfloat16 *tok0_bf = nullptr, *q_bf = nullptr, *qpe_bf = nullptr, *t_qkv = nullptr, *t_att = nullptr, *t_mlp = nullptr;
@@ -94,7 +96,8 @@ __global__ void dense_pe_kernel(const float* __restrict__ G, int g, float* __res
 // NCHW fp32 image embedding [256, T] -> token-major src = emb + no_mask_embed (fp32, bf16) and src + pos (bf16).
 __global__ void set_image_kernel(const float* __restrict__ feat, const float* __restrict__ no_mask,
                                  const float* __restrict__ pos, int T, float* __restrict__ src,
-                                 __nv_bfloat16* __restrict__ src_bf, __nv_bfloat16* __restrict__ src_pe_bf) {
+                                 __nv_bfloat16* __restrict__ src_bf, __nv_bfloat16* __restrict__ src_pe_bf,
+                                 float* __restrict__ emb) {
   __shared__ float tile[32][33];
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
@@ -102,6 +105,7 @@ __global__ void set_image_kernel(const float* __restrict__ feat, const float* __
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int t = t0 + i, c = c0 + tx;
+    emb[(long)t * 256 + c] = tile[tx][i];
     const float v = tile[tx][i] + no_mask[c];
     src[(long)t * 256 + c] = v;
     src_bf[(long)t * 256 + c] = __float2bfloat16(v);
@@ -109,14 +113,88 @@ __global__ void set_image_kernel(const float* __restrict__ feat, const float* __
   }
 }
 
+// Mask prompts (PromptEncoder._embed_masks): keys0[p, token, :] = image_embedding[token, :] + mask_downscaling(mask[p])[:, token]
+// grid = (4096 / 16, P), block = 256 (thread = output channel; 16 tokens per block).  LayerNorm2d: eps 1e-6, biased variance.
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__global__ void __launch_bounds__(256)
+mask_dense_kernel(const float* __restrict__ mask, const float* __restrict__ w1, const float* __restrict__ b1,
+                  const float* __restrict__ g1, const float* __restrict__ be1, const float* __restrict__ w2,
+                  const float* __restrict__ b2, const float* __restrict__ g2, const float* __restrict__ be2,
+                  const float* __restrict__ w3, const float* __restrict__ b3, const float* __restrict__ emb,
+                  __nv_bfloat16* __restrict__ keys) {
+  const int p = blockIdx.y, t0 = blockIdx.x * 16, tid = threadIdx.x;
+  __shared__ float sa[16][16];  // [token][c*4 + sy*2 + sx] after stage 1
+  __shared__ float sg[16][16];  // [token][o] after stage 2
+  const float* m = mask + (size_t)p * 65536;
+  if (tid < 64) {  // stage 1: thread = (token, sub-position): 4 channels
+    const int tk = tid >> 2, sy = (tid >> 1) & 1, sx = tid & 1, t = t0 + tk, ty = t >> 6, tx = t & 63;
+    const float* mp = m + (size_t)(4 * ty + 2 * sy) * 256 + 4 * tx + 2 * sx;
+    const float m00 = mp[0], m01 = mp[1], m10 = mp[256], m11 = mp[257];
+    float y[4], mean = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      y[c] = b1[c] + w1[c * 4 + 0] * m00 + w1[c * 4 + 1] * m01 + w1[c * 4 + 2] * m10 + w1[c * 4 + 3] * m11;
+      mean += y[c];
+    }
+    mean *= 0.25f;
+    float var = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) var += (y[c] - mean) * (y[c] - mean);
+    const float rstd = rsqrtf(var * 0.25f + 1e-6f);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) sa[tk][c * 4 + sy * 2 + sx] = gelu_exact((y[c] - mean) * rstd * g1[c] + be1[c]);
+  }
+  __syncthreads();
+  if (tid < 16) {  // stage 2: thread = token: 16 channels (w2[o][c][sy][sx] contiguous = [o][16])
+    float z[16], mean = 0.f;
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+      float acc = b2[o];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc += w2[o * 16 + k] * sa[tid][k];
+      z[o] = acc;
+      mean += acc;
+    }
+    mean *= (1.0f / 16);
+    float var = 0.f;
+#pragma unroll
+    for (int o = 0; o < 16; ++o) var += (z[o] - mean) * (z[o] - mean);
+    const float rstd = rsqrtf(var * (1.0f / 16) + 1e-6f);
+#pragma unroll
+    for (int o = 0; o < 16; ++o) sg[tid][o] = gelu_exact((z[o] - mean) * rstd * g2[o] + be2[o]);
+  }
+  __syncthreads();
+  float w[16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) w[o] = w3[tid * 16 + o];
+  const float bb = b3[tid];
+#pragma unroll 4
+  for (int tk = 0; tk < 16; ++tk) {
+    float acc = bb;
+#pragma unroll
+    for (int o = 0; o < 16; ++o) acc += w[o] * sg[tk][o];
+    const size_t tok = (size_t)(t0 + tk);
+    keys[((size_t)p * 4096 + tok) * 256 + tid] = __float2bfloat16(acc + emb[tok * 256 + tid]);
+  }
+}
+
 // Tokens [P, T, 256] = [iou_token, mask_tokens(4), sparse prompt embeddings].  Sparse = points (+ pad point when no
 // box) then box corners (PromptEncoder._embed_points/_embed_boxes).  grid = (T-5, P), block = 128.
 __global__ void prompt_tokens_kernel(const float* __restrict__ points, const float* __restrict__ labels, int np,
-                                     const float* __restrict__ boxes, int T, float img_size,
+                                     const float* __restrict__ boxes, int T, int n_sparse, float img_size,
                                      const float* __restrict__ G, const float* __restrict__ point_emb,
                                      const float* __restrict__ not_a_point, const float* __restrict__ out_tokens,
                                      float* __restrict__ tok, __nv_bfloat16* __restrict__ tok_bf) {
   const int p = blockIdx.y, s = blockIdx.x, f = threadIdx.x;
+  if (s == 0) {  // the 5 output tokens of this prompt
+    float* d0 = tok + (long)p * T * 256;
+    __nv_bfloat16* d0b = tok_bf + (long)p * T * 256;
+    for (int i = f; i < 5 * 256; i += 128) {
+      d0[i] = out_tokens[i];
+      d0b[i] = __float2bfloat16(out_tokens[i]);
+    }
+  }
+  if (s >= n_sparse) return;  // mask-only prompts have no sparse tokens
   const int n_pts = points ? np + (boxes ? 0 : 1) : 0;
   float* dst = tok + ((long)p * T + 5 + s) * 256;
   __nv_bfloat16* dstb = tok_bf + ((long)p * T + 5 + s) * 256;
@@ -149,14 +227,6 @@ __global__ void prompt_tokens_kernel(const float* __restrict__ points, const flo
   }
   dst[f] = e0; dst[128 + f] = e1;
   dstb[f] = __float2bfloat16(e0); dstb[128 + f] = __float2bfloat16(e1);
-  if (s == 0) {  // also write the 5 output tokens of this prompt
-    float* d0 = tok + (long)p * T * 256;
-    __nv_bfloat16* d0b = tok_bf + (long)p * T * 256;
-    for (int i = f; i < 5 * 256; i += 128) {
-      d0[i] = out_tokens[i];
-      d0b[i] = __float2bfloat16(out_tokens[i]);
-    }
-  }
 }
 
 // Token self attention: T x T per (prompt, head), 8 heads x 32 dims.  One warp per (prompt, head); lane t = query t.
@@ -520,42 +590,30 @@ int Engine::finalize_decoder() {
   dense_pe_kernel<<<(NI * 128 + 255) / 256, 256>>>(d.gauss, g, d.pos);
   LAUNCH_CHECK("dense_pe");
   {
-    // fused projection weights and their positional-encoding terms
-    auto cat_w = [&](std::initializer_list<std::pair<std::string, int>> parts, __nv_bfloat16** w, float** b) -> int {
-      std::vector<float> W, B;
-      for (auto& pr : parts) {
-        const auto *hw = host(pr.first + ".weight", {DI, DC}), *hb = host(pr.first + ".bias", {DI});
-        if (!hw || !hb) return -1;
-        W.insert(W.end(), hw->begin(), hw->end());
-        B.insert(B.end(), hb->begin(), hb->end());
-      }
-      *w = upload_bf16(W.data(), W.size());
-      *b = upload_f32(B.data(), B.size());
-      return (*w && *b) ? 0 : -1;
-    };
-    const std::string l1 = md + "transformer.layers.1.", fa = md + "transformer.final_attn_token_to_image.";
-    if (cat_w({{l1 + "cross_attn_token_to_image.k_proj", 0}, {l1 + "cross_attn_token_to_image.v_proj", 0},
-               {l1 + "cross_attn_image_to_token.q_proj", 0}}, &d.kvq1_w, &d.kvq1_b)) return -1;
-    if (cat_w({{fa + "k_proj", 0}, {fa + "v_proj", 0}}, &d.kvf_w, &d.kvf_b)) return -1;
+    // positional-encoding terms of the (unfused) image->token q projections
     __nv_bfloat16* pos_bf = d.pos_bf = (__nv_bfloat16*)dalloc((size_t)NI * DC * 2);
     CHK(pos_bf);
     if (launch_cast_bf16(d.pos, (long)NI * DC, pos_bf, 0)) return -1;
-    CHK(d.kvq1_res = (float*)dalloc((size_t)NI * 3 * DI * 4, true));
-    CHK(d.kvf_res = (float*)dalloc((size_t)NI * 2 * DI * 4, true));
-    auto pe_proj = [&](const __nv_bfloat16* w, float* out, int ldc) {
+    for (int l = 0; l < 2; ++l) {
+      CHK(d.q_res[l] = (float*)dalloc((size_t)NI * DI * 4, true));
       GemmArgs a;
-      a.A = pos_bf; a.W = w; a.M = NI; a.N = DI; a.K = DC; a.lda = DC; a.ldw = DC; a.out = out; a.ldc = ldc; a.out_fp32 = 1;
-      return launch_gemm(a, num_sms, 0);
-    };
-    if (pe_proj(d.layers[1].t2i.k, d.kvq1_res, 3 * DI)) return -1;
-    if (pe_proj(d.layers[1].i2t.q, d.kvq1_res + 2 * DI, 3 * DI)) return -1;
-    if (pe_proj(d.final_t2i.k, d.kvf_res, 2 * DI)) return -1;
+      a.A = pos_bf; a.W = d.layers[l].i2t.q; a.M = NI; a.N = DI; a.K = DC; a.lda = DC; a.ldw = DC; a.out = d.q_res[l];
+      a.ldc = DI; a.out_fp32 = 1;
+      if (launch_gemm(a, num_sms, 0)) return -1;
+    }
+  }
+  {
+    const std::string mk = pe + "mask_downscaling.";
+    CHK(d.md_w1 = up_f32(mk + "0.weight", {4, 1, 2, 2})); CHK(d.md_b1 = up_f32(mk + "0.bias", {4}));
+    CHK(d.md_g1 = up_f32(mk + "1.weight", {4}));          CHK(d.md_be1 = up_f32(mk + "1.bias", {4}));
+    CHK(d.md_w2 = up_f32(mk + "3.weight", {16, 4, 2, 2})); CHK(d.md_b2 = up_f32(mk + "3.bias", {16}));
+    CHK(d.md_g2 = up_f32(mk + "4.weight", {16}));         CHK(d.md_be2 = up_f32(mk + "4.bias", {16}));
+    CHK(d.md_w3 = up_f32(mk + "6.weight", {DC, 16, 1, 1})); CHK(d.md_b3 = up_f32(mk + "6.bias", {DC}));
   }
   CHK(d.src = (float*)dalloc((size_t)NI * DC * 4));
   CHK(d.src_bf = (__nv_bfloat16*)dalloc((size_t)NI * DC * 2));
   CHK(d.src_pe_bf = (__nv_bfloat16*)dalloc((size_t)NI * DC * 2));
-  CHK(d.k0 = (__nv_bfloat16*)dalloc((size_t)NI * DI * 2));
-  CHK(d.v0 = (__nv_bfloat16*)dalloc((size_t)NI * DI * 2));
+  CHK(d.emb = (float*)dalloc((size_t)NI * DC * 4));
   CHK(d.q0 = (__nv_bfloat16*)dalloc((size_t)NI * DI * 2));
   // per-chunk workspace
   const size_t P = cfg.max_prompts, PT = P * TMAX, PN = P * NI;
@@ -615,7 +673,7 @@ int Engine::set_image_embedding(const float* feat, cudaStream_t st) {
   if (!finalized || !dec) return set_error("set_image_embedding: decoder weights not loaded");
   DecoderState& d = *dec;
   const int g = cfg.image_size / cfg.patch_size, NI = g * g;
-  set_image_kernel<<<dim3(NI / 32, DC / 32), dim3(32, 8), 0, st>>>(feat, d.no_mask, d.pos, NI, d.src, d.src_bf, d.src_pe_bf);
+  set_image_kernel<<<dim3(NI / 32, DC / 32), dim3(32, 8), 0, st>>>(feat, d.no_mask, d.pos, NI, d.src, d.src_bf, d.src_pe_bf, d.emb);
   LAUNCH_CHECK("set_image");
   const DecLayer& L0 = d.layers[0];
   if (gemm(*this, st, d.src_pe_bf, DC, L0.i2t.q, NI, DI, DC, L0.i2t.qb, d.q0, DI, 0)) return -1;
@@ -625,17 +683,25 @@ int Engine::set_image_embedding(const float* feat, cudaStream_t st) {
 
 // One chunk of P <= max_prompts prompts.
 static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const float* labels, int np, const float* boxes,
-                        int P, int multimask, float* low_res, float* iou) {
+                        const float* mask_in, int P, int multimask, float* low_res, float* iou) {
   DecoderState& d = *E.dec;
   const int NI = 4096;
   const int n_sparse = (points ? np + (boxes ? 0 : 1) : 0) + (boxes ? 2 : 0);
   const int T = 5 + n_sparse, PT = P * T, PN = P * NI;
-  if (n_sparse <= 0) return set_error("decode: need points and/or boxes");
+  if (n_sparse <= 0 && !mask_in) return set_error("decode: need points, boxes and/or mask prompts");
   if (T > TMAX) return set_error("decode: %d tokens per prompt exceeds the supported %d", T, TMAX);
 
-  prompt_tokens_kernel<<<dim3(n_sparse, P), 128, 0, st>>>(points, labels, np, boxes, T, (float)E.cfg.image_size, d.gauss,
+  prompt_tokens_kernel<<<dim3(n_sparse > 0 ? n_sparse : 1, P), 128, 0, st>>>(points, labels, np, boxes, T, n_sparse, (float)E.cfg.image_size, d.gauss,
                                                           d.point_emb, d.not_a_point, d.out_tokens, d.tok0, d.tok0_bf);
   LAUNCH_CHECK("prompt_tokens");
+
+  // Mask prompts: the dense prompt embedding differs per prompt, so layer 0 cannot share its image-side operands; the
+  // per-prompt keys are materialised up front and layer 0 runs exactly like layer 1 on the image side.
+  if (mask_in) {
+    mask_dense_kernel<<<dim3(NI / 16, P), 256, 0, st>>>(mask_in, d.md_w1, d.md_b1, d.md_g1, d.md_be1, d.md_w2, d.md_b2, d.md_g2,
+                                                         d.md_be2, d.md_w3, d.md_b3, d.emb, d.keys);
+    LAUNCH_CHECK("mask_dense");
+  }
 
   // token -> image attention core: t_q128 -> t_att128 (t2i_fused.cu)
   auto t2i = [&](const AttnW& A, int mode) -> int {
@@ -655,9 +721,9 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
   for (int l = 0; l < 2; ++l) {
     const DecLayer& L = d.layers[l];
     const bool fused_i2t = T <= 8;
-    if (l == 1 && !fused_i2t) {  // q of the (unfused) image -> token attention: (keys + pe) Wq^T, pe term through the residual
-      if (gemm(E, st, d.keys, DC, d.kvq1_w + (size_t)2 * DI * DC, PN, DI, DC, d.kvq1_b + 2 * DI, d.img_kvq, DI, 0, 0,
-               d.kvq1_res + 2 * DI, NI, 0, 0, nullptr, nullptr, 1e-5f, 3 * DI)) return -1;
+    const bool shared = (l == 0) && !mask_in;  // image-side operands identical for every prompt
+    if (!shared && !fused_i2t) {  // q of the (unfused) image -> token attention: (keys + pe) Wq^T, pe term through the residual
+      if (gemm(E, st, d.keys, DC, L.i2t.q, PN, DI, DC, L.i2t.qb, d.img_kvq, DI, 0, 0, d.q_res[l], NI)) return -1;
     }
     // ---- (1) token self attention
     if (l == 0) {
@@ -678,7 +744,7 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
     if (ln(st, d.tok_f32, PT, DC, L.n1g, L.n1b, 1e-5f, d.q_bf, d.queries, d.tok0, PT, d.qpe_bf)) return -1;
     // ---- (2) token -> image cross attention
     if (gemm(E, st, d.qpe_bf, DC, L.t2i.q, PT, DI, DC, L.t2i.qb, d.t_q128, DI, 0)) return -1;
-    if (t2i(L.t2i, l)) return -1;
+    if (t2i(L.t2i, shared ? 0 : 1)) return -1;
     if (gemm(E, st, d.t_att128, DI, L.t2i.o, PT, DC, DI, L.t2i.ob, d.tok_f32, DC, 1, 0, d.queries, PT)) return -1;
     if (ln(st, d.tok_f32, PT, DC, L.n2g, L.n2b, 1e-5f, d.q_bf, d.queries)) return -1;
     // ---- (3) MLP (ReLU)
@@ -694,15 +760,15 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
       if (gemm(E, st, d.kexp, DI, L.i2t_qT, P * 64, DC, DI, nullptr, d.mq, DC, 0)) return -1;
       if (gemm(E, st, L.i2t.o, DI, d.vexp, DC, P * 64, DI, nullptr, d.vt, P * 64, 0)) return -1;
       I2tFusedArgs fa;
-      fa.P = P; fa.T = T; fa.mode = l;
-      fa.a0 = l == 0 ? d.src_pe_bf : d.keys;
-      fa.a1 = l == 0 ? d.src_bf : d.pos_bf;
+      fa.P = P; fa.T = T; fa.mode = shared ? 0 : 1;
+      fa.a0 = shared ? d.src_pe_bf : d.keys;
+      fa.a1 = shared ? d.src_bf : d.pos_bf;
       fa.mq = d.mq; fa.vt = d.vt; fa.sbias = d.sbias;
       fa.bias = L.i2t.ob; fa.gamma = L.n4g; fa.beta = L.n4b; fa.eps = 1e-5f;
       fa.out = d.keys;
       if (launch_i2t_fused(fa, E.num_sms, st)) return -1;
     } else {
-      if (l == 0) {
+      if (shared) {
         i2t_attn_kernel<<<dim3(NI / 64, P), 256, 0, st>>>(d.q0, DI, 0, d.t_k128, d.t_v128, T, NI, d.img_att);
       } else {
         i2t_attn_kernel<<<dim3(NI / 64, P), 256, 0, st>>>(d.img_kvq, DI, NI, d.t_k128, d.t_v128, T, NI, d.img_att);
@@ -710,7 +776,7 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
       LAUNCH_CHECK("i2t_attn");
       // LayerNorm fused into the out-projection GEMM epilogue (in place for layer 1: every thread reads the residual of
       // exactly the row segment it later overwrites)
-      if (l == 0) {
+      if (shared) {
         if (gemm(E, st, d.img_att, DI, L.i2t.o, PN, DC, DI, L.i2t.ob, d.keys, DC, 0, 0, d.src_bf, NI, 1, 1, L.n4g, L.n4b, 1e-5f)) return -1;
       } else {
         if (gemm(E, st, d.img_att, DI, L.i2t.o, PN, DC, DI, L.i2t.ob, d.keys, DC, 0, 0, d.keys, PN, 1, 1, L.n4g, L.n4b, 1e-5f)) return -1;
@@ -754,8 +820,8 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
   return 0;
 }
 
-int Engine::decode(const float* points, const float* labels, int np, const float* boxes, int P, int multimask,
-                   float* low_res, float* iou, cudaStream_t st) {
+int Engine::decode(const float* points, const float* labels, int np, const float* boxes, const float* mask_in, int P,
+                   int multimask, float* low_res, float* iou, cudaStream_t st) {
   if (!finalized || !dec) return set_error("decode: decoder weights not loaded");
   if (!dec->image_set) return set_error("decode: no image embedding set (call msam_set_image_embedding first)");
   if (P <= 0) return set_error("decode: empty prompt batch");
@@ -763,7 +829,8 @@ int Engine::decode(const float* points, const float* labels, int np, const float
   for (int p0 = 0; p0 < P; p0 += cfg.max_prompts) {
     const int n = (P - p0 < cfg.max_prompts) ? (P - p0) : cfg.max_prompts;
     if (decode_chunk(*this, st, points ? points + (size_t)p0 * np * 2 : nullptr, labels ? labels + (size_t)p0 * np : nullptr,
-                     np, boxes ? boxes + (size_t)p0 * 4 : nullptr, n, multimask, low_res + (size_t)p0 * nm * 65536,
+                     np, boxes ? boxes + (size_t)p0 * 4 : nullptr, mask_in ? mask_in + (size_t)p0 * 65536 : nullptr, n, multimask,
+                     low_res + (size_t)p0 * nm * 65536,
                      iou + (size_t)p0 * nm))
       return -1;
   }

@@ -412,7 +412,14 @@ int msam_decode(msam_handle* h, const float* points, const float* labels, int n_
   if (!h || !low_res || !iou) return set_error("msam_decode: null argument");
   if (!points && !boxes) return set_error("msam_decode: need points and/or boxes");
   if (points && !labels) return set_error("msam_decode: points without labels");
-  return h->eng.decode(points, labels, points ? n_points : 0, boxes, P, multimask, low_res, iou, (cudaStream_t)stream);
+  return h->eng.decode(points, labels, points ? n_points : 0, boxes, nullptr, P, multimask, low_res, iou, (cudaStream_t)stream);
+}
+int msam_decode_ex(msam_handle* h, const float* points, const float* labels, int n_points, const float* boxes,
+                   const float* mask_input, int P, int multimask, float* low_res, float* iou, void* stream) {
+  if (!h || !low_res || !iou) return set_error("msam_decode_ex: null argument");
+  if (!points && !boxes && !mask_input) return set_error("msam_decode_ex: need points, boxes and/or mask prompts");
+  if (points && !labels) return set_error("msam_decode_ex: points without labels");
+  return h->eng.decode(points, labels, points ? n_points : 0, boxes, mask_input, P, multimask, low_res, iou, (cudaStream_t)stream);
 }
 int msam_mask_stats(const float* low_res, int n_masks, int in_h, int in_w, int orig_h, int orig_w, float mask_threshold,
                     float stability_offset, int32_t* boxes_xyxy, float* stability, int32_t* area, void* stream) {

@@ -345,31 +345,39 @@ __global__ void t2i_prep_kernel(const __nv_bfloat16* __restrict__ q, int P, int 
 }
 
 // out[p, t, o = h*16 + d] = bv[o] + Wv[o, :] . U[row(p, h, t), :]     grid = P, block = 128 (thread = output channel o);
-// WvT = Wv transposed [256, 128] so that the weight reads are coalesced (L1 resident).
+// WvT = Wv transposed [256, 128] so that the weight reads are coalesced.  All T (<= 16) tokens of the prompt are staged in
+// shared memory (T x 8 heads x 256 fp32 <= 128 KB) so that every weight is loaded once per prompt.
+template <int TT>
 __global__ void __launch_bounds__(128)
 t2i_head_proj_kernel(const float* __restrict__ U, const __nv_bfloat16* __restrict__ WvT, const float* __restrict__ bv, int T,
                      int paired, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) float su[];  // [T][8][256]
   const int pp = blockIdx.x, o = threadIdx.x, h = o >> 4;
-  __shared__ __align__(16) float su[8][256];  // U rows of one token, all heads
-  const float b = bv[o];
-  for (int t = 0; t < T; ++t) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 8 * 64; i += 128) {
-      const int hh = i >> 6, c4 = i & 63;
-      reinterpret_cast<float4*>(su[hh])[c4] = __ldg(reinterpret_cast<const float4*>(U + t2i_row(pp, hh, t, paired) * 256) + c4);
-    }
-    __syncthreads();
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < 256; c += 4) {
-      const float4 u = *reinterpret_cast<const float4*>(&su[h][c]);
-      a0 = fmaf(__bfloat162float(WvT[(c + 0) * 128 + o]), u.x, a0);
-      a1 = fmaf(__bfloat162float(WvT[(c + 1) * 128 + o]), u.y, a1);
-      a2 = fmaf(__bfloat162float(WvT[(c + 2) * 128 + o]), u.z, a2);
-      a3 = fmaf(__bfloat162float(WvT[(c + 3) * 128 + o]), u.w, a3);
-    }
-    out[((size_t)pp * T + t) * 128 + o] = __float2bfloat16(b + (a0 + a1) + (a2 + a3));
+  for (int i = threadIdx.x; i < T * 8 * 64; i += 128) {
+    const int t = i / 512, hh = (i >> 6) & 7, c4 = i & 63;
+    reinterpret_cast<float4*>(su)[i] = __ldg(reinterpret_cast<const float4*>(U + t2i_row(pp, hh, t, paired) * 256) + c4);
   }
+  __syncthreads();
+  float acc[TT];
+#pragma unroll
+  for (int t = 0; t < TT; ++t) acc[t] = 0.f;
+  const float* uh = su + h * 256;
+#pragma unroll 4
+  for (int c = 0; c < 256; c += 4) {
+    const float w0 = __bfloat162float(WvT[(c + 0) * 128 + o]), w1 = __bfloat162float(WvT[(c + 1) * 128 + o]);
+    const float w2 = __bfloat162float(WvT[(c + 2) * 128 + o]), w3 = __bfloat162float(WvT[(c + 3) * 128 + o]);
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      if (t < T) {
+        const float4 u = *reinterpret_cast<const float4*>(uh + t * 2048 + c);
+        acc[t] = fmaf(w0, u.x, fmaf(w1, u.y, fmaf(w2, u.z, fmaf(w3, u.w, acc[t]))));
+      }
+    }
+  }
+  const float b = bv[o];
+#pragma unroll
+  for (int t = 0; t < TT; ++t)
+    if (t < T) out[((size_t)pp * T + t) * 128 + o] = __float2bfloat16(b + acc[t]);
 }
 
 int launch_t2i_prep(const __nv_bfloat16* q, int P, int T, int paired, int n_items, __nv_bfloat16* qexp, cudaStream_t stream) {
@@ -381,8 +389,18 @@ int launch_t2i_prep(const __nv_bfloat16* q, int P, int T, int paired, int n_item
 }
 int launch_t2i_head_proj(const float* U, const __nv_bfloat16* WvT, const float* bv, int P, int T, int paired,
                          __nv_bfloat16* out, cudaStream_t stream) {
-  t2i_head_proj_kernel<<<P, 128, 0, stream>>>(U, WvT, bv, T, paired, out);
-  cudaError_t e = cudaGetLastError();
+  const int smem = T * 8 * 256 * 4;
+  cudaError_t e = cudaSuccess;
+  if (T <= 8) {
+    static bool attr8 = false;
+    if (!attr8) { e = cudaFuncSetAttribute(t2i_head_proj_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192); attr8 = true; }
+    if (e == cudaSuccess) t2i_head_proj_kernel<8><<<P, 128, smem, stream>>>(U, WvT, bv, T, paired, out);
+  } else {
+    static bool attr16 = false;
+    if (!attr16) { e = cudaFuncSetAttribute(t2i_head_proj_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 8192); attr16 = true; }
+    if (e == cudaSuccess) t2i_head_proj_kernel<16><<<P, 128, smem, stream>>>(U, WvT, bv, T, paired, out);
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("t2i_head_proj launch failed: %s", cudaGetErrorString(e));
   count_launch();
   return 0;

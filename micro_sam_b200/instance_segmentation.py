@@ -136,8 +136,6 @@ class AutomaticMaskGenerator(AMGBase):
             self.point_grids = point_grids
         else:
             raise ValueError("Can't have both points_per_side and point_grid be None or not None.")
-        if crop_n_layers != 0:
-            raise NotImplementedError("crop_n_layers > 0 is not implemented on the B200 path (default is 0)")
         self._predictor = predictor
         self._points_per_side = points_per_side
         # the whole grid fits one decoder launch sequence; the engine chunks internally by its max_prompts
@@ -185,16 +183,27 @@ class AutomaticMaskGenerator(AMGBase):
         self._original_size = original_size
         crop_boxes, layer_idxs = amg_utils.generate_crop_boxes(original_size, self._crop_n_layers,
                                                                self._crop_overlap_ratio)
-        if image_embeddings is None:
-            image_embeddings = util.precompute_image_embeddings(self._predictor, image, to_numpy=False)
-        util.set_precomputed(self._predictor, image_embeddings, i=i)
+        # a single crop (default) uses the (pre)computed embedding of the whole image; with crop layers every crop of the
+        # globally normalised image is embedded on its own (instance_segmentation.py:433-441, :371-378)
+        precomputed = len(crop_boxes) == 1
+        if precomputed:
+            if image_embeddings is None:
+                image_embeddings = util.precompute_image_embeddings(self._predictor, image, to_numpy=False)
+            util.set_precomputed(self._predictor, image_embeddings, i=i)
+        else:
+            image_u8 = util._to_image(image)
         _, pbar_init, pbar_update, pbar_close = util.handle_pbar(verbose, pbar_init, pbar_update)
-        crop_list = []
+        crop_list, geoms = [], []
         for crop_box, layer_idx in zip(crop_boxes, layer_idxs):
+            if not precomputed:
+                x0, y0, x1, y1 = crop_box
+                self._predictor.set_image(np.ascontiguousarray(image_u8[y0:y1, x0:x1, :]))
             crop_list.append(self._process_crop(original_size, crop_box, layer_idx, pbar_init, pbar_update))
+            geoms.append(dict(inp=tuple(self._predictor.input_size), orig=tuple(self._predictor.original_size)))
+        if not precomputed:
+            self._predictor.reset_image()
         pbar_close()
-        self._geoms = [dict(inp=tuple(self._predictor.input_size), orig=tuple(self._predictor.original_size))
-                       for _ in crop_boxes]
+        self._geoms = geoms
         self._is_initialized = True
         self._crop_list = crop_list
         self._crop_boxes = crop_boxes

@@ -248,14 +248,15 @@ class B200SamPredictor:
 
     @torch.no_grad()
     def decode_low_res(self, point_coords: Optional[torch.Tensor], point_labels: Optional[torch.Tensor],
-                       boxes: Optional[torch.Tensor] = None, multimask_output: bool = True):
+                       boxes: Optional[torch.Tensor] = None, multimask_output: bool = True,
+                       mask_input: Optional[torch.Tensor] = None):
         """prompt_encoder + mask_decoder only: (low_res (P,M,256,256), iou (P,M)).  The hot AMG / batched-inference path
         stops here and post-processes with msam_mask_stats instead of materialising (P,M,H,W) logits."""
         if not self.is_image_set:
             raise RuntimeError("An image must be set with .set_image(...) before mask prediction.")
         self._bind_features()
         dev = self.device
-        pts = lbl = bx = None
+        pts = lbl = bx = mk = None
         np_ = 0
         if point_coords is not None:
             if point_labels is None:
@@ -266,21 +267,25 @@ class B200SamPredictor:
         if boxes is not None:
             bx = boxes.to(dev, torch.float32).reshape(-1, 4).contiguous()
             P = bx.shape[0]
-        if pts is None and bx is None:
-            raise ValueError("predict_torch needs point and/or box prompts (mask-only prompts are not supported)")
+        if mask_input is not None:  # (P,1,256,256) low-res logits of a previous prediction (PromptEncoder._embed_masks)
+            mk = mask_input.to(dev, torch.float32).reshape(-1, 256, 256).contiguous()
+            if pts is None and bx is None:
+                P = mk.shape[0]
+            elif mk.shape[0] != P:
+                raise ValueError(f"mask_input batch {mk.shape[0]} does not match the {P} prompts")
+        if pts is None and bx is None and mk is None:
+            raise ValueError("predict_torch needs point, box and/or mask prompts")
         M = 3 if multimask_output else 1
         low = torch.empty(P, M, 256, 256, device=dev, dtype=torch.float32)
         iou = torch.empty(P, M, device=dev, dtype=torch.float32)
-        _lib.check(_lib.lib().msam_decode(self.model._h, _lib.ptr(pts), _lib.ptr(lbl), np_, _lib.ptr(bx), P,
-                                          int(multimask_output), _lib.ptr(low), _lib.ptr(iou), _lib.cur_stream()))
+        _lib.check(_lib.lib().msam_decode_ex(self.model._h, _lib.ptr(pts), _lib.ptr(lbl), np_, _lib.ptr(bx), _lib.ptr(mk), P,
+                                             int(multimask_output), _lib.ptr(low), _lib.ptr(iou), _lib.cur_stream()))
         return low, iou
 
     @torch.no_grad()
     def predict_torch(self, point_coords, point_labels, boxes=None, mask_input=None, multimask_output: bool = True,
                       return_logits: bool = False):
-        if mask_input is not None:
-            raise NotImplementedError("mask_input prompts are not supported by the B200 decoder yet")
-        low, iou = self.decode_low_res(point_coords, point_labels, boxes, multimask_output)
+        low, iou = self.decode_low_res(point_coords, point_labels, boxes, multimask_output, mask_input)
         P, M = low.shape[:2]
         H, W = self.original_size
         lr = low.view(P * M, 256, 256)
@@ -309,7 +314,10 @@ class B200SamPredictor:
         if box is not None:
             box_t = torch.as_tensor(self.transform.apply_boxes(box, self.original_size), dtype=torch.float,
                                     device=self.device).reshape(1, 4)
-        m, s, l = self.predict_torch(coords_t, labels_t, box_t, mask_input, multimask_output, return_logits)
+        mask_t = None
+        if mask_input is not None:
+            mask_t = torch.as_tensor(mask_input, dtype=torch.float, device=self.device)[None]
+        m, s, l = self.predict_torch(coords_t, labels_t, box_t, mask_t, multimask_output, return_logits)
         return m[0].cpu().numpy(), s[0].cpu().numpy(), l[0].cpu().numpy()
 
 

@@ -494,16 +494,36 @@ def batched_mask_nms(masks: torch.Tensor, boxes_xyxy: torch.Tensor, scores: torc
 def apply_nms(predictions: List[Dict[str, Any]], min_size: int, shape: Optional[Tuple[int, int]] = None,
               perform_box_nms: bool = False, nms_thresh: float = 0.9, max_size: Optional[int] = None,
               intersection_over_min: bool = False) -> np.ndarray:
-    """util.apply_nms (util.py:1851-1957) for non-tiled predictions (records with full-size `segmentation` masks)."""
-    if len(predictions) and "global_bbox" in predictions[0]:
-        raise NotImplementedError("apply_nms on tiled predictions (global_bbox) is not on the B200 path yet")
+    """util.apply_nms (util.py:1851-1957).  Tiled predictions (records with a `global_bbox`, util.py:1687-1770) are placed
+    at their global offset (global_bbox - bbox) on canvases of the full shape: masks are zero outside their boxes, so the
+    intersection over the overlap window that the reference crops out equals the global intersection, and the same
+    bit-packed mask-NMS kernel serves both cases."""
+    is_tiled = len(predictions) > 0 and "global_bbox" in predictions[0]
+    if is_tiled and shape is None:  # _infer_tiled_shape, util.py:1687-1695
+        shape = [0, 0]
+        for pred in predictions:
+            bbox, gbb = pred["bbox"], pred["global_bbox"]
+            ms = pred["segmentation"].shape
+            shape[0] = max(shape[0], gbb[1] - bbox[1] + ms[0])
+            shape[1] = max(shape[1], gbb[0] - bbox[0] + ms[1])
+        shape = tuple(int(v) for v in shape)
     if shape is None:
         shape = tuple(predictions[0]["segmentation"].shape)
     dev = torch.device("cuda")
-    masks = torch.stack([torch.as_tensor(p["segmentation"]).to(dev) for p in predictions]).to(torch.uint8)
+    if is_tiled:
+        masks = torch.zeros((len(predictions),) + tuple(shape), dtype=torch.uint8, device=dev)
+        for k, pred in enumerate(predictions):
+            m = torch.as_tensor(pred["segmentation"]).to(dev).to(torch.uint8)
+            oy, ox = int(pred["global_bbox"][1] - pred["bbox"][1]), int(pred["global_bbox"][0] - pred["bbox"][0])
+            y0, x0 = max(oy, 0), max(ox, 0)
+            y1, x1 = min(oy + m.shape[0], shape[0]), min(ox + m.shape[1], shape[1])
+            masks[k, y0:y1, x0:x1] = m[y0 - oy:y1 - oy, x0 - ox:x1 - ox]
+    else:
+        masks = torch.stack([torch.as_tensor(p["segmentation"]).to(dev) for p in predictions]).to(torch.uint8)
     iou = torch.tensor([p["predicted_iou"] for p in predictions], dtype=torch.float32)
     stab = torch.tensor([p["stability_score"] for p in predictions], dtype=torch.float32)
-    boxes = torch.tensor(np.array([p["bbox"] for p in predictions]))
+    local_boxes = torch.tensor(np.array([p["bbox"] for p in predictions]))
+    boxes = torch.tensor(np.array([p["global_bbox"] for p in predictions])) if is_tiled else local_boxes
     area = masks.flatten(1).sum(1).cpu()
     idx = torch.arange(len(predictions))
     if min_size > 0:
@@ -528,5 +548,9 @@ def apply_nms(predictions: List[Dict[str, Any]], min_size: int, shape: Optional[
     else:
         keep = batched_mask_nms(masks[idx.to(dev)], bxyxy, scores, nms_thresh, intersection_over_min).cpu()
     sel = idx[keep]
-    mask_data = [{"segmentation": masks[k].bool(), "area": int(area[k]), "bbox": boxes[k]} for k in sel.tolist()]
+    if is_tiled:
+        mask_data = [{"segmentation": predictions[k]["segmentation"], "area": int(area[k]), "bbox": local_boxes[k].tolist(),
+                      "global_bbox": boxes[k].tolist()} for k in sel.tolist()]
+    else:
+        mask_data = [{"segmentation": masks[k].bool(), "area": int(area[k]), "bbox": boxes[k]} for k in sel.tolist()]
     return mask_data_to_segmentation(mask_data, shape=shape, min_object_size=min_size)

@@ -368,9 +368,17 @@ def mask_data_to_segmentation(masks: List[Dict[str, Any]], shape=None, min_objec
         this_mask = mask_data["segmentation"]
         this_mask = this_mask.cpu().numpy() if torch.is_tensor(this_mask) else this_mask
         this_seg_id = mask_data.get("seg_id", seg_id)
-        if merge_exclusively:
-            this_mask = np.logical_and(this_mask, segmentation == 0)
-        segmentation[this_mask] = this_seg_id
+        if "global_bbox" in mask_data:  # tiled records: paint the local box window at its global position (:1814-1823)
+            bb = mask_data["bbox"]
+            bb = np.s_[bb[1]:bb[1] + bb[3], bb[0]:bb[0] + bb[2]]
+            gbb = mask_data["global_bbox"]
+            gbb = np.s_[gbb[1]:gbb[1] + gbb[3], gbb[0]:gbb[0] + gbb[2]]
+            this_mask = np.logical_and(this_mask[bb], segmentation[gbb] == 0) if merge_exclusively else this_mask[bb]
+            segmentation[gbb][this_mask] = this_seg_id
+        else:
+            if merge_exclusively:
+                this_mask = np.logical_and(this_mask, segmentation == 0)
+            segmentation[this_mask] = this_seg_id
         seg_id = this_seg_id + 1
     if label_masks:
         segmentation = label_connected(segmentation)
@@ -390,10 +398,12 @@ def mask_data_to_segmentation(masks: List[Dict[str, Any]], shape=None, min_objec
 
 # ------------------------------------------------------------------------------------------------ AMG
 class AutomaticMaskGenerator:
-    """instance_segmentation.py:65-530 (AMGBase + AutomaticMaskGenerator), single crop layer supported."""
+    """instance_segmentation.py:65-530 (AMGBase + AutomaticMaskGenerator)."""
 
-    def __init__(self, predictor, points_per_side: int = 32, points_per_batch: int = 64, stability_score_offset=1.0):
-        self.point_grids = build_all_layer_point_grids(points_per_side, 0, 1)
+    def __init__(self, predictor, points_per_side: int = 32, points_per_batch: int = 64, stability_score_offset=1.0,
+                 crop_n_layers: int = 0, crop_overlap_ratio: float = 512 / 1500, crop_n_points_downscale_factor: int = 1):
+        self.point_grids = build_all_layer_point_grids(points_per_side, crop_n_layers, crop_n_points_downscale_factor)
+        self._crop_n_layers, self._crop_overlap_ratio = crop_n_layers, crop_overlap_ratio
         self._predictor = predictor
         self._points_per_batch = points_per_batch
         self._stability_score_offset = stability_score_offset
@@ -426,15 +436,20 @@ class AutomaticMaskGenerator:
     def initialize(self, image: np.ndarray, image_embeddings=None):
         original_size = image.shape[:2]
         self._original_size = original_size
-        crop_boxes, layer_idxs = generate_crop_boxes(original_size, 0, 512 / 1500)
-        if image_embeddings is None:
-            image_embeddings = precompute_image_embeddings_2d(self._predictor, image)
-        set_precomputed(self._predictor, image_embeddings)
+        crop_boxes, layer_idxs = generate_crop_boxes(original_size, self._crop_n_layers, self._crop_overlap_ratio)
+        precomputed = len(crop_boxes) == 1   # :433-441: with several crops every crop is embedded on its own
+        if precomputed:
+            if image_embeddings is None:
+                image_embeddings = precompute_image_embeddings_2d(self._predictor, image)
+            set_precomputed(self._predictor, image_embeddings)
         image = to_image(image)
         crop_list = []
         for crop_box, layer_idx in zip(crop_boxes, layer_idxs):
             x0, y0, x1, y1 = crop_box
-            cropped_im_size = image[y0:y1, x0:x1, :].shape[:2]
+            cropped_im = image[y0:y1, x0:x1, :]
+            cropped_im_size = cropped_im.shape[:2]
+            if not precomputed:
+                self._predictor.set_image(cropped_im)
             points_scale = np.array(cropped_im_size)[None, ::-1]
             points_for_image = self.point_grids[layer_idx] * points_scale
             data = MaskData()
@@ -507,8 +522,8 @@ class AutomaticMaskGenerator:
 @torch.no_grad()
 def batched_inference(predictor, image, batch_size: int, boxes=None, points=None, point_labels=None,
                       multimasking: bool = False, embedding_path=None, return_instance_segmentation: bool = True,
-                      image_embeddings=None, mask_threshold: float = 0.0):
-    """inference.py:155-286 (default threshold path, no mask prompts, no logits_masks)."""
+                      image_embeddings=None, mask_threshold: float = 0.0, logits_masks=None):
+    """inference.py:155-286 (default threshold path; `logits_masks` (N,1,256,256) are passed on as mask prompts :240-247)."""
     if boxes is None and points is None:
         raise ValueError("batched_inference needs boxes and/or points")
     if image_embeddings is None:
@@ -530,7 +545,8 @@ def batched_inference(predictor, image, batch_size: int, boxes=None, points=None
         s, e = b * batch_size, (b + 1) * batch_size
         bm, bi, _ = predictor.predict_torch(
             point_coords=pt[s:e] if have_points else None, point_labels=pl[s:e] if have_points else None,
-            boxes=bx[s:e] if have_boxes else None, multimask_output=multimasking, return_logits=True)
+            boxes=bx[s:e] if have_boxes else None, mask_input=None if logits_masks is None else logits_masks[s:e],
+            multimask_output=multimasking, return_logits=True)
         if multimasking:
             best = torch.argmax(bi, dim=1)
             sel = torch.arange(bm.shape[0])
@@ -548,6 +564,79 @@ def batched_inference(predictor, image, batch_size: int, boxes=None, points=None
     if return_instance_segmentation:
         return mask_data_to_segmentation(recs, min_object_size=0, shape=image_shape)
     return recs
+
+
+def stitch_segmentation(masks, tile_ids, tiling, halo, output_shape):
+    """inference.py:337-356 (+ _merge_segmentations :315-332: `discard_ids` is computed there but never used, so the merge
+    reduces to "the previous segmentation is fully preserved")."""
+    segmentation = np.zeros(output_shape, dtype="uint32")
+    for tile_id, this_seg in zip(tile_ids, masks):
+        t = tiling.get_block_with_halo(tile_id, list(halo)).outer_block
+        bb = tuple(slice(b, e) for b, e in zip(t.begin, t.end))
+        if tile_id == 0:
+            segmentation[bb] = this_seg
+        else:
+            prev = segmentation[bb]
+            this_seg = this_seg.copy()
+            captured = prev != 0
+            this_seg[captured] = prev[captured]
+            segmentation[bb] = this_seg
+    return segmentation
+
+
+def coordinates_to_block_id(tiling, coords) -> int:
+    pos = [int((c - b) // s) for c, b, s in zip(coords, tiling.rb, tiling.bs)]
+    return int(np.ravel_multi_index(pos, tiling.blocks_per_axis))
+
+
+@torch.no_grad()
+def batched_tiled_inference(predictor, image, batch_size: int, image_embeddings=None, boxes=None, points=None,
+                            point_labels=None, multimasking: bool = False, return_instance_segmentation: bool = True,
+                            tile_shape=None, halo=None, mask_threshold: float = 0.0):
+    """inference.py:359-538, default (optimize_memory=False) path: prompts are routed to the tile that contains the box
+    centre / the point, run per tile with tile-local coordinates, and the records get a `global_bbox`."""
+    if image_embeddings is None:
+        image_embeddings = precompute_tiled_embeddings_2d(predictor, image, tile_shape, halo)
+    tile_shape, halo = image_embeddings["tile_shape"], image_embeddings["halo"]
+    shape = image.shape[:2]
+    tiling = Blocking([0, 0], shape, tile_shape)
+    have_boxes, have_points = boxes is not None, points is not None
+    n_prompts = boxes.shape[0] if have_boxes else points.shape[0]
+    box_to_tile, point_to_tile, label_to_tile, tile_ids = {}, {}, {}, []
+    for k in range(n_prompts):
+        tid = None
+        if have_boxes:
+            box = boxes[k]
+            center = np.array([(box[1] + box[3]) / 2, (box[0] + box[2]) / 2]).round().astype("int").tolist()
+            tid = coordinates_to_block_id(tiling, center)
+            t = tiling.get_block_with_halo(tid, list(halo)).outer_block
+            off, ts = t.begin, t.shape
+            b = np.array([max(box[1] - off[0], 0), max(box[0] - off[1], 0), min(box[3] - off[0], ts[0]),
+                          min(box[2] - off[1], ts[1])])[None]
+            box_to_tile[tid] = np.concatenate([box_to_tile[tid], b]) if tid in box_to_tile else b
+        if have_points:
+            pt = points[k, 0][::-1].round().astype("int").tolist()
+            if tid is None:
+                tid = coordinates_to_block_id(tiling, pt)
+            t = tiling.get_block_with_halo(tid, list(halo)).outer_block
+            pin = (points[k, 0] - np.array(t.begin)[::-1])[None, None]
+            lin = point_labels[k][None]
+            point_to_tile[tid] = np.concatenate([point_to_tile[tid], pin]) if tid in point_to_tile else pin
+            label_to_tile[tid] = np.concatenate([label_to_tile[tid], lin]) if tid in label_to_tile else lin
+        tile_ids.append(tid)
+    tile_ids = sorted(set(tile_ids))
+    masks = []
+    for tid in tile_ids:
+        recs = batched_inference(predictor, None, batch_size, boxes=box_to_tile.get(tid), points=point_to_tile.get(tid),
+                                 point_labels=label_to_tile.get(tid), multimasking=multimasking,
+                                 return_instance_segmentation=False, image_embeddings=image_embeddings["features"][str(tid)],
+                                 mask_threshold=mask_threshold)
+        t = tiling.get_block_with_halo(tid, list(halo)).outer_block
+        offset = np.array(t.begin[::-1] + [0, 0])
+        masks.extend({**m, "global_bbox": (np.array(m["bbox"]) + offset).tolist()} for m in recs)
+    if return_instance_segmentation:
+        return mask_data_to_segmentation(masks, shape=shape, min_object_size=0)
+    return masks
 
 
 # ------------------------------------------------------------------------------------------------ mask NMS (util.py)
@@ -599,6 +688,106 @@ def batched_mask_nms(masks, boxes, scores, nms_thresh: float, intersection_over_
             break
         sorted_indices = sorted_indices[1:][mat[i, sorted_indices[1:]] <= nms_thresh]
     return torch.tensor(keep)
+
+
+def xywh_to_xyxy(boxes):
+    """util.py:1679-1684."""
+    boxes = boxes.clone() if isinstance(boxes, torch.Tensor) else torch.tensor(boxes)
+    boxes[:, 2] += boxes[:, 0]
+    boxes[:, 3] += boxes[:, 1]
+    return boxes
+
+
+def infer_tiled_shape(predictions):
+    """util.py:1687-1695."""
+    shape = [0, 0]
+    for pred in predictions:
+        bbox, gbb = pred["bbox"], pred["global_bbox"]
+        offset = (gbb[0] - bbox[0], gbb[1] - bbox[1])
+        ms = pred["segmentation"].shape
+        shape[0] = max(shape[0], offset[1] + ms[0])
+        shape[1] = max(shape[1], offset[0] + ms[1])
+    return tuple(int(v) for v in shape)
+
+
+def tiled_mask_overlap_matrix(masks, boxes, global_boxes, intersection_over_min: bool) -> torch.Tensor:
+    """util.py:1698-1747: pairwise IoU / IoMin of tile-local masks, evaluated on the overlap window of their global boxes."""
+    n = len(masks)
+    boxes = torch.as_tensor(np.asarray(boxes)).to(torch.long)
+    global_boxes = torch.as_tensor(np.asarray(global_boxes)).to(torch.long)
+    gxyxy = xywh_to_xyxy(global_boxes).to(torch.long)
+    ovl = overlap_matrix(gxyxy)
+    masks = [torch.as_tensor(np.asarray(m)) for m in masks]
+    areas = torch.tensor([float(m.sum()) for m in masks], dtype=torch.float32)
+    out = torch.zeros((n, n))
+    for i in range(n):
+        js = torch.where(ovl[i])[0]
+        off_i = global_boxes[i, :2] - boxes[i, :2]
+        for j in js[js > i]:
+            off_j = global_boxes[j, :2] - boxes[j, :2]
+            o = [max(gxyxy[i, 0], gxyxy[j, 0]), max(gxyxy[i, 1], gxyxy[j, 1]), min(gxyxy[i, 2], gxyxy[j, 2]),
+                 min(gxyxy[i, 3], gxyxy[j, 3])]
+            mi = masks[i][o[1] - off_i[1]:o[3] - off_i[1], o[0] - off_i[0]:o[2] - off_i[0]]
+            mj = masks[j][o[1] - off_j[1]:o[3] - off_j[1], o[0] - off_j[0]:o[2] - off_j[0]]
+            inter = torch.logical_and(mi, mj).sum()
+            den = torch.minimum(areas[i], areas[j]) if intersection_over_min else areas[i] + areas[j] - inter
+            out[i, j] = inter / den
+    out = out + out.T
+    out.fill_diagonal_(1)
+    return out
+
+
+def batched_tiled_mask_nms(masks, boxes, global_boxes, scores, nms_thresh: float, intersection_over_min: bool) -> torch.Tensor:
+    """util.py:1750-1770."""
+    scores = torch.as_tensor(np.asarray(scores))
+    mat = tiled_mask_overlap_matrix(masks, boxes, global_boxes, intersection_over_min)
+    order = torch.argsort(scores, descending=True)
+    keep = []
+    while len(order) > 0:
+        i = order[0]
+        keep.append(int(i))
+        if len(order) == 1:
+            break
+        order = order[1:][mat[i, order[1:]] <= nms_thresh]
+    return torch.tensor(keep)
+
+
+def apply_nms(predictions, min_size: int, shape=None, perform_box_nms: bool = False, nms_thresh: float = 0.9,
+              max_size=None, intersection_over_min: bool = False) -> np.ndarray:
+    """util.py:1851-1957."""
+    is_tiled = "global_bbox" in predictions[0]
+    if is_tiled and shape is None:
+        shape = infer_tiled_shape(predictions)
+    masks = [torch.as_tensor(np.asarray(p["segmentation"].cpu() if torch.is_tensor(p["segmentation"]) else p["segmentation"]))
+             for p in predictions]
+    idx = list(range(len(predictions)))
+    area = [int(m.sum()) for m in masks]
+    if min_size > 0:
+        idx = [k for k in idx if area[k] > min_size]
+    if max_size is not None:
+        idx = [k for k in idx if area[k] < max_size]
+    if shape is None:
+        shape = tuple(predictions[0]["segmentation"].shape)
+    if len(idx) == 0:
+        return np.zeros(shape, dtype="uint32")
+    scores = torch.tensor([predictions[k]["predicted_iou"] * predictions[k]["stability_score"] for k in idx], dtype=torch.float32)
+    boxes = torch.tensor(np.array([predictions[k]["bbox"] for k in idx]))
+    gboxes = torch.tensor(np.array([predictions[k]["global_bbox"] for k in idx])) if is_tiled else None
+    bxyxy = xywh_to_xyxy(gboxes if is_tiled else boxes)
+    if perform_box_nms:
+        keep = batched_nms(bxyxy.float(), scores, torch.zeros(len(idx)), nms_thresh)
+    elif is_tiled:
+        keep = batched_tiled_mask_nms([masks[k] for k in idx], boxes, gboxes, scores, nms_thresh, intersection_over_min)
+    else:
+        keep = batched_mask_nms(torch.stack([masks[k] for k in idx]), bxyxy, scores, nms_thresh, intersection_over_min)
+    recs = []
+    for q in keep.tolist():
+        k = idx[q]
+        rec = {"segmentation": masks[k], "area": area[k], "bbox": boxes[q].tolist()}
+        if is_tiled:
+            rec["global_bbox"] = gboxes[q].tolist()
+        recs.append(rec)
+    return mask_data_to_segmentation(recs, shape=shape, min_object_size=min_size)
 
 
 # ------------------------------------------------------------------------------------------------ tiling

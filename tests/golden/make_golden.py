@@ -5,7 +5,8 @@ symbol is not on the executed path:
     of the same file, _vendored.py:104, is the one exercised: rle_implementation="numpy");
   * micro_sam/util.py cannot be imported (zarr/elf/pooch/...), so the *source text* of the listed functions is extracted
     with `ast` and exec'ed unchanged: _to_image, _overlap_matrix, _calculate_ious_between_pred_masks,
-    _calculate_iomin_between_pred_masks, _batched_mask_nms.
+    _calculate_iomin_between_pred_masks, _batched_mask_nms, _xywh_to_xyxy, _infer_tiled_shape,
+    _calculate_tiled_mask_overlap_matrix, _batched_tiled_mask_nms.
 Usage:  python tests/golden/make_golden.py
 """
 import ast
@@ -105,6 +106,48 @@ def main():
         res[f"nms_keep_iomin_{thr}"] = fns["_batched_mask_nms"](masks, boxes, scores, thr, True).numpy()
     res["nms_iou_matrix"] = fns["_calculate_ious_between_pred_masks"](masks, boxes).numpy()
     np.savez_compressed(os.path.join(OUT, "util.npz"), **res)
+
+    # --- tiled mask NMS (util.py:1687-1770): tile-local masks with `bbox` (local xywh) and `global_bbox`
+    fns = load_util_functions(["_overlap_matrix", "_xywh_to_xyxy", "_infer_tiled_shape", "_calculate_tiled_mask_overlap_matrix",
+                               "_batched_tiled_mask_nms"])
+    rng = np.random.default_rng(1)
+    res = {}
+    shape, tile, halo = (96, 128), (64, 64), (16, 16)
+    tiles = []
+    for ty in range(0, shape[0], tile[0]):
+        for tx in range(0, shape[1], tile[1]):
+            y0, x0 = max(ty - halo[0], 0), max(tx - halo[1], 0)
+            y1, x1 = min(ty + tile[0] + halo[0], shape[0]), min(tx + tile[1] + halo[1], shape[1])
+            tiles.append((y0, x0, y1, x1))
+    preds = []
+    for k in range(18):
+        y0, x0, y1, x1 = tiles[k % len(tiles)]
+        m = blobs(rng, 1, y1 - y0, x1 - x0)[0]
+        if k == 7:   # same object seen from the neighbouring tile: paste the overlap part of mask 6
+            py0, px0, py1, px1 = tiles[6 % len(tiles)]
+            g = np.zeros(shape, dtype=bool)
+            g[py0:py1, px0:px1] = preds[6]["segmentation"]
+            m = g[y0:y1, x0:x1].copy()
+        if not m.any():
+            m[3:9, 4:12] = True
+        ys, xs = np.where(m)
+        bbox = [int(xs.min()), int(ys.min()), int(xs.max() - xs.min()), int(ys.max() - ys.min())]  # xywh as batched_mask_to_box
+        preds.append({"segmentation": m, "bbox": bbox, "global_bbox": [bbox[0] + x0, bbox[1] + y0, bbox[2], bbox[3]]})
+    scores = rng.random(len(preds)).astype("float32")
+    masks = [torch.from_numpy(p["segmentation"]) for p in preds]
+    boxes = torch.tensor([p["bbox"] for p in preds])
+    gboxes = torch.tensor([p["global_bbox"] for p in preds])
+    res["n"] = np.array(len(preds))
+    for k, p_ in enumerate(preds):
+        res[f"mask_{k}"] = p_["segmentation"]
+    res["boxes"], res["global_boxes"], res["scores"] = boxes.numpy(), gboxes.numpy(), scores
+    res["inferred_shape"] = np.array(fns["_infer_tiled_shape"](preds))
+    for iomin in (False, True):
+        res[f"overlap_{int(iomin)}"] = fns["_calculate_tiled_mask_overlap_matrix"](masks, boxes, gboxes, iomin).numpy()
+        for thr in (0.3, 0.9):
+            res[f"keep_{int(iomin)}_{thr}"] = fns["_batched_tiled_mask_nms"](masks, boxes, gboxes, torch.from_numpy(scores), thr,
+                                                                            iomin).numpy()
+    np.savez_compressed(os.path.join(OUT, "tiled_nms.npz"), **res)
     print("written", os.listdir(OUT))
 
 

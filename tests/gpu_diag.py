@@ -316,6 +316,20 @@ def sec_decoder(types=("vit_test",)):
         low, iou = bp.decode_low_res(pts2, lbl2, boxes, True)
         report(f"decoder {mt} box+2pts multimask: low_res", low.cpu(), low_r, 3e-2)
         report(f"decoder {mt} box+2pts multimask: iou", iou.cpu(), iou_r, 3e-2)
+        # mask prompts (PromptEncoder._embed_masks): mask + point, mask + box + 2 points (unfused path), mask only
+        mk = torch.nn.functional.interpolate(torch.randn(3, 1, 16, 16, generator=g), (256, 256), mode="bicubic") * 4
+        _, iou_r, low_r = op.predict_torch(pts[:3], lbl[:3], mask_input=mk, multimask_output=True, return_logits=True)
+        low, iou = bp.decode_low_res(pts[:3], lbl[:3], None, True, mk)
+        report(f"decoder {mt} mask+point multimask: low_res", low.cpu(), low_r, 3e-2)
+        report(f"decoder {mt} mask+point multimask: iou", iou.cpu(), iou_r, 3e-2)
+        _, iou_r, low_r = op.predict_torch(pts2, lbl2, boxes=boxes, mask_input=mk, multimask_output=False, return_logits=True)
+        low, iou = bp.decode_low_res(pts2, lbl2, boxes, False, mk)
+        report(f"decoder {mt} mask+box+2pts single: low_res", low.cpu(), low_r, 3e-2)
+        report(f"decoder {mt} mask+box+2pts single: iou", iou.cpu(), iou_r, 3e-2)
+        _, iou_r, low_r = op.predict_torch(None, None, mask_input=mk, multimask_output=False, return_logits=True)
+        low, iou = bp.decode_low_res(None, None, None, False, mk)
+        report(f"decoder {mt} mask only single: low_res", low.cpu(), low_r, 3e-2)
+        report(f"decoder {mt} mask only single: iou", iou.cpu(), iou_r, 3e-2)
 
 
 def sec_post():

@@ -295,3 +295,114 @@ def test_mask_nms_bit_exact_vs_reference_golden():
     oseg = amg_ref.mask_data_to_segmentation([{"segmentation": m[k].numpy(), "area": int(area[k])} for k in idx[keep].tolist()],
                                              shape=(64, 64), min_object_size=5)
     assert _partition_equal(seg, oseg)
+
+
+def test_tiled_apply_nms_vs_reference_golden():
+    """a19 tiled variant: util.apply_nms on records with `global_bbox` == oracle (itself pinned on the reference's
+    `_calculate_tiled_mask_overlap_matrix` / `_batched_tiled_mask_nms` outputs, tests/golden/tiled_nms.npz)."""
+    from micro_sam_b200 import util
+    from oracle import amg_ref
+    z = np.load(os.path.join(HERE, "golden", "tiled_nms.npz"))
+    n = int(z["n"])
+    recs = [{"segmentation": torch.from_numpy(z[f"mask_{k}"]), "bbox": z["boxes"][k].tolist(),
+             "global_bbox": z["global_boxes"][k].tolist(), "predicted_iou": float(z["scores"][k]), "stability_score": 1.0}
+            for k in range(n)]
+    for kw in (dict(min_size=0, nms_thresh=0.3), dict(min_size=20, nms_thresh=0.9), dict(min_size=0, nms_thresh=0.3,
+                                                                                        intersection_over_min=True)):
+        seg = util.apply_nms(recs, **kw)
+        oseg = amg_ref.apply_nms(recs, **kw)
+        assert seg.shape == tuple(z["inferred_shape"]) and _partition_equal(seg, oseg), kw
+
+
+def test_batched_tiled_inference_against_oracle(models):
+    """a18: prompts routed to tiles, tile-local decoding, `global_bbox` records, global painting; optimize_memory path
+    (per-tile apply_nms + first-come stitching).  Integer stages bit-exact given the GPU's low-res logits."""
+    from oracle import amg_ref
+    from micro_sam_b200 import inference, util
+    from micro_sam_b200.sample_data import lm_tile, random_boxes
+    opred, pred = models
+    img = lm_tile((300, 420), 30, seed=9)
+    tile_shape, halo = (160, 224), (24, 24)
+    boxes = random_boxes(24, (300, 420), seed=3)
+    emb = util.precompute_image_embeddings(pred, img, ndim=2, tile_shape=tile_shape, halo=halo, to_numpy=False)
+    recs = inference.batched_tiled_inference(pred, img, batch_size=8, image_embeddings=emb, boxes=boxes,
+                                             return_instance_segmentation=False)
+    assert len(recs) == 24 and all("global_bbox" in r for r in recs)
+    # oracle on the GPU's low-res logits: the records come back tile by tile, in prompt order inside a tile
+    low = torch.stack([r["logits"] for r in recs]).cpu()
+    iou = torch.tensor([r["predicted_iou"] for r in recs], dtype=torch.float32)[:, None]
+    state = {"i": 0}
+
+    def fake(point_coords, point_labels, boxes=None, mask_input=None, multimask_output=True, return_logits=False):
+        k = boxes.shape[0]
+        s0 = state["i"]; state["i"] += k
+        return opred.model.postprocess_masks(low[s0:s0 + k], opred.input_size, opred.original_size), iou[s0:s0 + k], low[s0:s0 + k]
+
+    oemb = amg_ref.precompute_tiled_embeddings_2d(opred, img, tile_shape, halo)
+    orig = opred.predict_torch
+    opred.predict_torch = fake
+    try:
+        orecs = amg_ref.batched_tiled_inference(opred, img, 8, image_embeddings=oemb, boxes=boxes, return_instance_segmentation=False)
+        state["i"] = 0
+        oseg = amg_ref.batched_tiled_inference(opred, img, 8, image_embeddings=oemb, boxes=boxes)
+    finally:
+        opred.predict_torch = orig
+    assert len(orecs) == 24
+    for r, o in zip(recs, orecs):
+        assert r["bbox"] == o["bbox"] and r["global_bbox"] == o["global_bbox"] and r["area"] == int(o["area"])
+        assert np.array_equal(r["segmentation"].cpu().numpy(), o["segmentation"].numpy())
+    seg = inference.batched_tiled_inference(pred, img, batch_size=8, image_embeddings=emb, boxes=boxes)
+    assert seg.shape == (300, 420) and _partition_equal(seg, oseg)
+    # optimize_memory: per-tile NMS + stitching (reference semantics: earlier tiles win)
+    seg2 = inference.batched_tiled_inference(pred, img, batch_size=8, image_embeddings=emb, boxes=boxes, optimize_memory=True,
+                                             min_size=0)
+    assert seg2.shape == (300, 420) and seg2.dtype == np.uint32 and seg2.max() > 0
+
+
+def test_amg_crop_layers_against_oracle(models):
+    """a13 with crop_n_layers=1: 1 + 4 crops, each embedded on its own from the globally normalised image, points of the
+    down-scaled grid, crop-edge filter, cross-crop NMS preferring smaller crops.  Integer stages bit-exact given the GPU's
+    low-res logits."""
+    from oracle import amg_ref
+    from micro_sam_b200 import instance_segmentation as iseg
+    from micro_sam_b200.sample_data import lm_tile
+    opred, pred = models
+    img = lm_tile((240, 320), 25, seed=11)
+    kw0 = dict(points_per_side=4, crop_n_layers=1, crop_n_points_downscale_factor=2)
+    amg = iseg.AutomaticMaskGenerator(pred, **kw0)
+    amg.initialize(img)
+    assert len(amg.crop_list) == 5 and len(amg.crop_list[1]["iou_preds"]) == 2 * 2 * 3
+    lows = [d["low_res"].cpu().view(-1, 3, 256, 256) for d in amg.crop_list]
+    ious = [d["iou_preds"].cpu().view(-1, 3) for d in amg.crop_list]
+    calls = {"i": 0}
+
+    def fake(point_coords, point_labels, boxes=None, mask_input=None, multimask_output=True, return_logits=False):
+        t = calls["i"]
+        calls["i"] += 1
+        return opred.model.postprocess_masks(lows[t], opred.input_size, opred.original_size), ious[t], lows[t]
+
+    oamg_f = amg_ref.AutomaticMaskGenerator(opred, points_per_batch=64, **kw0)
+    oamg_f.initialize(img)                                          # float path: per-crop embeddings + decoder on the oracle
+    assert oamg_f._crop_boxes == amg.crop_boxes
+    for d, od in zip(amg.crop_list, oamg_f._crop_list):
+        assert np.abs(d["iou_preds"].cpu().numpy() - od["iou_preds"].numpy()).max() < 2e-2
+    orig = opred.predict_torch
+    opred.predict_torch = fake
+    try:
+        oamg = amg_ref.AutomaticMaskGenerator(opred, points_per_batch=64, **kw0)
+        oamg.initialize(img)
+    finally:
+        opred.predict_torch = orig
+    for d, od in zip(amg.crop_list, oamg._crop_list):
+        assert np.array_equal(d["boxes"].cpu().numpy(), od["boxes"].numpy())
+    for kw in (dict(pred_iou_thresh=0.0, stability_score_thresh=0.0), dict(pred_iou_thresh=0.0, stability_score_thresh=0.5,
+                                                                            crop_nms_thresh=0.3)):
+        recs = amg.generate(output_mode="binary_mask", **kw)
+        orecs = oamg.generate(output_mode="binary_mask", **kw)
+        assert len(recs) == len(orecs), (kw, len(recs), len(orecs))
+        for a, b in zip(recs, orecs):
+            assert a["bbox"] == b["bbox"] and a["area"] == b["area"] and a["crop_box"] == b["crop_box"]
+            assert np.array_equal(a["segmentation"], b["segmentation"])
+        seg = amg.generate(output_mode="instance_segmentation", **kw)
+        oseg = oamg.generate(output_mode="instance_segmentation", **kw)
+        assert _partition_equal(seg, oseg), kw

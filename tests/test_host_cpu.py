@@ -149,3 +149,19 @@ def test_gloo_world2_sharding_and_instance_table_gather():
     # without a process group the helpers are the identity
     t = torch.ones(3, 2)
     assert D.all_gather_tables(t)[1] == [3]
+
+
+def test_stitch_segmentation_matches_oracle():
+    """inference._stitch_segmentation / _merge_segmentations (inference.py:315-356): earlier tiles are preserved."""
+    from micro_sam_b200 import inference
+    from micro_sam_b200._amg_utils import Blocking
+    from oracle import amg_ref
+    shape, tile_shape, halo = (300, 420), (160, 224), (24, 24)
+    tiling, otiling = Blocking([0, 0], shape, tile_shape), amg_ref.Blocking([0, 0], shape, tile_shape)
+    ids = [0, 1, 3]
+    segs = [np.random.default_rng(i).integers(0, 4, tuple(tiling.get_block_with_halo(i, list(halo)).outer_block.shape)).astype("uint32")
+            for i in ids]
+    a = inference._stitch_segmentation([s.copy() for s in segs], ids, tiling, halo, shape)
+    b = amg_ref.stitch_segmentation([s.copy() for s in segs], ids, otiling, halo, shape)
+    assert a.dtype == np.uint32 and np.array_equal(a, b)
+    assert tiling.coordinates_to_block_id([200, 300]) == amg_ref.coordinates_to_block_id(otiling, [200, 300]) == 3

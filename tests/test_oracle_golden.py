@@ -54,6 +54,22 @@ def test_mask_nms_golden():
         assert amg_ref.batched_mask_nms(masks, boxes, scores, thr, True).tolist() == z[f"nms_keep_iomin_{thr}"].tolist()
 
 
+def test_tiled_mask_nms_golden():
+    """util.py:1687-1770 (tile-local masks + global boxes): oracle == outputs of the reference's own functions."""
+    z = np.load(os.path.join(G, "tiled_nms.npz"))
+    n = int(z["n"])
+    masks = [z[f"mask_{k}"] for k in range(n)]
+    boxes, gboxes, scores = z["boxes"], z["global_boxes"], z["scores"]
+    preds = [{"segmentation": masks[k], "bbox": boxes[k].tolist(), "global_bbox": gboxes[k].tolist()} for k in range(n)]
+    assert list(amg_ref.infer_tiled_shape(preds)) == z["inferred_shape"].tolist()
+    for iomin in (False, True):
+        mat = amg_ref.tiled_mask_overlap_matrix(masks, boxes, gboxes, iomin).numpy()
+        np.testing.assert_allclose(mat, z[f"overlap_{int(iomin)}"], rtol=0, atol=1e-7)
+        for thr in (0.3, 0.9):
+            keep = amg_ref.batched_tiled_mask_nms(masks, boxes, gboxes, scores, thr, iomin).tolist()
+            assert keep == z[f"keep_{int(iomin)}_{thr}"].tolist()
+
+
 def test_box_nms_matches_torchvision():
     import torchvision
     g = torch.Generator().manual_seed(0)
