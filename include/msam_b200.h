@@ -79,6 +79,26 @@ int msam_decode_ex(msam_handle* h, const float* points, const float* labels, int
  * low_res [n,256,256]; boxes int32 [n,4] xyxy ([0,0,0,0] if empty); stability fp32 [n]; area int32 [n]. */
 int msam_mask_stats(const float* low_res, int n_masks, int in_h, int in_w, int orig_h, int orig_w, float mask_threshold,
                     float stability_offset, int32_t* boxes_xyxy, float* stability, int32_t* area, void* stream);
+/* segment_anything.utils.amg.remove_small_regions for a batch of materialised masks (AMGBase._postprocess_small_regions,
+ * instance_segmentation.py:146-186): masks uint8 [n,h,w] (0/1) are edited in place -- holes != 0: 8-connected background
+ * components smaller than area_thresh are filled; holes == 0: foreground components smaller than area_thresh are removed
+ * (the largest one is kept if all are small).  changed int32 [n]; workspace int32 [n*(2*h*w + 4)]. */
+int msam_remove_small_regions(uint8_t* masks, int n, int h, int w, int area_thresh, int holes, int32_t* changed,
+                              int32_t* workspace, void* stream);
+/* batched_mask_to_box (_vendored.py:33-85) + area for materialised uint8 masks [n,h,w]: boxes int32 [n,4] xyxy. */
+int msam_mask_boxes(const uint8_t* masks, int n, int h, int w, int32_t* boxes_xyxy, int32_t* area, void* stream);
+/* mask_threshold = "auto" (inference._local_otsu_threshold, inference.py:70-134): thresholds[n] = max over the pixels of the
+ * Otsu threshold of the 31x31 window (64 bins) of the min-max normalised low-res logits, mapped back and clamped at 0. */
+int msam_local_otsu_threshold(const float* low_res, int n_masks, float* thresholds, void* stream);
+/* msam_mask_stats / msam_upsample_masks / msam_paint with one threshold per mask (device fp32, indexed by the mask's
+ * position in low_res) instead of the scalar mask_threshold (inference._process_masks_for_batch, inference.py:137-151). */
+int msam_mask_stats_ex(const float* low_res, int n_masks, int in_h, int in_w, int orig_h, int orig_w, const float* thresholds,
+                       float stability_offset, int32_t* boxes_xyxy, float* stability, int32_t* area, void* stream);
+int msam_upsample_masks_ex(const float* low_res, const int32_t* sel, int n_sel, int in_h, int in_w, int orig_h, int orig_w,
+                           const float* thresholds, float* logits, uint8_t* binary, void* stream);
+int msam_paint_ex(const float* low_res, const int32_t* sel, const int32_t* boxes_xyxy, const int32_t* seg_ids, int n_sel,
+                  int in_h, int in_w, int orig_h, int orig_w, const float* thresholds, int exclusive, uint32_t* label,
+                  int ld_label, void* stream);
 /* Sam.postprocess_masks materialised for the selected masks `sel` (int32 [n_sel] device, or NULL = first n_sel):
  * logits fp32 [n_sel,H,W] and/or binary uint8 [n_sel,H,W] (either may be NULL). */
 int msam_upsample_masks(const float* low_res, const int32_t* sel, int n_sel, int in_h, int in_w, int orig_h, int orig_w,

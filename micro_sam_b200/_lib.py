@@ -48,6 +48,15 @@ def lib() -> ctypes.CDLL:
                                      c_void_p]
         L.msam_mask_stats.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p,
                                       c_void_p, c_void_p]
+        L.msam_remove_small_regions.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+        L.msam_mask_boxes.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+        L.msam_local_otsu_threshold.argtypes = [c_void_p, c_int, c_void_p, c_void_p]
+        L.msam_mask_stats_ex.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p,
+                                         c_void_p, c_void_p]
+        L.msam_upsample_masks_ex.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                             c_void_p, c_void_p]
+        L.msam_paint_ex.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                    c_void_p, c_int, c_void_p]
         L.msam_upsample_masks.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
                                           c_void_p, c_void_p]
         L.msam_paint.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int,

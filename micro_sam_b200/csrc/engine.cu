@@ -433,6 +433,37 @@ int msam_upsample_masks(const float* low_res, const int32_t* sel, int n_sel, int
                         float mask_threshold, float* logits, uint8_t* binary, void* stream) {
   return post_upsample(low_res, sel, n_sel, in_h, in_w, orig_h, orig_w, mask_threshold, logits, binary, (cudaStream_t)stream);
 }
+int msam_remove_small_regions(uint8_t* masks, int n, int h, int w, int area_thresh, int holes, int32_t* changed,
+                              int32_t* workspace, void* stream) {
+  if (!masks || !changed || !workspace) return set_error("msam_remove_small_regions: null argument");
+  return post_remove_small_regions(masks, n, h, w, area_thresh, holes, changed, workspace, (cudaStream_t)stream);
+}
+int msam_mask_boxes(const uint8_t* masks, int n, int h, int w, int32_t* boxes_xyxy, int32_t* area, void* stream) {
+  if (!masks || !boxes_xyxy || !area) return set_error("msam_mask_boxes: null argument");
+  return post_mask_boxes(masks, n, h, w, boxes_xyxy, area, (cudaStream_t)stream);
+}
+int msam_local_otsu_threshold(const float* low_res, int n_masks, float* thresholds, void* stream) {
+  if (!low_res || !thresholds) return set_error("msam_local_otsu_threshold: null argument");
+  return post_local_otsu(low_res, n_masks, thresholds, (cudaStream_t)stream);
+}
+int msam_mask_stats_ex(const float* low_res, int n_masks, int in_h, int in_w, int orig_h, int orig_w, const float* thresholds,
+                       float stability_offset, int32_t* boxes_xyxy, float* stability, int32_t* area, void* stream) {
+  if (!thresholds) return set_error("msam_mask_stats_ex: null thresholds");
+  return post_mask_stats(low_res, n_masks, in_h, in_w, orig_h, orig_w, 0.f, fabsf(stability_offset), boxes_xyxy, stability, area,
+                         (cudaStream_t)stream, stability_offset < 0.f, thresholds);
+}
+int msam_upsample_masks_ex(const float* low_res, const int32_t* sel, int n_sel, int in_h, int in_w, int orig_h, int orig_w,
+                           const float* thresholds, float* logits, uint8_t* binary, void* stream) {
+  if (!thresholds) return set_error("msam_upsample_masks_ex: null thresholds");
+  return post_upsample(low_res, sel, n_sel, in_h, in_w, orig_h, orig_w, 0.f, logits, binary, (cudaStream_t)stream, thresholds);
+}
+int msam_paint_ex(const float* low_res, const int32_t* sel, const int32_t* boxes_xyxy, const int32_t* seg_ids, int n_sel,
+                  int in_h, int in_w, int orig_h, int orig_w, const float* thresholds, int exclusive, uint32_t* label,
+                  int ld_label, void* stream) {
+  if (!thresholds) return set_error("msam_paint_ex: null thresholds");
+  return post_paint(low_res, sel, boxes_xyxy, seg_ids, n_sel, in_h, in_w, orig_h, orig_w, 0.f, exclusive, label, ld_label,
+                    (cudaStream_t)stream, thresholds);
+}
 int msam_paint(const float* low_res, const int32_t* sel, const int32_t* boxes_xyxy, const int32_t* seg_ids, int n_sel,
                int in_h, int in_w, int orig_h, int orig_w, float mask_threshold, int exclusive, uint32_t* label,
                int ld_label, void* stream) {

@@ -67,12 +67,18 @@ struct Engine {
 };
 
 // postprocess.cu
+int post_remove_small_regions(uint8_t* masks, int n, int h, int w, int area_thresh, int holes, int32_t* changed, int32_t* ws,
+                              cudaStream_t st);
+int post_mask_boxes(const uint8_t* masks, int n, int h, int w, int32_t* boxes, int32_t* area, cudaStream_t st);
+int post_local_otsu(const float* low_res, int n, float* thr_out, cudaStream_t st);
 int post_mask_stats(const float* low_res, int n, int in_h, int in_w, int out_h, int out_w, float thr, float off,
-                    int32_t* boxes, float* stability, int32_t* area, cudaStream_t st, bool force_generic = false);
+                    int32_t* boxes, float* stability, int32_t* area, cudaStream_t st, bool force_generic = false,
+                    const float* thr_arr = nullptr);
 int post_upsample(const float* low_res, const int32_t* sel, int n_sel, int in_h, int in_w, int out_h, int out_w, float thr,
-                  float* logits, uint8_t* bin, cudaStream_t st);
+                  float* logits, uint8_t* bin, cudaStream_t st, const float* thr_arr = nullptr);
 int post_paint(const float* low_res, const int32_t* sel, const int32_t* boxes, const int32_t* seg_ids, int n_sel, int in_h,
-               int in_w, int out_h, int out_w, float thr, int exclusive, uint32_t* label, int ld_label, cudaStream_t st);
+               int in_w, int out_h, int out_w, float thr, int exclusive, uint32_t* label, int ld_label, cudaStream_t st,
+               const float* thr_arr = nullptr);
 int post_to_image(const void* src, int dtype, int h, int w, int c, uint8_t* out, uint32_t* scratch6, cudaStream_t st);
 int post_paint_min_area(const float* low_res, const int32_t* sel, const int32_t* n_sel, const int32_t* boxes,
                         const int32_t* area, int in_h, int in_w, int out_h, int out_w, float thr, int32_t* label,

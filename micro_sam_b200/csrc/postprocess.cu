@@ -56,9 +56,10 @@ __device__ __forceinline__ float full_res(const float* __restrict__ lr, const Po
 
 // One CTA per mask.  stats: cnt(v > thr+off), cnt(v > thr-off), area = cnt(v > thr), bbox of (v > thr).
 __global__ void __launch_bounds__(256)
-mask_stats_kernel(const float* __restrict__ low_res, PostGeom g, float thr, float off, int32_t* __restrict__ boxes,
-                  float* __restrict__ stability, int32_t* __restrict__ area) {
+mask_stats_kernel(const float* __restrict__ low_res, PostGeom g, float thr, const float* __restrict__ thr_arr, float off,
+                  int32_t* __restrict__ boxes, float* __restrict__ stability, int32_t* __restrict__ area) {
   const long mi = blockIdx.x;
+  if (thr_arr) thr = thr_arr[mi];  // per-mask threshold (mask_threshold="auto", inference.py:137-151)
   const float* lr = low_res + mi * g.lr * g.lr;
   int hi = 0, lo = 0, ar = 0, x0 = 1 << 30, y0 = 1 << 30, x1 = -1, y1 = -1;
   const float t_hi = thr + off, t_lo = thr - off;
@@ -112,9 +113,10 @@ mask_stats_kernel(const float* __restrict__ low_res, PostGeom g, float thr, floa
 // 87 %, 27 instructions per pixel).  Same interp_axis / bilerp arithmetic as the generic kernel: bit-identical results.
 // grid = n_masks, block = 512 (two row ranges x 256 low-res columns).
 __global__ void __launch_bounds__(512)
-mask_stats_x4_kernel(const float* __restrict__ low_res, PostGeom g, float thr, float off, int32_t* __restrict__ boxes,
-                     float* __restrict__ stability, int32_t* __restrict__ area) {
+mask_stats_x4_kernel(const float* __restrict__ low_res, PostGeom g, float thr, const float* __restrict__ thr_arr, float off,
+                     int32_t* __restrict__ boxes, float* __restrict__ stability, int32_t* __restrict__ area) {
   const long mi = blockIdx.x;
+  if (thr_arr) thr = thr_arr[mi];
   const float* lr = low_res + mi * 65536;
   const int j = threadIdx.x & 255, part = threadIdx.x >> 8;
   Interp ix[4];
@@ -248,9 +250,11 @@ mask_stats_x4_kernel(const float* __restrict__ low_res, PostGeom g, float thr, f
 
 // Materialise selected masks: logits (fp32) and/or thresholded (uint8 0/1), each [n_sel, out_h, out_w].
 __global__ void upsample_kernel(const float* __restrict__ low_res, const int32_t* __restrict__ sel, PostGeom g,
-                                float thr, float* __restrict__ logits, uint8_t* __restrict__ bin) {
+                                float thr, const float* __restrict__ thr_arr, float* __restrict__ logits,
+                                uint8_t* __restrict__ bin) {
   const long k = blockIdx.y;
   const long mi = sel ? sel[k] : k;
+  if (thr_arr) thr = thr_arr[mi];
   const float* lr = low_res + mi * g.lr * g.lr;
   const long npx = (long)g.out_h * g.out_w;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long)gridDim.x * blockDim.x) {
@@ -265,7 +269,8 @@ __global__ void upsample_kernel(const float* __restrict__ low_res, const int32_t
 // exclusive = 1: the first mask covering a pixel wins (merge_exclusively=True); 0: the last one wins (AMG).
 __global__ void paint_kernel(const float* __restrict__ low_res, const int32_t* __restrict__ sel,
                              const int32_t* __restrict__ boxes /*xyxy per mask id*/, const int32_t* __restrict__ seg_ids,
-                             int n_sel, PostGeom g, float thr, int exclusive, uint32_t* __restrict__ label, int ld_label) {
+                             int n_sel, PostGeom g, float thr, const float* __restrict__ thr_arr, int exclusive,
+                             uint32_t* __restrict__ label, int ld_label) {
   extern __shared__ int32_t sbox[];  // [n_sel][4]
   for (int i = threadIdx.x; i < n_sel * 4; i += blockDim.x) sbox[i] = boxes[(long)sel[i / 4] * 4 + (i % 4)];
   __syncthreads();
@@ -275,7 +280,7 @@ __global__ void paint_kernel(const float* __restrict__ low_res, const int32_t* _
   for (int k = 0; k < n_sel; ++k) {
     if (x < sbox[4 * k] || x > sbox[4 * k + 2] || y < sbox[4 * k + 1] || y > sbox[4 * k + 3]) continue;
     const float v = full_res(low_res + (long)sel[k] * g.lr * g.lr, g, y, x);
-    if (v > thr) {
+    if (v > (thr_arr ? thr_arr[sel[k]] : thr)) {
       lab = (uint32_t)seg_ids[k];
       if (exclusive) break;
     }
@@ -413,21 +418,22 @@ static int make_geom(int in_h, int in_w, int out_h, int out_w, PostGeom* g) {
 }
 
 int post_mask_stats(const float* low_res, int n, int in_h, int in_w, int out_h, int out_w, float thr, float off,
-                    int32_t* boxes, float* stability, int32_t* area, cudaStream_t st, bool force_generic) {
+                    int32_t* boxes, float* stability, int32_t* area, cudaStream_t st, bool force_generic,
+                    const float* thr_arr) {
   PostGeom g;
   if (make_geom(in_h, in_w, out_h, out_w, &g)) return -1;
   if (n <= 0) return 0;
   if (g.identity2 && in_h == 1024 && in_w == 1024 && !force_generic) {
-    mask_stats_x4_kernel<<<n, 512, 0, st>>>(low_res, g, thr, off, boxes, stability, area);
+    mask_stats_x4_kernel<<<n, 512, 0, st>>>(low_res, g, thr, thr_arr, off, boxes, stability, area);
   } else {
-    mask_stats_kernel<<<n, 256, 0, st>>>(low_res, g, thr, off, boxes, stability, area);
+    mask_stats_kernel<<<n, 256, 0, st>>>(low_res, g, thr, thr_arr, off, boxes, stability, area);
   }
   LAUNCH_CHECK("mask_stats");
   return 0;
 }
 
 int post_upsample(const float* low_res, const int32_t* sel, int n_sel, int in_h, int in_w, int out_h, int out_w, float thr,
-                  float* logits, uint8_t* bin, cudaStream_t st) {
+                  float* logits, uint8_t* bin, cudaStream_t st, const float* thr_arr) {
   PostGeom g;
   if (make_geom(in_h, in_w, out_h, out_w, &g)) return -1;
   if (n_sel <= 0) return 0;
@@ -437,14 +443,15 @@ int post_upsample(const float* low_res, const int32_t* sel, int n_sel, int in_h,
   for (int k0 = 0; k0 < n_sel; k0 += 32768) {  // gridDim.y limit
     const int nk = (n_sel - k0 < 32768) ? n_sel - k0 : 32768;
     upsample_kernel<<<dim3(bx, nk), 256, 0, st>>>(low_res + (sel ? 0 : (long)k0 * 65536), sel ? sel + k0 : nullptr, g, thr,
-                                                  logits ? logits + (long)k0 * npx : nullptr, bin ? bin + (long)k0 * npx : nullptr);
+                                                  thr_arr ? thr_arr + (sel ? 0 : k0) : nullptr, logits ? logits + (long)k0 * npx : nullptr, bin ? bin + (long)k0 * npx : nullptr);
     LAUNCH_CHECK("upsample");
   }
   return 0;
 }
 
 int post_paint(const float* low_res, const int32_t* sel, const int32_t* boxes, const int32_t* seg_ids, int n_sel, int in_h,
-               int in_w, int out_h, int out_w, float thr, int exclusive, uint32_t* label, int ld_label, cudaStream_t st) {
+               int in_w, int out_h, int out_w, float thr, int exclusive, uint32_t* label, int ld_label, cudaStream_t st,
+               const float* thr_arr) {
   PostGeom g;
   if (make_geom(in_h, in_w, out_h, out_w, &g)) return -1;
   if (n_sel <= 0) return 0;
@@ -455,7 +462,7 @@ int post_paint(const float* low_res, const int32_t* sel, const int32_t* boxes, c
     attr = true;
   }
   paint_kernel<<<dim3((out_w + 255) / 256, out_h), 256, (size_t)n_sel * 16, st>>>(low_res, sel, boxes, seg_ids, n_sel, g, thr,
-                                                                                  exclusive, label, ld_label);
+                                                                                  thr_arr, exclusive, label, ld_label);
   LAUNCH_CHECK("paint");
   return 0;
 }
@@ -926,6 +933,260 @@ int post_mask_nms(const uint8_t* masks, int n, int h, int w, const float* boxes_
   }
   matrix_nms_kernel<<<1, 1024, (size_t)npow2 * 8 + n + 16, st>>>(matrix_ws, scores, n, thresh, keep, n_keep);
   LAUNCH_CHECK("matrix_nms");
+  return 0;
+}
+
+}  // namespace msam
+
+// =================================================================================================================
+// mask_threshold = "auto" (inference._local_otsu_threshold, inference.py:70-134): per mask, the maximum over all pixels of
+// the Otsu threshold of the 31x31 window (zero padded in the normalised domain) of the 64-bin quantised low-res logits.
+// One CTA per mask, thread = column; the window histogram slides down the column (31 bins in, 31 out per step) in shared
+// memory ([bin][thread] uint16: conflict free).  Arithmetic mirrors the reference run on the CPU: fp32 everywhere, cumsum
+// accumulated in double and rounded to fp32 per element (ATen's CPU cumsum), first maximal bin on ties, no FMA contraction.
+namespace msam {
+
+__global__ void __launch_bounds__(256)
+local_otsu_kernel(const float* __restrict__ low_res, float* __restrict__ thr_out) {
+  constexpr int N = 256, WIN = 31, PAD = 15, NB = 64;
+  const long mi = blockIdx.x;
+  const float* lr = low_res + mi * N * N;
+  extern __shared__ uint8_t osm[];
+  uint8_t* bins = osm;                                            // [256][256] quantised image
+  unsigned short* hist = reinterpret_cast<unsigned short*>(osm + N * N);  // [64][256]
+  __shared__ float red[2][8];
+  __shared__ int redi[8];
+  const int tid = threadIdx.x;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int i = tid; i < N * N; i += 256) { const float v = lr[i]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+  if ((tid & 31) == 0) { red[0][tid >> 5] = mn; red[1][tid >> 5] = mx; }
+  __syncthreads();
+  mn = red[0][0]; mx = red[1][0];
+  for (int w = 1; w < 8; ++w) { mn = fminf(mn, red[0][w]); mx = fmaxf(mx, red[1][w]); }
+  const float range = fmaxf(__fsub_rn(mx, mn), 1e-6f);
+  for (int i = tid; i < N * N; i += 256) {
+    const float xn = __fdiv_rn(__fsub_rn(lr[i], mn), range);
+    long b = (long)__fmul_rn(xn, 63.0f);
+    b = b < 0 ? 0 : (b > 63 ? 63 : b);
+    bins[i] = (uint8_t)b;
+  }
+  for (int b = 0; b < NB; ++b) hist[b * 256 + tid] = 0;
+  __syncthreads();
+  // this thread's column x: window columns [x-15, x+15]; out-of-image pixels are zeros of the normalised image -> bin 0
+  const int x = tid;
+  const int c0 = x - PAD, c1 = x + PAD;
+  auto add_row = [&](int y, int delta) {
+    if (y < 0 || y >= N) { hist[tid] = (unsigned short)(hist[tid] + delta * WIN); return; }
+    const uint8_t* row = bins + y * N;
+    int npad = 0;
+    for (int c = c0; c <= c1; ++c) {
+      if (c < 0 || c >= N) { ++npad; continue; }
+      const int b = row[c];
+      hist[b * 256 + tid] = (unsigned short)(hist[b * 256 + tid] + delta);
+    }
+    if (npad) hist[tid] = (unsigned short)(hist[tid] + delta * npad);
+  };
+  for (int y = -PAD; y <= PAD; ++y) add_row(y, 1);
+  int tmax = 0;
+  for (int y = 0; y < N; ++y) {
+    // Otsu on the current window (961 samples)
+    double om = 0.0, mu = 0.0;
+    float muT;
+    {
+      double m2 = 0.0;
+      for (int b = 0; b < NB; ++b) {
+        const float p = __fdiv_rn((float)hist[b * 256 + tid], 961.0f);
+        m2 += (double)__fmul_rn(p, (float)b);
+      }
+      muT = (float)m2;
+    }
+    float best = -1.0f;
+    int tb = 0;
+    for (int b = 0; b < NB; ++b) {
+      const float p = __fdiv_rn((float)hist[b * 256 + tid], 961.0f);
+      om += (double)p;
+      mu += (double)__fmul_rn(p, (float)b);
+      const float omega1 = (float)om, muf = (float)mu;
+      const float omega2 = __fsub_rn(1.0f, omega1);
+      const float mu1 = __fdiv_rn(muf, fmaxf(omega1, 1e-6f));
+      const float mu2 = __fdiv_rn(__fsub_rn(muT, muf), fmaxf(omega2, 1e-6f));
+      const float d = __fsub_rn(mu1, mu2);
+      const float sig = __fmul_rn(__fmul_rn(omega1, omega2), __fmul_rn(d, d));
+      if (sig > best) { best = sig; tb = b; }
+    }
+    tmax = max(tmax, tb);
+    if (y + 1 < N) { add_row(y - PAD, -1); add_row(y + 1 + PAD, 1); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+  if ((tid & 31) == 0) redi[tid >> 5] = tmax;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) tmax = max(tmax, redi[w]);
+    const float tn = __fdiv_rn((float)tmax, 63.0f);
+    thr_out[mi] = fmaxf(__fadd_rn(mn, __fmul_rn(tn, range)), 0.0f);
+  }
+}
+
+int post_local_otsu(const float* low_res, int n, float* thr_out, cudaStream_t st) {
+  if (n <= 0) return 0;
+  constexpr int SMEM = 256 * 256 + 64 * 256 * 2;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(local_otsu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    attr = true;
+  }
+  local_otsu_kernel<<<n, 256, SMEM, st>>>(low_res, thr_out);
+  LAUNCH_CHECK("local_otsu");
+  return 0;
+}
+
+}  // namespace msam
+
+// =================================================================================================================
+// min_mask_region_area > 0 (AMGBase._postprocess_small_regions, instance_segmentation.py:146-186; the per-mask work is
+// segment_anything.utils.amg.remove_small_regions: cv2.connectedComponentsWithStats(8-connectivity) on the mask ("islands")
+// or its complement ("holes"), components below `area_thresh` are removed / filled; if every island is small the largest
+// one (first in raster order on ties, like np.argmax over cv2's raster-ordered labels) is kept).  Batched over masks
+// (blockIdx.y), union-find with atomicMin roots as in the label-image CC above, 8-connectivity.
+namespace msam {
+
+__global__ void rsr_init_kernel(const uint8_t* __restrict__ masks, long npix, int holes, int* __restrict__ parent,
+                                int* __restrict__ size) {
+  const long m = blockIdx.y;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const bool working = (masks[m * npix + i] != 0) != (holes != 0);
+  parent[m * npix + i] = working ? (int)i : -1;
+  size[m * npix + i] = 0;
+}
+__global__ void rsr_merge_kernel(int h, int w, int* __restrict__ parent_all) {
+  const long m = blockIdx.y;
+  const long npix = (long)h * w;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  int* parent = parent_all + m * npix;
+  if (parent[i] < 0) return;
+  const int x = (int)(i % w), y = (int)(i / w);
+  if (x + 1 < w && parent[i + 1] >= 0) uf_union(parent, (int)i, (int)i + 1);
+  if (y + 1 < h) {
+    if (parent[i + w] >= 0) uf_union(parent, (int)i, (int)(i + w));
+    if (x + 1 < w && parent[i + w + 1] >= 0) uf_union(parent, (int)i, (int)(i + w + 1));
+    if (x > 0 && parent[i + w - 1] >= 0) uf_union(parent, (int)i, (int)(i + w - 1));
+  }
+}
+__global__ void rsr_flatten_kernel(long npix, int* __restrict__ parent_all, int* __restrict__ size_all) {
+  const long m = blockIdx.y;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  int* parent = parent_all + m * npix;
+  if (parent[i] < 0) return;
+  const int r = uf_find(parent, (int)i);
+  parent[i] = r;
+  atomicAdd(&size_all[m * npix + r], 1);
+}
+// per-mask statistics: st[0] = #small components, st[1] = #large components, best = packed (size, ~root) maximum
+__global__ void rsr_stats_kernel(long npix, const int* __restrict__ parent_all, const int* __restrict__ size_all, int area_thresh,
+                                 int* __restrict__ st, unsigned long long* __restrict__ best) {
+  const long m = blockIdx.y;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  if (parent_all[m * npix + i] != (int)i) return;
+  const int s = size_all[m * npix + i];
+  atomicAdd(&st[2 * m + (s < area_thresh ? 0 : 1)], 1);
+  atomicMax(&best[m], ((unsigned long long)(unsigned)s << 32) | (unsigned)(~(unsigned)i));
+}
+__global__ void rsr_apply_kernel(uint8_t* __restrict__ masks, long npix, int holes, const int* __restrict__ parent_all,
+                                 const int* __restrict__ size_all, int area_thresh, const int* __restrict__ st,
+                                 const unsigned long long* __restrict__ best, int32_t* __restrict__ changed) {
+  const long m = blockIdx.y;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) changed[m] = st[2 * m] > 0;
+  if (i >= npix || st[2 * m] == 0) return;  // no small component: the mask is returned unchanged
+  const int r = parent_all[m * npix + i];
+  if (holes) {
+    if (r >= 0 && size_all[m * npix + r] < area_thresh) masks[m * npix + i] = 1;   // fill the small holes
+  } else {
+    bool keep = false;
+    if (r >= 0) {
+      if (st[2 * m + 1] > 0) keep = size_all[m * npix + r] >= area_thresh;
+      else keep = r == (int)(~(unsigned)(best[m] & 0xffffffffu));                  // every island is small: keep the largest
+    }
+    masks[m * npix + i] = keep ? 1 : 0;
+  }
+}
+
+// masks [n, h, w] uint8 (0/1) in place; changed [n]; ws: n * (2*h*w) ints + n * 4 ints
+int post_remove_small_regions(uint8_t* masks, int n, int h, int w, int area_thresh, int holes, int32_t* changed, int32_t* ws,
+                              cudaStream_t st) {
+  if (n <= 0) return 0;
+  const long npix = (long)h * w;
+  if (npix >= (1l << 31)) return set_error("remove_small_regions: image too large");
+  int* parent = ws;
+  int* size = ws + (size_t)n * npix;
+  int* stats = ws + 2 * (size_t)n * npix;
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(stats + 2 * n);  // 2n ints: 8-byte aligned with ws
+  cudaMemsetAsync(stats, 0, (size_t)n * 4 * sizeof(int), st);
+  const dim3 grid((unsigned)((npix + 255) / 256), n);
+  rsr_init_kernel<<<grid, 256, 0, st>>>(masks, npix, holes, parent, size);
+  LAUNCH_CHECK("rsr_init");
+  rsr_merge_kernel<<<grid, 256, 0, st>>>(h, w, parent);
+  LAUNCH_CHECK("rsr_merge");
+  rsr_flatten_kernel<<<grid, 256, 0, st>>>(npix, parent, size);
+  LAUNCH_CHECK("rsr_flatten");
+  rsr_stats_kernel<<<grid, 256, 0, st>>>(npix, parent, size, area_thresh, stats, best);
+  LAUNCH_CHECK("rsr_stats");
+  rsr_apply_kernel<<<grid, 256, 0, st>>>(masks, npix, holes, parent, size, area_thresh, stats, best, changed);
+  LAUNCH_CHECK("rsr_apply");
+  return 0;
+}
+
+// batched_mask_to_box (_vendored.py:33-85) + area for materialised uint8 masks [n, h, w]: one CTA per mask
+__global__ void __launch_bounds__(256)
+mask_box_kernel(const uint8_t* __restrict__ masks, int h, int w, int32_t* __restrict__ boxes, int32_t* __restrict__ area) {
+  const long m = blockIdx.x;
+  const uint8_t* mk = masks + m * (long)h * w;
+  int ar = 0, x0 = 1 << 30, y0 = 1 << 30, x1 = -1, y1 = -1;
+  for (long i = threadIdx.x; i < (long)h * w; i += 256) {
+    if (mk[i]) {
+      const int x = (int)(i % w), y = (int)(i / w);
+      ++ar; x0 = min(x0, x); x1 = max(x1, x); y0 = min(y0, y); y1 = max(y1, y);
+    }
+  }
+  __shared__ int red[5][8];
+  int vals[5] = {ar, x0, y0, x1, y1};
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    int v = vals[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int t = __shfl_xor_sync(0xffffffffu, v, o);
+      v = (k == 0) ? v + t : ((k <= 2) ? min(v, t) : max(v, t));
+    }
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int r[5];
+    for (int k = 0; k < 5; ++k) {
+      int v = red[k][0];
+      for (int q = 1; q < 8; ++q) v = (k == 0) ? v + red[k][q] : ((k <= 2) ? min(v, red[k][q]) : max(v, red[k][q]));
+      r[k] = v;
+    }
+    area[m] = r[0];
+    const bool empty = r[0] == 0;
+    boxes[m * 4 + 0] = empty ? 0 : r[1];
+    boxes[m * 4 + 1] = empty ? 0 : r[2];
+    boxes[m * 4 + 2] = empty ? 0 : r[3];
+    boxes[m * 4 + 3] = empty ? 0 : r[4];
+  }
+}
+int post_mask_boxes(const uint8_t* masks, int n, int h, int w, int32_t* boxes, int32_t* area, cudaStream_t st) {
+  if (n <= 0) return 0;
+  mask_box_kernel<<<n, 256, 0, st>>>(masks, h, w, boxes, area);
+  LAUNCH_CHECK("mask_box");
   return 0;
 }
 

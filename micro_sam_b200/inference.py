@@ -16,7 +16,7 @@ import torch
 
 from . import _amg_utils as amg_utils
 from . import _lib, util
-from .sam import ResizeLongestSide, mask_stats
+from .sam import ResizeLongestSide, local_otsu_threshold, mask_stats
 
 
 def _validate_inputs(boxes, points, point_labels, multimasking, return_instance_segmentation, segmentation_ids,
@@ -50,8 +50,6 @@ def batched_inference(predictor, image: Optional[np.ndarray], batch_size: int, b
                       i: Optional[int] = None):
     n_prompts, have_boxes, have_points, have_logits = _validate_inputs(
         boxes, points, point_labels, multimasking, return_instance_segmentation, segmentation_ids, logits_masks)
-    if mask_threshold == "auto":
-        raise NotImplementedError("mask_threshold='auto' (local Otsu, inference.py:70-134) is not on the B200 path")
     if multimasking and not reduce_multimasking:
         raise NotImplementedError("multimasking without reduce_multimasking")
     if image is None:
@@ -68,7 +66,10 @@ def batched_inference(predictor, image: Optional[np.ndarray], batch_size: int, b
     if have_points:
         points_t = torch.tensor(tf.apply_coords(points, image_shape), dtype=torch.float32).to(device)
         labels_t = torch.tensor(point_labels, dtype=torch.float32).to(device)
-    thr = predictor.model.mask_threshold if mask_threshold is None else float(mask_threshold)
+    auto = isinstance(mask_threshold, str)
+    if auto and mask_threshold != "auto":
+        raise ValueError(f"Invalid mask_threshold {mask_threshold}")
+    thr = predictor.model.mask_threshold if (mask_threshold is None or auto) else float(mask_threshold)
 
     lows, ious = [], []
     for s in range(0, n_prompts, batch_size):
@@ -84,7 +85,8 @@ def batched_inference(predictor, image: Optional[np.ndarray], batch_size: int, b
         ious.append(iou[:, 0])
     low = torch.cat(lows).contiguous()
     iou = torch.cat(ious)
-    bxs, stab, area = mask_stats(low, predictor.input_size, image_shape, thr, 1.0)
+    thr_t = local_otsu_threshold(low) if auto else None   # one threshold per mask (inference.py:137-151)
+    bxs, stab, area = mask_stats(low, predictor.input_size, image_shape, thr_t if auto else thr, 1.0)
     H, W = image_shape
     inp = predictor.input_size
     seg_ids = np.arange(1, n_prompts + 1) if segmentation_ids is None else np.asarray(segmentation_ids, dtype=np.int64)
@@ -95,15 +97,24 @@ def batched_inference(predictor, image: Optional[np.ndarray], batch_size: int, b
         sel = order.to(torch.int32).contiguous()
         ids = torch.as_tensor(seg_ids, device=device)[order].to(torch.int32).contiguous()
         label = torch.zeros(H, W, dtype=torch.int32, device=device)
-        _lib.check(_lib.lib().msam_paint(_lib.ptr(low), _lib.ptr(sel), _lib.ptr(bxs), _lib.ptr(ids), n_prompts, int(inp[0]),
-                                         int(inp[1]), H, W, float(thr), 1, _lib.ptr(label), W, _lib.cur_stream()))
+        if auto:
+            _lib.check(_lib.lib().msam_paint_ex(_lib.ptr(low), _lib.ptr(sel), _lib.ptr(bxs), _lib.ptr(ids), n_prompts,
+                                                int(inp[0]), int(inp[1]), H, W, _lib.ptr(thr_t), 1, _lib.ptr(label), W,
+                                                _lib.cur_stream()))
+        else:
+            _lib.check(_lib.lib().msam_paint(_lib.ptr(low), _lib.ptr(sel), _lib.ptr(bxs), _lib.ptr(ids), n_prompts, int(inp[0]),
+                                             int(inp[1]), H, W, float(thr), 1, _lib.ptr(label), W, _lib.cur_stream()))
         return util._finish_segmentation(label.cpu().numpy().astype(np.uint32), min_object_size=0, label_masks=True,
                                          with_background=False)
 
     binm = torch.empty(n_prompts, H, W, dtype=torch.uint8, device=device)
     logits = torch.empty(n_prompts, H, W, dtype=torch.float32, device=device) if return_highres_logits else None
-    _lib.check(_lib.lib().msam_upsample_masks(_lib.ptr(low), None, n_prompts, int(inp[0]), int(inp[1]), H, W, float(thr),
-                                              _lib.ptr(logits), _lib.ptr(binm), _lib.cur_stream()))
+    if auto:
+        _lib.check(_lib.lib().msam_upsample_masks_ex(_lib.ptr(low), None, n_prompts, int(inp[0]), int(inp[1]), H, W,
+                                                     _lib.ptr(thr_t), _lib.ptr(logits), _lib.ptr(binm), _lib.cur_stream()))
+    else:
+        _lib.check(_lib.lib().msam_upsample_masks(_lib.ptr(low), None, n_prompts, int(inp[0]), int(inp[1]), H, W, float(thr),
+                                                  _lib.ptr(logits), _lib.ptr(binm), _lib.cur_stream()))
     binm = binm.bool()
     bx, io, st, ar = bxs.cpu().numpy(), iou.cpu().numpy(), stab.cpu().numpy(), area.cpu().numpy()
     return [{

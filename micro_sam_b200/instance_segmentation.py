@@ -214,13 +214,14 @@ class AutomaticMaskGenerator(AMGBase):
                  output_mode: str = "instance_segmentation", with_background: bool = True):
         if not self.is_initialized:
             raise RuntimeError("AutomaticMaskGenerator has not been initialized. Call initialize first.")
-        if min_mask_region_area > 0:
-            raise NotImplementedError("min_mask_region_area > 0 (cv2 hole/island removal) is not on the B200 path yet")
         if output_mode not in ("instance_segmentation", "binary_mask", "rle", "coco_rle"):
             raise ValueError(f"Invalid output mode {output_mode}.")
         if output_mode == "coco_rle":
             raise NotImplementedError("coco_rle needs pycocotools")
         geoms = getattr(self, "_geoms", None)
+        if min_mask_region_area > 0:
+            return self._generate_small_regions(pred_iou_thresh, stability_score_thresh, box_nms_thresh, crop_nms_thresh,
+                                                min_mask_region_area, output_mode, with_background, geoms)
         if output_mode == "instance_segmentation" and len(self.crop_list) == 1 and geoms and \
                 tuple(self.crop_boxes[0]) == (0, 0, self.original_size[1], self.original_size[0]):
             out = self.generate_device(pred_iou_thresh, stability_score_thresh, box_nms_thresh, with_background)
@@ -298,6 +299,64 @@ class AutomaticMaskGenerator(AMGBase):
         _lib.check(L.msam_finish_segmentation(_lib.ptr(label), H, W, 0, int(with_background), _lib.ptr(out), _lib.ptr(ws),
                                               _lib.cur_stream()))
         return out.cpu().numpy().view(np.uint32)
+
+    def _generate_small_regions(self, pred_iou_thresh, stability_score_thresh, box_nms_thresh, crop_nms_thresh, min_area,
+                                output_mode, with_background, geoms):
+        """generate(min_mask_region_area > 0): AMGBase._postprocess_small_regions (instance_segmentation.py:146-186) on the
+        device -- holes then islands smaller than `min_area` are filled / removed per mask (8-connected components,
+        `msam_remove_small_regions`), boxes are recomputed, and a box NMS that prefers unchanged masks drops new duplicates."""
+        recs = self._generate_multi(pred_iou_thresh, stability_score_thresh, box_nms_thresh, crop_nms_thresh, "binary_mask",
+                                    with_background, geoms)
+        H, W = self.original_size
+        dev = self._predictor.device
+        L = _lib.lib()
+        n = len(recs)
+        if n > 0:
+            masks = torch.from_numpy(np.stack([r["segmentation"] for r in recs])).to(dev).to(torch.uint8).contiguous()
+            changed = torch.zeros(n, dtype=torch.bool, device=dev)
+            CH = 128
+            ws = torch.empty(min(n, CH) * (2 * H * W + 4), dtype=torch.int32, device=dev)
+            for s0 in range(0, n, CH):
+                m = masks[s0:s0 + CH]
+                for holes in (1, 0):
+                    ch = torch.zeros(m.shape[0], dtype=torch.int32, device=dev)
+                    _lib.check(L.msam_remove_small_regions(_lib.ptr(m), m.shape[0], H, W, int(min_area), holes, _lib.ptr(ch),
+                                                           _lib.ptr(ws), _lib.cur_stream()))
+                    changed[s0:s0 + CH] |= ch != 0
+            boxes = torch.empty(n, 4, dtype=torch.int32, device=dev)
+            area = torch.empty(n, dtype=torch.int32, device=dev)
+            _lib.check(L.msam_mask_boxes(_lib.ptr(masks), n, H, W, _lib.ptr(boxes), _lib.ptr(area), _lib.cur_stream()))
+            scores = (~changed).to(torch.float32).contiguous()
+            keep = torch.empty(n, dtype=torch.int32, device=dev)
+            nk = torch.zeros(1, dtype=torch.int32, device=dev)
+            z4 = (ctypes.c_int32 * 4)(0, 0, 0, 0)
+            _lib.check(L.msam_amg_filter_nms(_lib.ptr(boxes), _lib.ptr(scores), _lib.ptr(scores), n, 0, 0.0, 0.0,
+                                             float(max(box_nms_thresh, crop_nms_thresh)), z4, z4, _lib.ptr(keep), _lib.ptr(nk),
+                                             _lib.cur_stream()))
+            keep = keep[: int(nk.item())].long()
+            ch_h, bx_h, ar_h = changed.cpu().numpy(), boxes.cpu().numpy().astype(np.int64), area.cpu().numpy()
+            out = []
+            for k in keep.tolist():
+                r = recs[k]
+                if ch_h[k]:   # only changed masks get a new mask / box / area (:176-182)
+                    r = dict(r, segmentation=masks[k].bool().cpu().numpy(), area=int(ar_h[k]),
+                             bbox=amg_utils.box_xyxy_to_xywh(bx_h[k]).tolist())
+                out.append(r)
+            recs = out
+        if output_mode == "binary_mask":
+            return recs
+        if output_mode == "rle":
+            return [dict(r, segmentation=amg_utils.mask_to_rle(r["segmentation"][None])[0]) for r in recs]
+        # instance segmentation: mask_data_to_segmentation(..., merge_exclusively=False): descending area, later overwrites
+        label = torch.zeros(H, W, dtype=torch.int32, device=dev)
+        order = sorted(range(len(recs)), key=lambda k: recs[k]["area"], reverse=True)
+        for sid, k in enumerate(order, 1):
+            label[torch.from_numpy(recs[k]["segmentation"]).to(dev)] = sid
+        out_t = torch.empty(H, W, dtype=torch.int32, device=dev)
+        ws2 = torch.empty(4 * H * W + 4096 + 8, dtype=torch.int32, device=dev)
+        _lib.check(L.msam_finish_segmentation(_lib.ptr(label), H, W, 0, int(with_background), _lib.ptr(out_t), _lib.ptr(ws2),
+                                              _lib.cur_stream()))
+        return out_t.cpu().numpy().view(np.uint32)
 
     @torch.no_grad()
     def generate_device(self, pred_iou_thresh: float = 0.88, stability_score_thresh: float = 0.95,

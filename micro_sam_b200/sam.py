@@ -321,9 +321,19 @@ class B200SamPredictor:
         return m[0].cpu().numpy(), s[0].cpu().numpy(), l[0].cpu().numpy()
 
 
-def mask_stats(low_res: torch.Tensor, input_size, original_size, mask_threshold: float = 0.0,
-               stability_offset: float = 1.0):
+def local_otsu_threshold(low_res: torch.Tensor) -> torch.Tensor:
+    """inference._local_otsu_threshold (inference.py:70-134) on (N,256,256) low-res logits -> fp32 thresholds [N]."""
+    lr = low_res.reshape(-1, 256, 256).to(torch.float32).contiguous()
+    if not lr.is_cuda:
+        raise RuntimeError("local_otsu_threshold needs CUDA tensors")
+    thr = torch.empty(lr.shape[0], device=lr.device, dtype=torch.float32)
+    _lib.check(_lib.lib().msam_local_otsu_threshold(_lib.ptr(lr), lr.shape[0], _lib.ptr(thr), _lib.cur_stream()))
+    return thr
+
+
+def mask_stats(low_res: torch.Tensor, input_size, original_size, mask_threshold=0.0, stability_offset: float = 1.0):
     """Fused postprocess_masks + stability score + threshold + box + area on (N,256,256) low-res logits.
+    `mask_threshold`: a float, or a device tensor [N] of per-mask thresholds (mask_threshold="auto").
     Returns (boxes int32 [N,4] xyxy, stability fp32 [N], area int32 [N]) on the device of `low_res`."""
     lr = low_res.reshape(-1, 256, 256)
     if not lr.is_cuda:
@@ -333,6 +343,13 @@ def mask_stats(low_res: torch.Tensor, input_size, original_size, mask_threshold:
     boxes = torch.empty(n, 4, device=lr.device, dtype=torch.int32)
     stab = torch.empty(n, device=lr.device, dtype=torch.float32)
     area = torch.empty(n, device=lr.device, dtype=torch.int32)
+    if torch.is_tensor(mask_threshold):
+        thr = mask_threshold.to(lr.device, torch.float32).reshape(-1).contiguous()
+        assert thr.shape[0] == n
+        _lib.check(_lib.lib().msam_mask_stats_ex(_lib.ptr(lr), n, int(input_size[0]), int(input_size[1]), int(original_size[0]),
+                                                 int(original_size[1]), _lib.ptr(thr), float(stability_offset),
+                                                 _lib.ptr(boxes), _lib.ptr(stab), _lib.ptr(area), _lib.cur_stream()))
+        return boxes, stab, area
     _lib.check(_lib.lib().msam_mask_stats(_lib.ptr(lr), n, int(input_size[0]), int(input_size[1]), int(original_size[0]),
                                           int(original_size[1]), float(mask_threshold), float(stability_offset),
                                           _lib.ptr(boxes), _lib.ptr(stab), _lib.ptr(area), _lib.cur_stream()))

@@ -165,6 +165,29 @@ def is_box_near_crop_edge(boxes: torch.Tensor, crop_box, orig_box, atol: float =
     return torch.any(near_crop_edge, dim=1)
 
 
+def remove_small_regions(mask: np.ndarray, area_thresh: float, mode: str):
+    """segment_anything.utils.amg.remove_small_regions (third party, unpinned; call site instance_segmentation.py:157-160).
+    Upstream uses cv2.connectedComponentsWithStats(working_mask, 8); cv2 is absent here, scipy.ndimage.label with the full
+    3x3 structure is the same 8-connected labelling in the same raster order of first pixels (parity unpinned: no cv2)."""
+    from scipy import ndimage
+    assert mode in ("holes", "islands")
+    correct_holes = mode == "holes"
+    working_mask = (correct_holes ^ mask).astype(np.uint8)
+    regions, n_labels = ndimage.label(working_mask, structure=np.ones((3, 3), dtype=int))
+    n_labels += 1  # cv2 counts the background label 0
+    sizes = np.bincount(regions.ravel(), minlength=n_labels)[1:]
+    small_regions = [i + 1 for i, s_ in enumerate(sizes) if s_ < area_thresh]
+    if len(small_regions) == 0:
+        return mask, False
+    fill_labels = [0] + small_regions
+    if not correct_holes:
+        fill_labels = [i for i in range(n_labels) if i not in fill_labels]
+        if len(fill_labels) == 0:  # every region is below the threshold: keep the largest
+            fill_labels = [int(np.argmax(sizes)) + 1]
+    mask = np.isin(regions, fill_labels)
+    return mask, True
+
+
 def box_xyxy_to_xywh(box_xyxy):
     box_xywh = deepcopy(box_xyxy)
     box_xywh[2] = box_xywh[2] - box_xywh[0]
@@ -482,8 +505,6 @@ class AutomaticMaskGenerator:
                  min_mask_region_area=0, output_mode="instance_segmentation", with_background=True):
         if not self._is_initialized:
             raise RuntimeError("AutomaticMaskGenerator has not been initialized. Call initialize first.")
-        if min_mask_region_area > 0:
-            raise NotImplementedError("oracle: min_mask_region_area > 0 needs cv2 connected components")
         data = MaskData()
         for data_, crop_box in zip(self._crop_list, self._crop_boxes):
             data.cat(self._postprocess_batch(deepcopy(data_), crop_box, self._original_size, pred_iou_thresh,
@@ -494,6 +515,26 @@ class AutomaticMaskGenerator:
                                       iou_threshold=crop_nms_thresh)
             data.filter(keep_by_nms)
         data.to_numpy()
+        if min_mask_region_area > 0 and len(data["rles"]) > 0:   # _postprocess_small_regions, :146-186
+            nms_thresh = max(box_nms_thresh, crop_nms_thresh)
+            new_masks, scores = [], []
+            for rle in data["rles"]:
+                mask = rle_to_mask(rle)
+                mask, changed = remove_small_regions(mask, min_mask_region_area, mode="holes")
+                unchanged = not changed
+                mask, changed = remove_small_regions(mask, min_mask_region_area, mode="islands")
+                unchanged = unchanged and not changed
+                new_masks.append(torch.as_tensor(mask, dtype=torch.int).unsqueeze(0))
+                scores.append(float(unchanged))   # NMS prefers masks that did not need post-processing
+            masks = torch.cat(new_masks, dim=0)
+            boxes = batched_mask_to_box(masks.to(torch.bool))
+            keep_by_nms = batched_nms(boxes.float(), torch.as_tensor(scores, dtype=torch.float), torch.zeros_like(boxes[:, 0]),
+                                      iou_threshold=nms_thresh)
+            for i_mask in keep_by_nms:
+                if scores[i_mask] == 0.0:
+                    data["rles"][i_mask] = mask_to_rle(masks[i_mask].unsqueeze(0).to(torch.bool))[0]
+                    data["boxes"][i_mask] = boxes[i_mask]
+            data.filter(keep_by_nms)
         if output_mode in ("binary_mask", "instance_segmentation"):
             segs = [rle_to_mask(rle) for rle in data["rles"]]
         elif output_mode == "rle":
@@ -519,6 +560,40 @@ class AutomaticMaskGenerator:
 
 
 # ------------------------------------------------------------------------------------------------ inference.py
+def local_otsu_threshold(images: torch.Tensor, window_size: int = 31, num_bins: int = 64, eps: float = 1e-6) -> torch.Tensor:
+    """inference.py:70-134, evaluated mask by mask (the reference unfolds the whole batch at once: same values, but
+    (B, 961, 65536) fp32 temporaries).  images (B,1,H,W) -> thresholds (B,1,1)."""
+    import torch.nn.functional as F
+    out = []
+    for b in range(images.shape[0]):
+        x = images[b:b + 1].to(torch.float32)
+        _, _, H, W = x.shape
+        x_min, x_max = x.min().view(1, 1, 1, 1), x.max().view(1, 1, 1, 1)
+        x_range = (x_max - x_min).clamp_min(eps)
+        x_norm = (x - x_min) / x_range
+        patches = F.unfold(x_norm, kernel_size=window_size, padding=window_size // 2)      # (1, P, L)
+        bin_idx = (patches * (num_bins - 1)).long().clamp(0, num_bins - 1)
+        L = bin_idx.shape[2]
+        one_hot = torch.zeros(1, L, num_bins, dtype=torch.float32)
+        idx = bin_idx.transpose(1, 2)
+        one_hot.scatter_add_(2, idx, torch.ones_like(idx, dtype=one_hot.dtype))
+        hist = one_hot.permute(0, 2, 1)
+        p = hist / hist.sum(dim=1, keepdim=True).clamp_min(eps)
+        bins = torch.arange(num_bins, dtype=torch.float32).view(1, num_bins, 1)
+        omega1 = torch.cumsum(p, dim=1)
+        mu = torch.cumsum(p * bins, dim=1)
+        mu_T = mu[:, -1:, :]
+        omega2 = 1.0 - omega1
+        mu1 = mu / omega1.clamp_min(eps)
+        mu2 = (mu_T - mu) / omega2.clamp_min(eps)
+        sigma_b2 = omega1 * omega2 * (mu1 - mu2) ** 2
+        t_bin = torch.argmax(sigma_b2, dim=1)
+        t_norm = t_bin.to(torch.float32) / (num_bins - 1)
+        thr_vals = (x_min.view(1, 1) + t_norm * x_range.view(1, 1)).clamp_min(0.0)
+        out.append(torch.amax(thr_vals.view(1, H, W), dim=(1, 2), keepdim=True))
+    return torch.cat(out)
+
+
 @torch.no_grad()
 def batched_inference(predictor, image, batch_size: int, boxes=None, points=None, point_labels=None,
                       multimasking: bool = False, embedding_path=None, return_instance_segmentation: bool = True,
@@ -543,17 +618,18 @@ def batched_inference(predictor, image, batch_size: int, boxes=None, points=None
     n_batches = int(np.ceil(float(n_prompts) / batch_size))
     for b in range(n_batches):
         s, e = b * batch_size, (b + 1) * batch_size
-        bm, bi, _ = predictor.predict_torch(
+        bm, bi, bl = predictor.predict_torch(
             point_coords=pt[s:e] if have_points else None, point_labels=pl[s:e] if have_points else None,
             boxes=bx[s:e] if have_boxes else None, mask_input=None if logits_masks is None else logits_masks[s:e],
             multimask_output=multimasking, return_logits=True)
         if multimasking:
             best = torch.argmax(bi, dim=1)
             sel = torch.arange(bm.shape[0])
-            bm, bi = bm[sel, best][:, None], bi[sel, best][:, None]
+            bm, bi, bl = bm[sel, best][:, None], bi[sel, best][:, None], bl[sel, best][:, None]
         data = MaskData(masks=bm.flatten(0, 1), iou_preds=bi.flatten(0, 1))
-        data["stability_scores"] = calculate_stability_score(data["masks"], mask_threshold, 1.0)
-        data["masks"] = (data["masks"] > mask_threshold).type(torch.bool)
+        thr_b = local_otsu_threshold(bl) if isinstance(mask_threshold, str) else mask_threshold   # inference.py:137-151
+        data["stability_scores"] = calculate_stability_score(data["masks"], thr_b, 1.0)
+        data["masks"] = (data["masks"] > thr_b).type(torch.bool)
         data["boxes"] = batched_mask_to_box(data["masks"])
         masks.cat(data)
     recs = [{

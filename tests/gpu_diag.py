@@ -5,6 +5,7 @@ import os
 import sys
 import time
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -333,11 +334,51 @@ def sec_decoder(types=("vit_test",)):
 
 
 def sec_post():
-    from oracle import sam_ref
+    from oracle import sam_ref, amg_ref
     from micro_sam_b200 import sam as bsam
     L = _lib.lib()
     osam = sam_ref.build_sam("vit_test")
     g = torch.Generator().manual_seed(5)
+    # mask_threshold="auto": local Otsu thresholds, bit-exact vs the CPU restatement (smooth, noisy, constant masks)
+    lo = torch.nn.functional.interpolate(torch.randn(4, 1, 12, 12, generator=g), (256, 256), mode="bicubic")[:, 0] * 4
+    lo[1] += torch.randn(256, 256, generator=g) * 0.5
+    lo[2] = lo[2] - 6.0
+    lo[3] = 1.5
+    thr = bsam.local_otsu_threshold(lo.to(DEV)).cpu()
+    thr_ref = amg_ref.local_otsu_threshold(lo[:, None]).view(-1)
+    same = bool(torch.equal(thr, thr_ref))
+    RESULTS.append(same)
+    print(f"[{'OK ' if same else 'BAD'}] local Otsu thresholds {thr.tolist()} vs oracle {thr_ref.tolist()}", flush=True)
+    b1, s1, a1 = bsam.mask_stats(lo.to(DEV), (1024, 1024), (1024, 1024), thr.to(DEV), 1.0)
+    ok = True
+    for k in range(4):
+        b0, s0, a0 = bsam.mask_stats(lo[k:k + 1].to(DEV), (1024, 1024), (1024, 1024), float(thr[k]), 1.0)
+        ok &= bool((b0[0] == b1[k]).all()) and int(a0[0]) == int(a1[k]) and bool(torch.equal(s0.nan_to_num(-1), s1[k:k + 1].nan_to_num(-1)))
+    RESULTS.append(ok)
+    print(f"[{'OK ' if ok else 'BAD'}] mask_stats with per-mask thresholds == scalar-threshold calls", flush=True)
+    # remove_small_regions (8-connected components) + mask boxes vs the oracle
+    rng = np.random.default_rng(3)
+    mk = (torch.nn.functional.interpolate(torch.randn(6, 1, 10, 14, generator=g), (96, 130), mode="bicubic")[:, 0] > 0.3).numpy()
+    mk |= rng.random(mk.shape) > 0.995                      # specks (islands)
+    mk &= ~(rng.random(mk.shape) > 0.99)                   # pin holes
+    mk[4] = False; mk[4, 10:12, 20:22] = True; mk[4, 50, 60] = True   # every island below the threshold -> keep the largest
+    mk[5] = False                                          # empty mask
+    dm = torch.from_numpy(mk).to(DEV).to(torch.uint8).contiguous()
+    ws = torch.empty(6 * (2 * 96 * 130 + 4), dtype=torch.int32, device=DEV)
+    ch = torch.zeros(2, 6, dtype=torch.int32, device=DEV)
+    ok = True
+    ref = mk.copy(); ref_ch = np.zeros((2, 6), dtype=bool)
+    for q, (holes, mode) in enumerate(((1, "holes"), (0, "islands"))):
+        _lib.check(L.msam_remove_small_regions(_lib.ptr(dm), 6, 96, 130, 12, holes, _lib.ptr(ch[q]), _lib.ptr(ws), _lib.cur_stream()))
+        for k in range(6):
+            ref[k], ref_ch[q, k] = amg_ref.remove_small_regions(ref[k], 12, mode)
+        ok &= bool(np.array_equal(dm.cpu().numpy().astype(bool), ref)) and bool(np.array_equal(ch[q].cpu().numpy() != 0, ref_ch[q]))
+    bx = torch.empty(6, 4, dtype=torch.int32, device=DEV); ar = torch.empty(6, dtype=torch.int32, device=DEV)
+    _lib.check(L.msam_mask_boxes(_lib.ptr(dm), 6, 96, 130, _lib.ptr(bx), _lib.ptr(ar), _lib.cur_stream()))
+    ok &= bool(np.array_equal(bx.cpu().numpy(), amg_ref.batched_mask_to_box(torch.from_numpy(ref)).numpy()))
+    ok &= bool(np.array_equal(ar.cpu().numpy(), ref.reshape(6, -1).sum(1)))
+    RESULTS.append(ok)
+    print(f"[{'OK ' if ok else 'BAD'}] remove_small_regions (holes, islands; changed {ref_ch.tolist()}) + mask boxes == oracle", flush=True)
     # smooth random low-res logits with both signs
     low = torch.nn.functional.interpolate(torch.randn(12, 1, 16, 16, generator=g), (256, 256), mode="bicubic")[:, 0] * 3
     low[3] = -5.0  # empty mask

@@ -186,6 +186,25 @@ def test_batched_inference_against_oracle(models):
     assert _partition_equal(seg, oseg)
     with pytest.raises(ValueError):
         inference.batched_inference(pred, img, batch_size=8)
+    # mask_threshold="auto" (local Otsu per mask, a16): same low-res logits -> identical thresholds, masks, boxes, painting
+    recs_a = inference.batched_inference(pred, img, batch_size=8, boxes=boxes[:6], return_instance_segmentation=False,
+                                         mask_threshold="auto")
+    low = torch.stack([r["logits"] for r in recs_a]).cpu()
+    iou = torch.tensor([r["predicted_iou"] for r in recs_a], dtype=torch.float32)[:, None]
+    state["i"] = 0
+    opred.predict_torch = fake
+    try:
+        orecs_a = amg_ref.batched_inference(opred, img, batch_size=8, boxes=boxes[:6], return_instance_segmentation=False,
+                                            mask_threshold="auto")
+        state["i"] = 0
+        oseg_a = amg_ref.batched_inference(opred, img, batch_size=8, boxes=boxes[:6], mask_threshold="auto")
+    finally:
+        opred.predict_torch = orig
+    for r, o in zip(recs_a, orecs_a):
+        assert r["bbox"] == o["bbox"] and r["area"] == int(o["area"])
+        assert np.array_equal(r["segmentation"].cpu().numpy(), o["segmentation"].numpy())
+    seg_a = inference.batched_inference(pred, img, batch_size=8, boxes=boxes[:6], mask_threshold="auto")
+    assert _partition_equal(seg_a, oseg_a)
 
 
 def test_device_to_image_and_finish_segmentation_bit_exact(models):
@@ -406,3 +425,11 @@ def test_amg_crop_layers_against_oracle(models):
         seg = amg.generate(output_mode="instance_segmentation", **kw)
         oseg = oamg.generate(output_mode="instance_segmentation", **kw)
         assert _partition_equal(seg, oseg), kw
+    # a15: min_mask_region_area > 0 (holes / islands removal, re-boxing, NMS preferring unchanged masks)
+    kw = dict(pred_iou_thresh=0.0, stability_score_thresh=0.0, box_nms_thresh=0.95, crop_nms_thresh=0.95, min_mask_region_area=40)
+    recs = amg.generate(output_mode="binary_mask", **kw)
+    orecs = oamg.generate(output_mode="binary_mask", **kw)
+    assert len(recs) == len(orecs) and len(recs) > 0
+    for a, b in zip(recs, orecs):
+        assert a["bbox"] == b["bbox"] and a["area"] == b["area"] and np.array_equal(a["segmentation"], b["segmentation"])
+    assert _partition_equal(amg.generate(output_mode="instance_segmentation", **kw), oamg.generate(output_mode="instance_segmentation", **kw))
