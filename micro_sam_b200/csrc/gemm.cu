@@ -50,6 +50,7 @@ struct GemmParams {
   const float* bias;      // [N] or null
   const void* residual;   // fp32 (or bf16 if res_bf16) [res_rows, ldr] or null; row index = row % res_rows
   int res_rows, ldr, res_bf16;
+  int res_tma;            // fp32 residual fetched by TMA into the staging tile (fp32 output, res_rows % 128 == 0)
   int out_fp32;
   int act;                // 0 none, 1 GELU(erf), 2 ReLU
   const float* ln_gamma;  // fused LayerNorm epilogues
@@ -102,7 +103,7 @@ template <int EPI> struct EpiCols { static constexpr int value = (EPI == 3) ? 32
 template <int BN, int EPI, bool SK>
 __global__ void __launch_bounds__(GemmCfg<BN, SK, EpiCols<EPI>::value>::THREADS, GemmCfg<BN, SK, EpiCols<EPI>::value>::MIN_CTAS)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   using Cfg = GemmCfg<BN, SK, EpiCols<EPI>::value>;
   constexpr int NG = Cfg::NG, CPW = Cfg::CPW;
   extern __shared__ uint8_t smem_raw[];
@@ -112,6 +113,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 3;  // [NG] residual tile landed in the staging buffer of the column group
   // statically declared so that the compiler emits LDS/STS (not generic LD/ST through the LG path)
   __shared__ __align__(16) float2 exch[2 * 4 * 128];  // EPI_LN256 statistics exchange, double buffered by tile parity
   __shared__ __align__(16) float rowp[768];           // [0,256) bias, [256,512) gamma, [512,768) beta (fused epilogues)
@@ -137,6 +139,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], NG * 4);  // one arrive per epilogue warp
     }
+    for (int i = 0; i < NG; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -214,6 +217,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool issuer = (quad == 0 && lane == 0);
     const int bar_id = 2 + grp;          // named barrier of this column group (128 threads)
     int it = 0;
+    uint32_t res_cnt = 0;  // residual tiles consumed by this column group (parity of res_bar)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
       const int as = it & 1;
@@ -243,6 +247,64 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       };
 
       if constexpr (EPI == EPI_PLAIN) {
+        if (p.res_tma) {
+          // fp32 output + fp32 residual: the residual tile [128 x 32] of each chunk is fetched by TMA straight into the
+          // staging tile (the row-per-thread 16-byte loads of the first version cost one L1 line per lane: 8K cycles per
+          // tile, more than the MMA time of a K = 768 tile -- profiles/r1_gemm_shapes_after_elect.log, "proj +res"),
+          // each thread then adds its accumulators in place and the same tile is stored.
+          const uint32_t stg_a = smem_u32(stg) + r * 128;
+          const int rrow = (m_blk * GEMM_BM) % p.res_rows;
+          const bool on0 = colbase < p.N, on1 = colbase + 32 < p.N;
+          if (issuer && on0) {  // chunk 0: prefetched while the tile is still being accumulated
+            tma_store_wait_read();
+            mbar_expect_tx(&res_bar[grp], STG_BYTES);
+            tma_load_2d(stg, &tmR, &res_bar[grp], colbase, rrow);
+          }
+          mbar_wait(&tfull_bar[as], aphase, 4);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            const int col0 = colbase + c * 32;
+            uint32_t v[32];
+            tmem_ld32(tcol + c * 32, v);
+            tmem_ld_wait();
+            if (c == 1) release_acc();
+            if (!(c ? on1 : on0)) continue;  // uniform across the column group
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+              }
+            }
+            if (p.act) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+            }
+            mbar_wait(&res_bar[grp], res_cnt & 1, 5);
+            ++res_cnt;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint32_t a = stg_a + ((q ^ (r & 7)) << 4);
+              const uint4 rr = ld_shared_v4(a);
+              st_shared_v4(a, make_uint4(__float_as_uint(f[4 * q] + __uint_as_float(rr.x)),
+                                         __float_as_uint(f[4 * q + 1] + __uint_as_float(rr.y)),
+                                         __float_as_uint(f[4 * q + 2] + __uint_as_float(rr.z)),
+                                         __float_as_uint(f[4 * q + 3] + __uint_as_float(rr.w))));
+            }
+            stg_publish(col0);
+            if (c == 0 && on1 && issuer) {  // residual of the second chunk, once the store has read the tile
+              tma_store_wait_read();
+              mbar_expect_tx(&res_bar[grp], STG_BYTES);
+              tma_load_2d(stg, &tmR, &res_bar[grp], col0 + 32, rrow);
+            }
+          }
+          __syncwarp();
+          continue;
+        }
         const bool has_res = p.residual != nullptr && row_ok;
         const float* res_f = nullptr;
         const __nv_bfloat16* res_b = nullptr;
@@ -446,12 +508,19 @@ static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     attr_set = true;
   }
   const int ldc = a.ldc > 0 ? a.ldc : a.N;
-  CUtensorMap tmA, tmB, tmC;
+  CUtensorMap tmA, tmB, tmC, tmR;
   if (make_tmap_bf16_2d(&tmA, a.A, a.M, a.K, a.lda, GEMM_BM)) return -1;
   if (make_tmap_bf16_2d(&tmB, a.W, a.N, a.K, a.ldw, BN)) return -1;
   if (EPI == EPI_HYPER) tmC = tmA;  // unused
   else if (make_tmap_2d(&tmC, a.out, a.out_fp32 ? 4 : 2, a.M, a.N, ldc, GEMM_BM)) return -1;
   GemmParams p;
+  const int res_rows = a.res_rows > 0 ? a.res_rows : a.M, ldr = a.ldr > 0 ? a.ldr : a.N;
+  p.res_tma = (EPI == EPI_PLAIN && a.residual && !a.res_bf16 && a.out_fp32 && res_rows % GEMM_BM == 0 && ldr % 4 == 0) ? 1 : 0;
+  if (p.res_tma) {
+    if (make_tmap_2d(&tmR, a.residual, 4, res_rows, a.N, ldr, GEMM_BM)) return -1;
+  } else {
+    tmR = tmA;  // unused
+  }
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.bias = a.bias;
   p.residual = a.residual;
@@ -472,7 +541,7 @@ static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     const double res_b = a.residual ? (double)(a.res_rows > 0 ? a.res_rows : a.M) * a.N * (a.res_bf16 ? 2 : 4) : 0.0;
     prof_begin(stream, PROF_GEMM_HBM, (double)a.M * a.K * 2 + (double)a.N * a.K * 2 + out_b + res_b);
   }
-  gemm_bf16_kernel<BN, EPI, SK><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+  gemm_bf16_kernel<BN, EPI, SK><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmR, p);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm launch failed: %s", cudaGetErrorString(e));

@@ -176,20 +176,26 @@ mask_stats_x4_kernel(const float* __restrict__ low_res, PostGeom g, float thr, c
   // the result stays bit-identical while the typical mask costs ~8x fewer instructions.
   const int i_begin = part == 0 ? 0 : 128, i_end = part == 0 ? 128 : 255;
   float B0 = __ldg(lr + i_begin * 256 + cm), B1 = __ldg(lr + i_begin * 256 + j), B2 = __ldg(lr + i_begin * 256 + cp);
+  int skip_test = 0;  // after a block that needed the per-pixel path the test is skipped for the next 3 (noisy masks: ~no overhead)
   for (int i = i_begin; i < i_end; ++i) {
     const float A0 = B0, A1 = B1, A2 = B2;
     const float* r1 = lr + (i + 1) * 256;
     B0 = __ldg(r1 + cm); B1 = __ldg(r1 + j); B2 = __ldg(r1 + cp);
-    const float mn = fminf(fminf(fminf(A0, A1), fminf(A2, B0)), fminf(B1, B2));
-    const float mx = fmaxf(fmaxf(fmaxf(A0, A1), fmaxf(A2, B0)), fmaxf(B1, B2));
-    const float slack = 1e-5f * fmaxf(fabsf(mn), fabsf(mx));
     const int y = 4 * i + 2;
-    if (mx < t_lo - slack) continue;  // every pixel is below every threshold
-    if (mn > t_hi + slack) {          // every pixel is above every threshold
-      hi += 16; lo += 16; ar += 16;
-      colbits[0] = colbits[1] = colbits[2] = colbits[3] = 0x80000000u;
-      y0 = min(y0, y); y1 = max(y1, y + 3);
-      continue;
+    if (skip_test == 0) {
+      const float mn = fminf(fminf(fminf(A0, A1), fminf(A2, B0)), fminf(B1, B2));
+      const float mx = fmaxf(fmaxf(fmaxf(A0, A1), fmaxf(A2, B0)), fmaxf(B1, B2));
+      const float slack = 1e-5f * fmaxf(fabsf(mn), fabsf(mx));
+      if (mx < t_lo - slack) continue;  // every pixel is below every threshold
+      if (mn > t_hi + slack) {          // every pixel is above every threshold
+        hi += 16; lo += 16; ar += 16;
+        colbits[0] = colbits[1] = colbits[2] = colbits[3] = 0x80000000u;
+        y0 = min(y0, y); y1 = max(y1, y + 3);
+        continue;
+      }
+      skip_test = 3;
+    } else {
+      --skip_test;
     }
     const float A[3] = {A0, A1, A2};
     const float B[3] = {B0, B1, B2};
