@@ -566,6 +566,10 @@ int launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream) {
       return set_error("gemm: fused hyper product needs N=128");
     return launch_gemm_bn<128, EPI_HYPER>(a, num_sms, stream);
   }
+  {  // large plain products (the encoder GEMMs): CTA-pair kernel
+    const int r2 = launch_gemm_2sm(a, num_sms, stream);
+    if (r2 != 0) return r2 < 0 ? -1 : 0;
+  }
   // BN=256 keeps the tensor pipe at its 1-CTA rate with the fewest smem bytes per flop; fall back to 128 / 64 when N is
   // not a multiple (or is small), to avoid wasted columns.
   if (a.N % 256 == 0) return launch_gemm_bn<256, EPI_PLAIN>(a, num_sms, stream);

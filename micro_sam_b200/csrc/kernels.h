@@ -38,6 +38,8 @@ struct GemmArgs {
   int hyper_m0 = 0, hyper_nm = 0;
 };
 int launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream);
+// gemm2.cu: 2-SM (cta_group::2) kernel for large plain products; returns 1 if launched, 0 if the problem does not qualify
+int launch_gemm_2sm(const GemmArgs& a, int num_sms, cudaStream_t stream);
 
 // ---- i2t_fused.cu : fused image -> token cross-attention block (q projection + attention + out projection + residual +
 // LayerNorm in one pass over the per-prompt image tokens); T <= 8 prompt tokens
