@@ -31,6 +31,7 @@ struct GCfg {
   static constexpr int TILE = NB * BOX;
   static constexpr int KST = 2;
   static constexpr int VST = (D == 64) ? 4 : 2;
+  static constexpr int STREAMS = (D == 64) ? 1 : 2;   // MMA / TMA issue streams (see the MMA issuer section)
   static constexpr int RTH_ROWS = 80, RTH_BOX = RTH_ROWS * 128, RTW_BOX = 128 * 128;
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + TILE;
@@ -65,7 +66,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 __device__ __forceinline__ void tmem_st_wait_g() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <int D>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
 attn_global_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmRTh,
                    const __grid_constant__ CUtensorMap tmRTw, const GParams p) {
   using C = GCfg<D>;
@@ -101,7 +102,7 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
     }
     for (int i = 0; i < 4; ++i) { mbar_init(&vfull[i], 1); mbar_init(&vempty[i], 1); }
-    mbar_init(o_full, 1);
+    mbar_init(o_full, C::STREAMS);  // the last P.V of each stream
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, 512);
@@ -113,14 +114,18 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   uint8_t* sK = smem + C::OFF_K;
   uint8_t* sV = smem + C::OFF_V;
 
-  if (warp == 8) {
-    // =========================================================== TMA producer
-    if (lane == 0) {
+  if (warp == 8 || warp == 11) {
+    // =========================================================== TMA producers: one per key-tile stream (warp 8: even tiles
+    // + Q and the rel-pos tables, warp 11: odd tiles), so that a stalled stream never delays the other one's loads
+    if (lane == 0 && (C::STREAMS == 2 || warp == 8)) {
+      const int sw = warp == 8 ? 0 : 1;
       const int qcol = head * D, kcol = p.d_model + head * D, vcol = 2 * p.d_model + head * D;
-      mbar_expect_tx(q_full, C::TILE + C::NB * (C::RTH_BOX + C::RTW_BOX));
-      for (int b = 0; b < C::NB; ++b) tma_load_2d(sQ + b * BOX, &tmQKV, q_full, qcol + b * 64, row0 + qt * 128);
-      for (int b = 0; b < C::NB; ++b) tma_load_2d(sV + b * C::RTH_BOX, &tmRTh, q_full, b * 64, qh0);
-      for (int b = 0; b < C::NB; ++b) tma_load_2d(sV + C::NB * C::RTH_BOX + b * C::RTW_BOX, &tmRTw, q_full, b * 64, 128);
+      if (sw == 0) {
+        mbar_expect_tx(q_full, C::TILE + C::NB * (C::RTH_BOX + C::RTW_BOX));
+        for (int b = 0; b < C::NB; ++b) tma_load_2d(sQ + b * BOX, &tmQKV, q_full, qcol + b * 64, row0 + qt * 128);
+        for (int b = 0; b < C::NB; ++b) tma_load_2d(sV + b * C::RTH_BOX, &tmRTh, q_full, b * 64, qh0);
+        for (int b = 0; b < C::NB; ++b) tma_load_2d(sV + C::NB * C::RTH_BOX + b * C::RTW_BOX, &tmRTw, q_full, b * 64, 128);
+      }
       auto load_k = [&](int j) {
         const int st = j & 1;
         mbar_wait(&kempty[st], ((j >> 1) & 1) ^ 1, 40);
@@ -133,15 +138,20 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         mbar_expect_tx(&vfull[st], C::TILE);
         for (int b = 0; b < C::NB; ++b) tma_load_2d(sV + st * C::TILE + b * BOX, &tmQKV, &vfull[st], vcol + b * 64, row0 + j * 128);
       };
-      load_k(0);
-      load_k(1);
+      load_k(sw);
+      if (C::STREAMS == 1) load_k(1);
       mbar_wait(t_full, 0, 42);  // the T MMAs have read the rel-pos tiles -> the V stages are free
-      load_v(0);
-      load_v(1);
-      for (int j = 2; j < NKT; ++j) { load_k(j); load_v(j); }
+      load_v(sw);
+      if (C::STREAMS == 1) load_v(1);
+      for (int j = sw + 2; j < NKT; j += C::STREAMS) { load_k(j); load_v(j); }
     }
-  } else if (warp == 9) {
-    // =========================================================== MMA issuer (warp-uniform, elected lane issues)
+  } else if (warp == 9 || warp == 10) {
+    // =========================================================== MMA issuers, warp-uniform control flow with an elected lane.
+    // STREAMS == 2 (d = 80): one in-order stream per softmax warpgroup (warp 9: even key tiles, warp 10: odd) -- a single
+    // issuer blocked on P of tile j cannot issue S of tile j+3 for the other warpgroup (ncu: 40 % of the stall samples on
+    // that wait, profiles/r1_ncu_attn_global_d80.txt; 870 -> 800 us per block).  d = 64 measured faster with one issuer.
+    const int sw = warp - 9;
+    if (C::STREAMS == 1 && sw == 1) goto done;
     constexpr uint32_t idescTh = make_idesc_bf16(128, C::RTH_ROWS);
     constexpr uint32_t idescS = make_idesc_bf16(128, 128);
     constexpr uint32_t idescO = make_idesc_bf16(128, D, 1);  // B (= V) is MN-major
@@ -151,18 +161,20 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     };
     mbar_wait(q_full, 0, 50);
     tc_fence_after();
-    if (elect_one()) {
+    if (sw == 0) {
+      if (elect_one()) {
 #pragma unroll
-      for (int ks = 0; ks < C::KSTEPS; ++ks)
-        umma_bf16(tmem + C::TM_TH, kdesc(aQ, BOX, ks), kdesc(aV, C::RTH_BOX, ks), idescTh, ks > 0);
+        for (int ks = 0; ks < C::KSTEPS; ++ks)
+          umma_bf16(tmem + C::TM_TH, kdesc(aQ, BOX, ks), kdesc(aV, C::RTH_BOX, ks), idescTh, ks > 0);
 #pragma unroll
-      for (int ks = 0; ks < C::KSTEPS; ++ks)
-        umma_bf16(tmem + C::TM_S, kdesc(aQ, BOX, ks), kdesc(aV + C::NB * C::RTH_BOX, C::RTW_BOX, ks), idescS, ks > 0);
-      umma_commit(t_full);
+        for (int ks = 0; ks < C::KSTEPS; ++ks)
+          umma_bf16(tmem + C::TM_S, kdesc(aQ, BOX, ks), kdesc(aV + C::NB * C::RTH_BOX, C::RTW_BOX, ks), idescS, ks > 0);
+        umma_commit(t_full);
+      }
+      __syncwarp();
+      mbar_wait(t_done, 0, 51);  // T_w (aliases S_0) has been gathered into registers
+      tc_fence_after();
     }
-    __syncwarp();
-    mbar_wait(t_done, 0, 51);  // both warpgroups have pulled T_w (aliases S_0) into registers
-    tc_fence_after();
     auto issue_S = [&](int j) {
       const int w = j & 1, n = j >> 1;
       mbar_wait(&kfull[w], n & 1, 52);
@@ -177,9 +189,9 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       }
       __syncwarp();
     };
-    issue_S(0);
-    issue_S(1);
-    for (int j = 0; j < NKT; ++j) {
+    issue_S(sw);
+    if (C::STREAMS == 1) issue_S(1);
+    for (int j = sw; j < NKT; j += C::STREAMS) {
       if (j + 2 < NKT) issue_S(j + 2);
       const int w = j & 1, n = j >> 1, vs = j % C::VST;
       mbar_wait(&p_full[w], n & 1, 54);
@@ -195,7 +207,7 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         }
         umma_commit(&p_empty[w]);
         umma_commit(&vempty[vs]);
-        if (j == NKT - 1) umma_commit(o_full);
+        if (j + C::STREAMS >= NKT) umma_commit(o_full);
       }
       __syncwarp();
     }
@@ -376,6 +388,7 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     }
   }
 
+done:
   tc_fence_before();
   __syncthreads();
   if (warp == 9) {
@@ -402,7 +415,7 @@ int launch_global_t(const AttnArgs& a, cudaStream_t stream) {
   GParams p;
   p.out = a.out; p.d_model = d_model; p.scale_log2 = a.scale * 1.4426950408889634f;
   prof_begin(stream, PROF_ATTN, (double)a.batch * a.heads * (4.0 * 4096 * 4096 * D + 4.0 * 4096 * 64 * D));
-  attn_global_kernel<D><<<dim3(32, a.heads, a.batch), 320, C::SMEM_BYTES, stream>>>(tmQKV, tmRTh, tmRTw, p);
+  attn_global_kernel<D><<<dim3(32, a.heads, a.batch), 384, C::SMEM_BYTES, stream>>>(tmQKV, tmRTh, tmRTw, p);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("global attention launch failed: %s", cudaGetErrorString(e));
