@@ -412,17 +412,25 @@ struct WinCfg {
   static constexpr int KSTEPS = D / 16;
   static constexpr int Q_BYTES = NB * ATT_BOX_BYTES;
   static constexpr int K_BYTES = NB * WIN_KBOX;
-  static constexpr int P_BYTES = 4 * ATT_BOX_BYTES;              // 4 blocks of 64 keys (last one 16 keys used)
-  static constexpr int R0_BYTES = (Q_BYTES + K_BYTES) > P_BYTES ? (Q_BYTES + K_BYTES) : P_BYTES;  // Q|K aliased by P
-  static constexpr int OFF_V = R0_BYTES;
-  static constexpr int OFF_RT = OFF_V + K_BYTES;
   static constexpr int RT_BOX = 64 * 128;
-  static constexpr int OFF_BAR = OFF_RT + NB * RT_BOX;
+  // COMPACT (head_dim 80, two 64-column boxes per operand): 152 KB in the plain layout = one CTA per SM, i.e. the serial
+  // load -> T -> S -> softmax -> P.V chain of a window runs unoverlapped.  Compact layout: P covers only keys [0,192) =
+  // 3 boxes = exactly Q|RT (48 KB); the last 4 real keys (192..195) are added on the CUDA cores in the epilogue; V is
+  // loaded over the dead K tile once S has been computed.  100 KB -> two CTAs per SM.
+  static constexpr bool COMPACT = (D == 80);
+  static constexpr int PV_KSTEPS = COMPACT ? 12 : WIN_NK / 16;
+  static constexpr int P_BYTES = (COMPACT ? 3 : 4) * ATT_BOX_BYTES;   // blocks of 64 keys
+  static constexpr int R0_BYTES = (Q_BYTES + K_BYTES) > P_BYTES ? (Q_BYTES + K_BYTES) : P_BYTES;  // Q|K aliased by P
+  static constexpr int OFF_K = COMPACT ? (Q_BYTES + NB * RT_BOX) : Q_BYTES;
+  static constexpr int OFF_V = COMPACT ? OFF_K : R0_BYTES;
+  static constexpr int OFF_RT = COMPACT ? Q_BYTES : OFF_V + K_BYTES;
+  static constexpr int OFF_BAR = COMPACT ? (OFF_K + K_BYTES) : (OFF_RT + NB * RT_BOX);
   static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static_assert(!COMPACT || P_BYTES <= Q_BYTES + NB * RT_BOX, "compact layout: P must fit over Q|RT");
 };
 
 template <int D>
-__global__ void __launch_bounds__(ATT_THREADS, (D == 64) ? 2 : 1)
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_window_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ CUtensorMap tmRT, const AttParams p) {
   using C = WinCfg<D>;
@@ -430,8 +438,8 @@ attn_window_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + C::Q_BYTES;
-  uint8_t* sP = smem;  // aliases Q|K once S has been computed
+  uint8_t* sK = smem + C::OFF_K;
+  uint8_t* sP = smem;  // aliases Q|K (compact: Q|RT) once S has been computed
   uint8_t* sV = smem + C::OFF_V;
   uint8_t* sRT = smem + C::OFF_RT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -470,6 +478,7 @@ attn_window_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_load_2d(sK + b * WIN_KBOX, &tmKV, ld_full, kcol + b * 64, row0);
         tma_load_2d(sRT + b * C::RT_BOX, &tmRT, ld_full, b * 64, 0);
       }
+      if (C::COMPACT) mbar_wait(s_full, 0, 44);  // S = Q K^T has been computed: V goes over the dead K tile
       mbar_expect_tx(v_full, C::K_BYTES);
       for (int b = 0; b < C::NB; ++b) tma_load_2d(sV + b * WIN_KBOX, &tmKV, v_full, vcol + b * 64, row0);
     }
@@ -498,7 +507,7 @@ attn_window_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(v_full, 0, 43);
       tc_fence_after();
 #pragma unroll
-      for (int ks = 0; ks < WIN_NK / 16; ++ks) {
+      for (int ks = 0; ks < C::PV_KSTEPS; ++ks) {
         const uint64_t da = make_desc_sw128(aP + (uint32_t)(ks >> 2) * ATT_BOX_BYTES + (uint32_t)(ks & 3) * 32u, 0, 1024);
         const uint64_t db = make_desc_sw128(aV + (uint32_t)ks * 2048u, WIN_KBOX, 1024);
         umma_bf16(tmem, da, db, idescO, ks > 0);   // O over the dead S columns [0, D)
@@ -558,6 +567,7 @@ attn_window_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     // pass B: p = exp2(s - m) -> bf16 P tile (K-major SW128 blocks of 64 keys) over the dead Q|K buffers
     float l = 0.f;
+    float ptail[4] = {0.f, 0.f, 0.f, 0.f};  // compact layout: probabilities of keys 192..195
 #pragma unroll
     for (int c = 0; c < 7; ++c) {
       uint32_t v[32];
@@ -575,7 +585,9 @@ attn_window_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (key + 1 < G) p1 = ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, yh[(key + 1) / S] + yw[(key + 1) % S]) - m);
         l += p0 + p1;
         pk[i >> 1] = pack_bf16(p0, p1);
+        if (C::COMPACT && c == 6 && i < 4) { ptail[i] = p0; ptail[i + 1] = p1; }
       }
+      if (C::COMPACT && c == 6) continue;  // keys 192.. are added in the epilogue
       uint8_t* prow = sP + (c >> 1) * ATT_BOX_BYTES + r * 128;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -604,6 +616,24 @@ attn_window_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       uint32_t v[16];
       tmem_ld16(tlane + c * 16, v);
       tmem_ld_wait();
+      if constexpr (C::COMPACT) {  // O += p[192..195] V[192..195]  (V tile: SW128 boxes of 64 dims, 208 rows of 128 B)
+        const uint32_t vb = smem_u32(sV) + (uint32_t)((c * 16) >> 6) * WIN_KBOX;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int row = 192 + k;
+#pragma unroll
+          for (int hx = 0; hx < 2; ++hx) {
+            const int ch = (((c * 16) & 63) >> 3) + hx;
+            const uint4 w4 = ld_shared_v4(vb + row * 128 + ((ch ^ (row & 7)) << 4));
+            const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[hx * 8 + 2 * e] = __float_as_uint(fmaf(ptail[k], __uint_as_float(ws[e] << 16), __uint_as_float(v[hx * 8 + 2 * e])));
+              v[hx * 8 + 2 * e + 1] = __float_as_uint(fmaf(ptail[k], __uint_as_float(ws[e] & 0xffff0000u), __uint_as_float(v[hx * 8 + 2 * e + 1])));
+            }
+          }
+        }
+      }
       if (out_row >= 0) {
         uint4 u0, u1;
         u0.x = pack_bf16(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
