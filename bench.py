@@ -269,10 +269,12 @@ def run_ours(args):
     gemm_ms, gemm_flops, gemm_n = prof[0], prof[1], prof[2]
     att_ms, att_flops, att_n = prof[3], prof[4], prof[5]
     hbm_ms, hbm_bytes, hbm_n = prof[6], prof[7], prof[8]
-    # dominant kernel of the step: the short-K decoder GEMMs with fused epilogues (HBM-bound) -> bytes / time vs HBM peak
+    # dominant kernels of the step: the decoder's image-side kernels (up-scaling GEMMs with fused LN / GELU / hyper-product
+    # epilogues and the two fused cross-attention blocks) -> algorithmic bytes / CUDA-event time vs the measured HBM peak
     hbm_gbs = hbm_bytes / (hbm_ms * 1e-3) / 1e9 if hbm_ms > 0 else 0.0
     enc_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    roof = {"bound": "hbm", "kernel": "gemm_bf16_kernel, K<512 instances (decoder GEMMs with fused LN/GELU/hyper epilogues)",
+    roof = {"bound": "hbm", "kernel": "decoder image-side kernels: gemm_bf16_kernel K<512 (conv-transpose GEMMs with fused LN2d+GELU / "
+                                     "GELU+hyper-product epilogues), i2t_fused_kernel, t2i_fused_kernel",
             "achieved": hbm_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / pk["hbm_gbs"], "traffic": None,
             "peak_source": f"{pk_src} hbm_gbs", "launches_per_step": hbm_n / args.steps, "share_of_step": hbm_ms / dev_ms,
             "algorithmic_bytes_per_step": hbm_bytes / args.steps,
