@@ -705,17 +705,21 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
 
   // token -> image attention core: t_q128 -> t_att128 (t2i_fused.cu)
   auto t2i = [&](const AttnW& A, int mode) -> int {
-    const int paired = (mode == 0 && T <= 8) ? 1 : 0;
-    const int n_items = paired ? (P + 1) / 2 : P;
-    if (launch_t2i_prep(d.t_q128, P, T, paired, n_items, d.qexp, st)) return -1;
-    if (gemm(E, st, d.qexp, DI, A.kT, n_items * 128, DC, DI, nullptr, d.qp, DC, 0)) return -1;
+    // T <= 8: 64 rows per prompt (row pp*64 + h*8 + t).  Shared image tokens (mode 0): two prompts per 128-row item;
+    // own keys (mode 1): one 64-row item per prompt (tcgen05 M = 64).  T > 8: 128 rows per prompt (h*16 + t).
+    const int small = T <= 8 ? 1 : 0;
+    const int prep_items = small ? (P + 1) / 2 : P;   // 128-row blocks of the Q' operand
+    if (launch_t2i_prep(d.t_q128, P, T, small, prep_items, d.qexp, st)) return -1;
+    if (gemm(E, st, d.qexp, DI, A.kT, prep_items * 128, DC, DI, nullptr, d.qp, DC, 0)) return -1;
     T2iFusedArgs ta;
-    ta.n_items = n_items; ta.mode = mode;
+    ta.mode = mode;
+    ta.rows = (small && mode) ? 64 : 128;
+    ta.n_items = (small && mode) ? P : prep_items;
     ta.x = mode ? d.keys : d.src_bf;
     ta.xs = mode ? d.pos_bf : d.src_pe_bf;
     ta.qp = d.qp; ta.out = d.un;
     if (launch_t2i_fused(ta, E.num_sms, st)) return -1;
-    return launch_t2i_head_proj(d.un, A.vT, A.vb, P, T, paired, d.t_att128, st);
+    return launch_t2i_head_proj(d.un, A.vT, A.vb, P, T, small, d.t_att128, st);
   };
 
   for (int l = 0; l < 2; ++l) {

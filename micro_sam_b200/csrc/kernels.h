@@ -64,7 +64,8 @@ int launch_i2t_prep(const __nv_bfloat16* ktok, const __nv_bfloat16* vtok, const 
 // ---- t2i_fused.cu : fused token -> image cross-attention (k / v projections folded into the query / output side; the image
 // tokens are read once and used as both K and V)
 struct T2iFusedArgs {
-  int n_items = 0;                    // work items of 128 Q' rows (one prompt, or two prompts when paired)
+  int n_items = 0;                    // work items of `rows` Q' rows
+  int rows = 128;                     // 128: one prompt (h*16 + t) or two prompts (pl*64 + h*8 + t); 64: one prompt, T <= 8
   int mode = 0;                       // 1: x = keys [n_items*4096, 256], xs = pe;  0: x = src (shared), xs = src + pe
   const __nv_bfloat16* x = nullptr;
   const __nv_bfloat16* xs = nullptr;

@@ -18,15 +18,23 @@
 namespace msam {
 
 namespace t2i {
-constexpr int XSTAGES = 3, PESLOTS = 4;
+constexpr int PESLOTS = 4;
 constexpr int XT = 64;                              // image tokens per tile
 constexpr int SUBX = XT * 128;                      // [64 tokens x 64 channels] sub-tile, 8 KB
 constexpr int XSTAGE_BYTES = 4 * SUBX;              // 32 KB
-constexpr int OFF_PE = XSTAGES * XSTAGE_BYTES;      // 98304
-constexpr int OFF_Q = OFF_PE + PESLOTS * SUBX;      // 131072: Q' 4 x [128 x 64]
-constexpr int OFF_P = OFF_Q + 4 * 16384;            // 196608: P [128 x 64]
-constexpr int OFF_BAR = OFF_P + 16384;              // 212992
-constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+// ROWS = Q' rows per work item: 128 (tcgen05 M = 128), or 64 for one prompt with T <= 8 tokens (M = 64: the accumulator
+// rows live in lanes 0..15 of each TMEM sub-partition, the A tiles and their shared-memory reads halve, and the space
+// buys a 4th image-token stage).
+template <int ROWS>
+struct Cfg {
+  static constexpr int XSTAGES = ROWS == 64 ? 4 : 3;
+  static constexpr int QSUB = ROWS * 128;           // one 64-channel slice of Q'
+  static constexpr int OFF_PE = XSTAGES * XSTAGE_BYTES;
+  static constexpr int OFF_Q = OFF_PE + PESLOTS * SUBX;
+  static constexpr int OFF_P = OFF_Q + 4 * QSUB;    // P [ROWS x 64]
+  static constexpr int OFF_BAR = OFF_P + QSUB;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+};
 constexpr int THREADS = 256;
 constexpr uint32_t TM_U = 0, TM_S = 256, TMEM_COLS = 512;
 constexpr int NTILES = 4096 / XT;
@@ -55,10 +63,13 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+template <int ROWS>
 __global__ void __launch_bounds__(t2i::THREADS, 1)
 t2i_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXS,
                  const __grid_constant__ CUtensorMap tmQ, const T2iParams p) {
   using namespace t2i;
+  using C = Cfg<ROWS>;
+  constexpr int XSTAGES = C::XSTAGES, QSUB = C::QSUB, OFF_PE = C::OFF_PE, OFF_Q = C::OFF_Q, OFF_P = C::OFF_P, OFF_BAR = C::OFF_BAR;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* xfull = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -98,9 +109,9 @@ t2i_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++ni) {
         mbar_wait(q_empty, (ni & 1) ^ 1, 20);
-        mbar_expect_tx(q_full, 4 * 16384);
+        mbar_expect_tx(q_full, 4 * QSUB);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) tma_load_2d(smem + OFF_Q + j * 16384, &tmQ, q_full, 64 * j, item * 128);
+        for (int j = 0; j < 4; ++j) tma_load_2d(smem + OFF_Q + j * QSUB, &tmQ, q_full, 64 * j, item * ROWS);
         const int row0 = p.mode ? item * 4096 : 0;
         for (int kt = 0; kt < NTILES; ++kt) {
           mbar_wait(&xempty[stage], phase ^ 1, 21);
@@ -131,8 +142,8 @@ t2i_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (warp-uniform control flow, elected lane issues)
     {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, XT);
-      constexpr uint32_t idesc_u = make_idesc_bf16(128, 256, 1);  // B = X consumed MN-major
+      constexpr uint32_t idesc_s = make_idesc_bf16(ROWS, XT);
+      constexpr uint32_t idesc_u = make_idesc_bf16(ROWS, 256, 1);  // B = X consumed MN-major
       const uint32_t aQ = smem_u32(smem + OFF_Q), aP = smem_u32(smem + OFF_P);
       int sstage = 0, vstage = 0, slot = 0, ni = 0;
       uint32_t sphase = 0, vphase = 0, pephase = 0;
@@ -172,7 +183,7 @@ t2i_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               for (int j = 0; j < 4; ++j) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_bf16(ts, make_desc_sw128(aQ + j * 16384 + k * 32, 0, 1024), make_desc_sw128(xb + j * SUBX + k * 32, 0, 1024),
+                  umma_bf16(ts, make_desc_sw128(aQ + j * QSUB + k * 32, 0, 1024), make_desc_sw128(xb + j * SUBX + k * 32, 0, 1024),
                             idesc_s, (j | k) != 0);
               }
             }
@@ -186,7 +197,7 @@ t2i_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_bf16(ts, make_desc_sw128(aQ + j * 16384 + k * 32, 0, 1024), make_desc_sw128(pb + k * 32, 0, 1024), idesc_s,
+                umma_bf16(ts, make_desc_sw128(aQ + j * QSUB + k * 32, 0, 1024), make_desc_sw128(pb + k * 32, 0, 1024), idesc_s,
                           (p.mode | j | k) != 0);
               umma_commit(&peempty[slot]);
               if (j == 3) {
@@ -207,7 +218,11 @@ t2i_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ softmax warps: thread = row (head, token)
-    const int quad = warp & 3, r = quad * 32 + lane;
+    // M = 128: row r <-> TMEM lane r.  M = 64: rows 16q .. 16q+15 live in lanes 0..15 of sub-partition q; lanes 16..31 idle
+    // (they still take part in the warp-collective tcgen05.ld / st and in the votes)
+    const int quad = warp & 3;
+    const bool active = ROWS == 128 || lane < 16;
+    const int r = ROWS == 128 ? quad * 32 + lane : quad * 16 + (lane & 15);
     const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t prow = smem_u32(smem + OFF_P) + r * 128;
     uint32_t ns = 0;
@@ -239,7 +254,7 @@ t2i_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (kt == 0) {
           m_used = mt;
         } else {
-          const bool need = mt > m_used + RESCALE_T;
+          const bool need = active && mt > m_used + RESCALE_T;
           if (__any_sync(0xffffffffu, need)) {  // lazy rescale of this warp's rows of U (warp-uniform: tcgen05.ld/st are collective)
             const float f = need ? ex2f(m_used - mt) : 1.0f;
 #pragma unroll 1
@@ -260,10 +275,12 @@ t2i_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < XT; ++j) { s[j] = ex2f(s[j] - m_used); ls[j & 3] += s[j]; }
         l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+        if (active) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          st_shared_v4(prow + ((c ^ (r & 7)) << 4), make_uint4(pack_bf16(s[8 * c], s[8 * c + 1]), pack_bf16(s[8 * c + 2], s[8 * c + 3]),
-                                                               pack_bf16(s[8 * c + 4], s[8 * c + 5]), pack_bf16(s[8 * c + 6], s[8 * c + 7])));
+          for (int c = 0; c < 8; ++c)
+            st_shared_v4(prow + ((c ^ (r & 7)) << 4), make_uint4(pack_bf16(s[8 * c], s[8 * c + 1]), pack_bf16(s[8 * c + 2], s[8 * c + 3]),
+                                                                 pack_bf16(s[8 * c + 4], s[8 * c + 5]), pack_bf16(s[8 * c + 6], s[8 * c + 7])));
+        }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
@@ -273,16 +290,18 @@ t2i_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       mbar_wait(u_full, ni & 1, 32);
       tc_fence_after();
       const float inv = 1.0f / l;
-      float* dst = p.out + ((size_t)item * 128 + r) * 256;
+      float* dst = p.out + ((size_t)item * ROWS + r) * 256;
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         uint32_t v[32];
         tmem_ld32(tlane + TM_U + 32 * c, v);
         tmem_ld_wait();
+        if (active) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(dst + 32 * c + j) = make_float4(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv,
-                                                                     __uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + 32 * c + j) = make_float4(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv,
+                                                                       __uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -298,12 +317,13 @@ t2i_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   }
 }
 
-int launch_t2i_fused(const T2iFusedArgs& a, int num_sms, cudaStream_t stream) {
+template <int ROWS>
+static int launch_t2i_fused_t(const T2iFusedArgs& a, int num_sms, cudaStream_t stream) {
   using namespace t2i;
-  if (a.n_items <= 0) return set_error("t2i_fused: empty problem");
+  using C = Cfg<ROWS>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(t2i_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(t2i_fused_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("t2i_fused: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -311,17 +331,24 @@ int launch_t2i_fused(const T2iFusedArgs& a, int num_sms, cudaStream_t stream) {
   const uint64_t xrows = a.mode ? (uint64_t)a.n_items * 4096 : 4096;
   if (make_tmap_bf16_2d(&tmX, a.x, xrows, 256, 256, XT)) return -1;
   if (make_tmap_bf16_2d(&tmXS, a.xs, 4096, 256, 256, XT)) return -1;
-  if (make_tmap_bf16_2d(&tmQ, a.qp, (uint64_t)a.n_items * 128, 256, 256, 128)) return -1;
+  if (make_tmap_bf16_2d(&tmQ, a.qp, (uint64_t)a.n_items * ROWS, 256, 256, ROWS)) return -1;
   T2iParams p;
   p.n_items = a.n_items; p.mode = a.mode; p.out = a.out;
   const int grid = a.n_items < num_sms ? a.n_items : num_sms;
-  prof_begin(stream, PROF_GEMM_HBM, (double)a.n_items * (128.0 * 256 * 2 + 128.0 * 256 * 4) + (a.mode ? (double)a.n_items * 4096 * 512 : 0.0));
-  t2i_fused_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmX, tmXS, tmQ, p);
+  prof_begin(stream, PROF_GEMM_HBM, (double)a.n_items * (ROWS * 256.0 * 2 + ROWS * 256.0 * 4) + (a.mode ? (double)a.n_items * 4096 * 512 : 0.0));
+  t2i_fused_kernel<ROWS><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tmX, tmXS, tmQ, p);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("t2i_fused launch failed: %s", cudaGetErrorString(e));
   count_launch();
   return 0;
+}
+
+int launch_t2i_fused(const T2iFusedArgs& a, int num_sms, cudaStream_t stream) {
+  if (a.n_items <= 0) return set_error("t2i_fused: empty problem");
+  if (a.rows == 64) return launch_t2i_fused_t<64>(a, num_sms, stream);
+  if (a.rows == 128) return launch_t2i_fused_t<128>(a, num_sms, stream);
+  return set_error("t2i_fused: rows per item must be 64 or 128 (%d)", a.rows);
 }
 
 // Row of prompt pp, head h, token t inside the Q' / U tensors.
