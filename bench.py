@@ -159,25 +159,31 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------------- our arm
 def vit_h_roofline(device, steps=3):
-    """ViT-H encoder forward on a batch of 8 tiles: ms/tile and fraction of the bf16 tensor roofline."""
+    """ViT-H encoder forward: ms/tile and fraction of the bf16 tensor roofline.  Measured at batch 4 and 8 tiles (distinct
+    uint8 tiles each step, so nothing is cached): at batch 4 the fp32 residual stream (84 MB) stays in the 126 MB L2,
+    at batch 8 it does not -- the better of the two is reported together with its batch."""
     from oracle import sam_ref  # weights only (seeded generator); nothing of the oracle is timed here
     from micro_sam_b200.sam import B200Sam
     sd = {k: v for k, v in sam_ref.seeded_state_dict("vit_h", seed=0).items() if k.startswith("image_encoder.")}
     sam = B200Sam("vit_h", sd, device=device, max_batch=8, max_prompts=1)
-    x = torch.randint(0, 255, (8, TILE, TILE, 3), dtype=torch.uint8, device=device)
-    for _ in range(2):
-        sam.encode_u8(x)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        sam.encode_u8(x)
-    e1.record()
-    torch.cuda.synchronize()
-    ms_tile = e0.elapsed_time(e1) / steps / 8
+    best = None
+    for batch in (8, 4):
+        xs = [torch.randint(0, 255, (batch, TILE, TILE, 3), dtype=torch.uint8, device=device) for _ in range(steps)]
+        for _ in range(2):
+            sam.encode_u8(xs[0])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            sam.encode_u8(xs[k])
+        e1.record()
+        torch.cuda.synchronize()
+        ms_tile = e0.elapsed_time(e1) / steps / batch
+        if best is None or ms_tile < best[0]:
+            best = (ms_tile, batch)
     del sam
     torch.cuda.empty_cache()
-    return ms_tile
+    return best
 
 
 def run_ours(args):
@@ -194,7 +200,7 @@ def run_ours(args):
     pk, pk_src = peaks()
 
     sd = sam_ref.seeded_state_dict(args.model, seed=0)
-    pred = util.get_sam_model(args.model, device=device, state_dict=sd, max_batch=N_TILES, max_prompts=args.max_prompts)
+    pred = util.get_sam_model(args.model, device=device, state_dict=sd, max_batch=args.enc_batch, max_prompts=args.max_prompts)
     sam = pred.model
     amg = iseg.AutomaticMaskGenerator(pred, points_per_side=GRID)
     tiles = make_tiles(seed0=rank * N_TILES)                                   # host uint16 (16,1024,1024)
@@ -302,10 +308,10 @@ def run_ours(args):
     if world == 1 and not args.no_vith:
         del pred, sam, amg
         torch.cuda.empty_cache()
-        ms_tile = vit_h_roofline(device)
+        ms_tile, vith_batch = vit_h_roofline(device)
         tf = ENC_FLOPS["vit_h"] / (ms_tile * 1e-3) / 1e12
         out["vit_h_encoder"] = {"ms_per_tile": ms_tile, "tflops": tf, "frac_of_peak": tf / pk["bf16_tflops_sustained"],
-                                "peak": pk["bf16_tflops_sustained"], "batch": 8, "algorithmic_tflop_per_tile": 5.6418}
+                                "peak": pk["bf16_tflops_sustained"], "batch": vith_batch, "algorithmic_tflop_per_tile": 5.6418}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -319,6 +325,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="vit_b")
     ap.add_argument("--max-prompts", type=int, default=1024)
+    ap.add_argument("--enc-batch", type=int, default=16, help="tiles per encoder pass (the engine chunks the 16-tile batch)")
     ap.add_argument("--pred-iou-thresh", type=float, default=0.88)
     ap.add_argument("--stability-score-thresh", type=float, default=0.95)
     ap.add_argument("--no-vith", action="store_true")

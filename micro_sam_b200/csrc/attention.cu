@@ -1,15 +1,7 @@
-// ViT-encoder attention for sm_100a: softmax(scale * Q K^T + rel_h[q,kh] + rel_w[q,kw]) V, one CTA per
-// (128-query tile, head, group) where a group is a 14x14 window (196 tokens incl. zero-pad tokens, which stay in the
-// key set with q=k=v=qkv.bias exactly like the reference) or a whole 64x64 image (global blocks).
-//
-// Restates segment_anything's Attention.forward + add_decomposed_rel_pos (oracle/sam_ref.py:Attention) as
-//   * tcgen05.mma (cta_group::1, kind::f16):  T = Q RT^T (all relative-position dot products, fp32 in TMEM),
-//     S = Q K^T (128x128 per key tile, double-buffered in TMEM), O += P V (V consumed MN-major straight from the
-//     TMA tile), all operands TMA-loaded with SWIZZLE_128B;
-//   * a two-pass exact softmax (pass A: row max over all key tiles; pass B: exp2 / row sum / bf16 P tile to shared
-//     memory in the UMMA K-major SW128 layout), so O accumulates in TMEM with no rescaling;
-//   * the decomposed bias is gathered from T: rel_w[q, 0..S) lives in registers (static indices after a per-lane
-//     log-step shift), rel_h[q, kh] is re-read from TMEM per key tile (global) or kept in registers (window).
+// Windowed ViT-encoder attention for sm_100a (14x14 windows, 196 keys incl. the zero-pad tokens, which stay in the key set
+// with q=k=v=qkv.bias exactly like the reference): softmax(scale * Q K^T + rel_h[q,kh] + rel_w[q,kw]) V, one CTA per
+// (128-query tile, head, window).  Restates segment_anything's Attention.forward + add_decomposed_rel_pos
+// (oracle/sam_ref.py:Attention).  The global (64x64) blocks live in attention_global.cu.
 // Warp roles: warps 0-3 softmax/epilogue (thread r <-> query row r <-> TMEM lane r), warp 4 TMA producer,
 // warp 5 TMEM allocator + MMA issuer.
 #include "kernels.h"
@@ -21,29 +13,6 @@ namespace msam {
 
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_BOX_BYTES = 128 * 128;  // 128 rows x 64 bf16
-
-template <int D, int S>
-struct AttCfg {
-  static constexpr int NB = (D + 63) / 64;        // 64-column TMA boxes per operand tile
-  static constexpr int KSTEPS = D / 16;           // UMMA K steps over the head dim
-  static constexpr int G = (S == 64) ? 4096 : S * S;   // tokens per group
-  static constexpr int NKT = (G + 127) / 128;     // key tiles == query tiles per group
-  static constexpr int NT = (S == 64) ? 256 : 64; // rows of the relative-position table tile
-  static constexpr int WOFF = (S == 64) ? 128 : 32;    // first rel_w row / T column
-  static constexpr int TILE_BYTES = NB * ATT_BOX_BYTES;
-  static constexpr int RT_BOX_BYTES = NT * 128;
-  static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = OFF_Q + TILE_BYTES;
-  static constexpr int OFF_V = OFF_K + 2 * TILE_BYTES;   // RT aliases the V stages until T has been computed
-  static constexpr int OFF_P = OFF_V + 2 * TILE_BYTES;
-  static constexpr int OFF_BAR = OFF_P + 2 * ATT_BOX_BYTES;
-  static constexpr int SMEM_BYTES_MIN = OFF_BAR + 256 + 1024;
-  // request > half of the SM's shared memory so that exactly one CTA (which allocates all 512 TMEM columns) is resident
-  static constexpr int SMEM_BYTES = SMEM_BYTES_MIN > 120 * 1024 ? SMEM_BYTES_MIN : 120 * 1024;
-  static_assert(NB * RT_BOX_BYTES <= 2 * TILE_BYTES, "rel table must fit in the V stages");
-};
-
-constexpr uint32_t TM_S0 = 128, TM_O = 384;  // TMEM column map: [0,128) T_h | [128,256) T_w then S0 | [256,384) S1 | O
 
 struct AttParams {
   __nv_bfloat16* out;
@@ -69,333 +38,6 @@ __device__ __forceinline__ void lane_shift(float (&x)[N], int sh) {
     for (int i = 0; i + step < N; ++i) x[i] = on ? x[i + step] : x[i];
   }
 }
-
-// Pre-softmax logit (in log2 units) of static column `col` of key tile `j`; returns false if the key is masked.
-template <int S, int JS>
-struct KeyIdx {
-  // window case: everything static
-  static __device__ __forceinline__ constexpr bool valid(int col) { return JS * 128 + col < S * S; }
-  static __device__ __forceinline__ constexpr int kh(int col) { return (JS * 128 + col) / S; }
-  static __device__ __forceinline__ constexpr int kw(int col) { return (JS * 128 + col) % S; }
-};
-
-template <int D, int S>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmRT, const AttParams p) {
-  using C = AttCfg<D, S>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem + C::OFF_Q;
-  uint8_t* sK = smem + C::OFF_K;
-  uint8_t* sV = smem + C::OFF_V;
-  uint8_t* sP = smem + C::OFF_P;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint64_t* q_full = bars + 0;
-  uint64_t* t_full = bars + 1;
-  uint64_t* t_done = bars + 2;
-  uint64_t* kfull = bars + 3;    // [2]
-  uint64_t* kempty = bars + 5;   // [2]
-  uint64_t* vfull = bars + 7;    // [2]
-  uint64_t* vempty = bars + 9;   // [2]
-  uint64_t* s_full = bars + 11;  // [2]
-  uint64_t* s_empty = bars + 13; // [2]
-  uint64_t* p_full = bars + 15;
-  uint64_t* p_empty = bars + 16;
-  uint64_t* o_full = bars + 17;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, head = blockIdx.y, group = blockIdx.z;
-
-  if (warp == 4 && lane == 0) {
-    prefetch_tmap(&tmQKV);
-    prefetch_tmap(&tmRT);
-    mbar_init(q_full, 1);
-    mbar_init(t_full, 1);
-    mbar_init(t_done, 128);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&kfull[i], 1);
-      mbar_init(&kempty[i], 1);
-      mbar_init(&vfull[i], 1);
-      mbar_init(&vempty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128);
-    }
-    mbar_init(p_full, 128);
-    mbar_init(p_empty, 1);
-    mbar_init(o_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 5) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  const int row0 = group * C::G;  // first token row of this group in the qkv buffer
-
-  if (warp == 4) {
-    // =========================================================== TMA producer
-    if (lane == 0) {
-      const int qcol = head * D, kcol = p.d_model + head * D, vcol = 2 * p.d_model + head * D;
-      mbar_expect_tx(q_full, C::TILE_BYTES + C::NB * C::RT_BOX_BYTES);
-      for (int b = 0; b < C::NB; ++b) tma_load_2d(sQ + b * ATT_BOX_BYTES, &tmQKV, q_full, qcol + b * 64, row0 + qt * 128);
-      for (int b = 0; b < C::NB; ++b) tma_load_2d(sV + b * C::RT_BOX_BYTES, &tmRT, q_full, b * 64, 0);
-      int kc = 0;
-      for (int j = 0; j < C::NKT; ++j, ++kc) {  // pass A: K only
-        const int st = kc & 1;
-        mbar_wait(&kempty[st], ((kc >> 1) & 1) ^ 1, 10);
-        mbar_expect_tx(&kfull[st], C::TILE_BYTES);
-        for (int b = 0; b < C::NB; ++b)
-          tma_load_2d(sK + st * C::TILE_BYTES + b * ATT_BOX_BYTES, &tmQKV, &kfull[st], kcol + b * 64, row0 + j * 128);
-      }
-      mbar_wait(t_full, 0, 11);  // the T MMAs have finished reading RT -> the V stages are free
-      for (int j = 0; j < C::NKT; ++j, ++kc) {  // pass B: K and V
-        const int st = kc & 1;
-        mbar_wait(&kempty[st], ((kc >> 1) & 1) ^ 1, 12);
-        mbar_expect_tx(&kfull[st], C::TILE_BYTES);
-        for (int b = 0; b < C::NB; ++b)
-          tma_load_2d(sK + st * C::TILE_BYTES + b * ATT_BOX_BYTES, &tmQKV, &kfull[st], kcol + b * 64, row0 + j * 128);
-        const int vs = j & 1;
-        mbar_wait(&vempty[vs], ((j >> 1) & 1) ^ 1, 13);
-        mbar_expect_tx(&vfull[vs], C::TILE_BYTES);
-        for (int b = 0; b < C::NB; ++b)
-          tma_load_2d(sV + vs * C::TILE_BYTES + b * ATT_BOX_BYTES, &tmQKV, &vfull[vs], vcol + b * 64, row0 + j * 128);
-      }
-    }
-  } else if (warp == 5) {
-    // =========================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idescT = make_idesc_bf16(128, C::NT);
-      constexpr uint32_t idescS = make_idesc_bf16(128, 128);
-      constexpr uint32_t idescO = make_idesc_bf16(128, D, 1);  // B (= V) is MN-major
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
-      // K-major operand, K step ks: box ks/4, +32 B per step inside the 128-B swizzle atom
-      auto kdesc = [](uint32_t base, uint32_t box_bytes, int ks) {
-        return make_desc_sw128(base + (uint32_t)(ks >> 2) * box_bytes + (uint32_t)(ks & 3) * 32u, 0, 1024);
-      };
-      mbar_wait(q_full, 0, 20);
-      tc_fence_after();
-#pragma unroll
-      for (int ks = 0; ks < C::KSTEPS; ++ks)
-        umma_bf16(tmem, kdesc(aQ, ATT_BOX_BYTES, ks), kdesc(aV, C::RT_BOX_BYTES, ks), idescT, ks > 0);
-      umma_commit(t_full);
-      mbar_wait(t_done, 0, 21);  // softmax warps have pulled T_w (aliases S0) into registers
-      tc_fence_after();
-
-      int kc = 0, sc = 0;
-      auto issue_S = [&]() {
-        const int st = kc & 1, sb = sc & 1;
-        mbar_wait(&kfull[st], (kc >> 1) & 1, 22);
-        mbar_wait(&s_empty[sb], ((sc >> 1) & 1) ^ 1, 23);
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < C::KSTEPS; ++ks)
-          umma_bf16(tmem + TM_S0 + sb * 128, kdesc(aQ, ATT_BOX_BYTES, ks),
-                    kdesc(aK + st * C::TILE_BYTES, ATT_BOX_BYTES, ks), idescS, ks > 0);
-        umma_commit(&s_full[sb]);
-        umma_commit(&kempty[st]);
-        ++kc;
-        ++sc;
-      };
-      for (int j = 0; j < C::NKT; ++j) issue_S();  // pass A
-      issue_S();                                   // pass B, tile 0
-      for (int j = 0; j < C::NKT; ++j) {
-        if (j + 1 < C::NKT) issue_S();
-        const int vs = j & 1;
-        mbar_wait(p_full, j & 1, 24);
-        mbar_wait(&vfull[vs], (j >> 1) & 1, 25);
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t da = make_desc_sw128(aP + (uint32_t)(ks >> 2) * ATT_BOX_BYTES + (uint32_t)(ks & 3) * 32u, 0, 1024);
-          // V tile: rows = keys (K), 128-B rows of 64 head-dim elements (MN); 16 keys = 2048 B; next 64-col block = 16 KB
-          const uint64_t db = make_desc_sw128(aV + vs * C::TILE_BYTES + (uint32_t)ks * 2048u, ATT_BOX_BYTES, 1024);
-          umma_bf16(tmem + TM_O, da, db, idescO, (j | ks) != 0);
-        }
-        umma_commit(p_empty);
-        umma_commit(&vempty[vs]);
-      }
-      umma_commit(o_full);
-    }
-  } else {
-    // =========================================================== softmax / epilogue warps (thread r <-> query row r)
-    const int r = threadIdx.x;  // 0..127
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
-    const int qi = qt * 128 + r;
-    constexpr float LOG2E = 1.4426950408889634f;
-    float yw[S];                          // rel_w[q, kw] * log2e
-    float yh[(S == 64) ? 1 : S];          // window: rel_h[q, kh] * log2e
-    int qh_u = 0;                         // global: warp-uniform query row (qi / 64)
-
-    mbar_wait(t_full, 0, 30);
-    tc_fence_after();
-    if constexpr (S == 64) {
-      qh_u = (qt * 128 + warp * 32) >> 6;
-      const int qw = qi & 63;
-      float x[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tlane + C::WOFF + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) x[c * 32 + i] = __uint_as_float(v[i]);
-      }
-      lane_shift<128, 6>(x, qw);          // x[i] = T_w[q][i + qw]
-#pragma unroll
-      for (int kw = 0; kw < 64; ++kw) yw[kw] = x[63 - kw] * LOG2E;   // T_w[q][qw - kw + 63]
-    } else {
-      int qh = qi / S, qw = qi % S;
-      if (qh > S - 1) qh = S - 1;         // rows beyond the group (discarded) must still index inside the table
-      float x[32];
-      uint32_t v[32];
-      tmem_ld32(tlane + 0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
-      lane_shift<32, 4>(x, qh);
-#pragma unroll
-      for (int kh = 0; kh < S; ++kh) yh[kh] = x[S - 1 - kh] * LOG2E;
-      tmem_ld32(tlane + C::WOFF, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
-      lane_shift<32, 4>(x, qw);
-#pragma unroll
-      for (int kw = 0; kw < S; ++kw) yw[kw] = x[S - 1 - kw] * LOG2E;
-    }
-    tc_fence_before();
-    mbar_arrive(t_done);
-
-    const float sl2 = p.scale_log2;
-    int sc = 0;
-    float m = -INFINITY, l = 0.f;
-
-    // One key tile.  JS >= 0: static tile index (window), JS < 0: dynamic tile index j (global).
-    auto tile = [&](auto js_tag, auto pb_tag, int j) {
-      constexpr int JS = decltype(js_tag)::value;
-      constexpr bool pass_b = decltype(pb_tag)::value;
-      const int sb = sc & 1;
-      mbar_wait(&s_full[sb], (sc >> 1) & 1, 31);
-      tc_fence_after();
-      float rh0 = 0.f, rh1 = 0.f;
-      if constexpr (S == 64) {
-        uint32_t a, b;
-        tmem_ld2(tlane + (uint32_t)(qh_u + 62 - 2 * j), a, b);  // T_h[q][qh+62-2j], T_h[q][qh+63-2j]
-        tmem_ld_wait();
-        rh1 = __uint_as_float(a) * LOG2E;  // kh = 2j+1
-        rh0 = __uint_as_float(b) * LOG2E;  // kh = 2j
-      }
-      if (pass_b) mbar_wait(p_empty, (j & 1) ^ 1, 32);  // PV of the previous tile has consumed the P buffer
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tlane + TM_S0 + sb * 128 + c * 32, v);
-        tmem_ld_wait();
-        float s[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = c * 32 + i;
-          float bias;
-          bool ok = true;
-          if constexpr (S == 64) {
-            bias = ((col < 64) ? rh0 : rh1) + yw[col & 63];
-          } else {
-            constexpr int JJ = JS < 0 ? 0 : JS;
-            ok = KeyIdx<S, JJ>::valid(col);
-            bias = ok ? yh[ok ? KeyIdx<S, JJ>::kh(col) : 0] + yw[KeyIdx<S, JJ>::kw(col)] : 0.f;
-          }
-          s[i] = ok ? fmaf(__uint_as_float(v[i]), sl2, bias) : -INFINITY;
-        }
-        if (!pass_b) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) m = fmaxf(m, s[i]);
-        } else {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2f(s[i] - m), p1 = ex2f(s[i + 1] - m);
-            l += p0 + p1;
-            pk[i >> 1] = pack_bf16(p0, p1);
-          }
-          // P tile, K-major SW128: row r = 128 B, logical 16-B chunk ch -> physical chunk ch ^ (r & 7)
-          uint8_t* prow = sP + (c >> 1) * ATT_BOX_BYTES + r * 128;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int ch = (c & 1) * 4 + q;
-            *reinterpret_cast<uint4*>(prow + ((ch ^ (r & 7)) << 4)) =
-                make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-          }
-        }
-      }
-      tc_fence_before();
-      if (pass_b) {
-        fence_proxy_async_smem();  // generic-proxy P writes -> visible to the UMMA (async proxy) reads
-        mbar_arrive(p_full);
-      }
-      mbar_arrive(&s_empty[sb]);
-      ++sc;
-    };
-
-    if constexpr (S == 64) {
-#pragma unroll 1
-      for (int j = 0; j < C::NKT; ++j) tile(std::integral_constant<int, -1>{}, std::false_type{}, j);
-#pragma unroll 1
-      for (int j = 0; j < C::NKT; ++j) tile(std::integral_constant<int, -1>{}, std::true_type{}, j);
-    } else {
-      static_assert(S == 64 || C::NKT == 2, "window path is written for two key tiles");
-      tile(std::integral_constant<int, 0>{}, std::false_type{}, 0);
-      tile(std::integral_constant<int, 1>{}, std::false_type{}, 1);
-      tile(std::integral_constant<int, 0>{}, std::true_type{}, 0);
-      tile(std::integral_constant<int, 1>{}, std::true_type{}, 1);
-    }
-
-    // ---- epilogue: O / l -> bf16 -> out[token row][head*D ...]
-    mbar_wait(o_full, 0, 33);
-    tc_fence_after();
-    const float inv = 1.0f / l;
-    long out_row = -1;
-    if constexpr (S == 64) {
-      out_row = (long)group * C::G + qi;
-    } else {
-      const int wpr = (p.grid + S - 1) / S;  // windows per image side (5)
-      const int b = group / (wpr * wpr), wy = (group / wpr) % wpr, wx = group % wpr;
-      const int y = wy * S + qi / S, x = wx * S + qi % S;
-      if (qi < C::G && y < p.grid && x < p.grid) out_row = (long)b * p.grid * p.grid + y * p.grid + x;
-    }
-    __nv_bfloat16* orow = p.out + (out_row < 0 ? 0 : out_row) * p.d_model + head * D;
-#pragma unroll
-    for (int c = 0; c < D / 16; ++c) {
-      uint32_t v[16];
-      tmem_ld16(tlane + TM_O + c * 16, v);
-      tmem_ld_wait();
-      if (out_row >= 0) {
-        uint4 u0, u1;
-        u0.x = pack_bf16(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
-        u0.y = pack_bf16(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
-        u0.z = pack_bf16(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
-        u0.w = pack_bf16(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
-        u1.x = pack_bf16(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
-        u1.y = pack_bf16(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
-        u1.z = pack_bf16(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
-        u1.w = pack_bf16(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
-        *reinterpret_cast<uint4*>(orow + c * 16) = u0;
-        *reinterpret_cast<uint4*>(orow + c * 16 + 8) = u1;
-      }
-      __syncwarp();
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 5) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
-  }
-}
-
 
 // =================================================================================================================
 // Windowed attention (14x14 windows, 196 keys incl. pad tokens): one CTA per (128-query tile, head, window).
@@ -483,29 +125,36 @@ attn_window_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int b = 0; b < C::NB; ++b) tma_load_2d(sV + b * WIN_KBOX, &tmKV, v_full, vcol + b * 64, row0);
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      constexpr uint32_t idescT = make_idesc_bf16(128, 64);
-      constexpr uint32_t idescS = make_idesc_bf16(128, WIN_NK);
-      constexpr uint32_t idescO = make_idesc_bf16(128, D, 1);
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), aRT = smem_u32(sRT);
-      auto kdesc = [](uint32_t base, uint32_t box_bytes, int ks) {
-        return make_desc_sw128(base + (uint32_t)(ks >> 2) * box_bytes + (uint32_t)(ks & 3) * 32u, 0, 1024);
-      };
-      mbar_wait(ld_full, 0, 40);
-      tc_fence_after();
+    // MMA issuer: warp-uniform control flow, one elected lane issues (see ptx.cuh:elect_one)
+    constexpr uint32_t idescT = make_idesc_bf16(128, 64);
+    constexpr uint32_t idescS = make_idesc_bf16(128, WIN_NK);
+    constexpr uint32_t idescO = make_idesc_bf16(128, D, 1);
+    const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), aRT = smem_u32(sRT);
+    auto kdesc = [](uint32_t base, uint32_t box_bytes, int ks) {
+      return make_desc_sw128(base + (uint32_t)(ks >> 2) * box_bytes + (uint32_t)(ks & 3) * 32u, 0, 1024);
+    };
+    mbar_wait(ld_full, 0, 40);
+    tc_fence_after();
+    if (elect_one()) {
 #pragma unroll
       for (int ks = 0; ks < C::KSTEPS; ++ks)
         umma_bf16(tmem, kdesc(aQ, ATT_BOX_BYTES, ks), kdesc(aRT, C::RT_BOX, ks), idescT, ks > 0);
       umma_commit(t_full);
-      mbar_wait(t_done, 0, 41);  // T (columns [0,64)) is in registers: S may overwrite it
-      tc_fence_after();
+    }
+    __syncwarp();
+    mbar_wait(t_done, 0, 41);  // T (columns [0,64)) is in registers: S may overwrite it
+    tc_fence_after();
+    if (elect_one()) {
 #pragma unroll
       for (int ks = 0; ks < C::KSTEPS; ++ks)
         umma_bf16(tmem, kdesc(aQ, ATT_BOX_BYTES, ks), kdesc(aK, WIN_KBOX, ks), idescS, ks > 0);
       umma_commit(s_full);
-      mbar_wait(p_full, 0, 42);  // P written (over Q|K) and S fully consumed
-      mbar_wait(v_full, 0, 43);
-      tc_fence_after();
+    }
+    __syncwarp();
+    mbar_wait(p_full, 0, 42);  // P written (over Q|K) and S fully consumed
+    mbar_wait(v_full, 0, 43);
+    tc_fence_after();
+    if (elect_one()) {
 #pragma unroll
       for (int ks = 0; ks < C::PV_KSTEPS; ++ks) {
         const uint64_t da = make_desc_sw128(aP + (uint32_t)(ks >> 2) * ATT_BOX_BYTES + (uint32_t)(ks & 3) * 32u, 0, 1024);
@@ -514,6 +163,7 @@ attn_window_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       umma_commit(o_full);
     }
+    __syncwarp();
   } else {
     const int r = threadIdx.x;
     const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
@@ -682,38 +332,6 @@ static int launch_attn_window(const AttnArgs& a, cudaStream_t stream) {
   prof_end(stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("window attention launch failed: %s", cudaGetErrorString(e));
-  count_launch();
-  return 0;
-}
-
-template <int D, int S>
-static int launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
-  using C = AttCfg<D, S>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<D, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    if (e != cudaSuccess) return set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  const int d_model = a.heads * D;
-  const int wpr = (S == 64) ? 1 : (a.grid + S - 1) / S;
-  const int groups = a.batch * wpr * wpr;
-  const long rows = (long)groups * C::G;
-  CUtensorMap tmQKV, tmRT;
-  if (make_tmap_bf16_2d(&tmQKV, a.qkv, rows, 3 * d_model, 3 * d_model, 128)) return -1;
-  if (make_tmap_bf16_2d(&tmRT, a.rel_table, C::NT, C::NB * 64, C::NB * 64, C::NT)) return -1;
-  AttParams p;
-  p.out = a.out;
-  p.d_model = d_model;
-  p.grid = a.grid;
-  p.scale_log2 = a.scale * 1.4426950408889634f;
-  dim3 grid(C::NKT, a.heads, groups);
-  // algorithmic FLOPs: QK^T + PV over the G keys of each group (+ the rel-pos dot products)
-  prof_begin(stream, PROF_ATTN, (double)groups * a.heads * (4.0 * C::G * C::G * D + 4.0 * C::G * S * D));
-  attn_kernel<D, S><<<grid, ATT_THREADS, C::SMEM_BYTES, stream>>>(tmQKV, tmRT, p);
-  prof_end(stream);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_error("attention launch failed: %s", cudaGetErrorString(e));
   count_launch();
   return 0;
 }

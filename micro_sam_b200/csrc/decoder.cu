@@ -279,92 +279,6 @@ __global__ void token_self_attn_kernel(const __nv_bfloat16* __restrict__ q, int 
   }
 }
 
-// token -> image attention core.  q [P*T,128] (bf16, projected), k/v [*, ld] image-side (kv_stride_rows = 0 when shared
-// by all prompts, else 4096 rows per prompt).  One CTA per prompt, warp = head (16 dims), lane = slice of image tokens;
-// per-(token, lane) online softmax with lazy rescaling (the running max rarely moves after the first keys), the next
-// key/value rows are prefetched into registers while the current ones are consumed; lanes are combined at the end.
-// Tokens are handled in groups of 8 (AMG / box prompts have T = 7).
-__global__ void __launch_bounds__(256)
-t2i_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
-                const __nv_bfloat16* __restrict__ v, int ld, long kv_stride_rows, int T, int NI,
-                __nv_bfloat16* __restrict__ out) {
-  const int p = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ __align__(16) float sq[TMAX][DI];
-  for (int i = threadIdx.x; i < T * DI; i += 256) sq[i / DI][i % DI] = __bfloat162float(q[(long)p * T * DI + i]) * 0.25f;
-  __syncthreads();
-  const __nv_bfloat16* kp = k + (long)p * kv_stride_rows * ld + h * 16;
-  const __nv_bfloat16* vp = v + (long)p * kv_stride_rows * ld + h * 16;
-  for (int t0 = 0; t0 < T; t0 += 8) {
-    const int nt = (T - t0 < 8) ? (T - t0) : 8;
-    float m[8], l[8], acc[8][16];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      m[t] = -1e30f; l[t] = 0.f;
-#pragma unroll
-      for (int d = 0; d < 16; ++d) acc[t][d] = 0.f;
-    }
-    uint4 ka = *reinterpret_cast<const uint4*>(kp + (long)lane * ld), kb = *reinterpret_cast<const uint4*>(kp + (long)lane * ld + 8);
-    uint4 va = *reinterpret_cast<const uint4*>(vp + (long)lane * ld), vb = *reinterpret_cast<const uint4*>(vp + (long)lane * ld + 8);
-    for (int n = lane; n < NI; n += 32) {
-      const uint32_t kw[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
-      const uint32_t vw[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-      if (n + 32 < NI) {  // prefetch the next rows of this lane
-        const long nn = (long)(n + 32) * ld;
-        ka = *reinterpret_cast<const uint4*>(kp + nn); kb = *reinterpret_cast<const uint4*>(kp + nn + 8);
-        va = *reinterpret_cast<const uint4*>(vp + nn); vb = *reinterpret_cast<const uint4*>(vp + nn + 8);
-      }
-      float kf[16], vf[16];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        kf[2 * i] = bf_lo(kw[i]); kf[2 * i + 1] = bf_hi(kw[i]);
-        vf[2 * i] = bf_lo(vw[i]); vf[2 * i + 1] = bf_hi(vw[i]);
-      }
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        if (t >= nt) break;
-        float s = 0.f;
-#pragma unroll
-        for (int d = 0; d < 16; d += 4) {
-          const float4 qq = *reinterpret_cast<const float4*>(&sq[t0 + t][h * 16 + d]);  // warp-uniform -> broadcast
-          s += qq.x * kf[d] + qq.y * kf[d + 1] + qq.z * kf[d + 2] + qq.w * kf[d + 3];
-        }
-        if (s > m[t]) {  // lazy rescale
-          const float corr = __expf(m[t] - s);
-          m[t] = s;
-          l[t] *= corr;
-#pragma unroll
-          for (int d = 0; d < 16; ++d) acc[t][d] *= corr;
-        }
-        const float pj = __expf(s - m[t]);
-        l[t] += pj;
-#pragma unroll
-        for (int d = 0; d < 16; ++d) acc[t][d] += pj * vf[d];
-      }
-    }
-    // combine the 32 lanes
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      if (t < nt) {
-        float mm = m[t];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
-        const float sc = __expf(m[t] - mm);
-        float ll = l[t] * sc;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
-        const float inv = 1.f / ll;
-#pragma unroll
-        for (int d = 0; d < 16; ++d) {
-          float a = acc[t][d] * sc;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-          if (lane == d) out[((long)p * T + t0 + t) * DI + h * 16 + d] = __float2bfloat16(a * inv);
-        }
-      }
-    }
-  }
-}
-
 // image -> token attention core.  q_img [*, ldq] (q_stride_rows = 0 when shared), k_tok / v_tok [P*T,128].
 // grid = (NI/64, P), block = 256: thread = (head = tid%8, two image tokens n0 = blockIdx.x*64 + tid/8 and n0 + 32);
 // token keys/values live in shared memory as 16-byte vectors (LDS.128, conflict-free with the 20-float pitch).
