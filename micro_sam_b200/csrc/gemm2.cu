@@ -78,11 +78,9 @@ __device__ __forceinline__ float g2_gelu_erf(float x) { return 0.5f * x * (1.0f 
 __device__ __forceinline__ float g2_gelu_fast(float x) {  // see gemm.cu
   const float z = fabsf(x);
   float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, z, 1.0f)));
-  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
-  poly = fmaf(poly, t, 0.5f * 1.421413741f);
-  poly = fmaf(poly, t, 0.5f * -0.284496736f);
-  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.47047f * 0.70710678118654752440f, z, 1.0f)));
+  float poly = fmaf(0.5f * 0.7478556f, t, 0.5f * -0.0958798f);
+  poly = fmaf(poly, t, 0.5f * 0.3480242f);
   poly *= t;
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * (x * -0.72134752044448170368f)));
