@@ -117,6 +117,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // statically declared so that the compiler emits LDS/STS (not generic LD/ST through the LG path)
   __shared__ __align__(16) float2 exch[2 * 4 * 128];  // EPI_LN256 statistics exchange, double buffered by tile parity
   __shared__ __align__(16) float rowp[768];           // [0,256) bias, [256,512) gamma, [512,768) beta (fused epilogues)
+  // EPI_HYPER: the hyper-network weights of the tile's prompt ([nm <= 4][32] fp32), one private copy per epilogue warp and
+  // tile parity, fetched before the accumulator is ready (the 24 dependent LDG.128 per thread of the first version showed
+  // up as long-scoreboard stalls on the dot products, profiles/r1_ncu_hyper_final.txt)
+  __shared__ __align__(16) float hyp_s[(EPI == EPI_HYPER) ? 16 * 2 * 128 : 4];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -384,6 +388,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)(row % p.res_rows) * p.ldr + colbase;
           prefetch_l1(rp);
         }
+        float* hyp_w = nullptr;
+        if constexpr (EPI == EPI_HYPER) {  // all 128 rows of a tile belong to one prompt (16384 rows per prompt)
+          hyp_w = hyp_s + ((warp - 4) * 2 + (it & 1)) * 128;
+          const int pp0 = (m_blk * GEMM_BM) >> 14;
+          if (lane < 8 * p.hyper_nm)
+            reinterpret_cast<float4*>(hyp_w)[lane] =
+                __ldg(reinterpret_cast<const float4*>(p.hyper + ((size_t)pp0 * 4 + p.hyper_m0) * 32) + lane);
+          __syncwarp();
+        }
         mbar_wait(&tfull_bar[as], aphase, 4);
         tc_fence_after();
 #pragma unroll
@@ -471,11 +484,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int sub = row & 3, tok = (row >> 2) & 4095, pp = row >> 14;
             const int Y = 4 * (tok >> 6) + 2 * (sub >> 1) + (grp >> 1), X = 4 * (tok & 63) + 2 * (sub & 1) + (grp & 1);
             for (int mi = 0; mi < p.hyper_nm; ++mi) {
-              const float* hw = p.hyper + ((size_t)pp * 4 + p.hyper_m0 + mi) * 32;
+              const float* hw = hyp_w + mi * 32;
               float a0 = 0.f, a1 = 0.f;
 #pragma unroll
               for (int c = 0; c < 32; c += 8) {
-                const float4 h4 = __ldg(reinterpret_cast<const float4*>(hw + c)), g4 = __ldg(reinterpret_cast<const float4*>(hw + c + 4));
+                const float4 h4 = *reinterpret_cast<const float4*>(hw + c), g4 = *reinterpret_cast<const float4*>(hw + c + 4);
                 a0 += h4.x * f[c] + h4.y * f[c + 1] + h4.z * f[c + 2] + h4.w * f[c + 3];
                 a1 += g4.x * f[c + 4] + g4.y * f[c + 5] + g4.z * f[c + 6] + g4.w * f[c + 7];
               }
