@@ -152,6 +152,50 @@ def rle_to_mask(rle: Dict[str, Any]) -> np.ndarray:
     return mask.reshape(w, h).transpose()
 
 
+def coco_encode_rle(uncompressed_rle: Dict[str, Any]) -> Dict[str, Any]:
+    """segment_anything.utils.amg.coco_encode_rle (call site instance_segmentation.py:192): the upstream function hands the
+    uncompressed column-major RLE to pycocotools (`frPyObjects`) and decodes the bytes to str.  pycocotools is absent here;
+    this is its `rleToString` (cocoapi common/maskApi.c): counts[i] (i > 2: minus counts[i-2]) as little-endian 5-bit groups,
+    bit 5 = continuation, + 48 -> ASCII.  Parity unpinned (no pycocotools vector in this image); round trip tested."""
+    counts = uncompressed_rle["counts"]
+    out = []
+    for i, c in enumerate(counts):
+        x = int(c)
+        if i > 2:
+            x -= int(counts[i - 2])
+        more = True
+        while more:
+            ch = x & 0x1F
+            x >>= 5
+            more = (x != -1) if (ch & 0x10) else (x != 0)
+            if more:
+                ch |= 0x20
+            out.append(chr(ch + 48))
+    h, w = uncompressed_rle["size"]
+    return {"size": [h, w], "counts": "".join(out)}
+
+
+def coco_decode_rle(rle: Dict[str, Any]) -> Dict[str, Any]:
+    """Inverse of coco_encode_rle (cocoapi rleFrString): compressed string -> uncompressed counts."""
+    s = rle["counts"]
+    counts: List[int] = []
+    p = 0
+    while p < len(s):
+        x, k, more = 0, 0, True
+        while more:
+            c = ord(s[p]) - 48
+            x |= (c & 0x1F) << (5 * k)
+            more = bool(c & 0x20)
+            p += 1
+            k += 1
+            if not more and (c & 0x10):
+                x |= -1 << (5 * k)
+        if len(counts) > 2:
+            x += counts[-2]
+        counts.append(x)
+    return {"size": list(rle["size"]), "counts": counts}
+
+
 def area_from_rle(rle: Dict[str, Any]) -> int:
     return sum(rle["counts"][1::2])
 

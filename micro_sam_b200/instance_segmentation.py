@@ -88,6 +88,8 @@ class AMGBase(ABC):
             segs = binm.cpu().numpy().astype(bool)
             if output_mode != "binary_mask":
                 segs = amg_utils.mask_to_rle(segs)
+            if output_mode == "coco_rle":
+                segs = [amg_utils.coco_encode_rle(r) for r in segs]
         anns = []
         for k in range(len(keep)):
             ann = {
@@ -216,8 +218,6 @@ class AutomaticMaskGenerator(AMGBase):
             raise RuntimeError("AutomaticMaskGenerator has not been initialized. Call initialize first.")
         if output_mode not in ("instance_segmentation", "binary_mask", "rle", "coco_rle"):
             raise ValueError(f"Invalid output mode {output_mode}.")
-        if output_mode == "coco_rle":
-            raise NotImplementedError("coco_rle needs pycocotools")
         geoms = getattr(self, "_geoms", None)
         if min_mask_region_area > 0:
             return self._generate_small_regions(pred_iou_thresh, stability_score_thresh, box_nms_thresh, crop_nms_thresh,
@@ -273,10 +273,12 @@ class AutomaticMaskGenerator(AMGBase):
                         full = np.zeros((H, W), dtype=bool)
                         full[y0:y1, x0:x1] = r["segmentation"]
                         r["segmentation"] = full
-                    elif output_mode == "rle" and (x1 - x0, y1 - y0) != (W, H):
+                    elif output_mode in ("rle", "coco_rle") and (x1 - x0, y1 - y0) != (W, H):
+                        rl = r["segmentation"] if output_mode == "rle" else amg_utils.coco_decode_rle(r["segmentation"])
                         full = np.zeros((H, W), dtype=bool)
-                        full[y0:y1, x0:x1] = amg_utils.rle_to_mask(r["segmentation"])
-                        r["segmentation"] = amg_utils.mask_to_rle(full[None])[0]
+                        full[y0:y1, x0:x1] = amg_utils.rle_to_mask(rl)
+                        rl = amg_utils.mask_to_rle(full[None])[0]
+                        r["segmentation"] = rl if output_mode == "rle" else amg_utils.coco_encode_rle(rl)
                     out[k] = r
             return out
         canvas = torch.full((H, W), -1, dtype=torch.int64, device=dev)
@@ -345,8 +347,11 @@ class AutomaticMaskGenerator(AMGBase):
             recs = out
         if output_mode == "binary_mask":
             return recs
-        if output_mode == "rle":
-            return [dict(r, segmentation=amg_utils.mask_to_rle(r["segmentation"][None])[0]) for r in recs]
+        if output_mode in ("rle", "coco_rle"):
+            rl = [amg_utils.mask_to_rle(r["segmentation"][None])[0] for r in recs]
+            if output_mode == "coco_rle":
+                rl = [amg_utils.coco_encode_rle(x) for x in rl]
+            return [dict(r, segmentation=x) for r, x in zip(recs, rl)]
         # instance segmentation: mask_data_to_segmentation(..., merge_exclusively=False): descending area, later overwrites
         label = torch.zeros(H, W, dtype=torch.int32, device=dev)
         order = sorted(range(len(recs)), key=lambda k: recs[k]["area"], reverse=True)

@@ -83,3 +83,24 @@ def test_box_nms_idempotent_and_sorted(n, seed, thr):
     assert int(keep[0]) == int(torch.argmax(scores)) and bool((ks[:-1] >= ks[1:]).all())
     again = amg_ref.nms(boxes[keep], scores[keep], thr)
     assert again.tolist() == list(range(len(keep)))
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 70), st.integers(1, 70), st.integers(0, 2 ** 31 - 1), st.floats(0.0, 1.0))
+def test_coco_rle_round_trip(h, w, seed, density):
+    """COCO compressed RLE string (cocoapi rleToString / rleFrString): decode(encode(rle)) == rle, printable ASCII only."""
+    rng = np.random.default_rng(seed)
+    mask = rng.random((1, h, w)) < density
+    rle = au.mask_to_rle(mask)[0]
+    enc = au.coco_encode_rle(rle)
+    assert enc["size"] == [h, w] and all(48 <= ord(c) < 48 + 64 for c in enc["counts"])
+    assert au.coco_decode_rle(enc)["counts"] == rle["counts"]
+
+
+def test_coco_rle_known_values():
+    """Hand-derived from the cocoapi algorithm: small counts are single characters ('0' + value), counts from the fourth on
+    are stored as differences to counts[i-2], values >= 16 need a continuation group, negative differences set bit 4."""
+    assert au.coco_encode_rle({"size": [2, 3], "counts": [3, 2, 1]})["counts"] == "321"
+    assert au.coco_encode_rle({"size": [1, 19], "counts": [5, 3, 7, 4]})["counts"] == "5371"       # 4 - 3 = 1
+    assert au.coco_encode_rle({"size": [1, 40], "counts": [40]})["counts"] == "X1"                # 40 = 8 + 32*1
+    assert au.coco_encode_rle({"size": [1, 30], "counts": [0, 10, 5, 7]})["counts"] == "0:5M"      # 7 - 10 = -3 -> 'M'
