@@ -170,6 +170,37 @@ def _stitch_segmentation(masks, tile_ids, tiling, halo, output_shape, verbose=Fa
     return segmentation
 
 
+def _route_prompts_to_tiles(tiling, halo, boxes, points, point_labels):
+    """Prompt -> tile assignment of batched_tiled_inference (inference.py:424-470), vectorised: every prompt goes to the tile
+    that holds its anchor (box centre, else the point) and keeps its original order inside the tile.  Tile-local boxes are
+    assembled exactly like the reference does (inference.py:438-445), i.e. as (y0, x0, y1, x1) clipped to the outer tile --
+    kept as is so that results stay identical.  Returns (sorted tile ids, boxes / points / labels per tile)."""
+    have_boxes, have_points = boxes is not None, points is not None
+    if have_boxes:
+        anchors = np.stack([(boxes[:, 1] + boxes[:, 3]) / 2, (boxes[:, 0] + boxes[:, 2]) / 2], axis=1)
+    else:
+        anchors = points[:, 0, ::-1]
+    anchors = np.asarray(anchors).round().astype("int")
+    tile_of = np.array([tiling.coordinates_to_block_id(a.tolist()) for a in anchors], dtype=np.int64)
+    if have_boxes and have_points:
+        pt_tiles = [tiling.coordinates_to_block_id(pt.tolist()) for pt in np.asarray(points[:, 0, ::-1]).round().astype("int")]
+        assert np.array_equal(tile_of, np.array(pt_tiles)), "box and point prompts of a pair must fall into the same tile"
+    tile_ids = sorted(set(tile_of.tolist()))
+    box_to_tile, point_to_tile, label_to_tile = {}, {}, {}
+    for tile_id in tile_ids:
+        sel = np.flatnonzero(tile_of == tile_id)
+        outer = tiling.get_block_with_halo(tile_id, list(halo)).outer_block
+        (oy, ox), (th, tw) = outer.begin, outer.shape
+        if have_boxes:
+            bx = boxes[sel]
+            box_to_tile[tile_id] = np.stack([np.maximum(bx[:, 1] - oy, 0), np.maximum(bx[:, 0] - ox, 0),
+                                             np.minimum(bx[:, 3] - oy, th), np.minimum(bx[:, 2] - ox, tw)], axis=1)
+        if have_points:
+            point_to_tile[tile_id] = points[sel] - np.array([ox, oy])[None, None]
+            label_to_tile[tile_id] = point_labels[sel]
+    return tile_ids, box_to_tile, point_to_tile, label_to_tile
+
+
 @torch.no_grad()
 def batched_tiled_inference(predictor, image: Optional[np.ndarray], batch_size: int, image_embeddings=None,
                             boxes: Optional[np.ndarray] = None, points: Optional[np.ndarray] = None,
@@ -190,35 +221,7 @@ def batched_tiled_inference(predictor, image: Optional[np.ndarray], batch_size: 
         predictor, image, image_embeddings, embedding_path, tile_shape, halo, verbose_embeddings)
 
     tiling = amg_utils.Blocking([0, 0], shape, tile_shape)
-    box_to_tile, point_to_tile, label_to_tile, tile_ids = {}, {}, {}, []
-    for prompt_id in range(n_prompts):
-        this_tile_id = None
-        if have_boxes:
-            box = boxes[prompt_id]
-            center = np.array([(box[1] + box[3]) / 2, (box[0] + box[2]) / 2]).round().astype("int").tolist()
-            this_tile_id = tiling.coordinates_to_block_id(center)
-            tile = tiling.get_block_with_halo(this_tile_id, list(halo)).outer_block
-            offset, this_tile_shape = tile.begin, tile.shape
-            box_in_tile = np.array([max(box[1] - offset[0], 0), max(box[0] - offset[1], 0),
-                                    min(box[3] - offset[0], this_tile_shape[0]), min(box[2] - offset[1], this_tile_shape[1])])[None]
-            box_to_tile[this_tile_id] = (np.concatenate([box_to_tile[this_tile_id], box_in_tile])
-                                         if this_tile_id in box_to_tile else box_in_tile)
-        if have_points:
-            point = points[prompt_id, 0][::-1].round().astype("int").tolist()
-            if this_tile_id is None:
-                this_tile_id = tiling.coordinates_to_block_id(point)
-            else:
-                assert this_tile_id == tiling.coordinates_to_block_id(point)
-            tile = tiling.get_block_with_halo(this_tile_id, list(halo)).outer_block
-            point_in_tile = (points[prompt_id, 0] - np.array(tile.begin)[::-1])[None, None]
-            label_in_tile = point_labels[prompt_id][None]
-            if this_tile_id in point_to_tile:
-                point_to_tile[this_tile_id] = np.concatenate([point_to_tile[this_tile_id], point_in_tile])
-                label_to_tile[this_tile_id] = np.concatenate([label_to_tile[this_tile_id], label_in_tile])
-            else:
-                point_to_tile[this_tile_id], label_to_tile[this_tile_id] = point_in_tile, label_in_tile
-        tile_ids.append(this_tile_id)
-    tile_ids = sorted(set(tile_ids))
+    tile_ids, box_to_tile, point_to_tile, label_to_tile = _route_prompts_to_tiles(tiling, halo, boxes, points, point_labels)
 
     masks, id_offset = [], 0
     for tile_id in tile_ids:

@@ -165,3 +165,35 @@ def test_stitch_segmentation_matches_oracle():
     b = amg_ref.stitch_segmentation([s.copy() for s in segs], ids, otiling, halo, shape)
     assert a.dtype == np.uint32 and np.array_equal(a, b)
     assert tiling.coordinates_to_block_id([200, 300]) == amg_ref.coordinates_to_block_id(otiling, [200, 300]) == 3
+
+
+def test_tiled_prompt_routing_matches_oracle_loop():
+    """inference._route_prompts_to_tiles (vectorised) == the reference's per-prompt loop as restated in the oracle
+    (inference.py:424-470), for boxes and for points."""
+    from micro_sam_b200 import inference
+    from micro_sam_b200._amg_utils import Blocking
+    from micro_sam_b200.sample_data import random_boxes
+    from oracle import amg_ref
+    shape, tile_shape, halo = (300, 420), (160, 224), (24, 24)
+    tiling, ot = Blocking([0, 0], shape, tile_shape), amg_ref.Blocking([0, 0], shape, tile_shape)
+    boxes = random_boxes(60, shape, seed=3)
+    ids, b2t, _, _ = inference._route_prompts_to_tiles(tiling, halo, boxes, None, None)
+    ref = {}
+    for box in boxes:
+        c = np.array([(box[1] + box[3]) / 2, (box[0] + box[2]) / 2]).round().astype("int").tolist()
+        tid = amg_ref.coordinates_to_block_id(ot, c)
+        t = ot.get_block_with_halo(tid, list(halo)).outer_block
+        b = np.array([max(box[1] - t.begin[0], 0), max(box[0] - t.begin[1], 0), min(box[3] - t.begin[0], t.shape[0]),
+                      min(box[2] - t.begin[1], t.shape[1])])[None]
+        ref[tid] = np.concatenate([ref[tid], b]) if tid in ref else b
+    assert ids == sorted(ref) and all(np.array_equal(b2t[t], ref[t]) for t in ids)
+    pts = (np.random.default_rng(0).random((50, 1, 2)) * [419, 299]).astype(np.float64)
+    lbl = np.ones((50, 1), dtype=np.int64)
+    ids, _, p2t, l2t = inference._route_prompts_to_tiles(tiling, halo, None, pts, lbl)
+    refp = {}
+    for k in range(50):
+        tid = amg_ref.coordinates_to_block_id(ot, pts[k, 0][::-1].round().astype("int").tolist())
+        t = ot.get_block_with_halo(tid, list(halo)).outer_block
+        pin = (pts[k, 0] - np.array(t.begin)[::-1])[None, None]
+        refp[tid] = np.concatenate([refp[tid], pin]) if tid in refp else pin
+    assert ids == sorted(refp) and all(np.array_equal(p2t[t], refp[t]) and len(l2t[t]) == len(refp[t]) for t in ids)
