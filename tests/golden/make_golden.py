@@ -148,6 +148,50 @@ def main():
             res[f"keep_{int(iomin)}_{thr}"] = fns["_batched_tiled_mask_nms"](masks, boxes, gboxes, torch.from_numpy(scores), thr,
                                                                             iomin).numpy()
     np.savez_compressed(os.path.join(OUT, "tiled_nms.npz"), **res)
+
+    # --- _merge_segmentations / _stitch_segmentation (inference.py:315-356), executed from the reference source.  The absent
+    # bioimage_cpp.segmentation_overlap is stubbed with an object that reports a 100 % overlap for every id: the reference
+    # collects such ids in `discard_ids` but never uses the list, so the stub cannot influence the result -- which is
+    # exactly the behaviour the oracle / product restate ("the previous segmentation is fully preserved").
+    class _Ovlp:
+        def overlaps_for_label_a(self, seg_id, normalize=True):
+            return {"label": np.array([0, 1]), "fraction": np.array([0.0, 1.0])}
+
+    class _Blk:
+        def __init__(self, b, e):
+            self.begin, self.end = list(b), list(e)
+
+    class _Tiling:  # nifty-style blocking with the camelCase API the reference calls
+        def __init__(self, shape, block):
+            self.shape, self.block = shape, block
+            self.grid = [-(-s // b) for s, b in zip(shape, block)]
+
+        def getBlockWithHalo(self, tile_id, halo):
+            pos = np.unravel_index(tile_id, self.grid)
+            ib = [p_ * b for p_, b in zip(pos, self.block)]
+            ie = [min(x + b, s_) for x, b, s_ in zip(ib, self.block, self.shape)]
+            outer = _Blk([max(x - h, 0) for x, h in zip(ib, halo)], [min(x + h, s_) for x, h, s_ in zip(ie, halo, self.shape)])
+            return types.SimpleNamespace(outerBlock=outer)
+
+    src = open(os.path.join(REF, "inference.py")).read()
+    ns = {"np": np, "segmentation_overlap": lambda a, b: _Ovlp(), "tqdm": lambda it, **kw: it}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("_merge_segmentations", "_stitch_segmentation"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "inference.py", "exec"), ns)
+    rng = np.random.default_rng(2)
+    shape, tile, halo = (300, 420), (160, 224), (24, 24)
+    tiling = _Tiling(shape, tile)
+    res = {"shape": np.array(shape), "tile_shape": np.array(tile), "halo": np.array(halo)}
+    for name, ids in (("all", [0, 1, 2, 3]), ("subset", [0, 2, 3]), ("no_first", [1, 3])):
+        segs = []
+        for t in ids:
+            ob = tiling.getBlockWithHalo(t, list(halo)).outerBlock
+            segs.append(rng.integers(0, 5, (ob.end[0] - ob.begin[0], ob.end[1] - ob.begin[1])).astype("uint32") * (t + 1))
+        res[f"{name}_ids"] = np.array(ids)
+        for k, sg in enumerate(segs):
+            res[f"{name}_seg{k}"] = sg
+        res[f"{name}_out"] = ns["_stitch_segmentation"]([sg.copy() for sg in segs], ids, tiling, halo, shape)
+    np.savez_compressed(os.path.join(OUT, "stitch.npz"), **res)
     print("written", os.listdir(OUT))
 
 

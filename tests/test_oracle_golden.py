@@ -1,4 +1,4 @@
-"""Pin oracle/amg_ref.py against (a) golden vectors produced by executing the reference's own code
+"""Pin oracle/amg_ref.py (and, where noted, the product's host code) against (a) golden vectors produced by executing the reference's own code
 (tests/golden/make_golden.py) and (b) the reference's own known-answer tests."""
 import os
 
@@ -68,6 +68,22 @@ def test_tiled_mask_nms_golden():
         for thr in (0.3, 0.9):
             keep = amg_ref.batched_tiled_mask_nms(masks, boxes, gboxes, scores, thr, iomin).tolist()
             assert keep == z[f"keep_{int(iomin)}_{thr}"].tolist()
+
+
+def test_stitch_segmentation_golden():
+    """inference._stitch_segmentation / _merge_segmentations: oracle AND product host code == the output of the reference's
+    own functions (tests/golden/stitch.npz), incl. tile subsets and a sequence that does not start with tile 0."""
+    from micro_sam_b200 import inference
+    from micro_sam_b200._amg_utils import Blocking
+    z = np.load(os.path.join(G, "stitch.npz"))
+    shape, tile_shape, halo = tuple(z["shape"].tolist()), tuple(z["tile_shape"].tolist()), tuple(z["halo"].tolist())
+    ot, pt = amg_ref.Blocking([0, 0], shape, tile_shape), Blocking([0, 0], shape, tile_shape)
+    for name in ("all", "subset", "no_first"):
+        ids = z[f"{name}_ids"].tolist()
+        segs = [z[f"{name}_seg{k}"] for k in range(len(ids))]
+        out = z[f"{name}_out"]
+        assert np.array_equal(amg_ref.stitch_segmentation([s.copy() for s in segs], ids, ot, halo, shape), out), name
+        assert np.array_equal(inference._stitch_segmentation([s.copy() for s in segs], ids, pt, halo, shape), out), name
 
 
 def test_box_nms_matches_torchvision():
