@@ -57,6 +57,15 @@ def blobs(rng, n, h, w):
     return out
 
 
+def otsu_inputs():
+    """(3,1,256,256) fp32 low-res logits: smooth, smooth + noise, shifted negative (seeded; also used by the tests)."""
+    g = torch.Generator().manual_seed(7)
+    lo = torch.nn.functional.interpolate(torch.randn(3, 1, 12, 12, generator=g), (256, 256), mode="bicubic") * 4
+    lo[1] += torch.randn(1, 256, 256, generator=g) * 0.5
+    lo[2] = lo[2] - 6.0
+    return lo
+
+
 def main():
     rng = np.random.default_rng(0)
     ven = load_vendored()
@@ -192,6 +201,17 @@ def main():
             res[f"{name}_seg{k}"] = sg
         res[f"{name}_out"] = ns["_stitch_segmentation"]([sg.copy() for sg in segs], ids, tiling, halo, shape)
     np.savez_compressed(os.path.join(OUT, "stitch.npz"), **res)
+
+    # --- _local_otsu_threshold (inference.py:70-134, mask_threshold="auto"), executed from the reference source on CPU.
+    # Inputs are regenerated from the seed by the tests (otsu_inputs below); their float64 sum is stored to detect drift.
+    import torch.nn.functional as F
+    ns = {"np": np, "torch": torch, "F": F}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name == "_local_otsu_threshold":
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "inference.py", "exec"), ns)
+    x = otsu_inputs()
+    thr = ns["_local_otsu_threshold"](x)
+    np.savez_compressed(os.path.join(OUT, "otsu.npz"), thresholds=thr.reshape(-1).numpy(), checksum=np.array(x.double().sum().item()))
     print("written", os.listdir(OUT))
 
 

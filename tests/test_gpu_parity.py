@@ -433,3 +433,4 @@ def test_amg_crop_layers_against_oracle(models):
     for a, b in zip(recs, orecs):
         assert a["bbox"] == b["bbox"] and a["area"] == b["area"] and np.array_equal(a["segmentation"], b["segmentation"])
     assert _partition_equal(amg.generate(output_mode="instance_segmentation", **kw), oamg.generate(output_mode="instance_segmentation", **kw))
+

@@ -86,6 +86,20 @@ def test_stitch_segmentation_golden():
         assert np.array_equal(inference._stitch_segmentation([s.copy() for s in segs], ids, pt, halo, shape), out), name
 
 
+def test_local_otsu_golden():
+    """mask_threshold="auto": the oracle's per-mask restatement == the reference's own `_local_otsu_threshold` (executed from
+    its source by tests/golden/make_golden.py) on the seeded inputs, bit for bit."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(G, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    z = np.load(os.path.join(G, "otsu.npz"))
+    x = mg.otsu_inputs()
+    assert abs(x.double().sum().item() - float(z["checksum"])) < 1e-6, "seeded inputs drifted"
+    thr = amg_ref.local_otsu_threshold(x).reshape(-1).numpy()
+    assert np.array_equal(thr, z["thresholds"])
+
+
 def test_box_nms_matches_torchvision():
     import torchvision
     g = torch.Generator().manual_seed(0)
