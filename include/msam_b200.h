@@ -34,12 +34,12 @@ const char* msam_last_error(void);
 /* number of CUDA kernels this library has launched from the calling thread since load */
 int64_t msam_launch_count(void);
 
-/* bench instrumentation: when enabled, CUDA events are recorded on the launching stream around every GEMM / attention
- * launch; msam_profile_summary synchronises and returns {ms, algorithmic work, launches} per category in out[9]:
- * 0 = long-K tcgen05 GEMMs (work = FLOPs), 1 = encoder attention (FLOPs), 2 = short-K GEMMs with fused epilogues
- * (HBM-bound, work = algorithmic bytes). */
+/* bench instrumentation: when enabled, CUDA events are recorded on the launching stream around every instrumented kernel
+ * launch; msam_profile_report synchronises and writes a JSON array with one object per kernel name
+ * {"name", "ms", "n", "flops", "bytes"} (CUDA-event time, launches, ALGORITHMIC flops / bytes summed over the launches)
+ * into buf[cap]; returns the length, < 0 on error. */
 int msam_profile(int enable);
-int msam_profile_summary(double* out);
+int msam_profile_report(char* buf, int cap);
 
 /* util.get_sam_model (util.py:441-458): build the model on `device`. */
 int msam_create(const msam_config* cfg, int device, msam_handle** out);
@@ -56,6 +56,10 @@ int msam_encode_f32(msam_handle* h, const float* nchw, int B, float* out, void* 
 /* Same, fusing Sam.preprocess (util.py:670; trainable_sam.py:24-47): B resized uint8 HWC images, each (hh, ww, 3)
  * with max(hh, ww) <= S, contiguous [B, hh, ww, 3]. */
 int msam_encode_u8(msam_handle* h, const uint8_t* hwc, int B, int hh, int ww, float* out, void* stream);
+
+/* Parity localisation (tests): patch embedding + the first n_blocks transformer blocks of msam_encode_u8; x_out receives the
+ * fp32 residual stream [B*4096, embed_dim] (token-major), to be compared with the oracle's activations block by block. */
+int msam_encode_u8_blocks(msam_handle* h, const uint8_t* hwc, int B, int hh, int ww, int n_blocks, float* x_out, void* stream);
 
 /* SamPredictor.features assignment (util.py:676-679 / set_precomputed util.py:1248-1256): bind a (256,64,64) fp32
  * NCHW image embedding as the decoder's current image; precomputes the prompt-independent layer-0 projections. */

@@ -54,10 +54,15 @@ class MaskData:
             else:
                 raise TypeError(f"MaskData key {k} has an unsupported type {type(v)}.")
 
-    def cat(self, new_stats: "MaskData") -> None:
+    def cat(self, new_stats: "MaskData", copy: bool = True) -> None:
+        """copy=False adopts the first batch's tensors instead of cloning them (the AMG path hands over freshly computed
+        per-batch tensors; cloning [3072, 256, 256] fp32 low-res logits is an 805 MB device copy per tile)."""
         for k, v in new_stats.items():
             if k not in self._stats or self._stats[k] is None:
-                self._stats[k] = v.clone() if isinstance(v, torch.Tensor) else deepcopy(v)
+                if isinstance(v, torch.Tensor):
+                    self._stats[k] = v.clone() if copy else v
+                else:
+                    self._stats[k] = deepcopy(v)
             elif isinstance(v, torch.Tensor):
                 self._stats[k] = torch.cat([self._stats[k], v], dim=0)
             elif isinstance(v, np.ndarray):

@@ -73,7 +73,8 @@ def lib() -> ctypes.CDLL:
         L.msam_mask_nms.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p]
         L.msam_profile.argtypes = [c_int]
-        L.msam_profile_summary.argtypes = [POINTER(ctypes.c_double)]
+        L.msam_profile_report.argtypes = [ctypes.c_char_p, c_int]
+        L.msam_encode_u8_blocks.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
         _lib = L
     return _lib
 
@@ -81,6 +82,16 @@ def lib() -> ctypes.CDLL:
 def check(rc: int) -> None:
     if rc != 0:
         raise RuntimeError("libmsam_b200: " + lib().msam_last_error().decode())
+
+
+def profile_report():
+    """Per-kernel CUDA-event times since msam_profile(1): list of {"name", "ms", "n", "flops", "bytes"}."""
+    import json
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = lib().msam_profile_report(buf, len(buf))
+    if n < 0:
+        raise RuntimeError("libmsam_b200: " + lib().msam_last_error().decode())
+    return json.loads(buf.value.decode())
 
 
 def launch_count() -> int:

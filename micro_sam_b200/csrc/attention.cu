@@ -327,7 +327,8 @@ static int launch_attn_window(const AttnArgs& a, cudaStream_t stream) {
   if (make_tmap_bf16_2d(&tmRT, a.rel_table, 64, C::NB * 64, C::NB * 64, 64)) return -1;
   AttParams p;
   p.out = a.out; p.d_model = d_model; p.grid = a.grid; p.scale_log2 = a.scale * 1.4426950408889634f;
-  prof_begin(stream, PROF_ATTN, (double)groups * a.heads * (4.0 * 196 * 196 * D + 4.0 * 196 * S * D));
+  prof_begin(stream, D == 64 ? "attn_window<64>" : "attn_window<80>", (double)groups * a.heads * (4.0 * 196 * 196 * D + 4.0 * 196 * S * D),
+             (double)groups * 196 * a.heads * D * 2 * 4);
   attn_window_kernel<D><<<dim3(2, a.heads, groups), ATT_THREADS, C::SMEM_BYTES, stream>>>(tmQ, tmKV, tmRT, p);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();

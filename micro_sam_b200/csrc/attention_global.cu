@@ -414,7 +414,8 @@ int launch_global_t(const AttnArgs& a, cudaStream_t stream) {
   if (make_tmap_bf16_2d(&tmRTw, a.rel_table, 256, C::NB * 64, C::NB * 64, 128)) return -1;
   GParams p;
   p.out = a.out; p.d_model = d_model; p.scale_log2 = a.scale * 1.4426950408889634f;
-  prof_begin(stream, PROF_ATTN, (double)a.batch * a.heads * (4.0 * 4096 * 4096 * D + 4.0 * 4096 * 64 * D));
+  prof_begin(stream, D == 64 ? "attn_global<64>" : "attn_global<80>", (double)a.batch * a.heads * (4.0 * 4096 * 4096 * D + 4.0 * 4096 * 64 * D),
+             (double)a.batch * 4096 * a.heads * D * 2 * 4);
   attn_global_kernel<D><<<dim3(32, a.heads, a.batch), 384, C::SMEM_BYTES, stream>>>(tmQKV, tmRTh, tmRTw, p);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();

@@ -149,9 +149,11 @@ int launch_layernorm(const LnArgs& a, cudaStream_t stream) {
   if (a.rows <= 0) return 0;
   const int warps_per_block = 8;
   const unsigned blocks = (unsigned)((a.rows + warps_per_block - 1) / warps_per_block);
+  prof_begin(stream, "layernorm_rows", 0.0, (double)a.rows * a.D * (4 + (a.out ? 2 : 0) + (a.out2 ? 2 : 0) + (a.out_f32 ? 4 : 0)));
   layernorm_rows_kernel<<<blocks, warps_per_block * 32, 0, stream>>>(a.x, a.rows, a.D, a.gamma, a.beta, a.eps, a.out,
                                                                     a.window_mode, a.grid, a.ws, a.add, a.add_rows,
                                                                     a.out2, a.out_f32, a.act);
+  prof_end(stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("layernorm launch failed: %s", cudaGetErrorString(e));
   count_launch();

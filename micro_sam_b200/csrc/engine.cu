@@ -20,16 +20,17 @@ int set_error(const char* fmt, ...) {
 }
 void count_launch() { ++g_launches; }
 
-struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+struct ProfRec { cudaEvent_t a, b; const char* name; double flops, bytes; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
-void prof_begin(cudaStream_t st, int cat, double work) {
+void prof_begin(cudaStream_t st, const char* name, double flops, double bytes) {
   if (!g_prof_on) return;
   ProfRec r;
   cudaEventCreate(&r.a);
   cudaEventCreate(&r.b);
-  r.cat = cat;
-  r.work = work;
+  r.name = name;
+  r.flops = flops;
+  r.bytes = bytes;
   cudaEventRecord(r.a, st);
   g_prof.push_back(r);
 }
@@ -215,7 +216,8 @@ int Engine::alloc_encoder_ws() {
 }
 
 // ------------------------------------------------------------------------------------------------ encoder forward
-int Engine::encode(const uint8_t* u8, const float* f32, int B, int hh, int ww, float* out, cudaStream_t st) {
+int Engine::encode(const uint8_t* u8, const float* f32, int B, int hh, int ww, float* out, cudaStream_t st, int stop_after,
+                   float* x_out) {
   if (!finalized) return set_error("msam_encode: weights not finalized");
   if (B <= 0) return set_error("msam_encode: empty batch");
   const int D = cfg.embed_dim, hd = D / cfg.num_heads, g = cfg.image_size / cfg.patch_size, T = g * g, C = cfg.out_chans;
@@ -236,7 +238,9 @@ int Engine::encode(const uint8_t* u8, const float* f32, int B, int hh, int ww, f
       a.bias = enc.patch_b; a.residual = enc.pos_embed; a.res_rows = T; a.out = ws.x; a.out_fp32 = 1;
       if (launch_gemm(a, num_sms, st)) return -1;
     }
+    int blk_idx = 0;
     for (const EncBlock& b : enc.blocks) {
+      if (stop_after >= 0 && blk_idx++ >= stop_after) break;
       LnArgs l;
       l.x = ws.x; l.rows = M; l.D = D; l.gamma = b.ln1_g; l.beta = b.ln1_b; l.eps = 1e-6f;
       l.grid = g; l.ws = cfg.window_size;
@@ -276,6 +280,11 @@ int Engine::encode(const uint8_t* u8, const float* f32, int B, int hh, int ww, f
         a.bias = b.fc2_b; a.residual = ws.x; a.out = ws.x; a.out_fp32 = 1;
         if (launch_gemm(a, num_sms, st)) return -1;
       }
+    }
+    if (stop_after >= 0) {  // debug / parity localisation: the fp32 residual stream after `stop_after` blocks
+      if (cudaMemcpyAsync(x_out + (size_t)b0 * T * D, ws.x, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return set_error("encode_blocks: copy failed");
+      continue;
     }
     // neck: conv1x1 -> LN2d -> conv3x3 (im2col GEMM) -> LN2d (NCHW out)
     if (launch_cast_bf16(ws.x, (long)M * D, ws.xn, st)) return -1;
@@ -322,19 +331,32 @@ int msam_profile(int enable) {
   g_prof_on = enable != 0;
   return 0;
 }
-// out[3*cat + 0] = total ms, [3*cat + 1] = total work, [3*cat + 2] = launches.  Synchronises the device.
-int msam_profile_summary(double* out) {
-  if (!out) return set_error("msam_profile_summary: null argument");
+// JSON array, one object per kernel name: {"name", "ms" (sum of CUDA-event times), "n" (launches), "flops", "bytes"
+// (algorithmic work summed over the launches)}.  Synchronises the device.  Returns the length written, < 0 on error.
+int msam_profile_report(char* buf, int cap) {
+  if (!buf || cap < 4) return set_error("msam_profile_report: null argument");
   if (cudaDeviceSynchronize() != cudaSuccess) return set_error("profile: %s", cudaGetErrorString(cudaGetLastError()));
-  for (int i = 0; i < 3 * PROF_NCAT; ++i) out[i] = 0.0;
+  struct Agg { double ms = 0, n = 0, flops = 0, bytes = 0; };
+  std::vector<std::pair<std::string, Agg>> agg;
   for (auto& r : g_prof) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
-    out[3 * r.cat] += ms;
-    out[3 * r.cat + 1] += r.work;
-    out[3 * r.cat + 2] += 1.0;
+    Agg* a = nullptr;
+    for (auto& kv : agg) if (kv.first == r.name) { a = &kv.second; break; }
+    if (!a) { agg.emplace_back(r.name, Agg()); a = &agg.back().second; }
+    a->ms += ms; a->n += 1; a->flops += r.flops; a->bytes += r.bytes;
   }
-  return 0;
+  std::string s = "[";
+  char tmp[512];
+  for (size_t i = 0; i < agg.size(); ++i) {
+    snprintf(tmp, sizeof(tmp), "%s{\"name\": \"%s\", \"ms\": %.6f, \"n\": %.0f, \"flops\": %.6e, \"bytes\": %.6e}", i ? ", " : "",
+             agg[i].first.c_str(), agg[i].second.ms, agg[i].second.n, agg[i].second.flops, agg[i].second.bytes);
+    s += tmp;
+  }
+  s += "]";
+  if ((int)s.size() + 1 > cap) return set_error("msam_profile_report: buffer too small (%zu needed)", s.size() + 1);
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return (int)s.size();
 }
 
 int msam_create(const msam_config* cfg, int device, msam_handle** out) {
@@ -401,6 +423,11 @@ int msam_encode_f32(msam_handle* h, const float* nchw, int B, float* out, void* 
 int msam_encode_u8(msam_handle* h, const uint8_t* hwc, int B, int hh, int ww, float* out, void* stream) {
   if (!h || !hwc || !out) return set_error("msam_encode_u8: null argument");
   return h->eng.encode(hwc, nullptr, B, hh, ww, out, (cudaStream_t)stream);
+}
+
+int msam_encode_u8_blocks(msam_handle* h, const uint8_t* hwc, int B, int hh, int ww, int n_blocks, float* x_out, void* stream) {
+  if (!h || !hwc || !x_out || n_blocks < 0) return set_error("msam_encode_u8_blocks: bad argument");
+  return h->eng.encode(hwc, nullptr, B, hh, ww, nullptr, (cudaStream_t)stream, n_blocks, x_out);
 }
 
 int msam_set_image_embedding(msam_handle* h, const float* feat, void* stream) {

@@ -60,7 +60,8 @@ struct Engine {
   int finalize_encoder();
   int alloc_encoder_ws();
   int finalize_decoder();  // decoder.cu
-  int encode(const uint8_t* u8, const float* f32, int B, int hh, int ww, float* out, cudaStream_t st);
+  int encode(const uint8_t* u8, const float* f32, int B, int hh, int ww, float* out, cudaStream_t st, int stop_after = -1,
+             float* x_out = nullptr);
   int set_image_embedding(const float* feat, cudaStream_t st);  // decoder.cu
   int decode(const float* points, const float* labels, int np, const float* boxes, const float* mask_in, int P, int multimask,
              float* low_res, float* iou, cudaStream_t st);  // decoder.cu

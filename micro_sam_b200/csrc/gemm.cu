@@ -547,12 +547,14 @@ static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   const int tiles = ((a.M + GEMM_BM - 1) / GEMM_BM) * ((a.N + BN - 1) / BN);
   const int max_ctas = num_sms * Cfg::MIN_CTAS;
   const int grid = tiles < max_ctas ? tiles : max_ctas;
-  if (a.K >= 512) {
-    prof_begin(stream, PROF_GEMM, 2.0 * a.M * a.N * a.K);
-  } else {  // HBM-bound: algorithmic bytes
+  {
     const double out_b = EPI == EPI_HYPER ? (double)a.M * a.hyper_nm * 16.0 : (double)a.M * a.N * (a.out_fp32 ? 4 : 2);
     const double res_b = a.residual ? (double)(a.res_rows > 0 ? a.res_rows : a.M) * a.N * (a.res_bf16 ? 2 : 4) : 0.0;
-    prof_begin(stream, PROF_GEMM_HBM, (double)a.M * a.K * 2 + (double)a.N * a.K * 2 + out_b + res_b);
+    const char* nm = EPI == EPI_HYPER ? "gemm_bf16<128,hyper> (convT2+GELU+hyper)"
+                     : EPI == EPI_LN64_GELU ? "gemm_bf16<256,ln64gelu> (convT1+LN2d+GELU)"
+                     : EPI == EPI_LN256 ? "gemm_bf16<256,ln256>"
+                     : (a.K >= 512 ? "gemm_bf16 plain K>=512" : "gemm_bf16 plain K<512");
+    prof_begin(stream, nm, 2.0 * a.M * a.N * a.K, (double)a.M * a.K * 2 + (double)a.N * a.K * 2 + out_b + res_b);
   }
   gemm_bf16_kernel<BN, EPI, SK><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmR, p);
   prof_end(stream);

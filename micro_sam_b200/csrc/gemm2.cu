@@ -303,7 +303,8 @@ int launch_gemm_2sm(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   const int tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * (a.N / BN);
   const int max_clusters = num_sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  prof_begin(stream, PROF_GEMM, 2.0 * a.M * a.N * a.K);
+  prof_begin(stream, "gemm2_bf16 (2-SM, encoder)", 2.0 * a.M * a.N * a.K,
+             (double)a.M * a.K * 2 + (double)a.N * a.K * 2 + (double)a.M * a.N * (a.out_fp32 ? 4 : 2) * (a.residual ? 2 : 1));
   gemm2_bf16_kernel<<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmR, p);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();

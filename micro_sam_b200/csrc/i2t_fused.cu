@@ -336,7 +336,7 @@ int launch_i2t_fused(const I2tFusedArgs& a, int num_sms, cudaStream_t stream) {
   const long total = (long)a.P * TILES;
   const int grid = total < num_sms ? (int)total : num_sms;
   const double bytes = (double)a.P * 4096 * 256 * 2 * (a.mode ? 2 : 1) + (double)a.P * 64 * 256 * 2 * 2;
-  prof_begin(stream, PROF_GEMM_HBM, bytes);
+  prof_begin(stream, a.mode ? "i2t_fused (own keys)" : "i2t_fused (shared image)", (double)a.P * 4096 * (2.0 * 256 * 64 * (a.mode ? 2 : 1) + 2.0 * 64 * 256), bytes);
   i2t_fused_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmA0, tmA1, tmM, tmV, tmOut, p);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();

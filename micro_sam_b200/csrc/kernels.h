@@ -9,11 +9,9 @@ namespace msam {
 int set_error(const char* fmt, ...);  // records msam_last_error(); returns -1
 void count_launch();                  // per-thread launch counter (msam_launch_count)
 
-// Optional per-kernel timing (bench.py roofline): CUDA events recorded on the launching stream around a launch.
-// GEMM launches are split by what bounds them: long-K (encoder) GEMMs -> tensor pipe, work = FLOPs; short-K (decoder)
-// GEMMs with fused epilogues -> HBM, work = algorithmic bytes (A + W + residual + output).
-enum ProfCat { PROF_GEMM = 0, PROF_ATTN = 1, PROF_GEMM_HBM = 2, PROF_NCAT = 3 };
-void prof_begin(cudaStream_t st, int cat, double work);  // work = algorithmic FLOPs (or bytes) of the launch
+// Optional per-kernel timing (bench.py roofline / per-stage table): CUDA events recorded on the launching stream around a
+// launch, aggregated by `name` (a string literal) in msam_profile_report; flops / bytes = ALGORITHMIC work of the launch.
+void prof_begin(cudaStream_t st, const char* name, double flops, double bytes);
 void prof_end(cudaStream_t st);
 
 // ---- gemm.cu :  out[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual[row % res_rows])

@@ -429,11 +429,13 @@ int post_mask_stats(const float* low_res, int n, int in_h, int in_w, int out_h, 
   PostGeom g;
   if (make_geom(in_h, in_w, out_h, out_w, &g)) return -1;
   if (n <= 0) return 0;
+  prof_begin(st, "mask_stats", 0.0, (double)n * (65536.0 * 4 + 24));
   if (g.identity2 && in_h == 1024 && in_w == 1024 && !force_generic) {
     mask_stats_x4_kernel<<<n, 512, 0, st>>>(low_res, g, thr, thr_arr, off, boxes, stability, area);
   } else {
     mask_stats_kernel<<<n, 256, 0, st>>>(low_res, g, thr, thr_arr, off, boxes, stability, area);
   }
+  prof_end(st);
   LAUNCH_CHECK("mask_stats");
   return 0;
 }
@@ -493,7 +495,9 @@ int post_filter_nms(const int32_t* boxes, const float* scores, const float* stab
     cudaFuncSetAttribute(filter_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     attr = true;
   }
+  prof_begin(st, "filter_nms", 0.0, (double)n * 28);
   filter_nms_kernel<<<1, 1024, smem, st>>>(boxes, scores, stab, p, keep, n_keep);
+  prof_end(st);
   LAUNCH_CHECK("filter_nms");
   return 0;
 }
@@ -609,8 +613,10 @@ int post_paint_min_area(const float* low_res, const int32_t* sel, const int32_t*
                         int ld_label, cudaStream_t st) {
   PostGeom g;
   if (make_geom(in_h, in_w, out_h, out_w, &g)) return -1;
+  prof_begin(st, "paint_min_area", 0.0, (double)out_h * out_w * 4);
   paint_min_area_kernel<<<dim3((out_w + 255) / 256, out_h), 256, 0, st>>>(low_res, sel, n_sel, boxes, area, g, thr, label,
                                                                         ld_label);
+  prof_end(st);
   LAUNCH_CHECK("paint_min_area");
   return 0;
 }
@@ -745,6 +751,7 @@ int post_finish_segmentation(const int32_t* seg, int h, int w, int min_size, int
   unsigned long long* best = reinterpret_cast<unsigned long long*>(bg + 2);
   cudaMemsetAsync(bg, 0, 6 * sizeof(int), st);
   const unsigned blocks = (unsigned)((n + 255) / 256);
+  prof_begin(st, "finish_segmentation (8 kernels)", 0.0, (double)n * 4 * 12);
   cc_init_kernel<<<blocks, 256, 0, st>>>(seg, n, parent, size);
   LAUNCH_CHECK("cc_init");
   cc_merge_kernel<<<blocks, 256, 0, st>>>(seg, h, w, parent);
@@ -760,6 +767,7 @@ int post_finish_segmentation(const int32_t* seg, int h, int w, int min_size, int
   scan_sums_kernel<<<1, 1024, 0, st>>>(bsums, nb);
   LAUNCH_CHECK("scan_sums");
   cc_relabel_kernel<<<blocks, 256, 0, st>>>(n, parent, flag, scan, bsums, out);
+  prof_end(st);
   LAUNCH_CHECK("cc_relabel");
   return 0;
 }

@@ -335,7 +335,8 @@ static int launch_t2i_fused_t(const T2iFusedArgs& a, int num_sms, cudaStream_t s
   T2iParams p;
   p.n_items = a.n_items; p.mode = a.mode; p.out = a.out;
   const int grid = a.n_items < num_sms ? a.n_items : num_sms;
-  prof_begin(stream, PROF_GEMM_HBM, (double)a.n_items * (ROWS * 256.0 * 2 + ROWS * 256.0 * 4) + (a.mode ? (double)a.n_items * 4096 * 512 : 0.0));
+  prof_begin(stream, ROWS == 64 ? "t2i_fused<64>" : "t2i_fused<128>", (double)a.n_items * 4096 * ROWS * 256 * 2.0 * 3,
+             (double)a.n_items * (ROWS * 256.0 * 2 + ROWS * 256.0 * 4) + (a.mode ? (double)a.n_items * 4096 * 512 : 0.0));
   t2i_fused_kernel<ROWS><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tmX, tmXS, tmQ, p);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();

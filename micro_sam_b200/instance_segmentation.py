@@ -105,6 +105,18 @@ class AMGBase(ABC):
             anns.append(ann)
         return anns
 
+    def _crop_geoms(self):
+        """Per-crop (input_size, original_size) of the predictor while the crop was decoded -- a pure function of the crop
+        boxes (the crop is what `set_image` / the tile embedding saw; input_size = ResizeLongestSide of it), so a state
+        restored with set_state() needs nothing beyond the reference's three keys."""
+        from .sam import get_preprocess_shape
+        H, W = self.original_size
+        geoms = []
+        for x0, y0, x1, y1 in self.crop_boxes:
+            h, w = min(int(y1), H) - int(y0), min(int(x1), W) - int(x0)
+            geoms.append(dict(inp=get_preprocess_shape(h, w, self._predictor.transform.target_length), orig=(h, w)))
+        return geoms
+
     def get_state(self) -> Dict[str, Any]:
         if not self.is_initialized:
             raise RuntimeError("The state has not been computed yet. Call initialize first.")
@@ -172,7 +184,7 @@ class AutomaticMaskGenerator(AMGBase):
         if pbar_init is not None:
             pbar_init(n_batches, "Predict masks for point grid prompts")
         for (points,) in amg_utils.batch_iterator(self._points_per_batch, points_for_image):
-            data.cat(self._process_batch(points, cropped_im_size, crop_box, self.original_size))
+            data.cat(self._process_batch(points, cropped_im_size, crop_box, self.original_size), copy=False)
             if pbar_update is not None:
                 pbar_update(1)
         return data
@@ -195,17 +207,15 @@ class AutomaticMaskGenerator(AMGBase):
         else:
             image_u8 = util._to_image(image)
         _, pbar_init, pbar_update, pbar_close = util.handle_pbar(verbose, pbar_init, pbar_update)
-        crop_list, geoms = [], []
+        crop_list = []
         for crop_box, layer_idx in zip(crop_boxes, layer_idxs):
             if not precomputed:
                 x0, y0, x1, y1 = crop_box
                 self._predictor.set_image(np.ascontiguousarray(image_u8[y0:y1, x0:x1, :]))
             crop_list.append(self._process_crop(original_size, crop_box, layer_idx, pbar_init, pbar_update))
-            geoms.append(dict(inp=tuple(self._predictor.input_size), orig=tuple(self._predictor.original_size)))
         if not precomputed:
             self._predictor.reset_image()
         pbar_close()
-        self._geoms = geoms
         self._is_initialized = True
         self._crop_list = crop_list
         self._crop_boxes = crop_boxes
@@ -218,7 +228,7 @@ class AutomaticMaskGenerator(AMGBase):
             raise RuntimeError("AutomaticMaskGenerator has not been initialized. Call initialize first.")
         if output_mode not in ("instance_segmentation", "binary_mask", "rle", "coco_rle"):
             raise ValueError(f"Invalid output mode {output_mode}.")
-        geoms = getattr(self, "_geoms", None)
+        geoms = self._crop_geoms()
         if min_mask_region_area > 0:
             return self._generate_small_regions(pred_iou_thresh, stability_score_thresh, box_nms_thresh, crop_nms_thresh,
                                                 min_mask_region_area, output_mode, with_background, geoms)
@@ -373,7 +383,7 @@ class AutomaticMaskGenerator(AMGBase):
             raise RuntimeError("AutomaticMaskGenerator has not been initialized. Call initialize first.")
         if len(self.crop_list) != 1:
             raise NotImplementedError("device-side generate supports a single crop")
-        data, crop_box, geom = self.crop_list[0], self.crop_boxes[0], self._geoms[0]
+        data, crop_box, geom = self.crop_list[0], self.crop_boxes[0], self._crop_geoms()[0]
         H, W = self.original_size
         dev = data["low_res"].device
         keep = self._filter_nms(data, crop_box, self.original_size, pred_iou_thresh, stability_score_thresh,
@@ -434,16 +444,14 @@ class TiledAutomaticMaskGenerator(AutomaticMaskGenerator):
         crop_boxes = [[t.begin[1], t.begin[0], t.end[1], t.end[0]] for t in tiles]
         _, pbar_init, pbar_update, pbar_close = util.handle_pbar(verbose, pbar_init, pbar_update)
         pbar_init(len(crop_boxes), "Compute masks for tile")
-        mask_data, geoms = [], []
+        mask_data = []
         for idx, tile_id in enumerate(tile_ids):
             f = feats[str(tile_id)]
             util.set_precomputed(self._predictor, {"features": f, "input_size": f.attrs["input_size"],
                                                    "original_size": f.attrs["original_size"]}, i)
             mask_data.append(self._process_crop(original_size, crop_boxes[idx], 0))
-            geoms.append(dict(inp=tuple(self._predictor.input_size), orig=tuple(self._predictor.original_size)))
             pbar_update(1)
         pbar_close()
-        self._geoms = geoms
         self._is_initialized = True
         self._crop_list = mask_data
         self._crop_boxes = crop_boxes

@@ -20,7 +20,9 @@ def _hf_model(model_type):
     return SamModel(cfg).eval()
 
 
-@pytest.mark.parametrize("model_type", ["vit_test", "vit_test80"])
+# vit_b = a real architecture of micro_sam/models/build_sam.py:40-76: 12 heads (head-major qkv split), 4 global blocks
+# (2, 5, 8, 11), depth 12 -- the toy shapes alone would not pin those.
+@pytest.mark.parametrize("model_type", ["vit_test", "vit_test80", "vit_b"])
 def test_oracle_matches_hf(model_type):
     torch.manual_seed(0)
     sd = sam_ref.seeded_state_dict(model_type, seed=1)
