@@ -57,8 +57,17 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
   return make_tmap_2d(out, gptr, 2, rows, cols, ld, box_rows);
 }
 
+static int make_tmap_typed(CUtensorMap* out, const void* gptr, int elem_bytes, int f16, uint64_t rows, uint64_t cols,
+                           uint64_t ld, uint32_t box_rows);
 int make_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows) {
+  return make_tmap_typed(out, gptr, elem_bytes, 0, rows, cols, ld, box_rows);
+}
+int make_tmap_f16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  return make_tmap_typed(out, gptr, 2, 1, rows, cols, ld, box_rows);
+}
+static int make_tmap_typed(CUtensorMap* out, const void* gptr, int elem_bytes, int f16, uint64_t rows, uint64_t cols,
+                           uint64_t ld, uint32_t box_rows) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   if (elem_bytes != 2 && elem_bytes != 4) return set_error("tensor map: unsupported element size %d", elem_bytes);
@@ -69,7 +78,8 @@ int make_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t ro
   cuuint64_t strides[1] = {ld * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+  CUresult r = enc(out, elem_bytes == 2 ? (f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)
+                                        : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<void*>(gptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -111,6 +121,17 @@ __nv_bfloat16* Engine::upload_bf16(const float* src, size_t n) {
   std::vector<__nv_bfloat16> tmp(n);
   for (size_t i = 0; i < n; ++i) tmp[i] = __float2bfloat16(src[i]);
   auto* d = static_cast<__nv_bfloat16*>(dalloc(n * 2));
+  if (!d) return nullptr;
+  if (cudaMemcpy(d, tmp.data(), n * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("H2D copy failed");
+    return nullptr;
+  }
+  return d;
+}
+__half* Engine::upload_f16(const float* src, size_t n) {
+  std::vector<__half> tmp(n);
+  for (size_t i = 0; i < n; ++i) tmp[i] = __float2half(src[i]);
+  auto* d = static_cast<__half*>(dalloc(n * 2));
   if (!d) return nullptr;
   if (cudaMemcpy(d, tmp.data(), n * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
     set_error("H2D copy failed");

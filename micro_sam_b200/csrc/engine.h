@@ -5,6 +5,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "../../include/msam_b200.h"
 #include "kernels.h"
 #include "tensormap.h"
@@ -53,6 +55,7 @@ struct Engine {
   void* dalloc(size_t bytes, bool zero = false);
   const std::vector<float>* host(const std::string& name, std::initializer_list<int64_t> shape);
   __nv_bfloat16* upload_bf16(const float* src, size_t n);
+  __half* upload_f16(const float* src, size_t n);
   float* upload_f32(const float* src, size_t n);
   __nv_bfloat16* up_bf16(const std::string& name, std::initializer_list<int64_t> shape);
   float* up_f32(const std::string& name, std::initializer_list<int64_t> shape);

@@ -39,6 +39,22 @@ int launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream);
 // gemm2.cu: 2-SM (cta_group::2) kernel for large plain products; returns 1 if launched, 0 if the problem does not qualify
 int launch_gemm_2sm(const GemmArgs& a, int num_sms, cudaStream_t stream);
 
+// ---- upscale_fused.cu : conv-transpose 1 + LayerNorm2d + GELU + conv-transpose 2 + GELU + hyper-network product in one pass
+struct UpscaleFusedArgs {
+  int P = 0, nm = 3, m0 = 1;          // prompts; masks written per prompt = hyper rows [m0, m0 + nm)
+  const __nv_bfloat16* keys = nullptr;  // [P*4096, 256] image tokens after the transformer
+  const __nv_bfloat16* w1 = nullptr;    // conv-transpose-1 weight as GEMM operand [(sub-pixel, out-ch) = 256, 256]
+  const void* w2_f16 = nullptr;         // conv-transpose-2 weight, fp16 [(sub-sub-pixel, out-ch) = 128, 64]
+  const float* b1 = nullptr;            // [256]
+  const float* gamma = nullptr;         // LayerNorm2d(64)
+  const float* beta = nullptr;
+  float eps = 1e-6f;
+  const float* b2 = nullptr;            // [128]
+  const float* hyper = nullptr;         // [P, 4, 32]
+  float* out = nullptr;                 // [P, nm, 256, 256] low-res mask logits
+};
+int launch_upscale_fused(const UpscaleFusedArgs& a, int num_sms, cudaStream_t stream);
+
 // ---- i2t_fused.cu : fused image -> token cross-attention block (q projection + attention + out projection + residual +
 // LayerNorm in one pass over the per-prompt image tokens); T <= 8 prompt tokens
 struct I2tFusedArgs {

@@ -18,5 +18,7 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
 // row-major 2D tensor of bf16 (elem_bytes 2) or fp32 (4); box = [box_rows, 128 / elem_bytes cols] (128-B rows, SWIZZLE_128B)
 int make_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows);
+// fp16 variant of make_tmap_bf16_2d
+int make_tmap_f16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
 }  // namespace msam

@@ -3,20 +3,24 @@
 Mirrors (reference file:line): get_sam_model util.py:318-476, _to_image :618-651, _compute_embeddings_batched
 :654-681, tiled / 3-D drivers :765-1041, precompute_image_embeddings :1133-1212, set_precomputed :1215-1258,
 mask_data_to_segmentation :1773-1848.
-Out of scope: the zarr on-disk container (`save_path`), pooch downloads.  Embeddings are returned in
-memory with the same dict layout; tiled embeddings use an in-memory group with the same keys/attrs as the zarr one.
+`save_path` stores the embeddings in the reference's zarr layout (group attrs = embedding signature, `features` dataset or
+per-tile datasets, util.py:684-747 / :1044-1096) through micro_sam_b200/zarr_store.py (zarr itself is not in this image; the
+written directory is a plain zarr-v2 store), including the signature check and the resume of partial 3-D runs.  Without
+`save_path` embeddings stay in memory (optionally on the device, `to_numpy=False`) with the same dict / group layout.
+Out of scope: pooch downloads.
 """
 from __future__ import annotations
 
+import hashlib
 import os
-import pickle
 import warnings
+from concurrent import futures
 from typing import Any, Callable, Dict, List, Optional, Tuple, Union
 
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, zarr_store
 from ._amg_utils import Blocking
 from .sam import ARCH, B200Sam, B200SamPredictor, validate_model_type
 
@@ -166,15 +170,37 @@ def _needs_no_resize(predictor, image) -> bool:
         and np.dtype(image.dtype) in _DTYPE_CODES
 
 
+def _host_pool() -> futures.ThreadPoolExecutor:
+    """Host threads for the per-tile numpy / PIL work (min-max normalisation, ResizeLongestSide): both release the GIL, and
+    at B200 encoder speeds (a few ms per tile) a single Python thread would be the bottleneck."""
+    global _POOL
+    if _POOL is None:
+        _POOL = futures.ThreadPoolExecutor(max(1, min(32, (os.cpu_count() or 2) - 1)))
+    return _POOL
+
+
+_POOL = None
+
+
+def _prepare_tiles(predictor, raw_tiles):
+    """_to_image + ResizeLongestSide.apply_image for a list of raw tiles, in parallel on the host pool."""
+    def one(raw):
+        img = _to_image(raw)
+        return img.shape[:2], predictor.transform.apply_image(img)
+    return list(_host_pool().map(one, raw_tiles)) if len(raw_tiles) > 1 else [one(t) for t in raw_tiles]
+
+
 @torch.no_grad()
-def _compute_embeddings_batched(predictor, batched_images):
+def _compute_embeddings_batched(predictor, batched_images, prepared=None):
     """util.py:654-681: resize each image, then ONE encoder call for the batch (preprocess is fused in the kernel when
-    all resized images share a shape, which is always the case for tiles of one tiling)."""
+    all resized images share a shape, which is always the case for tiles of one tiling).  `prepared`: output of
+    `_prepare_tiles` for the same images (then `batched_images` is ignored)."""
     predictor.reset_image()
     resized, original_sizes, input_sizes = [], [], []
-    for image in batched_images:
-        t = predictor.transform.apply_image(image)
-        original_sizes.append(image.shape[:2])
+    if prepared is None:
+        prepared = [(image.shape[:2], predictor.transform.apply_image(image)) for image in batched_images]
+    for osz, t in prepared:
+        original_sizes.append(tuple(osz))
         input_sizes.append(tuple(t.shape[:2]))
         resized.append(t)
     sam = predictor.model
@@ -269,15 +295,73 @@ def _get_tiles_in_mask(mask, tiling, halo, z=None):
     return out
 
 
+def _compute_data_signature(input_) -> str:
+    """util.py:1044-1046."""
+    return hashlib.sha1(np.asarray(input_).tobytes()).hexdigest()
+
+
+def _get_embedding_signature(input_, predictor, tile_shape, halo, data_signature=None):
+    """util.py:1050-1064."""
+    from . import __version__
+    if data_signature is None:
+        data_signature = _compute_data_signature(input_)
+    return {
+        "data_signature": data_signature,
+        "tile_shape": tile_shape if tile_shape is None else list(tile_shape),
+        "halo": halo if halo is None else list(halo),
+        "model_type": predictor.model_type,
+        "model_name": predictor.model_name,
+        "micro_sam_version": __version__,
+        "model_hash": getattr(predictor, "_hash", None),
+    }
+
+
+def _write_embedding_signature(f, input_, predictor, tile_shape, halo, input_size, original_size):
+    """util.py:1070-1074: the signature is written LAST -- its `input_size` key is what marks a container as complete."""
+    signature = _get_embedding_signature(input_, predictor, tile_shape, halo)
+    signature.update({"input_size": None if input_size is None else list(input_size),
+                      "original_size": None if original_size is None else list(original_size)})
+    f.attrs.update(signature)
+
+
+def _check_saved_embeddings(input_, predictor, f, save_path, tile_shape, halo):
+    """util.py:1077-1102."""
+    if "input_size" not in f.attrs:   # empty / partial container: embeddings will be (re)computed
+        return
+    signature = _get_embedding_signature(input_, predictor, tile_shape, halo)
+    for key, val in signature.items():
+        if key not in f.attrs or f.attrs[key] != val:
+            if key in ("micro_sam_version", "model_hash", "model_name"):
+                warnings.warn(f"The signature for {key} in embeddings file {save_path} has a mismatch: "
+                              f"{f.attrs.get(key)} != {val}. This key was recently added, so your embeddings are likely "
+                              "correct. But please recompute them if model predictions don't look as expected.")
+            else:
+                raise RuntimeError(f"Embeddings file {save_path} is invalid due to mismatch in {key}: "
+                                   f"{f.attrs.get(key)} != {val}. Please recompute embeddings in a new file.")
+
+
+def _write_chunks(jobs):
+    """util._write_batch's thread pool (util.py:743-747): jobs = [(dataset, index, host array)]; chunk files are
+    independent, so the writes run concurrently while the GPU computes the next batch."""
+    if not jobs:
+        return
+    with futures.ThreadPoolExecutor(min(8, len(jobs))) as tp:
+        list(tp.map(lambda j: j[0].__setitem__(j[1], j[2]), jobs))
+
+
 def _compute_tiled_features(predictor, input_, is3d, tile_shape, halo, pbar_init, pbar_update, batch_size, mask, to_numpy,
-                            rank: int = 0, world_size: int = 1):
+                            rank: int = 0, world_size: int = 1, zgroup=None):
     """util.py:765-899 (_compute_tiled_features_2d/_3d + _BatchProvider): (z, tile) pairs in row-major order, batches of
     `batch_size`, each tile normalised on its own (_to_image) -- tiled embeddings are NOT crops of a global embedding.
     rank/world_size: static block partition of that order for multi-GPU sharding -- each rank fills only
-    its own (z, tile) entries; no collective."""
+    its own (z, tile) entries; no collective.  zgroup: zarr group to write into (`save_path`), else an in-memory group."""
     plane_shape = input_.shape[1:3] if is3d else input_.shape[:2]
     tiling = Blocking([0, 0], plane_shape, tile_shape)
-    features = _MemGroup()
+    if zgroup is not None:
+        features = zgroup.require_group("features")
+        to_numpy = True
+    else:
+        features = _MemGroup()
     features.attrs["shape"] = tuple(plane_shape)
     features.attrs["tile_shape"] = tuple(tile_shape)
     features.attrs["halo"] = tuple(halo)
@@ -291,15 +375,38 @@ def _compute_tiled_features(predictor, input_, is3d, tile_shape, halo, pbar_init
     lo, hi = (len(work) * rank) // world_size, (len(work) * (rank + 1)) // world_size
     my_work = work[lo:hi]
     pbar_init(len(my_work), "Compute Image Embeddings tiled")
-    for b0 in range(0, len(my_work), batch_size):
-        chunk = my_work[b0:b0 + batch_size]
-        images = []
+
+    def prepare(chunk):   # host side of a batch: crop, normalise per tile, resize -- runs one batch ahead of the GPU
+        raw = []
         for z, tile_id in chunk:
             tile = tiling.get_block_with_halo(tile_id, list(halo))
             outer = tuple(slice(b, e) for b, e in zip(tile.outer_block.begin, tile.outer_block.end))
-            images.append(_to_image(input_[(z,) + outer] if is3d else input_[outer]))
-        emb, original_sizes, input_sizes = _compute_embeddings_batched(predictor, images)
+            raw.append(input_[(z,) + outer] if is3d else input_[outer])
+        return _prepare_tiles(predictor, raw)
+
+    chunks = [my_work[b0:b0 + batch_size] for b0 in range(0, len(my_work), batch_size)]
+    ahead = futures.ThreadPoolExecutor(1)
+    nxt = ahead.submit(prepare, chunks[0]) if chunks else None
+    for ci, chunk in enumerate(chunks):
+        prepared = nxt.result()
+        nxt = ahead.submit(prepare, chunks[ci + 1]) if ci + 1 < len(chunks) else None
+        emb, original_sizes, input_sizes = _compute_embeddings_batched(predictor, None, prepared=prepared)
         emb_host = emb.cpu().numpy() if to_numpy else emb
+        if zgroup is not None:   # _write_batch (util.py:710-747): datasets first (creation is not thread-safe), then chunks
+            jobs = []
+            for k, (z, tile_id) in enumerate(chunk):
+                name = str(tile_id)
+                eshape = tuple(emb.shape[1:])
+                if name not in features:
+                    shape = ((n_slices, 1) if is3d else (1,)) + eshape
+                    chunks = ((1, 1) if is3d else (1,)) + eshape
+                    ds = features.create_dataset(name, shape=shape, dtype="float32", chunks=chunks)
+                    ds.attrs["original_size"] = original_sizes[k]
+                    ds.attrs["input_size"] = input_sizes[k]
+                jobs.append((features[name], z if is3d else slice(None), emb_host[k][None]))
+            _write_chunks(jobs)
+            pbar_update(len(chunk))
+            continue
         for k, (z, tile_id) in enumerate(chunk):
             name = str(tile_id)
             if is3d:
@@ -312,9 +419,82 @@ def _compute_tiled_features(predictor, input_, is3d, tile_shape, halo, pbar_init
                 features[name] = _MemDataset(emb_host[k][None], {"original_size": original_sizes[k],
                                                                    "input_size": input_sizes[k]})
         pbar_update(len(chunk))
+    ahead.shutdown()
     if mask is not None:
         features.attrs["tiles_in_mask"] = tiles_in_mask if is3d else tiles_in_mask["0"]
+    if zgroup is not None and rank == 0:   # every rank's chunks are in place once the caller's barrier has passed
+        _write_embedding_signature(zgroup, input_, predictor, tile_shape, halo, input_size=None, original_size=None)
     return features
+
+
+def _precompute_saved(predictor, input_, save_path, lazy_loading, ndim, tile_shape, halo, pbar_init, pbar_update, batch_size,
+                      mask, rank, world_size):
+    """precompute_image_embeddings with a zarr container (util.py:1183-1211 + _compute_2d / _compute_3d / _compute_tiled_*)."""
+    existed = os.path.exists(save_path)
+    f = zarr_store.open_group(save_path, mode="a")
+    if existed:
+        _check_saved_embeddings(input_, predictor, f, save_path, tile_shape, halo)
+    complete = "input_size" in f.attrs
+    if tile_shape is not None:
+        if complete:   # _compute_tiled_2d/_3d: cached
+            return {"features": f["features"], "input_size": f.attrs["input_size"], "original_size": f.attrs["original_size"]}
+        feats = _compute_tiled_features(predictor, input_, ndim == 3, tuple(tile_shape), tuple(halo), pbar_init, pbar_update,
+                                        batch_size, mask, True, rank, world_size, zgroup=f)
+        return {"features": feats, "input_size": None, "original_size": None}
+    if ndim == 2:
+        if complete:   # _compute_2d: load and set
+            emb = {"features": f["features"][:], "input_size": tuple(f.attrs["input_size"]),
+                   "original_size": tuple(f.attrs["original_size"])}
+            set_precomputed(predictor, emb)
+            return emb
+        pbar_init(1, "Compute Image Embeddings 2D")
+        if _needs_no_resize(predictor, input_):
+            _compute_embeddings_batched_raw(predictor, [input_])
+        else:
+            predictor.reset_image()
+            predictor.set_image(_to_image(input_))
+        feats = predictor.get_image_embedding().cpu().numpy()
+        pbar_update(1)
+        f.create_dataset("features", data=feats)
+        _write_embedding_signature(f, input_, predictor, None, None, predictor.input_size, predictor.original_size)
+        return {"features": feats, "input_size": predictor.input_size, "original_size": predictor.original_size}
+    # ---- 3-D (util.py:950-1022), resumable: slices whose chunk is already non-zero are skipped
+    if complete:
+        feats = f["features"] if lazy_loading else f["features"][:]
+        return {"features": feats, "input_size": tuple(f.attrs["input_size"]), "original_size": tuple(f.attrs["original_size"])}
+    n = input_.shape[0]
+    eshape = (1, 256, 64, 64)
+    shape, chunks = (n,) + eshape, (1,) + eshape
+    partial = "features" in f
+    if partial:
+        feats = f["features"]
+        if feats.shape != shape or feats.chunks != chunks:
+            raise RuntimeError("Invalid partial features")
+    else:
+        feats = f.create_dataset("features", shape=shape, chunks=chunks, dtype="float32")
+    todo = [z for z in range(n) if not (partial and np.count_nonzero(feats[z]) != 0)]
+    lo, hi = (len(todo) * rank) // world_size, (len(todo) * (rank + 1)) // world_size
+    todo = todo[lo:hi]
+    pbar_init(len(todo), "Compute Image Embeddings 3D")
+    original_sizes = input_sizes = None
+    for b0 in range(0, len(todo), batch_size):
+        zs = todo[b0:b0 + batch_size]
+        raw = [input_[z] for z in zs]
+        if all(_needs_no_resize(predictor, im) for im in raw):
+            e, original_sizes, input_sizes = _compute_embeddings_batched_raw(predictor, raw)
+        else:
+            e, original_sizes, input_sizes = _compute_embeddings_batched(predictor, [_to_image(im) for im in raw])
+        host = e.cpu().numpy()
+        _write_chunks([(feats, z, host[k][None]) for k, z in enumerate(zs)])
+        pbar_update(len(zs))
+    if original_sizes is None:   # nothing left to compute on this rank: sizes follow from the geometry
+        from .sam import get_preprocess_shape
+        h, w = input_.shape[1:3]
+        original_sizes, input_sizes = [(h, w)], [get_preprocess_shape(h, w, predictor.transform.target_length)]
+    if rank == 0:
+        _write_embedding_signature(f, input_, predictor, None, None, input_sizes[-1], original_sizes[-1])
+    out = feats if (lazy_loading or world_size > 1) else feats[:]
+    return {"features": out, "input_size": tuple(input_sizes[-1]), "original_size": tuple(original_sizes[-1])}
 
 
 def precompute_image_embeddings(predictor, input_: np.ndarray, save_path=None, lazy_loading: bool = False,
@@ -324,12 +504,17 @@ def precompute_image_embeddings(predictor, input_: np.ndarray, save_path=None, l
                                 to_numpy: bool = True, rank: int = 0, world_size: int = 1) -> ImageEmbeddings:
     """util.precompute_image_embeddings (util.py:1133).  `to_numpy=False` keeps the embeddings on the device (skips the
     reference's D2H, util.py:917); rank/world_size shard tiled work across processes."""
-    if save_path is not None:
-        raise NotImplementedError("zarr embedding containers (save_path=...) are outside the B200 hot path (8f-3)")
     ndim = input_.ndim if ndim is None else ndim
     _, pbar_init, pbar_update, pbar_close = handle_pbar(verbose, pbar_init, pbar_update)
     if tile_shape is not None and halo is None:
         raise ValueError("To compute tiled embeddings the parameters tile_shape and halo have to be passed.")
+    if ndim not in (2, 3):
+        raise ValueError(f"Invalid dimesionality {input_.ndim}, expect 2 or 3 dim data.")
+    if save_path is not None:
+        emb = _precompute_saved(predictor, input_, save_path, lazy_loading, ndim, tile_shape, halo, pbar_init, pbar_update,
+                                batch_size, mask, rank, world_size)
+        pbar_close()
+        return emb
     if ndim == 2 and tile_shape is None:
         pbar_init(1, "Compute Image Embeddings 2D")
         if _needs_no_resize(predictor, input_):
