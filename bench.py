@@ -37,10 +37,14 @@ GRID = 32
 # algorithmic FLOPs
 ENC_FLOPS = {"vit_b": 0.9376e12, "vit_l": 2.8370e12, "vit_h": 5.6418e12}
 DEC_FLOPS_PER_PROMPT = 2.817e9      # hoisted decoder; + 0.805e9 once per tile
-# generate() thresholds of the benchmark (both arms).  With the seeded random-init weights iou_pred ~ N(0.0, 0.24) and the
-# stability scores sit around 0.2 (noise masks), so the reference defaults (0.88 / 0.95) filter everything; these values are
-# fixed quantiles of the seeded vit_b model's predictions on tile 0 (see `threshold_calibration` in the JSON line).
-BENCH_THRESH = {"pred_iou_thresh": 0.25, "stability_score_thresh": 0.2, "box_nms_thresh": 0.7}
+# generate() thresholds of the benchmark (both arms).  With the seeded random-init weights the predicted IoUs have median
+# 0.23 / 90 % quantile 0.51 and the stability scores median 0.125 (noise masks), so the reference defaults (0.88 / 0.95)
+# filter everything; and because every noise mask has a near-full-tile box (pairwise box IoU ~ 0.99) the default box-NMS
+# threshold 0.7 keeps exactly one mask per tile.  The benchmark therefore uses ~ the 90 % / 50 % quantiles of the seeded
+# vit_b model's predictions (`threshold_calibration` in the JSON line) and box_nms_thresh 1.0 (NMS runs but suppresses
+# nothing): O(100-200) survivors per tile reach the NMS, the painter and the connected-component pass, which is the order
+# of a real LM tile.  The thresholds-0.0 worst case (all 3072 masks into the NMS) is reported as `worst_case`.
+BENCH_THRESH = {"pred_iou_thresh": 0.5, "stability_score_thresh": 0.125, "box_nms_thresh": 1.0}
 
 
 def workload_config(args):

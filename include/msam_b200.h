@@ -78,6 +78,19 @@ int msam_decode(msam_handle* h, const float* points, const float* labels, int n_
 int msam_decode_ex(msam_handle* h, const float* points, const float* labels, int n_points, const float* boxes,
                    const float* mask_input, int P, int multimask, float* low_res, float* iou, void* stream);
 
+/* The model-level calls of the Sam duck type (training/trainable_sam.py:88-106, models/build_sam.py:115-133):
+ * sam.prompt_encoder(points=(coords, labels)|None, boxes|None, masks|None) -> sparse [P, n_sparse, 256] (n_sparse = n_points
+ * (+1 padding point when no box is given) + 2 box corners) and, for mask prompts, dense [P, 256, 64, 64] (NCHW fp32; without
+ * a mask prompt the dense embedding is the broadcast no_mask_embed and dense_out is not written);
+ * sam.prompt_encoder.get_dense_pe() -> token-major [4096, 256] (the caller views it as (1, 256, 64, 64));
+ * sam.mask_decoder(image_embeddings = the bound embedding, image_pe = get_dense_pe(), sparse, dense|NULL = no mask,
+ * multimask_output) -> low_res [P, M, 256, 256], iou [P, M]. */
+int msam_prompt_encode(msam_handle* h, const float* points, const float* labels, int n_points, const float* boxes,
+                       const float* mask_input, int P, float* sparse_out, float* dense_out, void* stream);
+int msam_get_dense_pe(msam_handle* h, float* out_4096x256, void* stream);
+int msam_mask_decode(msam_handle* h, const float* sparse, int n_sparse, const float* dense, int P, int multimask, float* low_res,
+                     float* iou, void* stream);
+
 /* Sam.postprocess_masks + calculate_stability_score + threshold + batched_mask_to_box + area, fused, never
  * materialising the upsampled logits (instance_segmentation.py:229-255; inference.py:137-151; _vendored.py:33-85).
  * low_res [n,256,256]; boxes int32 [n,4] xyxy ([0,0,0,0] if empty); stability fp32 [n]; area int32 [n]. */

@@ -123,7 +123,7 @@ mask_dense_kernel(const float* __restrict__ mask, const float* __restrict__ w1, 
                   const float* __restrict__ g1, const float* __restrict__ be1, const float* __restrict__ w2,
                   const float* __restrict__ b2, const float* __restrict__ g2, const float* __restrict__ be2,
                   const float* __restrict__ w3, const float* __restrict__ b3, const float* __restrict__ emb,
-                  __nv_bfloat16* __restrict__ keys) {
+                  __nv_bfloat16* __restrict__ keys, float* __restrict__ dense_out) {
   const int p = blockIdx.y, t0 = blockIdx.x * 16, tid = threadIdx.x;
   __shared__ float sa[16][16];  // [token][c*4 + sy*2 + sx] after stage 1
   __shared__ float sg[16][16];  // [token][o] after stage 2
@@ -176,7 +176,36 @@ mask_dense_kernel(const float* __restrict__ mask, const float* __restrict__ w1, 
 #pragma unroll
     for (int o = 0; o < 16; ++o) acc += w[o] * sg[tk][o];
     const size_t tok = (size_t)(t0 + tk);
-    keys[((size_t)p * 4096 + tok) * 256 + tid] = __float2bfloat16(acc + emb[tok * 256 + tid]);
+    if (dense_out) dense_out[((size_t)p * 256 + tid) * 4096 + tok] = acc;   // PromptEncoder output (NCHW fp32)
+    else keys[((size_t)p * 4096 + tok) * 256 + tid] = __float2bfloat16(acc + emb[tok * 256 + tid]);
+  }
+}
+
+// Tokens from GIVEN sparse prompt embeddings (the `mask_decoder(sparse_prompt_embeddings=...)` call of
+// training/trainable_sam.py:88-106): tok[p, 0..4] = output tokens, tok[p, 5 + s] = sparse[p, s].  grid = (T, P), block = 128.
+__global__ void tokens_from_sparse_kernel(const float* __restrict__ sparse, int n_sparse, int T,
+                                          const float* __restrict__ out_tokens, float* __restrict__ tok,
+                                          __nv_bfloat16* __restrict__ tok_bf) {
+  const int p = blockIdx.y, t = blockIdx.x, f = threadIdx.x;
+  const float* src = t < 5 ? out_tokens + t * 256 : sparse + ((long)p * n_sparse + (t - 5)) * 256;
+  const long o = ((long)p * T + t) * 256;
+  const float a = src[f], b = src[128 + f];
+  tok[o + f] = a; tok[o + 128 + f] = b;
+  tok_bf[o + f] = __float2bfloat16(a); tok_bf[o + 128 + f] = __float2bfloat16(b);
+}
+
+// keys0[p, token, c] = image_embedding[token, c] + dense[p, c, token]  for GIVEN dense prompt embeddings (NCHW fp32
+// [P, 256, 4096]).  grid = (4096/32, 256/32, P), block = (32, 8): transposed through shared memory.
+__global__ void dense_to_keys_kernel(const float* __restrict__ dense, const float* __restrict__ emb,
+                                     __nv_bfloat16* __restrict__ keys) {
+  __shared__ float tile[32][33];
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32, p = blockIdx.z, tx = threadIdx.x, ty = threadIdx.y;
+  const float* d = dense + (size_t)p * 256 * 4096;
+  for (int i = ty; i < 32; i += 8) tile[i][tx] = d[(size_t)(c0 + i) * 4096 + t0 + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const size_t tok = (size_t)(t0 + i);
+    keys[((size_t)p * 4096 + tok) * 256 + c0 + tx] = __float2bfloat16(tile[tx][i] + emb[tok * 256 + c0 + tx]);
   }
 }
 
@@ -601,25 +630,35 @@ int Engine::set_image_embedding(const float* feat, cudaStream_t st) {
 
 // One chunk of P <= max_prompts prompts.
 static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const float* labels, int np, const float* boxes,
-                        const float* mask_in, int P, int multimask, float* low_res, float* iou) {
+                        const float* mask_in, int P, int multimask, float* low_res, float* iou,
+                        const float* sparse = nullptr, int n_sparse_given = 0, const float* dense = nullptr) {
   DecoderState& d = *E.dec;
   const int NI = 4096;
-  const int n_sparse = (points ? np + (boxes ? 0 : 1) : 0) + (boxes ? 2 : 0);
+  const int n_sparse = sparse ? n_sparse_given : (points ? np + (boxes ? 0 : 1) : 0) + (boxes ? 2 : 0);
   const int T = 5 + n_sparse, PT = P * T, PN = P * NI;
-  if (n_sparse <= 0 && !mask_in) return set_error("decode: need points, boxes and/or mask prompts");
+  if (n_sparse <= 0 && !mask_in && !dense) return set_error("decode: need points, boxes and/or mask prompts");
   if (T > TMAX) return set_error("decode: %d tokens per prompt exceeds the supported %d", T, TMAX);
 
-  prompt_tokens_kernel<<<dim3(n_sparse > 0 ? n_sparse : 1, P), 128, 0, st>>>(points, labels, np, boxes, T, n_sparse, (float)E.cfg.image_size, d.gauss,
-                                                          d.point_emb, d.not_a_point, d.out_tokens, d.tok0, d.tok0_bf);
-  LAUNCH_CHECK("prompt_tokens");
+  if (sparse || n_sparse_given < 0) {  // given sparse embeddings (model-level mask_decoder call)
+    tokens_from_sparse_kernel<<<dim3(T, P), 128, 0, st>>>(sparse, n_sparse, T, d.out_tokens, d.tok0, d.tok0_bf);
+    LAUNCH_CHECK("tokens_from_sparse");
+  } else {
+    prompt_tokens_kernel<<<dim3(n_sparse > 0 ? n_sparse : 1, P), 128, 0, st>>>(points, labels, np, boxes, T, n_sparse, (float)E.cfg.image_size, d.gauss,
+                                                            d.point_emb, d.not_a_point, d.out_tokens, d.tok0, d.tok0_bf);
+    LAUNCH_CHECK("prompt_tokens");
+  }
 
-  // Mask prompts: the dense prompt embedding differs per prompt, so layer 0 cannot share its image-side operands; the
-  // per-prompt keys are materialised up front and layer 0 runs exactly like layer 1 on the image side.
+  // Mask prompts / given dense embeddings: the dense prompt embedding differs per prompt, so layer 0 cannot share its
+  // image-side operands; the per-prompt keys are materialised up front and layer 0 runs exactly like layer 1 on the image side.
   if (mask_in) {
     mask_dense_kernel<<<dim3(NI / 16, P), 256, 0, st>>>(mask_in, d.md_w1, d.md_b1, d.md_g1, d.md_be1, d.md_w2, d.md_b2, d.md_g2,
-                                                         d.md_be2, d.md_w3, d.md_b3, d.emb, d.keys);
+                                                         d.md_be2, d.md_w3, d.md_b3, d.emb, d.keys, nullptr);
     LAUNCH_CHECK("mask_dense");
+  } else if (dense) {
+    dense_to_keys_kernel<<<dim3(NI / 32, DC / 32, P), dim3(32, 8), 0, st>>>(dense, d.emb, d.keys);
+    LAUNCH_CHECK("dense_to_keys");
   }
+  const bool own_keys = mask_in || dense;
 
   // token -> image attention core: t_q128 -> t_att128 (t2i_fused.cu)
   auto t2i = [&](const AttnW& A, int mode) -> int {
@@ -643,7 +682,7 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
   for (int l = 0; l < 2; ++l) {
     const DecLayer& L = d.layers[l];
     const bool fused_i2t = T <= 8;
-    const bool shared = (l == 0) && !mask_in;  // image-side operands identical for every prompt
+    const bool shared = (l == 0) && !own_keys;  // image-side operands identical for every prompt
     if (!shared && !fused_i2t) {  // q of the (unfused) image -> token attention: (keys + pe) Wq^T, pe term through the residual
       if (gemm(E, st, d.keys, DC, L.i2t.q, PN, DI, DC, L.i2t.qb, d.img_kvq, DI, 0, 0, d.q_res[l], NI)) return -1;
     }
@@ -763,6 +802,66 @@ int Engine::decode(const float* points, const float* labels, int np, const float
                      iou + (size_t)p0 * nm))
       return -1;
   }
+  return 0;
+}
+
+// PromptEncoder.forward as a stand-alone call: sparse [P, n_sparse, 256] (points incl. the padding point when no box is
+// given, then the two box corners) and, for mask prompts, the dense embedding [P, 256, 64, 64] (NCHW fp32).
+int Engine::prompt_encode(const float* points, const float* labels, int np, const float* boxes, const float* mask_in, int P,
+                          float* sparse_out, float* dense_out, cudaStream_t st) {
+  if (!finalized || !dec) return set_error("prompt_encode: decoder weights not loaded");
+  DecoderState& d = *dec;
+  const int n_sparse = (points ? np + (boxes ? 0 : 1) : 0) + (boxes ? 2 : 0), T = 5 + n_sparse;
+  if (T > TMAX) return set_error("prompt_encode: %d tokens per prompt exceeds the supported %d", T, TMAX);
+  for (int p0 = 0; p0 < P; p0 += cfg.max_prompts) {
+    const int n = (P - p0 < cfg.max_prompts) ? (P - p0) : cfg.max_prompts;
+    if (n_sparse > 0) {
+      if (!sparse_out) return set_error("prompt_encode: sparse_out is null");
+      prompt_tokens_kernel<<<dim3(n_sparse, n), 128, 0, st>>>(points ? points + (size_t)p0 * np * 2 : nullptr,
+                                                             labels ? labels + (size_t)p0 * np : nullptr, np,
+                                                             boxes ? boxes + (size_t)p0 * 4 : nullptr, T, n_sparse,
+                                                             (float)cfg.image_size, d.gauss, d.point_emb, d.not_a_point,
+                                                             d.out_tokens, d.tok0, d.tok0_bf);
+      LAUNCH_CHECK("prompt_tokens");
+      if (cudaMemcpy2DAsync(sparse_out + (size_t)p0 * n_sparse * 256, (size_t)n_sparse * 1024, d.tok0 + 5 * 256, (size_t)T * 1024,
+                            (size_t)n_sparse * 1024, n, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return set_error("prompt_encode: copy failed");
+    }
+    if (mask_in) {
+      if (!dense_out) return set_error("prompt_encode: dense_out is null");
+      mask_dense_kernel<<<dim3(4096 / 16, n), 256, 0, st>>>(mask_in + (size_t)p0 * 65536, d.md_w1, d.md_b1, d.md_g1, d.md_be1,
+                                                           d.md_w2, d.md_b2, d.md_g2, d.md_be2, d.md_w3, d.md_b3, d.emb, nullptr,
+                                                           dense_out + (size_t)p0 * 256 * 4096);
+      LAUNCH_CHECK("mask_dense");
+    }
+  }
+  return 0;
+}
+
+// MaskDecoder.forward on given prompt embeddings (training/trainable_sam.py:88-106): sparse [P, n_sparse, 256]; dense
+// [P, 256, 64, 64] or NULL = the no-mask embedding (shared fast path).  The image embedding must have been bound.
+int Engine::mask_decode(const float* sparse, int n_sparse, const float* dense, int P, int multimask, float* low_res,
+                        float* iou, cudaStream_t st) {
+  if (!finalized || !dec) return set_error("mask_decode: decoder weights not loaded");
+  if (!dec->image_set) return set_error("mask_decode: no image embedding set");
+  if (P <= 0) return set_error("mask_decode: empty prompt batch");
+  if (n_sparse < 0 || (n_sparse > 0 && !sparse)) return set_error("mask_decode: bad sparse embeddings");
+  if (n_sparse == 0 && !dense) return set_error("mask_decode: need sparse and/or dense prompt embeddings");
+  const int nm = multimask ? 3 : 1;
+  for (int p0 = 0; p0 < P; p0 += cfg.max_prompts) {
+    const int n = (P - p0 < cfg.max_prompts) ? (P - p0) : cfg.max_prompts;
+    if (decode_chunk(*this, st, nullptr, nullptr, 0, nullptr, nullptr, n, multimask, low_res + (size_t)p0 * nm * 65536,
+                     iou + (size_t)p0 * nm, n_sparse > 0 ? sparse + (size_t)p0 * n_sparse * 256 : nullptr,
+                     n_sparse > 0 ? n_sparse : -1, dense ? dense + (size_t)p0 * 256 * 4096 : nullptr))
+      return -1;
+  }
+  return 0;
+}
+
+int Engine::dense_pe(float* out_tokmajor, cudaStream_t st) {
+  if (!finalized || !dec) return set_error("dense_pe: decoder weights not loaded");
+  if (cudaMemcpyAsync(out_tokmajor, dec->pos, (size_t)4096 * 256 * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+    return set_error("dense_pe: copy failed");
   return 0;
 }
 

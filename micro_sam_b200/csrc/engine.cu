@@ -469,6 +469,21 @@ int msam_decode_ex(msam_handle* h, const float* points, const float* labels, int
   if (points && !labels) return set_error("msam_decode_ex: points without labels");
   return h->eng.decode(points, labels, points ? n_points : 0, boxes, mask_input, P, multimask, low_res, iou, (cudaStream_t)stream);
 }
+int msam_prompt_encode(msam_handle* h, const float* points, const float* labels, int n_points, const float* boxes,
+                       const float* mask_input, int P, float* sparse_out, float* dense_out, void* stream) {
+  if (!h) return set_error("msam_prompt_encode: null handle");
+  if (points && !labels) return set_error("msam_prompt_encode: points without labels");
+  return h->eng.prompt_encode(points, labels, points ? n_points : 0, boxes, mask_input, P, sparse_out, dense_out, (cudaStream_t)stream);
+}
+int msam_get_dense_pe(msam_handle* h, float* out_4096x256, void* stream) {
+  if (!h || !out_4096x256) return set_error("msam_get_dense_pe: null argument");
+  return h->eng.dense_pe(out_4096x256, (cudaStream_t)stream);
+}
+int msam_mask_decode(msam_handle* h, const float* sparse, int n_sparse, const float* dense, int P, int multimask, float* low_res,
+                     float* iou, void* stream) {
+  if (!h || !low_res || !iou) return set_error("msam_mask_decode: null argument");
+  return h->eng.mask_decode(sparse, n_sparse, dense, P, multimask, low_res, iou, (cudaStream_t)stream);
+}
 int msam_mask_stats(const float* low_res, int n_masks, int in_h, int in_w, int orig_h, int orig_w, float mask_threshold,
                     float stability_offset, int32_t* boxes_xyxy, float* stability, int32_t* area, void* stream) {
   // a negative stability_offset selects the generic (any-geometry) kernel with |offset| (used by the parity tests to

@@ -68,6 +68,11 @@ struct Engine {
   int set_image_embedding(const float* feat, cudaStream_t st);  // decoder.cu
   int decode(const float* points, const float* labels, int np, const float* boxes, const float* mask_in, int P, int multimask,
              float* low_res, float* iou, cudaStream_t st);  // decoder.cu
+  int prompt_encode(const float* points, const float* labels, int np, const float* boxes, const float* mask_in, int P,
+                    float* sparse_out, float* dense_out, cudaStream_t st);  // decoder.cu
+  int mask_decode(const float* sparse, int n_sparse, const float* dense, int P, int multimask, float* low_res, float* iou,
+                  cudaStream_t st);  // decoder.cu
+  int dense_pe(float* out_tokmajor, cudaStream_t st);  // decoder.cu
 };
 
 // postprocess.cu

@@ -94,6 +94,9 @@ class _ImageEncoder:
 
 
 class _PromptEncoder:
+    """Callable stand-in for `sam.prompt_encoder` (segment_anything PromptEncoder as used at
+    micro_sam/training/trainable_sam.py:88-96): `(points=(coords, labels)|None, boxes=(P,4)|None, masks=(P,1,256,256)|None)`
+    -> `(sparse (P, n, 256), dense (P, 256, 64, 64))`, plus `get_dense_pe()`."""
     embed_dim = 256
 
     def __init__(self, sam: "B200Sam"):
@@ -101,6 +104,92 @@ class _PromptEncoder:
         g = sam.image_size // 16
         self.image_embedding_size = (g, g)
         self.input_image_size = (sam.image_size, sam.image_size)
+        self.mask_input_size = (4 * g, 4 * g)
+        self._dense_pe = None
+        nm = sam._state.get("prompt_encoder.no_mask_embed.weight")
+        self._no_mask = None if nm is None else nm.to(sam.device, torch.float32).reshape(1, -1, 1, 1).contiguous()
+
+    def get_dense_pe(self) -> torch.Tensor:
+        if self._dense_pe is None:
+            sam = self._sam
+            g = self.image_embedding_size[0]
+            pe = torch.empty(g * g, 256, device=sam.device, dtype=torch.float32)
+            _lib.check(_lib.lib().msam_get_dense_pe(sam._h, _lib.ptr(pe), _lib.cur_stream()))
+            self._dense_pe = pe.view(g, g, 256).permute(2, 0, 1)[None].contiguous()
+        return self._dense_pe
+
+    def is_no_mask_dense(self, dense: torch.Tensor) -> bool:
+        """True if `dense` is the broadcast no-mask embedding this object handed out (the decoder's shared fast path)."""
+        return (self._no_mask is not None and dense.device == self._no_mask.device
+                and dense.untyped_storage().data_ptr() == self._no_mask.untyped_storage().data_ptr()
+                and tuple(dense.stride()) == (0, 1, 0, 0))
+
+    @torch.no_grad()
+    def __call__(self, points=None, boxes=None, masks=None):
+        sam, dev = self._sam, self._sam.device
+        pts = lbl = bx = mk = None
+        np_, P = 0, None
+        if points is not None:
+            coords, labels = points
+            pts = coords.to(dev, torch.float32).contiguous()
+            lbl = labels.to(dev, torch.float32).contiguous()
+            P, np_ = pts.shape[0], pts.shape[1]
+        if boxes is not None:
+            bx = boxes.to(dev, torch.float32).reshape(-1, 4).contiguous()
+            P = bx.shape[0]
+        if masks is not None:
+            mk = masks.to(dev, torch.float32).reshape(-1, *self.mask_input_size).contiguous()
+            P = mk.shape[0] if P is None else P
+        if P is None:
+            P = 1   # PromptEncoder._get_batch_size
+        n_sparse = (np_ + (0 if bx is not None else 1) if pts is not None else 0) + (2 if bx is not None else 0)
+        sparse = torch.empty(P, n_sparse, 256, device=dev, dtype=torch.float32)
+        g = self.image_embedding_size[0]
+        dense = torch.empty(P, 256, g, g, device=dev, dtype=torch.float32) if mk is not None else None
+        if n_sparse > 0 or mk is not None:
+            _lib.check(_lib.lib().msam_prompt_encode(sam._h, _lib.ptr(pts), _lib.ptr(lbl), np_, _lib.ptr(bx), _lib.ptr(mk), P,
+                                                     _lib.ptr(sparse) if n_sparse > 0 else None, _lib.ptr(dense),
+                                                     _lib.cur_stream()))
+        if dense is None:
+            dense = self._no_mask.expand(P, -1, g, g)
+        return sparse, dense
+
+    forward = __call__
+
+
+class _MaskDecoder:
+    """Callable stand-in for `sam.mask_decoder` (kwargs as at micro_sam/training/trainable_sam.py:98-104)."""
+    num_mask_tokens = 4
+    num_multimask_outputs = 3
+    transformer_dim = 256
+
+    def __init__(self, sam: "B200Sam"):
+        self._sam = sam
+
+    @torch.no_grad()
+    def __call__(self, image_embeddings: torch.Tensor, image_pe: torch.Tensor, sparse_prompt_embeddings: torch.Tensor,
+                 dense_prompt_embeddings: torch.Tensor, multimask_output: bool):
+        sam, dev = self._sam, self._sam.device
+        if image_embeddings.numel() != 256 * 64 * 64:
+            raise ValueError(f"mask_decoder expects ONE image embedding (1,256,64,64), got {tuple(image_embeddings.shape)}")
+        if image_pe is not None and tuple(image_pe.shape[-3:]) != (256, 64, 64):
+            raise ValueError(f"image_pe must have shape (1,256,64,64), got {tuple(image_pe.shape)}")
+        sam.bind_embedding(image_embeddings)
+        sp = sparse_prompt_embeddings.to(dev, torch.float32).contiguous()
+        P, n_sparse = sp.shape[0], sp.shape[1]
+        dn = dense_prompt_embeddings
+        if sam.prompt_encoder.is_no_mask_dense(dn):
+            dn = None
+        else:
+            dn = dn.to(dev, torch.float32).expand(P, -1, -1, -1).contiguous()
+        M = 3 if multimask_output else 1
+        low = torch.empty(P, M, 256, 256, device=dev, dtype=torch.float32)
+        iou = torch.empty(P, M, device=dev, dtype=torch.float32)
+        _lib.check(_lib.lib().msam_mask_decode(sam._h, _lib.ptr(sp) if n_sparse > 0 else None, n_sparse, _lib.ptr(dn), P,
+                                               int(multimask_output), _lib.ptr(low), _lib.ptr(iou), _lib.cur_stream()))
+        return low, iou
+
+    forward = __call__
 
 
 class B200Sam:
@@ -126,9 +215,22 @@ class B200Sam:
         ga = list(a["global_attn_indexes"]) + [-1] * (8 - len(a["global_attn_indexes"]))
         cfg = _lib.MsamConfig(a["embed_dim"], a["depth"], a["num_heads"], (ctypes.c_int32 * 8)(*ga), 14, image_size, 16,
                               256, max_batch, max_prompts)
+        self._cfg = cfg
+        self._h = None
+        self._build_engine(state_dict)
+        self.pixel_mean = torch.tensor([123.675, 116.28, 103.53], device=self.device).view(-1, 1, 1)
+        self.pixel_std = torch.tensor([58.395, 57.12, 57.375], device=self.device).view(-1, 1, 1)
+
+    def _build_engine(self, state_dict) -> None:
+        """(Re)create the device engine from an upstream-keyed state dict: weights are packed (bf16 GEMM operands, fused /
+        transposed layouts) at load time, so `load_state_dict` rebuilds the engine rather than patching buffers."""
+        L = _lib.lib()
+        if self._h:
+            L.msam_destroy(self._h)
         self._h = ctypes.c_void_p()
+        self._bound_key = self._bound_src = self._bound_tensor = None
         with torch.cuda.device(self.device):
-            _lib.check(L.msam_create(ctypes.byref(cfg), self.device.index, ctypes.byref(self._h)))
+            _lib.check(L.msam_create(ctypes.byref(self._cfg), self.device.index, ctypes.byref(self._h)))
             self._state = {}
             for k, v in state_dict.items():
                 v = v.detach().to("cpu", torch.float32).contiguous()
@@ -136,17 +238,54 @@ class B200Sam:
                 shape = (ctypes.c_int64 * max(v.ndim, 1))(*v.shape)
                 _lib.check(L.msam_load_weight(self._h, k.encode(), ctypes.c_void_p(v.data_ptr()), shape, v.ndim))
             _lib.check(L.msam_finalize_weights(self._h))
-        self.pixel_mean = torch.tensor([123.675, 116.28, 103.53], device=self.device).view(-1, 1, 1)
-        self.pixel_std = torch.tensor([58.395, 57.12, 57.375], device=self.device).view(-1, 1, 1)
         self.image_encoder = _ImageEncoder(self)
         self.prompt_encoder = _PromptEncoder(self)
+        self.mask_decoder = _MaskDecoder(self)
 
-    # --- nn.Module-ish surface used by micro-sam
+    # --- nn.Module-ish surface used by micro-sam (util.py:457-458, training/util.py:131, trainable_sam.py:40-106)
     def state_dict(self):
         return dict(self._state)
 
+    def load_state_dict(self, state_dict, strict: bool = True):
+        missing = [k for k in self._state if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in self._state]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"Error(s) in loading state_dict: missing {missing[:4]}..., unexpected {unexpected[:4]}...")
+        merged = dict(self._state)
+        merged.update({k: v for k, v in state_dict.items() if k in self._state})
+        self._build_engine(merged)
+        return missing, unexpected
+
+    def named_parameters(self):
+        """Host copies of the weights under their upstream names (frozen: the B200 core is an inference engine; the training
+        surface of cfg 5 is documented in DESIGN.md)."""
+        for k, v in self._state.items():
+            yield k, torch.nn.Parameter(v, requires_grad=False)
+
+    def parameters(self):
+        for _, p in self.named_parameters():
+            yield p
+
     def eval(self):
         return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("micro_sam_b200 has no backward kernels yet (cfg 5, DESIGN.md)")
+        return self
+
+    def bind_embedding(self, f: torch.Tensor) -> None:
+        """Bind a (1,256,64,64) image embedding as the decoder's current image (SamPredictor.features assignment).  The
+        engine caches prompt-independent decoder state per bound embedding; the cache key lives HERE, with the engine it
+        describes, so that several predictors sharing one model cannot decode against each other's image."""
+        key = (f.data_ptr(), f._version, tuple(f.shape), str(f.device), f.dtype)
+        if self._bound_key == key and self._bound_src is f:
+            return
+        feat = f.detach().to(self.device, torch.float32).contiguous()
+        if feat.numel() != 256 * 64 * 64:
+            raise ValueError(f"features must have shape (1,256,64,64), got {tuple(f.shape)}")
+        _lib.check(_lib.lib().msam_set_image_embedding(self._h, _lib.ptr(feat), _lib.cur_stream()))
+        self._bound_key, self._bound_src, self._bound_tensor = key, f, feat  # keeps both alive: the address cannot be reused
 
     def to(self, device):
         if torch.device(device).type != "cuda":
@@ -194,7 +333,6 @@ class B200SamPredictor:
     def __init__(self, sam_model: B200Sam):
         self.model = sam_model
         self.transform = ResizeLongestSide(sam_model.image_size)
-        self._bound_features = None
         self.reset_image()
 
     @property
@@ -232,19 +370,12 @@ class B200SamPredictor:
             raise RuntimeError("An image must be set with .set_image(...) to generate an embedding.")
         return self.features
 
-    # -- the engine caches prompt-independent decoder state per bound embedding; re-bind when `features` was reassigned
+    # -- re-bind when `features` was reassigned (by this or any other predictor of the same model)
     def _bind_features(self) -> None:
         f = self.features
         if f is None:
             raise RuntimeError("An image must be set with .set_image(...) before mask prediction.")
-        key = (f.data_ptr(), f._version, tuple(f.shape))
-        if self._bound_features != key:
-            feat = f.to(self.device, torch.float32).contiguous()
-            if feat.numel() != 256 * 64 * 64:
-                raise ValueError(f"features must have shape (1,256,64,64), got {tuple(f.shape)}")
-            _lib.check(_lib.lib().msam_set_image_embedding(self.model._h, _lib.ptr(feat), _lib.cur_stream()))
-            self._bound_features = key
-            self._bound_tensor = feat  # keep alive
+        self.model.bind_embedding(f)
 
     @torch.no_grad()
     def decode_low_res(self, point_coords: Optional[torch.Tensor], point_labels: Optional[torch.Tensor],
