@@ -642,31 +642,53 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
     b = old;
   }
 }
-__global__ void cc_init_kernel(const int32_t* __restrict__ seg, int n, int* __restrict__ parent, int* __restrict__ size) {
+// Initial forest: every pixel points at the first pixel of its horizontal run inside the warp's 32-pixel segment (found with
+// one ballot), so the union phase starts from runs instead of single pixels: the chains that uf_find walks are 32x shorter
+// and most horizontal unions disappear.  (Roots stay the smallest index of their set, as the relabelling order requires.)
+__global__ void cc_init_kernel(const int32_t* __restrict__ seg, int n, int w, int* __restrict__ parent, int* __restrict__ size) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { parent[i] = seg[i] != 0 ? i : -1; size[i] = 0; }
+  const int lane = threadIdx.x & 31;
+  const int s = i < n ? seg[i] : 0;
+  const int left = __shfl_up_sync(0xffffffffu, s, 1);
+  // run boundary: first lane, first pixel of an image row, or a label change
+  const bool head = lane == 0 || (i % w) == 0 || left != s;
+  const unsigned heads = __ballot_sync(0xffffffffu, head);
+  if (i < n) {
+    const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));   // nearest head at or below this lane
+    parent[i] = s != 0 ? i - (lane - start) : -1;
+    size[i] = 0;
+  }
 }
+// Unions: horizontally only across warp-segment boundaries (inside a segment the run already shares a parent); vertically
+// only where the link is not implied by the left neighbours (i-1 ~ i and i-1+w ~ i+w by their runs, i-1 ~ i-1+w by the left
+// pixel's own link), i.e. at the first column of every vertical contact between two runs.
 __global__ void cc_merge_kernel(const int32_t* __restrict__ seg, int h, int w, int* __restrict__ parent) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= h * w) return;
   const int s = seg[i];
   if (s == 0) return;
   const int x = i % w, y = i / w;
-  if (x + 1 < w && seg[i + 1] == s) uf_union(parent, i, i + 1);
-  if (y + 1 < h && seg[i + w] == s) uf_union(parent, i, i + w);
+  if ((threadIdx.x & 31) == 0 && x > 0 && seg[i - 1] == s) uf_union(parent, i - 1, i);
+  if (y + 1 < h && seg[i + w] == s) {
+    const bool implied = x > 0 && seg[i - 1] == s && seg[i + w - 1] == s;
+    if (!implied) uf_union(parent, i, i + w);
+  }
 }
 __global__ void cc_flatten_count_kernel(int n, int* __restrict__ parent, int* __restrict__ size, int* __restrict__ bg_count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int bg = 0;
+  int bg = 0, r = -1;
   if (i < n) {
     if (parent[i] >= 0) {
-      const int r = uf_find(parent, i);
+      r = uf_find(parent, i);
       parent[i] = r;
-      atomicAdd(&size[r], 1);
     } else {
       bg = 1;
     }
   }
+  // one atomic per distinct root per warp (neighbouring pixels mostly share their root; a large component would otherwise
+  // take hundreds of thousands of same-address atomics)
+  const unsigned same = __match_any_sync(0xffffffffu, r);
+  if (r >= 0 && (threadIdx.x & 31) == (unsigned)(__ffs(same) - 1)) atomicAdd(&size[r], __popc(same));
   const unsigned m = __ballot_sync(0xffffffffu, bg);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(bg_count, __popc(m));
 }
@@ -752,7 +774,7 @@ int post_finish_segmentation(const int32_t* seg, int h, int w, int min_size, int
   cudaMemsetAsync(bg, 0, 6 * sizeof(int), st);
   const unsigned blocks = (unsigned)((n + 255) / 256);
   prof_begin(st, "finish_segmentation (8 kernels)", 0.0, (double)n * 4 * 12);
-  cc_init_kernel<<<blocks, 256, 0, st>>>(seg, n, parent, size);
+  cc_init_kernel<<<blocks, 256, 0, st>>>(seg, n, w, parent, size);
   LAUNCH_CHECK("cc_init");
   cc_merge_kernel<<<blocks, 256, 0, st>>>(seg, h, w, parent);
   LAUNCH_CHECK("cc_merge");

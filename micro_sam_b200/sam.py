@@ -53,6 +53,12 @@ class ResizeLongestSide:
         from PIL import Image  # same PIL bilinear(+antialias) uint8 resize the reference reaches via torchvision
         return np.array(Image.fromarray(image).resize((tw, th), Image.BILINEAR))
 
+    def apply_image_torch(self, image: torch.Tensor) -> torch.Tensor:
+        """(B, C, H, W) float tensor -> longest side `target_length` (bilinear, antialiased), the torch twin used by
+        training/trainable_sam.py:36 and prompt_based_segmentation.py:100."""
+        th, tw = get_preprocess_shape(image.shape[2], image.shape[3], self.target_length)
+        return torch.nn.functional.interpolate(image, (th, tw), mode="bilinear", align_corners=False, antialias=True)
+
     def apply_coords(self, coords: np.ndarray, original_size: Tuple[int, ...]) -> np.ndarray:
         old_h, old_w = original_size
         new_h, new_w = get_preprocess_shape(old_h, old_w, self.target_length)

@@ -434,3 +434,61 @@ def test_amg_crop_layers_against_oracle(models):
         assert a["bbox"] == b["bbox"] and a["area"] == b["area"] and np.array_equal(a["segmentation"], b["segmentation"])
     assert _partition_equal(amg.generate(output_mode="instance_segmentation", **kw), oamg.generate(output_mode="instance_segmentation", **kw))
 
+
+
+def test_model_level_prompt_encoder_and_mask_decoder(models):
+    """Row (b): the `predictor.model` duck type -- `prompt_encoder(points, boxes, masks)`, `get_dense_pe()`,
+    `mask_decoder(image_embeddings, image_pe, sparse, dense, multimask_output)`, `load_state_dict` -- used the way
+    micro_sam/training/trainable_sam.py:88-106 uses it, against the oracle modules on the same image embedding."""
+    opred, pred = models
+    osam, sam = opred.model, pred.model
+    from micro_sam_b200.sample_data import lm_tile
+    from micro_sam_b200 import util
+    img = util._to_image(lm_tile((1024, 1024), 60, seed=4))
+    opred.set_image(img)
+    feat = opred.features
+    pe = sam.prompt_encoder.get_dense_pe()
+    assert pe.shape == (1, 256, 64, 64)
+    assert torch.allclose(pe.cpu(), osam.prompt_encoder.get_dense_pe(), atol=2e-5)
+    g = torch.Generator().manual_seed(0)
+    P = 9
+    pts = torch.rand(P, 2, 2, generator=g) * 1024
+    lbl = torch.tensor([[1, 0], [1, 1], [1, -1]] * 3)
+    boxes = torch.sort(torch.rand(P, 2, 2, generator=g) * 1024, dim=1)[0].reshape(P, 4)
+    masks = torch.randn(P, 1, 256, 256, generator=g) * 4
+    cases = [dict(points=(pts, lbl), boxes=None, masks=None), dict(points=None, boxes=boxes, masks=None),
+             dict(points=(pts, lbl), boxes=boxes, masks=None), dict(points=None, boxes=None, masks=masks),
+             dict(points=(pts[:, :1], lbl[:, :1]), boxes=None, masks=masks)]
+    for kw in cases:
+        with torch.no_grad():
+            osp, ode = osam.prompt_encoder(**kw)
+        sp, de = sam.prompt_encoder(**kw)
+        assert sp.shape == osp.shape and de.shape == ode.shape, (sp.shape, osp.shape, de.shape, ode.shape)
+        assert torch.allclose(sp.cpu(), osp, atol=1e-4)
+        assert torch.allclose(de.cpu(), ode, atol=2e-3, rtol=1e-3)
+        for mm in (True, False):
+            with torch.no_grad():
+                olow, oiou = osam.mask_decoder(image_embeddings=feat, image_pe=osam.prompt_encoder.get_dense_pe(),
+                                               sparse_prompt_embeddings=osp, dense_prompt_embeddings=ode, multimask_output=mm)
+            low, iou = sam.mask_decoder(image_embeddings=feat.cuda(), image_pe=pe, sparse_prompt_embeddings=sp,
+                                        dense_prompt_embeddings=de, multimask_output=mm)
+            assert low.shape == olow.shape and iou.shape == oiou.shape
+            rel = float((low.cpu() - olow).norm() / olow.norm())
+            assert rel < 3e-2 and float((iou.cpu() - oiou).abs().max()) < 2e-2, (list(kw), mm, rel)
+    # a dense embedding that is NOT the prompt encoder's no-mask view takes the general (per-prompt keys) path: same result
+    sp, de = sam.prompt_encoder(points=(pts, lbl), boxes=None, masks=None)
+    low_fast, _ = sam.mask_decoder(image_embeddings=feat.cuda(), image_pe=pe, sparse_prompt_embeddings=sp,
+                                   dense_prompt_embeddings=de, multimask_output=True)
+    low_gen, _ = sam.mask_decoder(image_embeddings=feat.cuda(), image_pe=pe, sparse_prompt_embeddings=sp,
+                                  dense_prompt_embeddings=de.clone(), multimask_output=True)
+    assert float((low_fast - low_gen).norm() / low_fast.norm()) < 2e-2
+    # load_state_dict rebuilds the engine; identical weights -> identical outputs; perturbed weights -> different outputs
+    sd = sam.state_dict()
+    assert set(dict(sam.named_parameters())) == set(sd) and len(list(sam.parameters())) == len(sd)
+    sam.load_state_dict(sd)
+    low2, _ = sam.mask_decoder(image_embeddings=feat.cuda(), image_pe=sam.prompt_encoder.get_dense_pe(),
+                               sparse_prompt_embeddings=sp, dense_prompt_embeddings=sam.prompt_encoder(points=(pts, lbl))[1],
+                               multimask_output=True)
+    assert torch.equal(low2, low_fast)
+    with pytest.raises(RuntimeError):
+        sam.load_state_dict({"nope": torch.zeros(1)})
