@@ -144,7 +144,7 @@ int msam_paint_min_area(const float* low_res, const int32_t* sel, const int32_t*
                         int32_t* label, int ld_label, void* stream);
 /* util.mask_data_to_segmentation tail (util.py:1831-1848): connected components of equal labels (4-connectivity), drop
  * components smaller than min_object_size and (with_background) the largest segment, relabel consecutively in raster
- * order.  workspace: int32 [4*h*w + 4096 + 8]. */
+ * order.  workspace: int32 [4*h*w + max(4096, ceil(h*w/1024)) + 8] (any image size below 2^31 pixels). */
 int msam_finish_segmentation(const int32_t* painted, int h, int w, int min_object_size, int with_background, uint32_t* out,
                              int32_t* workspace, void* stream);
 

@@ -295,7 +295,9 @@ __global__ void paint_kernel(const float* __restrict__ low_res, const int32_t* _
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Fused AMG filter + greedy box NMS (single CTA, N <= NMS_MAX).  keep[] receives indices in descending-score order.
+// Fused AMG filter + greedy box NMS (single CTA).  keep[] receives indices in descending-score order.  Up to NMS_MAX
+// candidates the sort keys / boxes / alive flags live in shared memory; larger inputs (points_per_side 64, the cross-tile NMS
+// of a large tiled image) run the same algorithm on a global-memory workspace (L2 resident, slower but unbounded).
 constexpr int NMS_MAX = 8192;
 
 struct NmsParams {
@@ -313,8 +315,9 @@ __device__ __forceinline__ uint32_t orderable(float f) {
 
 __global__ void __launch_bounds__(1024)
 filter_nms_kernel(const int32_t* __restrict__ boxes, const float* __restrict__ scores, const float* __restrict__ stab,
-                  NmsParams p, int32_t* __restrict__ keep, int32_t* __restrict__ n_keep) {
-  extern __shared__ unsigned long long skey[];  // [npow2] sort keys, then reused
+                  NmsParams p, int32_t* __restrict__ keep, int32_t* __restrict__ n_keep, unsigned long long* gws) {
+  extern __shared__ unsigned long long skey_smem[];  // [npow2] sort keys, then reused
+  unsigned long long* skey = gws ? gws : skey_smem;
   __shared__ int s_cnt, s_cur;
   int npow2 = 1;
   while (npow2 < p.n) npow2 <<= 1;
@@ -478,7 +481,7 @@ int post_paint(const float* low_res, const int32_t* sel, const int32_t* boxes, c
 int post_filter_nms(const int32_t* boxes, const float* scores, const float* stab, int n, int use_filters, float iou_thresh,
                     float stab_thresh, float nms_thresh, const int32_t* crop_box, const int32_t* orig_box, int32_t* keep,
                     int32_t* n_keep, cudaStream_t st) {
-  if (n > NMS_MAX) return set_error("filter_nms: n=%d exceeds %d", n, NMS_MAX);
+  if (n > (1 << 22)) return set_error("filter_nms: n=%d exceeds %d", n, 1 << 22);
   if (n <= 0) {
     cudaMemsetAsync(n_keep, 0, 4, st);
     return 0;
@@ -495,9 +498,13 @@ int post_filter_nms(const int32_t* boxes, const float* scores, const float* stab
     cudaFuncSetAttribute(filter_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     attr = true;
   }
+  unsigned long long* gws = nullptr;
+  if (n > NMS_MAX && cudaMallocAsync(reinterpret_cast<void**>(&gws), smem, st) != cudaSuccess)
+    return set_error("filter_nms: workspace allocation of %zu bytes failed", smem);
   prof_begin(st, "filter_nms", 0.0, (double)n * 28);
-  filter_nms_kernel<<<1, 1024, smem, st>>>(boxes, scores, stab, p, keep, n_keep);
+  filter_nms_kernel<<<1, 1024, gws ? 0 : smem, st>>>(boxes, scores, stab, p, keep, n_keep, gws);
   prof_end(st);
+  if (gws) cudaFreeAsync(gws, st);
   LAUNCH_CHECK("filter_nms");
   return 0;
 }
@@ -737,16 +744,29 @@ __global__ void scan_block_kernel(const int* __restrict__ in, int n, int* __rest
   if (i < n) out[i] = s[threadIdx.x];
   if (threadIdx.x == 1023) block_sums[blockIdx.x] = s[1023];
 }
-__global__ void scan_sums_kernel(int* __restrict__ block_sums, int nb) {  // single block, nb <= 4096
-  __shared__ int s[4096];
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) s[i] = block_sums[i];
+// exclusive scan of the per-block sums in place: single block of 1024 threads, chunks of 1024 sums with a running carry
+// (any nb: a 16k x 16k label image has 262144 block sums)
+__global__ void scan_sums_kernel(int* __restrict__ block_sums, int nb) {
+  __shared__ int s[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int i = 0; i < nb; ++i) { const int t = s[i]; s[i] = acc; acc += t; }
+  for (int base = 0; base < nb; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nb ? block_sums[i] : 0;
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+      __syncthreads();
+      s[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < nb) block_sums[i] = carry + s[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += s[1023];
+    __syncthreads();
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) block_sums[i] = s[i];
 }
 __global__ void cc_relabel_kernel(int n, const int* __restrict__ parent, const int* __restrict__ flag,
                                   const int* __restrict__ scan, const int* __restrict__ block_offs,
@@ -760,16 +780,16 @@ __global__ void cc_relabel_kernel(int n, const int* __restrict__ parent, const i
 }
 
 int post_finish_segmentation(const int32_t* seg, int h, int w, int min_size, int with_background, uint32_t* out,
-                             int32_t* ws /* 4*h*w + 4096 + 8 ints */, cudaStream_t st) {
+                             int32_t* ws /* 4*h*w + max(4096, ceil(h*w/1024)) + 8 ints */, cudaStream_t st) {
+  if ((long)h * w >= (1l << 31) - 1024) return set_error("finish_segmentation: image too large (%d x %d)", h, w);
   const int n = h * w;
   const int nb = (n + 1023) / 1024;
-  if (nb > 4096) return set_error("finish_segmentation: image too large (%d x %d)", h, w);
   int* parent = ws;
   int* size = ws + n;
-  int* flag = ws + 2 * n;
-  int* scan = ws + 3 * n;
+  int* flag = ws + 2 * (size_t)n;
+  int* scan = ws + 3 * (size_t)n;
   int* bsums = ws + 4 * (size_t)n;
-  int* bg = bsums + 4096;
+  int* bg = bsums + (nb > 4096 ? nb : 4096);
   unsigned long long* best = reinterpret_cast<unsigned long long*>(bg + 2);
   cudaMemsetAsync(bg, 0, 6 * sizeof(int), st);
   const unsigned blocks = (unsigned)((n + 255) / 256);

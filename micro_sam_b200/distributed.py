@@ -46,3 +46,20 @@ def exclusive_id_offsets(local_max_ids: torch.Tensor, group=None) -> torch.Tenso
     rank = dist.get_rank(group) if (dist.is_available() and dist.is_initialized()) else 0
     lo = sum(counts[:rank])
     return scan[lo: lo + local_max_ids.numel()]
+
+
+def gather_instance_tables(tables: dict, group=None) -> Tuple[dict, List[int]]:
+    """The exchange step of a multi-rank stitched result: every rank contributes the per-instance tensors of
+    the tiles it owns (same keys / trailing shapes / dtypes on all ranks, first dimension = its number of instances) and
+    receives the concatenation over ranks in rank order -- which is tile order, because ranks own contiguous tile ranges,
+    so the gathered list is exactly the list a single process would have built."""
+    out, counts = {}, None
+    for k in sorted(tables):
+        t = tables[k]
+        flat = t.reshape(t.shape[0], -1) if t.ndim > 1 else t.reshape(-1, 1)
+        g, c = all_gather_tables(flat.contiguous(), group)
+        if counts is not None and c != counts:
+            raise RuntimeError(f"gather_instance_tables: inconsistent row counts for {k}: {c} != {counts}")
+        counts = c
+        out[k] = g.reshape((g.shape[0],) + tuple(t.shape[1:]))
+    return out, counts or []

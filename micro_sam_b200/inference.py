@@ -50,8 +50,6 @@ def batched_inference(predictor, image: Optional[np.ndarray], batch_size: int, b
                       i: Optional[int] = None):
     n_prompts, have_boxes, have_points, have_logits = _validate_inputs(
         boxes, points, point_labels, multimasking, return_instance_segmentation, segmentation_ids, logits_masks)
-    if multimasking and not reduce_multimasking:
-        raise NotImplementedError("multimasking without reduce_multimasking")
     if image is None:
         predictor.get_image_embedding()
     else:
@@ -77,14 +75,19 @@ def batched_inference(predictor, image: Optional[np.ndarray], batch_size: int, b
         low, iou = predictor.decode_low_res(points_t[s:e] if have_points else None, labels_t[s:e] if have_points else None,
                                             boxes_t[s:e] if have_boxes else None, multimask_output=multimasking,
                                             mask_input=logits_masks[s:e] if have_logits else None)
-        if multimasking:  # keep the mask with the highest predicted IoU (inference.py:259-263)
+        if multimasking and reduce_multimasking:  # keep the mask with the highest predicted IoU (inference.py:259-263)
             best = iou.argmax(dim=1)
             sel = torch.arange(low.shape[0], device=device)
             low, iou = low[sel, best][:, None], iou[sel, best][:, None]
-        lows.append(low[:, 0])
-        ious.append(iou[:, 0])
+        # without the reduction all three masks of every prompt become records (flattened prompt-major, :266-269)
+        lows.append(low.flatten(0, 1))
+        ious.append(iou.flatten(0, 1))
     low = torch.cat(lows).contiguous()
     iou = torch.cat(ious)
+    if low.shape[0] != n_prompts:
+        if segmentation_ids is not None:
+            raise ValueError("segmentation_ids cannot be combined with multimasking without reduce_multimasking")
+        n_prompts = low.shape[0]
     thr_t = local_otsu_threshold(low) if auto else None   # one threshold per mask (inference.py:137-151)
     bxs, stab, area = mask_stats(low, predictor.input_size, image_shape, thr_t if auto else thr, 1.0)
     H, W = image_shape
@@ -104,8 +107,12 @@ def batched_inference(predictor, image: Optional[np.ndarray], batch_size: int, b
         else:
             _lib.check(_lib.lib().msam_paint(_lib.ptr(low), _lib.ptr(sel), _lib.ptr(bxs), _lib.ptr(ids), n_prompts, int(inp[0]),
                                              int(inp[1]), H, W, float(thr), 1, _lib.ptr(label), W, _lib.cur_stream()))
-        return util._finish_segmentation(label.cpu().numpy().astype(np.uint32), min_object_size=0, label_masks=True,
-                                         with_background=False)
+        # connected components + consecutive relabelling on the device (util.py:1831-1848), like the AMG path
+        out = torch.empty(H, W, dtype=torch.int32, device=device)
+        ws = torch.empty(util.finish_ws_size(H, W), dtype=torch.int32, device=device)
+        _lib.check(_lib.lib().msam_finish_segmentation(_lib.ptr(label), H, W, 0, 0, _lib.ptr(out), _lib.ptr(ws),
+                                                       _lib.cur_stream()))
+        return out.cpu().numpy().view(np.uint32)
 
     binm = torch.empty(n_prompts, H, W, dtype=torch.uint8, device=device)
     logits = torch.empty(n_prompts, H, W, dtype=torch.float32, device=device) if return_highres_logits else None

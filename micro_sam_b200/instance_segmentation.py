@@ -306,7 +306,7 @@ class AutomaticMaskGenerator(AMGBase):
                                            _lib.ptr(canvas), W, _lib.cur_stream()))
         label = torch.empty(H, W, dtype=torch.int32, device=dev)
         out = torch.empty(H, W, dtype=torch.int32, device=dev)
-        ws = torch.empty(4 * H * W + 4096 + 8, dtype=torch.int32, device=dev)
+        ws = torch.empty(util.finish_ws_size(H, W), dtype=torch.int32, device=dev)
         _lib.check(L.msam_canvas_to_label(_lib.ptr(canvas), H * W, _lib.ptr(label), _lib.cur_stream()))
         _lib.check(L.msam_finish_segmentation(_lib.ptr(label), H, W, 0, int(with_background), _lib.ptr(out), _lib.ptr(ws),
                                               _lib.cur_stream()))
@@ -368,7 +368,7 @@ class AutomaticMaskGenerator(AMGBase):
         for sid, k in enumerate(order, 1):
             label[torch.from_numpy(recs[k]["segmentation"]).to(dev)] = sid
         out_t = torch.empty(H, W, dtype=torch.int32, device=dev)
-        ws2 = torch.empty(4 * H * W + 4096 + 8, dtype=torch.int32, device=dev)
+        ws2 = torch.empty(util.finish_ws_size(H, W), dtype=torch.int32, device=dev)
         _lib.check(L.msam_finish_segmentation(_lib.ptr(label), H, W, 0, int(with_background), _lib.ptr(out_t), _lib.ptr(ws2),
                                               _lib.cur_stream()))
         return out_t.cpu().numpy().view(np.uint32)
@@ -391,7 +391,7 @@ class AutomaticMaskGenerator(AMGBase):
         bufs = getattr(self, "_dev_bufs", None)
         if bufs is None or bufs[0].shape != (H, W) or bufs[0].device != dev:
             bufs = (torch.empty(H, W, dtype=torch.int32, device=dev), torch.empty(H, W, dtype=torch.int32, device=dev),
-                    torch.empty(4 * H * W + 4096 + 8, dtype=torch.int32, device=dev))
+                    torch.empty(util.finish_ws_size(H, W), dtype=torch.int32, device=dev))
             self._dev_bufs = bufs
         painted, out, ws = bufs
         L = _lib.lib()
@@ -410,24 +410,104 @@ class TiledAutomaticMaskGenerator(AutomaticMaskGenerator):
     """instance_segmentation.py:564-680: AMG over tiled embeddings; every (outer) tile acts as a crop, `generate` is the
     inherited multi-crop path (per-tile filters + NMS, cross-tile NMS, global painting)."""
 
+    @torch.no_grad()
+    def generate(self, pred_iou_thresh: float = 0.88, stability_score_thresh: float = 0.95, box_nms_thresh: float = 0.7,
+                 crop_nms_thresh: float = 0.7, min_mask_region_area: int = 0, output_mode: str = "instance_segmentation",
+                 with_background: bool = True, group=None):
+        if self._world_size == 1:
+            return super().generate(pred_iou_thresh, stability_score_thresh, box_nms_thresh, crop_nms_thresh,
+                                    min_mask_region_area, output_mode, with_background)
+        if not self.is_initialized:
+            raise RuntimeError("TiledAutomaticMaskGenerator has not been initialized. Call initialize first.")
+        if output_mode != "instance_segmentation" or min_mask_region_area > 0:
+            raise NotImplementedError("multi-rank generate() produces the stitched instance segmentation")
+        return self._generate_distributed(pred_iou_thresh, stability_score_thresh, box_nms_thresh, crop_nms_thresh,
+                                          with_background, group)
+
+    def _generate_distributed(self, pred_iou_thresh, stability_score_thresh, box_nms_thresh, crop_nms_thresh, with_background,
+                              group):
+        """instance_segmentation.py:499-529 across ranks: per-tile filters + box NMS on the owner rank, ONE all-gather of
+        the survivors' instance tables (global box, tile id, tile-local box, area, low-res logits), then the cross-tile
+        NMS that prefers smaller tiles (:511-521) and the painting (util.py:1799-1829) on the gathered list, identically
+        on every rank (so every rank returns the full label image)."""
+        from . import distributed as D
+        H, W = self.original_size
+        dev = self._predictor.device
+        geoms = self._crop_geoms()
+        tabs = dict(gbox=[], lbox=[], area=[], tile=[], low=[])
+        for k, data in enumerate(self.crop_list):
+            ci = self._tile_lo + k
+            crop_box = self.crop_boxes[ci]
+            keep = self._filter_nms(data, crop_box, self.original_size, pred_iou_thresh, stability_score_thresh, box_nms_thresh)
+            off = torch.tensor([crop_box[0], crop_box[1], crop_box[0], crop_box[1]], dtype=torch.int32, device=dev)
+            tabs["gbox"].append(data["boxes"][keep] + off)
+            tabs["lbox"].append(data["boxes"][keep])
+            tabs["area"].append(data["area"][keep])
+            tabs["tile"].append(torch.full((len(keep),), ci, dtype=torch.int32, device=dev))
+            tabs["low"].append(data["low_res"][keep])
+        empty = dict(gbox=(0, 4), lbox=(0, 4), area=(0,), tile=(0,), low=(0, 256, 256))
+        local = {k: (torch.cat(v) if v else torch.zeros(empty[k], dtype=torch.float32 if k == "low" else torch.int32, device=dev))
+                 for k, v in tabs.items()}
+        tab, _ = D.gather_instance_tables(local, group)          # <- the one collective of the stitched path
+        n = int(tab["gbox"].shape[0])
+        crop_id = tab["tile"].long()
+        order = torch.arange(n, device=dev)
+        L = _lib.lib()
+        if len(self.crop_boxes) > 1 and n > 0:
+            cb = torch.tensor(self.crop_boxes, dtype=torch.float32, device=dev)
+            scores = (1.0 / ((cb[:, 2] - cb[:, 0]) * (cb[:, 3] - cb[:, 1])))[crop_id].contiguous()
+            keep2 = torch.empty(n, dtype=torch.int32, device=dev)
+            n2 = torch.zeros(1, dtype=torch.int32, device=dev)
+            zero4 = (ctypes.c_int32 * 4)(0, 0, 0, 0)
+            gb = tab["gbox"].contiguous()
+            _lib.check(L.msam_amg_filter_nms(_lib.ptr(gb), _lib.ptr(scores), _lib.ptr(scores), n, 0, 0.0, 0.0,
+                                             float(crop_nms_thresh), zero4, zero4, _lib.ptr(keep2), _lib.ptr(n2),
+                                             _lib.cur_stream()))
+            order = keep2[: int(n2.item())].long()
+        crop_id = crop_id[order]
+        low, lbox, area = tab["low"].contiguous(), tab["lbox"].contiguous(), tab["area"].contiguous()
+        canvas = torch.full((H, W), -1, dtype=torch.int64, device=dev)
+        for ci, crop_box in enumerate(self.crop_boxes):
+            pos = (crop_id == ci).nonzero()[:, 0]
+            if len(pos) == 0:
+                continue
+            sel = order[pos].to(torch.int32).contiguous()      # rows of the gathered table
+            gpos = pos.to(torch.int32).contiguous()            # position in the NMS-ordered global list
+            g = geoms[ci]
+            _lib.check(L.msam_paint_canvas(_lib.ptr(low), _lib.ptr(sel), _lib.ptr(gpos), len(sel), _lib.ptr(lbox), _lib.ptr(area),
+                                           g["inp"][0], g["inp"][1], g["orig"][0], g["orig"][1], 0.0, int(crop_box[0]),
+                                           int(crop_box[1]), _lib.ptr(canvas), W, _lib.cur_stream()))
+        label = torch.empty(H, W, dtype=torch.int32, device=dev)
+        out = torch.empty(H, W, dtype=torch.int32, device=dev)
+        ws = torch.empty(util.finish_ws_size(H, W), dtype=torch.int32, device=dev)
+        _lib.check(L.msam_canvas_to_label(_lib.ptr(canvas), H * W, _lib.ptr(label), _lib.cur_stream()))
+        _lib.check(L.msam_finish_segmentation(_lib.ptr(label), H, W, 0, int(with_background), _lib.ptr(out), _lib.ptr(ws),
+                                              _lib.cur_stream()))
+        return out.cpu().numpy().view(np.uint32)
+
     def __init__(self, predictor, points_per_side: Optional[int] = 32, points_per_batch: Optional[int] = None,
                  point_grids: Optional[List[np.ndarray]] = None, stability_score_offset: float = 1.0) -> None:
         super().__init__(predictor=predictor, points_per_side=points_per_side, points_per_batch=points_per_batch,
                          point_grids=point_grids, stability_score_offset=stability_score_offset)
+        self._rank, self._world_size, self._tile_lo = 0, 1, 0
 
     @torch.no_grad()
     def initialize(self, image: np.ndarray, image_embeddings: Optional[util.ImageEmbeddings] = None,
                    i: Optional[int] = None, tile_shape=None, halo=None, verbose: bool = False,
                    pbar_init: Optional[Callable] = None, pbar_update: Optional[Callable] = None, batch_size: int = 1,
-                   mask=None) -> None:
+                   mask=None, rank: int = 0, world_size: int = 1) -> None:
+        """rank / world_size (one process per GPU, `torch.distributed` initialised): this rank embeds and decodes only its
+        contiguous share of the tiles; `generate()` then all-gathers the per-tile instance tables (one exchange, NCCL) so
+        that the cross-tile NMS and the painting see every instance -- the result is the single-process result bit for bit."""
         original_size = image.shape[:2]
         self._original_size = original_size
+        self._rank, self._world_size = int(rank), int(world_size)
         if image_embeddings is None:
             if tile_shape is None or halo is None:
                 raise ValueError("To compute tiled embeddings the parameters tile_shape and halo have to be passed.")
             image_embeddings = util.precompute_image_embeddings(self._predictor, image, tile_shape=tile_shape, halo=halo,
                                                                 verbose=verbose, batch_size=batch_size, mask=mask,
-                                                                to_numpy=False)
+                                                                to_numpy=False, rank=rank, world_size=world_size)
         feats = image_embeddings["features"]
         tile_shape_, halo_ = tuple(feats.attrs["tile_shape"]), tuple(feats.attrs["halo"])
         if tile_shape is not None and tuple(tile_shape) != tile_shape_:
@@ -439,13 +519,16 @@ class TiledAutomaticMaskGenerator(AutomaticMaskGenerator):
         if tiles_in_mask is not None and i is not None:
             tiles_in_mask = tiles_in_mask[str(i)]
         tiling = amg_utils.Blocking([0, 0], original_size, tile_shape)
-        tile_ids = range(tiling.number_of_blocks) if tiles_in_mask is None else tiles_in_mask
+        tile_ids = list(range(tiling.number_of_blocks) if tiles_in_mask is None else tiles_in_mask)
         tiles = [tiling.get_block_with_halo(t, list(halo)).outer_block for t in tile_ids]
         crop_boxes = [[t.begin[1], t.begin[0], t.end[1], t.end[0]] for t in tiles]
+        # this rank's contiguous share of the tile list (the same partition precompute_image_embeddings uses in 2-D)
+        lo, hi = (len(tile_ids) * self._rank) // self._world_size, (len(tile_ids) * (self._rank + 1)) // self._world_size
+        self._tile_lo = lo
         _, pbar_init, pbar_update, pbar_close = util.handle_pbar(verbose, pbar_init, pbar_update)
-        pbar_init(len(crop_boxes), "Compute masks for tile")
+        pbar_init(hi - lo, "Compute masks for tile")
         mask_data = []
-        for idx, tile_id in enumerate(tile_ids):
+        for idx, tile_id in list(enumerate(tile_ids))[lo:hi]:
             f = feats[str(tile_id)]
             util.set_precomputed(self._predictor, {"features": f, "input_size": f.attrs["input_size"],
                                                    "original_size": f.attrs["original_size"]}, i)

@@ -574,6 +574,11 @@ def set_precomputed(predictor, image_embeddings: ImageEmbeddings, i: Optional[in
 
 
 # ------------------------------------------------------------------------------------------------ label image assembly
+def finish_ws_size(h: int, w: int) -> int:
+    """int32 workspace elements of msam_finish_segmentation (include/msam_b200.h)."""
+    return 4 * h * w + max(4096, (h * w + 1023) // 1024) + 8
+
+
 def _label_connected(seg: np.ndarray) -> np.ndarray:
     """Connected components of a label image (what elf.parallel.label does at util.py:1831-1834): 4-connectivity,
     components of equal non-zero label, ids in raster order of first pixel."""

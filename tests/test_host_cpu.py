@@ -119,6 +119,13 @@ def _dist_worker(rank, world, port, ret):
         table[:, 1] = rank
         full, counts = D.all_gather_tables(table)
         offs = D.exclusive_id_offsets(torch.arange(lo, hi) + 1)
+        # the instance-table exchange of the multi-rank tiled AMG: several tensors of different trailing shapes / dtypes
+        tabs = {"gbox": torch.arange(lo, hi, dtype=torch.int32)[:, None].repeat(1, 4), "tile": torch.full((hi - lo,), rank, dtype=torch.int32),
+                "low": torch.arange(lo, hi, dtype=torch.float32)[:, None, None] * torch.ones(1, 2, 3)}
+        g, c = D.gather_instance_tables(tabs)
+        assert c == counts and g["gbox"].shape == (11, 4) and g["low"].shape == (11, 2, 3) and g["tile"].dtype == torch.int32
+        assert g["gbox"][:, 0].tolist() == list(range(11)) and g["low"][:, 1, 2].tolist() == list(map(float, range(11)))
+        assert g["tile"].tolist() == [0] * counts[0] + [1] * counts[1]
         ret[rank] = (lo, hi, full.tolist(), counts, offs.tolist())
     finally:
         dist.destroy_process_group()
