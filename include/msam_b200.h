@@ -132,6 +132,13 @@ int msam_amg_filter_nms(const int32_t* boxes_xyxy, const float* iou_preds, const
                         float pred_iou_thresh, float stability_thresh, float box_nms_thresh, const int32_t* crop_box_host,
                         const int32_t* orig_box_host, int32_t* keep, int32_t* n_keep, void* stream);
 
+/* Loss statistics of the fine-tuning step (training/sam_trainer.py:122-172: dice loss on sigmoid(masks) + true IoU for the
+ * IoU-regression target), fused with Sam.postprocess_masks: low_res [n_obj*M, 256, 256] logits, targets uint8 [n_obj, H, W]
+ * (0/1 object masks; mask k belongs to object k / M) -> out5 fp32 [n_obj*M, 5] = {sum sigmoid(v) t, sum sigmoid(v)^2, sum t,
+ * |{v>0} and t|, |{v>0} or t|} over the H x W pixels of the up-sampled logits v (never materialised). */
+int msam_mask_loss_stats(const float* low_res, const uint8_t* targets, int n_obj, int M, int in_h, int in_w, int orig_h, int orig_w,
+                         float* out5, void* stream);
+
 /* util._to_image (util.py:618-651): H x W x C raw image (device; dtype 0 u8, 1 u16, 2 f32, 3 i16, 4 f64; C = 1..)
  * -> H x W x 3 uint8 with per-channel min-max normalisation in the reference's exact float32 arithmetic.
  * scratch6: 6 x uint32 device scratch. */

@@ -67,6 +67,7 @@ def lib() -> ctypes.CDLL:
                                  c_void_p, c_int, c_void_p]
         L.msam_amg_filter_nms.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float,
                                           POINTER(c_int32), POINTER(c_int32), c_void_p, c_void_p, c_void_p]
+        L.msam_mask_loss_stats.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
         L.msam_to_image.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
         L.msam_paint_min_area.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                           c_float, c_void_p, c_int, c_void_p]

@@ -540,6 +540,11 @@ int msam_amg_filter_nms(const int32_t* boxes_xyxy, const float* iou_preds, const
                          box_nms_thresh, crop_box_host, orig_box_host, keep, n_keep, (cudaStream_t)stream);
 }
 
+int msam_mask_loss_stats(const float* low_res, const uint8_t* targets, int n_obj, int M, int in_h, int in_w, int orig_h, int orig_w,
+                         float* out5, void* stream) {
+  if (!low_res || !targets || !out5) return set_error("msam_mask_loss_stats: null argument");
+  return post_mask_loss_stats(low_res, targets, n_obj, M, in_h, in_w, orig_h, orig_w, out5, (cudaStream_t)stream);
+}
 int msam_to_image(const void* src, int dtype, int h, int w, int c, uint8_t* out_hwc3, uint32_t* scratch6, void* stream) {
   return post_to_image(src, dtype, h, w, c, out_hwc3, scratch6, (cudaStream_t)stream);
 }

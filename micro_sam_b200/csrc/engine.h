@@ -101,6 +101,8 @@ int post_paint_canvas(const float* low_res, const int32_t* sel, const int32_t* g
                       const int32_t* area, int in_h, int in_w, int out_h, int out_w, float thr, int off_x, int off_y,
                       unsigned long long* canvas, int ld_canvas, cudaStream_t st);
 int post_canvas_to_label(const unsigned long long* canvas, long n, int32_t* label, cudaStream_t st);
+int post_mask_loss_stats(const float* low_res, const uint8_t* targets, int n_obj, int M, int in_h, int in_w, int out_h, int out_w,
+                         float* out, cudaStream_t st);
 int post_filter_nms(const int32_t* boxes, const float* scores, const float* stab, int n, int use_filters, float iou_thresh,
                     float stab_thresh, float nms_thresh, const int32_t* crop_box, const int32_t* orig_box, int32_t* keep,
                     int32_t* n_keep, cudaStream_t st);

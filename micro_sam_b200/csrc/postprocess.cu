@@ -591,16 +591,111 @@ int post_to_image(const void* src, int dtype, int h, int w, int c, uint8_t* out,
 }
 
 // =================================================================================================================
+// Loss statistics of the fine-tuning step (training/sam_trainer.py:122-172, _compute_iou + _compute_loss): for every
+// predicted mask m of object o the five sums over the H x W pixels that the dice loss (torch_em DiceLoss(reduce_channel=
+// None) on sigmoid(masks)) and the IoU regression target need --
+//   out[mi] = { sum sigmoid(v) t,  sum sigmoid(v)^2,  sum t,  |{v > 0} and t|,  |{v > 0} or t| }      (t = target in {0,1})
+// -- computed straight from the 256 x 256 low-res logits: v = Sam.postprocess_masks(low_res) is evaluated per pixel
+// (same interpolation code as mask_stats) and never written.  One CTA per predicted mask; target of mask mi = targets[mi / M].
+__global__ void __launch_bounds__(256)
+mask_loss_stats_kernel(const float* __restrict__ low_res, const uint8_t* __restrict__ targets, int M, PostGeom g,
+                       float* __restrict__ out) {
+  const long mi = blockIdx.x;
+  const float* lr = low_res + mi * g.lr * g.lr;
+  const uint8_t* tg = targets + (mi / M) * (long)g.out_h * g.out_w;
+  float s_pt = 0.f, s_pp = 0.f;
+  int s_t = 0, s_and = 0, s_or = 0;
+  for (int y = threadIdx.x >> 5; y < g.out_h; y += 8) {
+    for (int x = threadIdx.x & 31; x < g.out_w; x += 32) {
+      const float v = full_res(lr, g, y, x);
+      const int t = tg[(long)y * g.out_w + x] != 0;
+      const float p = 1.0f / (1.0f + __expf(-v));
+      s_pt += t ? p : 0.f;
+      s_pp = fmaf(p, p, s_pp);
+      const int b = v > 0.f;  // sigmoid(v) > 0.5
+      s_t += t; s_and += b & t; s_or += b | t;
+    }
+  }
+  __shared__ float redf[2][8];
+  __shared__ int redi[3][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s_pt += __shfl_xor_sync(0xffffffffu, s_pt, o); s_pp += __shfl_xor_sync(0xffffffffu, s_pp, o);
+    s_t += __shfl_xor_sync(0xffffffffu, s_t, o); s_and += __shfl_xor_sync(0xffffffffu, s_and, o);
+    s_or += __shfl_xor_sync(0xffffffffu, s_or, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    const int w = threadIdx.x >> 5;
+    redf[0][w] = s_pt; redf[1][w] = s_pp; redi[0][w] = s_t; redi[1][w] = s_and; redi[2][w] = s_or;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    int c = 0, d = 0, e = 0;
+    for (int w = 0; w < 8; ++w) { a += redf[0][w]; b += redf[1][w]; c += redi[0][w]; d += redi[1][w]; e += redi[2][w]; }
+    out[mi * 5 + 0] = a; out[mi * 5 + 1] = b; out[mi * 5 + 2] = (float)c; out[mi * 5 + 3] = (float)d; out[mi * 5 + 4] = (float)e;
+  }
+}
+
+int post_mask_loss_stats(const float* low_res, const uint8_t* targets, int n_obj, int M, int in_h, int in_w, int out_h, int out_w,
+                         float* out, cudaStream_t st) {
+  PostGeom g;
+  if (make_geom(in_h, in_w, out_h, out_w, &g)) return -1;
+  if (n_obj <= 0 || M <= 0) return 0;
+  prof_begin(st, "mask_loss_stats", 0.0, (double)n_obj * M * 65536.0 * 4 + (double)n_obj * out_h * out_w);
+  mask_loss_stats_kernel<<<n_obj * M, 256, 0, st>>>(low_res, targets, M, g, out);
+  prof_end(st);
+  LAUNCH_CHECK("mask_loss_stats");
+  return 0;
+}
+
+// =================================================================================================================
 // AMG painting without a host round trip: n_sel is read from device memory (the NMS kernel's n_keep) and the
 // "descending area, later overwrites" order of mask_data_to_segmentation(merge_exclusively=False) is evaluated per pixel
 // as: the covering mask with the smallest (area, -position) wins.  Ids are position + 1 (any unique id works: the
 // connected-component pass re-assigns ids in raster order afterwards).
-__global__ void paint_min_area_kernel(const float* __restrict__ low_res, const int32_t* __restrict__ sel,
-                                      const int32_t* __restrict__ n_sel_ptr, const int32_t* __restrict__ boxes,
-                                      const int32_t* __restrict__ area, PostGeom g, float thr, int32_t* __restrict__ label,
-                                      int ld_label) {
+// Survivors are visited in ascending (area, -position) order -- sorted once per block in shared memory (<= PAINT_SORT_MAX
+// masks; a block is one row segment of 256 pixels) -- so the FIRST covering mask is the winner and the loop stops there:
+// with hundreds of overlapping masks that is ~2 bilinear evaluations per pixel instead of one per mask.
+constexpr int PAINT_SORT_MAX = 4096;
+__global__ void __launch_bounds__(256)
+paint_min_area_kernel(const float* __restrict__ low_res, const int32_t* __restrict__ sel,
+                      const int32_t* __restrict__ n_sel_ptr, const int32_t* __restrict__ boxes,
+                      const int32_t* __restrict__ area, PostGeom g, float thr, int32_t* __restrict__ label,
+                      int ld_label) {
+  __shared__ unsigned long long skey[PAINT_SORT_MAX];  // (area << 32) | (0xFFFFFFFF - position): ascending = winner first
   const int n_sel = *n_sel_ptr;
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (n_sel <= PAINT_SORT_MAX) {
+    int npow2 = 1;
+    while (npow2 < n_sel) npow2 <<= 1;
+    for (int k = threadIdx.x; k < npow2; k += 256)
+      skey[k] = k < n_sel ? (((unsigned long long)(unsigned)area[sel[k]] << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)k)) : ~0ull;
+    __syncthreads();
+    for (int kk = 2; kk <= npow2; kk <<= 1) {
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        for (int i = threadIdx.x; i < npow2; i += 256) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const unsigned long long a = skey[i], b = skey[ixj];
+            if (((i & kk) == 0) ? (a > b) : (a < b)) { skey[i] = b; skey[ixj] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (x >= g.out_w) return;
+    int best_pos = -1;
+    for (int k = 0; k < n_sel; ++k) {
+      const int pos = (int)(0xFFFFFFFFu - (unsigned)(skey[k] & 0xFFFFFFFFull));
+      const int mi = sel[pos];
+      const int4 b = *reinterpret_cast<const int4*>(boxes + 4L * mi);
+      if (x < b.x || x > b.z || y < b.y || y > b.w) continue;
+      if (full_res(low_res + (long)mi * g.lr * g.lr, g, y, x) > thr) { best_pos = pos; break; }
+    }
+    label[(long)y * ld_label + x] = best_pos + 1;
+    return;
+  }
   if (x >= g.out_w) return;
   int best_pos = -1, best_area = 0x7fffffff;
   for (int k = 0; k < n_sel; ++k) {

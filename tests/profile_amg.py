@@ -21,7 +21,7 @@ for t in range(n + 1):
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
     amg.initialize(tiles[t])
-    amg.generate_device()
+    amg.generate_device(pred_iou_thresh=0.5, stability_score_thresh=0.125, box_nms_thresh=1.0)   # bench.py BENCH_THRESH
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print("done")

@@ -492,3 +492,51 @@ def test_model_level_prompt_encoder_and_mask_decoder(models):
     assert torch.equal(low2, low_fast)
     with pytest.raises(RuntimeError):
         sam.load_state_dict({"nope": torch.zeros(1)})
+
+
+def test_trainable_sam_forward_and_loss(models):
+    """a21 / a22 (forward half of cfg 5): TrainableSAM.preprocess / image_embeddings_oft / forward and SamTrainer._compute_loss
+    on the B200 kernels against the oracle restatement (oracle/train_ref.py): floats within the usual tolerances; the loss
+    statistics kernel is additionally checked against the oracle loss evaluated on the GPU's OWN logits (tight tolerance)."""
+    from oracle import train_ref
+    from micro_sam_b200 import training
+    from micro_sam_b200.sample_data import lm_tile
+    opred, pred = models
+    om, m = train_ref.TrainableSAM(opred.model), training.TrainableSAM(pred.model)
+    g = torch.Generator().manual_seed(0)
+    B, n_obj, H, W = 2, 5, 96, 128
+    imgs = [torch.from_numpy(np.repeat(lm_tile((H, W), 12, seed=20 + b, dtype="uint8")[None], 3, 0).astype("float32")) for b in range(B)]
+    pts = [torch.rand(n_obj, 1, 2, generator=g) * torch.tensor([1024.0, 768.0]) for _ in range(B)]
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    y_one_hot = [torch.stack([(((yy - 20 - 12 * k) ** 2 + (xx - 30 - 18 * k) ** 2) < (8 + 2 * k) ** 2).float()[None] for k in range(n_obj)])
+                 for _ in range(B)]
+
+    def records():
+        return [{"image": im.clone(), "original_size": (H, W), "point_coords": p.clone(), "point_labels": torch.ones(n_obj, 1)}
+                for im, p in zip(imgs, pts)]
+    with torch.no_grad():
+        oemb, orecs = om.image_embeddings_oft(records())
+    emb, recs = m.image_embeddings_oft(records())
+    assert tuple(recs[0]["input_size"]) == tuple(orecs[0]["input_size"]) == (768, 1024)
+    assert float((emb.cpu() - oemb).norm() / oemb.norm()) < 2e-2
+    for mm in (True, False):
+        with torch.no_grad():
+            oout = om(orecs, oemb, multimask_output=mm)
+            oloss = train_ref.compute_loss(oout, y_one_hot)
+        out = m(recs, emb, multimask_output=mm)
+        for a, b in zip(out, oout):
+            assert a["masks"].shape == b["masks"].shape == (n_obj, 3 if mm else 1, H, W)
+            assert float((a["low_res_masks"].cpu() - b["low_res_masks"]).norm() / b["low_res_masks"].norm()) < 3e-2
+            assert float((a["masks"].cpu() - b["masks"]).norm() / b["masks"].norm()) < 3e-2
+            assert float((a["iou_predictions"].cpu() - b["iou_predictions"]).abs().max()) < 2e-2
+        loss = training.compute_loss(m(recs, emb, multimask_output=mm, return_masks=False), y_one_hot)
+        for got, ref in zip(loss, oloss):
+            assert abs(float(got) - float(ref)) < 2e-2, (mm, [float(v) for v in loss], [float(v) for v in oloss])
+        # the loss kernel itself: oracle loss on the GPU's own logits (bit-identical interpolation, fp32 sums)
+        same = [{"masks": a["masks"].cpu(), "iou_predictions": a["iou_predictions"].cpu()} for a in out]
+        with torch.no_grad():
+            eloss = train_ref.compute_loss(same, y_one_hot)
+        for got, ref in zip(loss, eloss):
+            assert abs(float(got) - float(ref)) < 2e-4, (mm, [float(v) for v in loss], [float(v) for v in eloss])
+    best_masks, best_logits = training.get_best_masks(out)
+    assert best_masks.shape == (B, n_obj, 1, H, W) and best_logits.shape == (B, n_obj, 1, 256, 256)
