@@ -176,6 +176,9 @@ int msam_mask_nms(const uint8_t* masks, int n, int h, int w, const float* boxes_
  * out bf16 (out_fp32=0) or fp32; act: 0 none, 1 GELU(erf), 2 ReLU. */
 int msam_op_gemm(const void* A, const void* W, int M, int N, int K, const float* bias, const float* residual,
                  int res_rows, void* out, int out_fp32, int act, void* stream);
+/* Weight gradient of a linear layer (first piece of msam_*_backward, cfg 5): out[M,N] fp32 = A[K,M]^T B[K,N], A = dY
+ * (tokens x out-features), B = X (tokens x in-features), both bf16 row-major -- torch autograd's dW = dY^T X. */
+int msam_op_gemm_tn(const void* A, const void* B, int M, int N, int K, float* out, void* stream);
 /* LayerNorm over rows of fp32 x[rows, D] -> bf16; window_mode=1 scatters into the 14x14 window-partitioned layout. */
 int msam_op_layernorm(const float* x, int rows, int D, const float* gamma, const float* beta, float eps, void* out_bf16,
                       int window_mode, void* stream);

@@ -35,6 +35,7 @@ constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr int THREADS = 128 + 128 + 512;  // 4 control warps, 4 softmax warps, 16 LayerNorm warps
 constexpr uint32_t TM_O = 0, TM_S = 256, TMEM_COLS = 512;
 constexpr int TILES = 32;                      // 4096 image tokens / 128 rows
+constexpr int PF_AHEAD = 2;                    // L2 prefetch distance in work items
 }  // namespace i2t
 
 struct I2tParams {
@@ -120,6 +121,11 @@ i2t_fused_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           cur_p = pp; ++nload;
         }
         const int row0 = (p.mode ? pp * 4096 : 0) + rt * 128, row1 = rt * 128;
+        if (p.mode && item + PF_AHEAD < it_end) {  // per-prompt keys of a later item -> L2 (HBM latency off the critical path)
+          const int pr = ((item + PF_AHEAD) / TILES) * 4096 + ((item + PF_AHEAD) % TILES) * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_prefetch_2d(&tmA0, 64 * j, pr);
+        }
         for (int j = 0; j < 4; ++j) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 11);
           uint8_t* sa = smem + stage * STAGE_BYTES;

@@ -39,6 +39,10 @@ int launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream);
 // gemm2.cu: 2-SM (cta_group::2) kernel for large plain products; returns 1 if launched, 0 if the problem does not qualify
 int launch_gemm_2sm(const GemmArgs& a, int num_sms, cudaStream_t stream);
 
+// ---- gemm_tn.cu : out[M,N] fp32 = A[K,M]^T B[K,N]  (weight gradient dW = dY^T X; both operands MN-major)
+int launch_gemm_tn(const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K, int lda, int ldb, float* out, int ldc,
+                   cudaStream_t stream);
+
 // ---- upscale_fused.cu : conv-transpose 1 + LayerNorm2d + GELU + conv-transpose 2 + GELU + hyper-network product in one pass
 struct UpscaleFusedArgs {
   int P = 0, nm = 3, m0 = 1;          // prompts; masks written per prompt = hyper rows [m0, m0 + nm)

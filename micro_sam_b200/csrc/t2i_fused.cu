@@ -114,6 +114,10 @@ t2i_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (int j = 0; j < 4; ++j) tma_load_2d(smem + OFF_Q + j * QSUB, &tmQ, q_full, 64 * j, item * ROWS);
         const int row0 = p.mode ? item * 4096 : 0;
         for (int kt = 0; kt < NTILES; ++kt) {
+          if (p.mode && kt + 8 < NTILES) {  // own keys: a tile 8 steps ahead -> L2
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_prefetch_2d(&tmX, 64 * j, row0 + (kt + 8) * XT);
+          }
           mbar_wait(&xempty[stage], phase ^ 1, 21);
           uint8_t* sx = smem + stage * XSTAGE_BYTES;
           mbar_expect_tx(&xfull[stage], XSTAGE_BYTES);

@@ -125,6 +125,11 @@ upscale_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       uint32_t phase = 0;
       for (int item = it_begin; item < it_end; ++item) {
         const int row0 = (item / TILES) * 4096 + (item % TILES) * 128;
+        if (item + 2 < it_end) {  // keys tile of a later item -> L2
+          const int pr = ((item + 2) / TILES) * 4096 + ((item + 2) % TILES) * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_prefetch_2d(&tmX, 64 * j, pr);
+        }
         for (int j = 0; j < 4; ++j) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 40);
           uint8_t* sa = smem + stage * STAGE_BYTES;

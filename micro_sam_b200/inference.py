@@ -47,7 +47,9 @@ def batched_inference(predictor, image: Optional[np.ndarray], batch_size: int, b
                       segmentation_ids: Optional[list] = None, reduce_multimasking: bool = True,
                       logits_masks: Optional[torch.Tensor] = None, verbose_embeddings: bool = False,
                       mask_threshold: Optional[Union[float, str]] = None, return_highres_logits: bool = False,
-                      i: Optional[int] = None):
+                      i: Optional[int] = None, device_result: bool = False):
+    """`device_result=True` (extension): the instance segmentation stays on the device (int32 (H, W) tensor holding the
+    uint32 ids), skipping the D2H copy the reference's numpy return implies."""
     n_prompts, have_boxes, have_points, have_logits = _validate_inputs(
         boxes, points, point_labels, multimasking, return_instance_segmentation, segmentation_ids, logits_masks)
     if image is None:
@@ -112,7 +114,7 @@ def batched_inference(predictor, image: Optional[np.ndarray], batch_size: int, b
         ws = torch.empty(util.finish_ws_size(H, W), dtype=torch.int32, device=device)
         _lib.check(_lib.lib().msam_finish_segmentation(_lib.ptr(label), H, W, 0, 0, _lib.ptr(out), _lib.ptr(ws),
                                                        _lib.cur_stream()))
-        return out.cpu().numpy().view(np.uint32)
+        return out if device_result else out.cpu().numpy().view(np.uint32)
 
     binm = torch.empty(n_prompts, H, W, dtype=torch.uint8, device=device)
     logits = torch.empty(n_prompts, H, W, dtype=torch.float32, device=device) if return_highres_logits else None

@@ -115,6 +115,33 @@ def sec_gemm():
     print(f"[perf] cublas same shape: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
 
 
+def sec_wgrad():
+    """First backward piece (cfg 5): dW = dY^T X through msam_op_gemm_tn (MN-major operands) against torch AUTOGRAD of
+    nn.Linear on the same bf16 inputs (fp32 accumulation both sides)."""
+    g = torch.Generator(device="cpu").manual_seed(1)
+    for (T, O, I) in ((256, 128, 128), (4096, 768, 768), (4096 * 2, 2304, 768), (1000, 256, 200), (4096, 3072, 768)):
+        x = (torch.randn(T, I, generator=g) * 0.5).to(DEV).bfloat16()
+        dy = (torch.randn(T, O, generator=g) * 0.5).to(DEV).bfloat16()
+        lin = torch.nn.Linear(I, O, bias=False).to(DEV)
+        y = lin(x.float())
+        y.backward(dy.float())
+        out = torch.empty(O, I, device=DEV, dtype=torch.float32)
+        try:
+            _lib.check(_lib.lib().msam_op_gemm_tn(_lib.ptr(dy), _lib.ptr(x), O, I, T, _lib.ptr(out), _lib.cur_stream()))
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            RESULTS.append(False)
+            print(f"[BAD] wgrad T={T} O={O} I={I}: EXCEPTION {e}", flush=True)
+            continue
+        report(f"wgrad dW = dY^T X  T={T} O={O} I={I} (vs autograd)", out, lin.weight.grad, 1e-5)
+    T, O, I = 16 * 4096, 3072, 768
+    x, dy = torch.randn(T, I, device=DEV).bfloat16(), torch.randn(T, O, device=DEV).bfloat16()
+    out = torch.empty(O, I, device=DEV, dtype=torch.float32)
+    f = lambda: _lib.check(_lib.lib().msam_op_gemm_tn(_lib.ptr(dy), _lib.ptr(x), O, I, T, _lib.ptr(out), _lib.cur_stream()))  # noqa: E731
+    ms = _time(f)
+    print(f"wgrad {O}x{I} over {T} tokens: {ms:.3f} ms = {2.0 * T * O * I / ms / 1e9:.0f} TFLOP/s", flush=True)
+
+
 def sec_gemmperf():
     """Event-timed throughput of the encoder GEMM shapes (batch of 4 tiles), next to cuBLAS for the bare product."""
     L = _lib.lib()
@@ -447,7 +474,7 @@ def sec_nms():
             print(f"[{'OK ' if ok else 'BAD'}] filter_nms n={n} filters={use_f}: kept {len(got)} (ref {len(ref)})", flush=True)
 
 
-SECTIONS = {"gemm": sec_gemm, "gemmperf": sec_gemmperf, "ln": sec_ln, "attn": sec_attn, "encoder": sec_encoder, "decoder": sec_decoder,
+SECTIONS = {"gemm": sec_gemm, "wgrad": sec_wgrad, "gemmperf": sec_gemmperf, "ln": sec_ln, "attn": sec_attn, "encoder": sec_encoder, "decoder": sec_decoder,
             "post": sec_post, "nms": sec_nms}
 
 if __name__ == "__main__":

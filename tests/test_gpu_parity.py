@@ -22,7 +22,7 @@ def _diag():
     return mod
 
 
-@pytest.mark.parametrize("section", ["gemm", "ln", "attn", "encoder", "decoder", "post", "nms"])
+@pytest.mark.parametrize("section", ["gemm", "wgrad", "ln", "attn", "encoder", "decoder", "post", "nms"])
 def test_ops(section):
     d = _diag()
     d.SECTIONS[section]()
@@ -540,3 +540,38 @@ def test_trainable_sam_forward_and_loss(models):
             assert abs(float(got) - float(ref)) < 2e-4, (mm, [float(v) for v in loss], [float(v) for v in eloss])
     best_masks, best_logits = training.get_best_masks(out)
     assert best_masks.shape == (B, n_obj, 1, H, W) and best_logits.shape == (B, n_obj, 1, 256, 256)
+
+
+def test_interactive_segmentation_against_oracle(models):
+    """f1: `B200SamPredictor.predict` through micro_sam's interactive entry points (segment_from_points / _box /
+    _box_and_points / _mask incl. the mask-prompt logits) against the oracle predictor fed the same prompts."""
+    from micro_sam_b200 import prompt_based_segmentation as pbs, util
+    from micro_sam_b200.sample_data import lm_tile
+    opred, pred = models
+    img = util._to_image(lm_tile((300, 420), 30, seed=21))
+    opred.set_image(img)
+    pred.set_image(img)
+    assert pred.original_size == (300, 420) and tuple(pred.input_size) == tuple(opred.input_size)
+
+    def check(got, ref, what):
+        (m, s, l), (om, os_, ol) = got, ref
+        assert m.shape == om.shape and s.shape == os_.shape and l.shape == ol.shape, what
+        assert np.abs(s - os_).max() < 2e-2, (what, s, os_)
+        assert np.linalg.norm(l - ol) / np.linalg.norm(ol) < 3e-2, what
+        assert (m == om).mean() > 0.98, (what, (m == om).mean())
+
+    pts, lbl = np.array([[150, 200], [40, 60]]), np.array([1, 0])
+    got = pbs.segment_from_points(pred, pts, lbl, return_all=True)
+    check(got, opred.predict(point_coords=pts[:, ::-1], point_labels=lbl, multimask_output=False), "points")
+    got = pbs.segment_from_points(pred, pts[:1], lbl[:1], return_all=True)          # single positive point: best of 3
+    om, os_, ol = opred.predict(point_coords=pts[:1, ::-1], point_labels=lbl[:1], multimask_output=True)
+    assert got[0].shape == (1, 300, 420) and (got[0][0] == om[np.argmax(os_)]).mean() > 0.98
+    box = np.array([50, 80, 200, 300])
+    check(pbs.segment_from_box(pred, box, return_all=True), opred.predict(box=box[[1, 0, 3, 2]], multimask_output=False), "box")
+    check(pbs.segment_from_box_and_points(pred, box, pts, lbl, return_all=True),
+          opred.predict(point_coords=pts[:, ::-1], point_labels=lbl, box=box[[1, 0, 3, 2]], multimask_output=False), "box+points")
+    mask = np.zeros((300, 420), "uint8")
+    mask[60:180, 100:260] = 1
+    got = pbs.segment_from_mask(pred, mask, return_all=True)
+    ref = opred.predict(mask_input=pbs._compute_logits_from_mask(mask), box=pbs._compute_box_from_mask(mask), multimask_output=False)
+    check(got, ref, "mask+box")
