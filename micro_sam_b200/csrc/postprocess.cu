@@ -710,14 +710,100 @@ paint_min_area_kernel(const float* __restrict__ low_res, const int32_t* __restri
   label[(long)y * ld_label + x] = best_pos + 1;
 }
 
+// Tile version for the common geometry input_size == original_size == (1024, 1024): one block paints a 32 x 32 pixel region
+// for ALL survivors.  The region depends on a 10 x 10 patch of each mask's low-res logits only, which the block stages in
+// shared memory (double buffered: the next mask's patch is fetched while the current one is evaluated) -- 0.1 global loads
+// per (pixel, mask) instead of 4, which is what bounded the per-pixel kernel with hundreds of overlapping survivors
+// (1.0 ms per tile at ~190 survivors, profiles/r2_launches_amg_vit_b_1tile.txt).  Survivors are visited in ascending
+// (area, -position) order (block-local bitonic sort), so a pixel is final at its first hit and the block stops as soon as
+// all its 1024 pixels are decided.  Same interp_axis / bilerp arithmetic as `stage1`: bit-identical results.
+__global__ void __launch_bounds__(256)
+paint_min_area_x4_kernel(const float* __restrict__ low_res, const int32_t* __restrict__ sel,
+                         const int32_t* __restrict__ n_sel_ptr, const int32_t* __restrict__ boxes,
+                         const int32_t* __restrict__ area, PostGeom g, float thr, int32_t* __restrict__ label, int ld_label) {
+  __shared__ unsigned long long skey[PAINT_SORT_MAX];
+  __shared__ float patch[2][10][12];
+  const int n_sel = *n_sel_ptr;
+  const int tid = threadIdx.x;
+  const bool sorted = n_sel <= PAINT_SORT_MAX;
+  if (sorted) {
+    int npow2 = 1;
+    while (npow2 < n_sel) npow2 <<= 1;
+    for (int k = tid; k < npow2; k += 256)
+      skey[k] = k < n_sel ? (((unsigned long long)(unsigned)area[sel[k]] << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)k)) : ~0ull;
+    __syncthreads();
+    for (int kk = 2; kk <= npow2; kk <<= 1) {
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < npow2; i += 256) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const unsigned long long a = skey[i], b = skey[ixj];
+            if (((i & kk) == 0) ? (a > b) : (a < b)) { skey[i] = b; skey[ixj] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+  const int X0 = blockIdx.x * 32, Y0 = blockIdx.y * 32;
+  const int py0 = (Y0 >> 2) - 1, px0 = (X0 >> 2) - 1;          // low-res origin of the patch (may be -1: never referenced)
+  const int y = Y0 + (tid >> 3), xb = X0 + (tid & 7) * 4;       // this thread: pixels (y, xb .. xb+3)
+  const Interp iy = interp_axis(y, g.s1, g.lr);
+  Interp ix[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) ix[q] = interp_axis(xb + q, g.s1, g.lr);
+  unsigned long long best[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+  const int pr = tid / 10, pc = tid % 10;                        // patch element fetched by threads 0..99
+  const int gy = min(max(py0 + pr, 0), g.lr - 1), gx = min(max(px0 + pc, 0), g.lr - 1);
+  auto pos_of = [&](int k) -> int { return sorted ? (int)(0xFFFFFFFFu - (unsigned)(skey[k] & 0xFFFFFFFFull)) : k; };
+  float nxt = 0.f;
+  if (n_sel > 0 && tid < 100) nxt = __ldg(low_res + (long)sel[pos_of(0)] * g.lr * g.lr + gy * g.lr + gx);
+  for (int k = 0; k < n_sel; ++k) {
+    const int buf = k & 1;
+    if (tid < 100) patch[buf][pr][pc] = nxt;
+    const int pos = pos_of(k), mi = sel[pos];
+    const unsigned long long key = ((unsigned long long)(unsigned)area[mi] << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)pos);
+    if (k + 1 < n_sel && tid < 100) nxt = __ldg(low_res + (long)sel[pos_of(k + 1)] * g.lr * g.lr + gy * g.lr + gx);
+    __syncthreads();   // patch[buf] complete; the previous iteration's readers of patch[buf ^ 1] ... are done (they passed this barrier)
+    const int4 b = *reinterpret_cast<const int4*>(boxes + 4L * mi);
+    bool open = false;
+    if (y >= b.y && y <= b.w) {
+      const float* r0 = &patch[buf][iy.i0 - py0][0];
+      const float* r1 = &patch[buf][iy.i1 - py0][0];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int x = xb + q;
+        if (key < best[q] && x >= b.x && x <= b.z) {
+          const float v = bilerp(r0[ix[q].i0 - px0], r0[ix[q].i1 - px0], r1[ix[q].i0 - px0], r1[ix[q].i1 - px0], iy, ix[q]);
+          if (v > thr) best[q] = key;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) open = open || best[q] == ~0ull;
+    // sorted order: a decided pixel is final -> stop when the whole region is decided (one barrier per mask either way)
+    if (sorted && !__syncthreads_or(open)) break;
+  }
+  int4 o;
+  o.x = best[0] == ~0ull ? 0 : (int)(0xFFFFFFFFu - (unsigned)(best[0] & 0xFFFFFFFFull)) + 1;
+  o.y = best[1] == ~0ull ? 0 : (int)(0xFFFFFFFFu - (unsigned)(best[1] & 0xFFFFFFFFull)) + 1;
+  o.z = best[2] == ~0ull ? 0 : (int)(0xFFFFFFFFu - (unsigned)(best[2] & 0xFFFFFFFFull)) + 1;
+  o.w = best[3] == ~0ull ? 0 : (int)(0xFFFFFFFFu - (unsigned)(best[3] & 0xFFFFFFFFull)) + 1;
+  *reinterpret_cast<int4*>(label + (long)y * ld_label + xb) = o;
+}
+
 int post_paint_min_area(const float* low_res, const int32_t* sel, const int32_t* n_sel, const int32_t* boxes,
                         const int32_t* area, int in_h, int in_w, int out_h, int out_w, float thr, int32_t* label,
                         int ld_label, cudaStream_t st) {
   PostGeom g;
   if (make_geom(in_h, in_w, out_h, out_w, &g)) return -1;
   prof_begin(st, "paint_min_area", 0.0, (double)out_h * out_w * 4);
-  paint_min_area_kernel<<<dim3((out_w + 255) / 256, out_h), 256, 0, st>>>(low_res, sel, n_sel, boxes, area, g, thr, label,
-                                                                        ld_label);
+  if (g.identity2 && in_h == 1024 && in_w == 1024 && ld_label % 4 == 0 && (reinterpret_cast<uintptr_t>(label) & 15) == 0) {
+    paint_min_area_x4_kernel<<<dim3(32, 32), 256, 0, st>>>(low_res, sel, n_sel, boxes, area, g, thr, label, ld_label);
+  } else {
+    paint_min_area_kernel<<<dim3((out_w + 255) / 256, out_h), 256, 0, st>>>(low_res, sel, n_sel, boxes, area, g, thr, label,
+                                                                          ld_label);
+  }
   prof_end(st);
   LAUNCH_CHECK("paint_min_area");
   return 0;

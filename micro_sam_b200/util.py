@@ -399,8 +399,7 @@ def _compute_tiled_features(predictor, input_, is3d, tile_shape, halo, pbar_init
                 eshape = tuple(emb.shape[1:])
                 if name not in features:
                     shape = ((n_slices, 1) if is3d else (1,)) + eshape
-                    chunks = ((1, 1) if is3d else (1,)) + eshape
-                    ds = features.create_dataset(name, shape=shape, dtype="float32", chunks=chunks)
+                    ds = features.create_dataset(name, shape=shape, dtype="float32", chunks=((1, 1) if is3d else (1,)) + eshape)
                     ds.attrs["original_size"] = original_sizes[k]
                     ds.attrs["input_size"] = input_sizes[k]
                 jobs.append((features[name], z if is3d else slice(None), emb_host[k][None]))

@@ -133,7 +133,11 @@ def test_tiled_containers_and_rank_shards(tmp_path):
     for rank in (1, 0):
         util.precompute_image_embeddings(_FakePredictor(), vol, save_path=p3, tile_shape=(256, 256), halo=(16, 16), batch_size=4,
                                          rank=rank, world_size=2)
+    p3b = str(tmp_path / "tiled3d_single.zarr")   # single rank, three batches (regression: the batch list must survive dataset creation)
+    util.precompute_image_embeddings(_FakePredictor(), vol, save_path=p3b, tile_shape=(256, 256), halo=(16, 16), batch_size=5)
     got = zarr_store.open_group(p3)["features"]
+    for t in "0123":
+        assert np.array_equal(zarr_store.open_group(p3b)["features"][t][:], got[t][:])
     ref = util.precompute_image_embeddings(pred, vol, tile_shape=(256, 256), halo=(16, 16), batch_size=5)["features"]
     assert sorted(got.keys()) == ["0", "1", "2", "3"]
     for t in "0123":
