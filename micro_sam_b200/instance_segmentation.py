@@ -83,7 +83,8 @@ class AMGBase(ABC):
             H, W = geom["orig"]
             sel = keep.to(torch.int32).contiguous()
             binm = torch.empty(len(keep), H, W, dtype=torch.uint8, device=sel.device)
-            _lib.check(_lib.lib().msam_upsample_masks(_lib.ptr(data["low_res"]), _lib.ptr(sel), len(keep), geom["inp"][0],
+            low_dev, sel = self._logits_rows(data, keep, sel.device)
+            _lib.check(_lib.lib().msam_upsample_masks(_lib.ptr(low_dev), _lib.ptr(sel), len(keep), geom["inp"][0],
                                                       geom["inp"][1], H, W, 0.0, None, _lib.ptr(binm), _lib.cur_stream()))
             segs = binm.cpu().numpy().astype(bool)
             if output_mode != "binary_mask":
@@ -116,6 +117,25 @@ class AMGBase(ABC):
             h, w = min(int(y1), H) - int(y0), min(int(x1), W) - int(x0)
             geoms.append(dict(inp=get_preprocess_shape(h, w, self._predictor.transform.target_length), orig=(h, w)))
         return geoms
+
+    @staticmethod
+    def _logits_rows(data, rows: torch.Tensor, device):
+        """Low-res logits of the given masks on `device` + their row indices in the returned tensor.  The state normally
+        keeps all logits on the device (rows index them directly); an OFFLOADED state (`offload_state`, pinned host memory)
+        ships only the requested rows -- the survivors of filters + NMS, a few hundred of the 3072 masks of a tile."""
+        low = data["low_res"]
+        if low.device == device:
+            return low, rows.to(torch.int32).contiguous()
+        picked = low.index_select(0, rows.to("cpu", torch.long))
+        return picked.to(device, non_blocking=True), torch.arange(len(rows), dtype=torch.int32, device=device)
+
+    def _offload(self, data) -> None:
+        """Move a crop's low-res logits (805 MB per 32x32-grid tile) to pinned host memory; the small per-mask statistics stay
+        on the device.  This is the reference's memory model (its state holds CPU RLEs, instance_segmentation.py:229-255)."""
+        low = data["low_res"]
+        host = torch.empty(low.shape, dtype=low.dtype, pin_memory=True)
+        host.copy_(low, non_blocking=False)
+        data["low_res"] = host
 
     def get_state(self) -> Dict[str, Any]:
         if not self.is_initialized:
@@ -233,6 +253,7 @@ class AutomaticMaskGenerator(AMGBase):
             return self._generate_small_regions(pred_iou_thresh, stability_score_thresh, box_nms_thresh, crop_nms_thresh,
                                                 min_mask_region_area, output_mode, with_background, geoms)
         if output_mode == "instance_segmentation" and len(self.crop_list) == 1 and geoms and \
+                self.crop_list[0]["low_res"].device == self.crop_list[0]["iou_preds"].device and \
                 tuple(self.crop_boxes[0]) == (0, 0, self.original_size[1], self.original_size[0]):
             out = self.generate_device(pred_iou_thresh, stability_score_thresh, box_nms_thresh, with_background)
             return out.cpu().numpy().view(np.uint32)
@@ -297,11 +318,14 @@ class AutomaticMaskGenerator(AMGBase):
             pos = (crop_id == ci).nonzero()[:, 0]
             if len(pos) == 0:
                 continue
-            sel = local[pos].to(torch.int32).contiguous()
+            low_dev, sel = self._logits_rows(data, local[pos], dev)
             gpos = pos.to(torch.int32).contiguous()
             g = geoms[ci]
-            _lib.check(L.msam_paint_canvas(_lib.ptr(data["low_res"]), _lib.ptr(sel), _lib.ptr(gpos), len(sel),
-                                           _lib.ptr(data["boxes"]), _lib.ptr(data["area"]), g["inp"][0], g["inp"][1],
+            bx_t, ar_t = data["boxes"], data["area"]
+            if low_dev is not data["low_res"]:   # offloaded state: the compacted logits are indexed 0..n-1, so are box / area
+                bx_t, ar_t = data["boxes"][local[pos]].contiguous(), data["area"][local[pos]].contiguous()
+            _lib.check(L.msam_paint_canvas(_lib.ptr(low_dev), _lib.ptr(sel), _lib.ptr(gpos), len(sel),
+                                           _lib.ptr(bx_t), _lib.ptr(ar_t), g["inp"][0], g["inp"][1],
                                            g["orig"][0], g["orig"][1], 0.0, int(crop_box[0]), int(crop_box[1]),
                                            _lib.ptr(canvas), W, _lib.cur_stream()))
         label = torch.empty(H, W, dtype=torch.int32, device=dev)
@@ -385,7 +409,9 @@ class AutomaticMaskGenerator(AMGBase):
             raise NotImplementedError("device-side generate supports a single crop")
         data, crop_box, geom = self.crop_list[0], self.crop_boxes[0], self._crop_geoms()[0]
         H, W = self.original_size
-        dev = data["low_res"].device
+        dev = data["iou_preds"].device
+        if data["low_res"].device != dev:
+            raise NotImplementedError("device-side generate needs the state on the device (offload_state=False)")
         keep = self._filter_nms(data, crop_box, self.original_size, pred_iou_thresh, stability_score_thresh,
                                 box_nms_thresh, sync=False)
         bufs = getattr(self, "_dev_bufs", None)
@@ -444,7 +470,7 @@ class TiledAutomaticMaskGenerator(AutomaticMaskGenerator):
             tabs["lbox"].append(data["boxes"][keep])
             tabs["area"].append(data["area"][keep])
             tabs["tile"].append(torch.full((len(keep),), ci, dtype=torch.int32, device=dev))
-            tabs["low"].append(data["low_res"][keep])
+            tabs["low"].append(self._logits_rows(data, keep, dev)[0] if data["low_res"].device != dev else data["low_res"][keep])
         empty = dict(gbox=(0, 4), lbox=(0, 4), area=(0,), tile=(0,), low=(0, 256, 256))
         local = {k: (torch.cat(v) if v else torch.zeros(empty[k], dtype=torch.float32 if k == "low" else torch.int32, device=dev))
                  for k, v in tabs.items()}
@@ -495,10 +521,12 @@ class TiledAutomaticMaskGenerator(AutomaticMaskGenerator):
     def initialize(self, image: np.ndarray, image_embeddings: Optional[util.ImageEmbeddings] = None,
                    i: Optional[int] = None, tile_shape=None, halo=None, verbose: bool = False,
                    pbar_init: Optional[Callable] = None, pbar_update: Optional[Callable] = None, batch_size: int = 1,
-                   mask=None, rank: int = 0, world_size: int = 1) -> None:
+                   mask=None, rank: int = 0, world_size: int = 1, offload_state: Optional[bool] = None) -> None:
         """rank / world_size (one process per GPU, `torch.distributed` initialised): this rank embeds and decodes only its
         contiguous share of the tiles; `generate()` then all-gathers the per-tile instance tables (one exchange, NCCL) so
-        that the cross-tile NMS and the painting see every instance -- the result is the single-process result bit for bit."""
+        that the cross-tile NMS and the painting see every instance -- the result is the single-process result bit for bit.
+        offload_state: keep the per-tile low-res logits (805 MB per tile at the default 32x32 grid) in pinned host memory
+        instead of HBM; None = automatically when this rank's tiles would need more than half of the free device memory."""
         original_size = image.shape[:2]
         self._original_size = original_size
         self._rank, self._world_size = int(rank), int(world_size)
@@ -528,11 +556,17 @@ class TiledAutomaticMaskGenerator(AutomaticMaskGenerator):
         _, pbar_init, pbar_update, pbar_close = util.handle_pbar(verbose, pbar_init, pbar_update)
         pbar_init(hi - lo, "Compute masks for tile")
         mask_data = []
+        if offload_state is None:
+            n_pts = sum(len(g) for g in self.point_grids[:1])
+            need = (hi - lo) * n_pts * 3 * 256 * 256 * 4
+            offload_state = need > 0.5 * torch.cuda.mem_get_info(self._predictor.device)[0]
         for idx, tile_id in list(enumerate(tile_ids))[lo:hi]:
             f = feats[str(tile_id)]
             util.set_precomputed(self._predictor, {"features": f, "input_size": f.attrs["input_size"],
                                                    "original_size": f.attrs["original_size"]}, i)
             mask_data.append(self._process_crop(original_size, crop_boxes[idx], 0))
+            if offload_state:
+                self._offload(mask_data[-1])
             pbar_update(1)
         pbar_close()
         self._is_initialized = True

@@ -290,6 +290,18 @@ def test_tiled_amg_against_oracle(models):
         seg = amg.generate(output_mode="instance_segmentation", **kw)
         oseg = oamg.generate(output_mode="instance_segmentation", **kw)
         assert seg.shape == (300, 420) and _partition_equal(seg, oseg), kw
+    # offloaded state (per-tile logits in pinned host memory, only the survivors travel back): identical results
+    amg_off = iseg.TiledAutomaticMaskGenerator(pred, points_per_side=4)
+    amg_off.initialize(img, tile_shape=tile_shape, halo=halo, batch_size=2, offload_state=True)
+    assert not amg_off.crop_list[0]["low_res"].is_cuda and amg_off.crop_list[0]["boxes"].is_cuda
+    kw = dict(pred_iou_thresh=0.1, stability_score_thresh=0.6)
+    assert np.array_equal(amg_off.generate(**kw), amg.generate(**kw))
+    for a, b in zip(amg_off.generate(output_mode="binary_mask", **kw), amg.generate(output_mode="binary_mask", **kw)):
+        assert a["bbox"] == b["bbox"] and np.array_equal(a["segmentation"], b["segmentation"])
+    state = amg_off.get_state()          # AMG state round trip into a fresh generator (no hidden geometry)
+    fresh = iseg.TiledAutomaticMaskGenerator(pred, points_per_side=4)
+    fresh.set_state(state)
+    assert np.array_equal(fresh.generate(**kw), amg.generate(**kw))
 
 
 def test_mask_nms_bit_exact_vs_reference_golden():
@@ -575,3 +587,38 @@ def test_interactive_segmentation_against_oracle(models):
     got = pbs.segment_from_mask(pred, mask, return_all=True)
     ref = opred.predict(mask_input=pbs._compute_logits_from_mask(mask), box=pbs._compute_box_from_mask(mask), multimask_output=False)
     check(got, ref, "mask+box")
+
+
+def test_large_inputs_beyond_the_former_size_caps():
+    """Advisor finding (round 1): filter_nms rejected n > 8192 and finish_segmentation images above 2048 x 2048.  Both run on
+    global-memory workspaces now: 12288 boxes (points_per_side 64 x 3 masks) against the oracle NMS, a 2304 x 2560 label image
+    against the host assembly."""
+    import ctypes
+    from oracle import amg_ref
+    from micro_sam_b200 import _lib, util
+    g = torch.Generator().manual_seed(5)
+    n = 12288
+    xy = torch.rand(n, 2, generator=g) * 1800
+    wh = torch.rand(n, 2, generator=g) * 200 + 8
+    boxes = torch.cat([xy, xy + wh], 1).round().to(torch.int32)
+    scores = torch.rand(n, generator=g)
+    keep = torch.empty(n, dtype=torch.int32, device="cuda")
+    nk = torch.zeros(1, dtype=torch.int32, device="cuda")
+    z4 = (ctypes.c_int32 * 4)(0, 0, 0, 0)
+    bd, sd = boxes.cuda().contiguous(), scores.cuda().contiguous()
+    _lib.check(_lib.lib().msam_amg_filter_nms(_lib.ptr(bd), _lib.ptr(sd), _lib.ptr(sd), n, 0, 0.0, 0.0, 0.5, z4, z4, _lib.ptr(keep),
+                                              _lib.ptr(nk), _lib.cur_stream()))
+    got = keep[: int(nk.item())].cpu().long()
+    ref = amg_ref.nms(boxes.float(), scores, 0.5)
+    assert len(got) == len(ref) > 1000 and torch.equal(got, ref)
+    rng = np.random.default_rng(0)
+    H, W = 2304, 2560
+    seg = np.zeros((H, W), np.int32)
+    for k in range(300):
+        cy, cx, r = rng.integers(0, H), rng.integers(0, W), rng.integers(10, 120)
+        seg[max(cy - r, 0):cy + r, max(cx - r, 0):cx + r] = k + 1
+    d = torch.from_numpy(seg).cuda()
+    out = torch.empty(H, W, dtype=torch.int32, device="cuda")
+    ws = torch.empty(util.finish_ws_size(H, W), dtype=torch.int32, device="cuda")
+    _lib.check(_lib.lib().msam_finish_segmentation(_lib.ptr(d), H, W, 50, 1, _lib.ptr(out), _lib.ptr(ws), _lib.cur_stream()))
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), util._finish_segmentation(seg.astype(np.uint32), 50, True, True))
