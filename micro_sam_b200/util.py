@@ -88,34 +88,51 @@ def get_sam_model(model_type: str = "vit_b", device: Optional[Union[str, torch.d
 
 
 # ------------------------------------------------------------------------------------------------ input pipeline
+def _normalize_channel(ch: np.ndarray) -> np.ndarray:
+    """One channel of util._to_image (util.py:643-647): uint8(((x - min) / (max(x - min) + 1e-7)) * 255) in float32 arithmetic.
+    Integer inputs go through a lookup table (the map is a pure function of the pixel value once min / max are known, so
+    the table -- built with the very same float32 operations -- gives bit-identical results at a fraction of the passes)."""
+    eps = np.float32(1e-7)
+    if ch.dtype.kind in "ui" and ch.dtype.itemsize <= 2:
+        info = np.iinfo(ch.dtype)
+        mn = ch.min()
+        span = np.float32(ch.max()) - np.float32(mn)           # exact: |values| < 2^24
+        vals = np.arange(info.min, info.max + 1, dtype=np.int32).astype(np.float32)
+        vals -= np.float32(mn)
+        vals /= (span + eps)
+        lut = (vals * 255).astype(np.uint8)                     # entries outside [min, max] are never read
+        return lut[ch.astype(np.int32) - info.min] if info.min < 0 else lut[ch]
+    x = np.ascontiguousarray(ch, dtype=np.float32)
+    x = x - x.min()
+    x /= (x.max() + eps)
+    return (x * 255).astype(np.uint8)
+
+
 def _to_image(image):
-    """util.py:618-651: any grayscale / 2-ch / RGB input -> per-channel min-max normalised uint8 HxWx3."""
-    input_ = image
-    ndim = input_.ndim
-    n_channels = 1 if ndim == 2 else input_.shape[-1]
+    """util._to_image (util.py:618-651): grey / 1-3(+) channel input of any dtype -> uint8 H x W x 3, every channel min-max
+    normalised on its own; a 2-channel input gets an all-zero third channel (normalised like the others: 0 / 1e-7 = 0), more
+    than 3 channels are cut with a warning.  Channel-wise formulation of the reference's whole-array expression (the
+    reductions run over contiguous planes); pinned bit for bit on vectors produced by the reference's own function
+    (tests/golden/util.npz)."""
+    ndim = image.ndim
     if ndim == 2:
-        input_ = np.concatenate([input_[..., None]] * 3, axis=-1)
-    elif ndim == 3 and n_channels == 1:
-        input_ = np.concatenate([input_] * 3, axis=-1)
-    elif ndim == 3 and n_channels == 2:
-        zero_channel = np.zeros(input_.shape[:2] + (1,), dtype=input_.dtype)
-        input_ = np.concatenate([input_, zero_channel], axis=-1)
-    elif input_.ndim == 3 and n_channels == 3:
-        pass
-    elif input_.ndim == 3 and n_channels > 3:
-        warnings.warn(f"You provided an input with {n_channels} channels. Only the first three will be used.")
-        input_ = input_[..., :3]
-    else:
+        c = _normalize_channel(image)
+        return np.stack([c, c, c], axis=-1)
+    if ndim != 3:
         raise ValueError(
             f"Invalid input dimensionality {ndim}. Expect either a 2D input (=grayscale image) "
             "or a 3D input (= image with channels)."
         )
-    assert input_.ndim == 3 and input_.shape[-1] == 3
-    input_ = input_.astype("float32")
-    input_ -= input_.min(axis=(0, 1))[None, None]
-    input_ /= (input_.max(axis=(0, 1))[None, None] + 1e-7)
-    input_ = (input_ * 255).astype("uint8")
-    return np.array(input_)
+    n_channels = image.shape[-1]
+    if n_channels == 1:
+        c = _normalize_channel(image[..., 0])
+        return np.stack([c, c, c], axis=-1)
+    if n_channels > 3:
+        warnings.warn(f"You provided an input with {n_channels} channels. Only the first three will be used.")
+    chans = [_normalize_channel(image[..., k]) for k in range(min(n_channels, 3))]
+    if n_channels == 2:
+        chans.append(np.zeros(image.shape[:2], dtype=np.uint8))
+    return np.stack(chans, axis=-1)
 
 
 _DTYPE_CODES = {np.dtype("uint8"): 0, np.dtype("uint16"): 1, np.dtype("float32"): 2, np.dtype("int16"): 3,
@@ -386,14 +403,14 @@ def _compute_tiled_features(predictor, input_, is3d, tile_shape, halo, pbar_init
 
     chunks = [my_work[b0:b0 + batch_size] for b0 in range(0, len(my_work), batch_size)]
     ahead = futures.ThreadPoolExecutor(1)
+    ahead_w, pending = futures.ThreadPoolExecutor(1), []
     nxt = ahead.submit(prepare, chunks[0]) if chunks else None
     for ci, chunk in enumerate(chunks):
         prepared = nxt.result()
         nxt = ahead.submit(prepare, chunks[ci + 1]) if ci + 1 < len(chunks) else None
         emb, original_sizes, input_sizes = _compute_embeddings_batched(predictor, None, prepared=prepared)
-        emb_host = emb.cpu().numpy() if to_numpy else emb
         if zgroup is not None:   # _write_batch (util.py:710-747): datasets first (creation is not thread-safe), then chunks
-            jobs = []
+            targets = []
             for k, (z, tile_id) in enumerate(chunk):
                 name = str(tile_id)
                 eshape = tuple(emb.shape[1:])
@@ -402,10 +419,17 @@ def _compute_tiled_features(predictor, input_, is3d, tile_shape, halo, pbar_init
                     ds = features.create_dataset(name, shape=shape, dtype="float32", chunks=((1, 1) if is3d else (1,)) + eshape)
                     ds.attrs["original_size"] = original_sizes[k]
                     ds.attrs["input_size"] = input_sizes[k]
-                jobs.append((features[name], z if is3d else slice(None), emb_host[k][None]))
-            _write_chunks(jobs)
+                targets.append((features[name], z if is3d else slice(None)))
+
+            def flush(emb=emb, targets=targets):   # D2H + chunk files off the critical path: the GPU encodes the next batch
+                host = emb.cpu().numpy()
+                _write_chunks([(ds, idx, host[k][None]) for k, (ds, idx) in enumerate(targets)])
+            pending.append(ahead_w.submit(flush))
+            if len(pending) > 2:                   # bound the embeddings held on the device to a few batches
+                pending.pop(0).result()
             pbar_update(len(chunk))
             continue
+        emb_host = emb.cpu().numpy() if to_numpy else emb
         for k, (z, tile_id) in enumerate(chunk):
             name = str(tile_id)
             if is3d:
@@ -419,6 +443,9 @@ def _compute_tiled_features(predictor, input_, is3d, tile_shape, halo, pbar_init
                                                                    "input_size": input_sizes[k]})
         pbar_update(len(chunk))
     ahead.shutdown()
+    for fut in pending:
+        fut.result()
+    ahead_w.shutdown()
     if mask is not None:
         features.attrs["tiles_in_mask"] = tiles_in_mask if is3d else tiles_in_mask["0"]
     if zgroup is not None and rank == 0:   # every rank's chunks are in place once the caller's barrier has passed
