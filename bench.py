@@ -355,16 +355,15 @@ def run_ours(args):
             return r
         return inner
 
-    orig = (sam.encode_u8, pred.decode_low_res, iseg.mask_stats, amg._filter_nms, L.msam_paint_min_area,
-            L.msam_finish_segmentation)
+    orig = (sam.encode_u8, pred.decode_low_res)
     sam.encode_u8 = wrap("encode", sam.encode_u8)
     pred.decode_low_res = wrap("decode", pred.decode_low_res)
-    iseg.mask_stats = wrap("mask_stats", iseg.mask_stats)
-    amg._filter_nms = wrap("filter_nms", amg._filter_nms)
 
     class _LWrap:  # the two generate() tail calls go through the ctypes handle
         def __init__(self, lib):
             self._lib = lib
+            self.msam_mask_stats_lazy = wrap("mask_stats (lazy: masks passing the IoU filter)", lib.msam_mask_stats_lazy)
+            self.msam_amg_filter_nms = wrap("filter_nms", lib.msam_amg_filter_nms)
             self.msam_paint_min_area = wrap("paint", lib.msam_paint_min_area)
             self.msam_finish_segmentation = wrap("finish_segmentation", lib.msam_finish_segmentation)
 
@@ -376,7 +375,7 @@ def run_ours(args):
     step_device(count=True)
     torch.cuda.synchronize()
     _lib._lib = L
-    sam.encode_u8, pred.decode_low_res, iseg.mask_stats, amg._filter_nms = orig[:4]
+    sam.encode_u8, pred.decode_low_res = orig
     stages = {k: sum(a.elapsed_time(b) for a, b in v) / N_TILES for k, v in stage.items()}
     surv = [int(s.item()) for s in survivors]
     # per-stage survivor counts of the last tile (filters evaluated with torch on the device's own statistics)

@@ -96,6 +96,13 @@ int msam_mask_decode(msam_handle* h, const float* sparse, int n_sparse, const fl
  * low_res [n,256,256]; boxes int32 [n,4] xyxy ([0,0,0,0] if empty); stability fp32 [n]; area int32 [n]. */
 int msam_mask_stats(const float* low_res, int n_masks, int in_h, int in_w, int orig_h, int orig_w, float mask_threshold,
                     float stability_offset, int32_t* boxes_xyxy, float* stability, int32_t* area, void* stream);
+/* The same, evaluated lazily for automatic mask generation: AMGBase._postprocess_batch (instance_segmentation.py:99-132)
+ * applies the predicted-IoU filter first, so the statistics of a mask are only ever read once `iou_preds[k] >
+ * pred_iou_thresh` holds (pred_iou_thresh <= 0: no filter).  Masks with done[k] != 0 or failing the filter are skipped,
+ * the others are computed and marked in `done` (uint8 [n_masks], device, zero-initialised by the caller). */
+int msam_mask_stats_lazy(const float* low_res, int n_masks, int in_h, int in_w, int orig_h, int orig_w, float mask_threshold,
+                         float stability_offset, const float* iou_preds, float pred_iou_thresh, uint8_t* done,
+                         int32_t* boxes_xyxy, float* stability, int32_t* area, void* stream);
 /* segment_anything.utils.amg.remove_small_regions for a batch of materialised masks (AMGBase._postprocess_small_regions,
  * instance_segmentation.py:146-186): masks uint8 [n,h,w] (0/1) are edited in place -- holes != 0: 8-connected background
  * components smaller than area_thresh are filled; holes == 0: foreground components smaller than area_thresh are removed

@@ -53,6 +53,8 @@ def lib() -> ctypes.CDLL:
         L.msam_mask_decode.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
         L.msam_mask_stats.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p,
                                       c_void_p, c_void_p]
+        L.msam_mask_stats_lazy.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_float,
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
         L.msam_remove_small_regions.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
         L.msam_mask_boxes.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
         L.msam_local_otsu_threshold.argtypes = [c_void_p, c_int, c_void_p, c_void_p]

@@ -46,7 +46,7 @@ struct DecoderState {
   DecLayer layers[2];
   AttnW final_t2i;
   float *nfg, *nfb;
-  __nv_bfloat16 *ct1 = nullptr, *ct2 = nullptr;  // conv-transpose weights as GEMM operands
+  __nv_bfloat16* ct1 = nullptr;                   // conv-transpose 1 weight as GEMM operand
   __half* ct2_f16 = nullptr;                      // conv-transpose 2 in fp16 (upscale_fused.cu)
   float *ct1b = nullptr, *ct2b = nullptr, *upln_g = nullptr, *upln_b = nullptr;
   Mlp3 hyper[4], iou_head;
@@ -71,7 +71,6 @@ struct DecoderState {
   float* sbias = nullptr;
   __nv_bfloat16 *qexp = nullptr, *qp = nullptr;  // fused t2i operands (t2i_fused.cu)
   float* un = nullptr;
-  __nv_bfloat16* up1 = nullptr;       // [P*4096*4, 64] after conv-transpose 1 + LN2d + GELU
   __nv_bfloat16 *h1 = nullptr, *h2 = nullptr;
   float *hyper_in = nullptr, *iou_out = nullptr;
 };
@@ -523,7 +522,6 @@ int Engine::finalize_decoder() {
         for (int s = 0; s < 4; ++s) W[((size_t)s * 32 + o) * 64 + c] = (*w)[((size_t)c * 32 + o) * 4 + s];
     for (int s = 0; s < 4; ++s)
       for (int o = 0; o < 32; ++o) B[s * 32 + o] = (*b)[o];
-    CHK(d.ct2 = upload_bf16(W.data(), W.size()));
     CHK(d.ct2_f16 = upload_f16(W.data(), W.size()));
     CHK(d.ct2b = upload_f32(B.data(), B.size()));
   }
@@ -579,8 +577,6 @@ int Engine::finalize_decoder() {
   CHK(d.keys = (__nv_bfloat16*)dalloc(PN * DC * 2));
   CHK(d.img_kvq = (__nv_bfloat16*)dalloc(PN * 3 * DI * 2));
   CHK(d.img_att = (__nv_bfloat16*)dalloc(PN * DI * 2));
-  static const bool legacy_up = getenv("MSAM_LEGACY_UPSCALE") != nullptr;  // two-kernel up-scaling (A/B measurements only)
-  if (legacy_up) CHK(d.up1 = (__nv_bfloat16*)dalloc(PN * 4 * 64 * 2));
   CHK(d.kexp = (__nv_bfloat16*)dalloc(P * 64 * DI * 2));
   CHK(d.vexp = (__nv_bfloat16*)dalloc(P * 64 * DI * 2));
   CHK(d.mq = (__nv_bfloat16*)dalloc(P * 64 * DC * 2));
@@ -765,23 +761,14 @@ static int decode_chunk(Engine& E, cudaStream_t st, const float* points, const f
       if (gemm(E, st, d.h2, DC, hm.w[2], P, 32, DC, hm.b[2], d.hyper_in + i * 32, 128, 1)) return -1;
     }
   }
-  // ---- output upscaling: convT(256->64) -> LN2d(64) -> GELU -> convT(64->32) -> GELU, then the hyper product
-  // convT1 + LayerNorm2d(64) + GELU in one GEMM; convT2 + GELU + hyper-network product in the next: neither the fp32
-  // conv output nor the 32-channel up-scaled embedding ever reaches HBM.
+  // ---- output upscaling: convT(256->64) -> LN2d(64) -> GELU -> convT(64->32) -> GELU, then the hyper product: neither
+  // up-scaled embedding ever reaches HBM.
   const int m0 = multimask ? 1 : 0, nm = multimask ? 3 : 1;
-  if (!d.up1) {  // one fused kernel (upscale_fused.cu)
+  {  // convT1 + LN2d + GELU + convT2 + GELU + hyper product: one fused kernel (upscale_fused.cu)
     UpscaleFusedArgs ua;
     ua.P = P; ua.nm = nm; ua.m0 = m0; ua.keys = d.keys; ua.w1 = d.ct1; ua.w2_f16 = d.ct2_f16; ua.b1 = d.ct1b;
     ua.gamma = d.upln_g; ua.beta = d.upln_b; ua.eps = 1e-6f; ua.b2 = d.ct2b; ua.hyper = d.hyper_in; ua.out = low_res;
     if (launch_upscale_fused(ua, E.num_sms, st)) return -1;
-  } else {
-  if (gemm(E, st, d.keys, DC, d.ct1, PN, 256, DC, d.ct1b, d.up1, 256, 0, 0, nullptr, 0, 0, 2, d.upln_g, d.upln_b, 1e-6f)) return -1;
-  {
-    GemmArgs a;
-    a.A = d.up1; a.W = d.ct2; a.M = PN * 4; a.N = 128; a.K = 64; a.lda = 64; a.ldw = 64; a.bias = d.ct2b; a.act = 1;
-    a.epi = 3; a.hyper = d.hyper_in; a.hyper_m0 = m0; a.hyper_nm = nm; a.out = low_res; a.out_fp32 = 1;
-    if (launch_gemm(a, E.num_sms, st)) return -1;
-  }
   }
   gather_iou_kernel<<<(P * nm + 127) / 128, 128, 0, st>>>(d.iou_out, P, m0, nm, iou);
   LAUNCH_CHECK("gather_iou");

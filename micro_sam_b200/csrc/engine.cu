@@ -492,6 +492,13 @@ int msam_mask_stats(const float* low_res, int n_masks, int in_h, int in_w, int o
   return post_mask_stats(low_res, n_masks, in_h, in_w, orig_h, orig_w, mask_threshold, fabsf(stability_offset), boxes_xyxy,
                          stability, area, (cudaStream_t)stream, generic);
 }
+int msam_mask_stats_lazy(const float* low_res, int n_masks, int in_h, int in_w, int orig_h, int orig_w, float mask_threshold,
+                         float stability_offset, const float* iou_preds, float pred_iou_thresh, uint8_t* done,
+                         int32_t* boxes_xyxy, float* stability, int32_t* area, void* stream) {
+  if (!iou_preds || !done) return set_error("msam_mask_stats_lazy: null argument");
+  return post_mask_stats(low_res, n_masks, in_h, in_w, orig_h, orig_w, mask_threshold, fabsf(stability_offset), boxes_xyxy,
+                         stability, area, (cudaStream_t)stream, stability_offset < 0.f, nullptr, iou_preds, pred_iou_thresh, done);
+}
 int msam_upsample_masks(const float* low_res, const int32_t* sel, int n_sel, int in_h, int in_w, int orig_h, int orig_w,
                         float mask_threshold, float* logits, uint8_t* binary, void* stream) {
   return post_upsample(low_res, sel, n_sel, in_h, in_w, orig_h, orig_w, mask_threshold, logits, binary, (cudaStream_t)stream);

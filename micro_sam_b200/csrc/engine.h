@@ -82,7 +82,8 @@ int post_mask_boxes(const uint8_t* masks, int n, int h, int w, int32_t* boxes, i
 int post_local_otsu(const float* low_res, int n, float* thr_out, cudaStream_t st);
 int post_mask_stats(const float* low_res, int n, int in_h, int in_w, int out_h, int out_w, float thr, float off,
                     int32_t* boxes, float* stability, int32_t* area, cudaStream_t st, bool force_generic = false,
-                    const float* thr_arr = nullptr);
+                    const float* thr_arr = nullptr, const float* lazy_iou = nullptr, float lazy_iou_thresh = 0.f,
+                    uint8_t* lazy_done = nullptr);
 int post_upsample(const float* low_res, const int32_t* sel, int n_sel, int in_h, int in_w, int out_h, int out_w, float thr,
                   float* logits, uint8_t* bin, cudaStream_t st, const float* thr_arr = nullptr);
 int post_paint(const float* low_res, const int32_t* sel, const int32_t* boxes, const int32_t* seg_ids, int n_sel, int in_h,

@@ -2,8 +2,7 @@
 //   * operands: TMA (SWIZZLE_128B boxes of 64 K-elements) -> shared memory ring (mbarrier full/empty)
 //   * math:     tcgen05.mma cta_group::1 kind::f16, M=128 x N=BN x K=16, fp32 accumulators in TMEM (2 stages)
 //   * epilogue: BN/64 column groups x 4 warps (warp%4 = TMEM lane quadrant); tcgen05.ld 32x32b -> registers ->
-//               bias / GELU(erf) / ReLU / residual (fp32 or bf16, row modulus), or a fused row epilogue
-//               (LayerNorm over N=256, LayerNorm over 64-column groups + GELU, GELU + hyper-network mask product) ->
+//               bias / GELU(erf) / ReLU / residual (fp32 or bf16, row modulus), or a fused LayerNorm over N=256 ->
 //               128-byte rows in a swizzled shared-memory staging tile -> TMA store (cp.async.bulk.tensor, coalesced,
 //               asynchronous: the row-per-thread global stores of the first version saturated the LSU queue --
 //               ncu: stall lg_throttle 8.9, tensor pipe 51 %, profiles/r1_ncu_gemm_plain_v1.txt).
@@ -23,7 +22,7 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int STG_BYTES = 128 * 128; // staging tile of one column group: 128 rows x 128 B
 
-enum { EPI_PLAIN = 0, EPI_LN256 = 1, EPI_LN64_GELU = 2, EPI_HYPER = 3 };
+enum { EPI_PLAIN = 0, EPI_LN256 = 1 };
 
 // SK = two shallow CTAs per SM (2 pipeline stages, BN = 128) for short-K GEMMs.  Measured SLOWER than one deep CTA on
 // every decoder GEMM (profiles/r1_launches_amg_vit_b_1tile_sk.txt: hyper 3.4 -> 5.3 ms, kvq 1.8 -> 2.1 ms, LN64 1.7 -> 2.4 ms;
@@ -56,9 +55,6 @@ struct GemmParams {
   const float* ln_gamma;  // fused LayerNorm epilogues
   const float* ln_beta;
   float ln_eps;
-  const float* hyper;     // EPI_HYPER: [P, 4, 32] hyper-network outputs
-  float* hyper_out;       // EPI_HYPER: low-res masks [P, hyper_nm, 256, 256]
-  int hyper_m0, hyper_nm;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -97,8 +93,7 @@ __device__ __forceinline__ void stg_write(uint8_t* stg, int r, int ch, const uin
   st_shared_v4(smem_u32(stg) + r * 128 + ((ch ^ (r & 7)) << 4), v);
 }
 
-// the hyper-product epilogue is ALU bound (GELU + 3 dot products per element): 32 columns per thread -> 16 epilogue warps
-template <int EPI> struct EpiCols { static constexpr int value = (EPI == 3) ? 32 : 64; };
+template <int EPI> struct EpiCols { static constexpr int value = 64; };
 
 template <int BN, int EPI, bool SK>
 __global__ void __launch_bounds__(GemmCfg<BN, SK, EpiCols<EPI>::value>::THREADS, GemmCfg<BN, SK, EpiCols<EPI>::value>::MIN_CTAS)
@@ -117,10 +112,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // statically declared so that the compiler emits LDS/STS (not generic LD/ST through the LG path)
   __shared__ __align__(16) float2 exch[2 * 4 * 128];  // EPI_LN256 statistics exchange, double buffered by tile parity
   __shared__ __align__(16) float rowp[768];           // [0,256) bias, [256,512) gamma, [512,768) beta (fused epilogues)
-  // EPI_HYPER: the hyper-network weights of the tile's prompt ([nm <= 4][32] fp32), one private copy per epilogue warp and
-  // tile parity, fetched before the accumulator is ready (the 24 dependent LDG.128 per thread of the first version showed
-  // up as long-scoreboard stalls on the dot products, profiles/r1_ncu_hyper_final.txt)
-  __shared__ __align__(16) float hyp_s[(EPI == EPI_HYPER) ? 16 * 2 * 128 : 4];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -132,7 +123,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    if constexpr (EPI != EPI_HYPER) prefetch_tmap(&tmC);
+    prefetch_tmap(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
@@ -151,7 +142,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int i = threadIdx.x; i < p.N && i < 256; i += Cfg::THREADS) {
       rowp[i] = p.bias ? p.bias[i] : 0.f;
       if constexpr (EPI == EPI_LN256) { rowp[256 + i] = p.ln_gamma[i]; rowp[512 + i] = p.ln_beta[i]; }
-      if constexpr (EPI == EPI_LN64_GELU) { rowp[256 + i] = p.ln_gamma[i & 63]; rowp[512 + i] = p.ln_beta[i & 63]; }
     }
   }
   tc_fence_before();
@@ -388,15 +378,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)(row % p.res_rows) * p.ldr + colbase;
           prefetch_l1(rp);
         }
-        float* hyp_w = nullptr;
-        if constexpr (EPI == EPI_HYPER) {  // all 128 rows of a tile belong to one prompt (16384 rows per prompt)
-          hyp_w = hyp_s + ((warp - 4) * 2 + (it & 1)) * 128;
-          const int pp0 = (m_blk * GEMM_BM) >> 14;
-          if (lane < 8 * p.hyper_nm)
-            reinterpret_cast<float4*>(hyp_w)[lane] =
-                __ldg(reinterpret_cast<const float4*>(p.hyper + ((size_t)pp0 * 4 + p.hyper_m0) * 32) + lane);
-          __syncwarp();
-        }
         mbar_wait(&tfull_bar[as], aphase, 4);
         tc_fence_after();
 #pragma unroll
@@ -452,49 +433,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                   pack_bf16(y[6], y[7])));
           }
           stg_publish(colbase);
-        } else if constexpr (EPI == EPI_LN64_GELU) {
-          // LayerNorm2d over one 64-channel group (= one conv-transpose sub-pixel) + GELU
-          float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int j = 0; j < CPW; ++j) s4[j & 3] += f[j];
-          const float mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / CPW);
-          float q4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int j = 0; j < CPW; ++j) { const float d = f[j] - mean; q4[j & 3] = fmaf(d, d, q4[j & 3]); }
-          const float rstd = rsqrtf(((q4[0] + q4[1]) + (q4[2] + q4[3])) * (1.0f / CPW) + p.ln_eps);
-          stg_acquire();
-#pragma unroll
-          for (int j = 0; j < CPW; j += 8) {
-            float y[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              y[q] = gelu_fast((f[j + q] - mean) * rstd * rowp[256 + j + q] + rowp[512 + j + q]);
-            stg_write(stg, r, j >> 3, make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]),
-                                                  pack_bf16(y[6], y[7])));
-          }
-          stg_publish(colbase);
-        } else if constexpr (EPI == EPI_HYPER) {
-          // second conv-transpose (N = 128 = 4 sub-sub-pixels x 32 channels; bias added above) + GELU + hyper product:
-          // masks[p, mi, Y, X] = sum_ch hyper[p, m0+mi, ch] * gelu(up[row, ss*32 + ch]).  GEMM row = (prompt p, token
-          // (y,x), sub-pixel (dy,dx)); this thread holds sub-sub-pixel ss = grp = ey*2 + ex (CPW == 32).
-          static_assert(EPI != EPI_HYPER || CPW == 32, "one sub-sub-pixel per thread");
-          if (row_ok) {
-#pragma unroll
-            for (int j = 0; j < CPW; ++j) f[j] = gelu_fast(f[j]);
-            const int sub = row & 3, tok = (row >> 2) & 4095, pp = row >> 14;
-            const int Y = 4 * (tok >> 6) + 2 * (sub >> 1) + (grp >> 1), X = 4 * (tok & 63) + 2 * (sub & 1) + (grp & 1);
-            for (int mi = 0; mi < p.hyper_nm; ++mi) {
-              const float* hw = hyp_w + mi * 32;
-              float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-              for (int c = 0; c < 32; c += 8) {
-                const float4 h4 = *reinterpret_cast<const float4*>(hw + c), g4 = *reinterpret_cast<const float4*>(hw + c + 4);
-                a0 += h4.x * f[c] + h4.y * f[c + 1] + h4.z * f[c + 2] + h4.w * f[c + 3];
-                a1 += g4.x * f[c + 4] + g4.y * f[c + 5] + g4.z * f[c + 6] + g4.w * f[c + 7];
-              }
-              p.hyper_out[(((size_t)pp * p.hyper_nm + mi) * 256 + Y) * 256 + X] = a0 + a1;
-            }
-          }
         }
       }
       __syncwarp();
@@ -524,8 +462,7 @@ static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   CUtensorMap tmA, tmB, tmC, tmR;
   if (make_tmap_bf16_2d(&tmA, a.A, a.M, a.K, a.lda, GEMM_BM)) return -1;
   if (make_tmap_bf16_2d(&tmB, a.W, a.N, a.K, a.ldw, BN)) return -1;
-  if (EPI == EPI_HYPER) tmC = tmA;  // unused
-  else if (make_tmap_2d(&tmC, a.out, a.out_fp32 ? 4 : 2, a.M, a.N, ldc, GEMM_BM)) return -1;
+  if (make_tmap_2d(&tmC, a.out, a.out_fp32 ? 4 : 2, a.M, a.N, ldc, GEMM_BM)) return -1;
   GemmParams p;
   const int res_rows = a.res_rows > 0 ? a.res_rows : a.M, ldr = a.ldr > 0 ? a.ldr : a.N;
   p.res_tma = (EPI == EPI_PLAIN && a.residual && !a.res_bf16 && a.out_fp32 && res_rows % GEMM_BM == 0 && ldr % 4 == 0) ? 1 : 0;
@@ -543,16 +480,13 @@ static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   p.out_fp32 = a.out_fp32;
   p.act = a.act;
   p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;
-  p.hyper = a.hyper; p.hyper_m0 = a.hyper_m0; p.hyper_nm = a.hyper_nm; p.hyper_out = reinterpret_cast<float*>(a.out);
   const int tiles = ((a.M + GEMM_BM - 1) / GEMM_BM) * ((a.N + BN - 1) / BN);
   const int max_ctas = num_sms * Cfg::MIN_CTAS;
   const int grid = tiles < max_ctas ? tiles : max_ctas;
   {
-    const double out_b = EPI == EPI_HYPER ? (double)a.M * a.hyper_nm * 16.0 : (double)a.M * a.N * (a.out_fp32 ? 4 : 2);
+    const double out_b = (double)a.M * a.N * (a.out_fp32 ? 4 : 2);
     const double res_b = a.residual ? (double)(a.res_rows > 0 ? a.res_rows : a.M) * a.N * (a.res_bf16 ? 2 : 4) : 0.0;
-    const char* nm = EPI == EPI_HYPER ? "gemm_bf16<128,hyper> (convT2+GELU+hyper)"
-                     : EPI == EPI_LN64_GELU ? "gemm_bf16<256,ln64gelu> (convT1+LN2d+GELU)"
-                     : EPI == EPI_LN256 ? "gemm_bf16<256,ln256>"
+    const char* nm = EPI == EPI_LN256 ? "gemm_bf16<256,ln256>"
                      : (a.K >= 512 ? "gemm_bf16 plain K>=512" : "gemm_bf16 plain K<512");
     prof_begin(stream, nm, 2.0 * a.M * a.N * a.K, (double)a.M * a.K * 2 + (double)a.N * a.K * 2 + out_b + res_b);
   }
@@ -569,18 +503,13 @@ int launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   if (a.N % 32 != 0) return set_error("gemm: N=%d must be a multiple of 32", a.N);
   if (a.K % 8 != 0 || a.lda % 8 != 0 || a.ldw % 8 != 0)
     return set_error("gemm: K/lda/ldw must be multiples of 8 (16-byte TMA strides)");
-  if (a.epi == EPI_LN256 || a.epi == EPI_LN64_GELU) {
+  if (a.epi == EPI_LN256) {
     if (a.N != 256 || a.out_fp32 || !a.ln_gamma || !a.ln_beta || a.act)
       return set_error("gemm: fused LN needs N=256, bf16 out, gamma/beta, no act");
     if (a.residual && !a.res_bf16) return set_error("gemm: fused LN takes a bf16 residual");
-    if (a.epi == EPI_LN256) return launch_gemm_bn<256, EPI_LN256>(a, num_sms, stream);
-    return launch_gemm_bn<256, EPI_LN64_GELU>(a, num_sms, stream);
+    return launch_gemm_bn<256, EPI_LN256>(a, num_sms, stream);
   }
-  if (a.epi == EPI_HYPER) {
-    if (a.N != 128 || !a.hyper || a.hyper_nm < 1 || a.hyper_nm > 4 || a.residual)
-      return set_error("gemm: fused hyper product needs N=128");
-    return launch_gemm_bn<128, EPI_HYPER>(a, num_sms, stream);
-  }
+  if (a.epi != EPI_PLAIN) return set_error("gemm: unknown epilogue %d", a.epi);
   {  // large plain products (the encoder GEMMs): CTA-pair kernel
     const int r2 = launch_gemm_2sm(a, num_sms, stream);
     if (r2 != 0) return r2 < 0 ? -1 : 0;

@@ -26,14 +26,11 @@ struct GemmArgs {
   int ldc = 0;
   int out_fp32 = 0;
   int act = 0;  // 0 none, 1 GELU(erf), 2 ReLU
-  // fused row epilogues (gemm.cu): 0 plain, 1 LayerNorm over N=256, 2 LayerNorm over 64-col groups + GELU (N=256),
-  // 3 hyper-network mask product (N=128; out = fp32 low-res masks [P, hyper_nm, 256, 256])
+  // fused row epilogue (gemm.cu): 0 plain, 1 LayerNorm over N=256
   int epi = 0;
   const float* ln_gamma = nullptr;
   const float* ln_beta = nullptr;
   float ln_eps = 1e-5f;
-  const float* hyper = nullptr;
-  int hyper_m0 = 0, hyper_nm = 0;
 };
 int launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream);
 // gemm2.cu: 2-SM (cta_group::2) kernel for large plain products; returns 1 if launched, 0 if the problem does not qualify

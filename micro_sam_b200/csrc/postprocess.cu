@@ -54,11 +54,26 @@ __device__ __forceinline__ float full_res(const float* __restrict__ lr, const Po
                 stage1(lr, g, iy.i1, ix.i1), iy, ix);
 }
 
+// Lazy evaluation (AMG): the statistics of a mask are only needed once it passes the predicted-IoU filter of generate(), so
+// initialize() can leave them pending; a launch with `lazy.done != nullptr` skips masks that are already done or that the
+// filter rejects (iou_pred > thresh fails; thresh <= 0 = no filter, as in AMGBase._postprocess_batch) and marks the rest.
+struct LazyStats {
+  const float* iou;
+  float iou_thresh;
+  uint8_t* done;
+};
+__device__ __forceinline__ bool lazy_skip(const LazyStats& z, long mi) {
+  if (!z.done) return false;
+  if (z.done[mi]) return true;
+  return z.iou_thresh > 0.f && !(z.iou[mi] > z.iou_thresh);
+}
+
 // One CTA per mask.  stats: cnt(v > thr+off), cnt(v > thr-off), area = cnt(v > thr), bbox of (v > thr).
 __global__ void __launch_bounds__(256)
 mask_stats_kernel(const float* __restrict__ low_res, PostGeom g, float thr, const float* __restrict__ thr_arr, float off,
-                  int32_t* __restrict__ boxes, float* __restrict__ stability, int32_t* __restrict__ area) {
+                  int32_t* __restrict__ boxes, float* __restrict__ stability, int32_t* __restrict__ area, LazyStats lazy) {
   const long mi = blockIdx.x;
+  if (lazy_skip(lazy, mi)) return;
   if (thr_arr) thr = thr_arr[mi];  // per-mask threshold (mask_threshold="auto", inference.py:137-151)
   const float* lr = low_res + mi * g.lr * g.lr;
   int hi = 0, lo = 0, ar = 0, x0 = 1 << 30, y0 = 1 << 30, x1 = -1, y1 = -1;
@@ -96,6 +111,7 @@ mask_stats_kernel(const float* __restrict__ low_res, PostGeom g, float thr, cons
     }
     stability[mi] = (float)r[0] / (float)r[1];  // 0/0 -> NaN like torch; NaN fails ">= thresh" downstream
     area[mi] = r[2];
+    if (lazy.done) lazy.done[mi] = 1;
     const bool empty = r[2] == 0;
     boxes[mi * 4 + 0] = empty ? 0 : r[3];
     boxes[mi * 4 + 1] = empty ? 0 : r[4];
@@ -114,8 +130,9 @@ mask_stats_kernel(const float* __restrict__ low_res, PostGeom g, float thr, cons
 // grid = n_masks, block = 512 (two row ranges x 256 low-res columns).
 __global__ void __launch_bounds__(512)
 mask_stats_x4_kernel(const float* __restrict__ low_res, PostGeom g, float thr, const float* __restrict__ thr_arr, float off,
-                     int32_t* __restrict__ boxes, float* __restrict__ stability, int32_t* __restrict__ area) {
+                     int32_t* __restrict__ boxes, float* __restrict__ stability, int32_t* __restrict__ area, LazyStats lazy) {
   const long mi = blockIdx.x;
+  if (lazy_skip(lazy, mi)) return;
   if (thr_arr) thr = thr_arr[mi];
   const float* lr = low_res + mi * 65536;
   const int j = threadIdx.x & 255, part = threadIdx.x >> 8;
@@ -246,6 +263,7 @@ mask_stats_x4_kernel(const float* __restrict__ low_res, PostGeom g, float thr, c
     }
     stability[mi] = (float)r[0] / (float)r[1];
     area[mi] = r[2];
+    if (lazy.done) lazy.done[mi] = 1;
     const bool empty = r[2] == 0;
     boxes[mi * 4 + 0] = empty ? 0 : r[3];
     boxes[mi * 4 + 1] = empty ? 0 : r[4];
@@ -428,15 +446,16 @@ static int make_geom(int in_h, int in_w, int out_h, int out_w, PostGeom* g) {
 
 int post_mask_stats(const float* low_res, int n, int in_h, int in_w, int out_h, int out_w, float thr, float off,
                     int32_t* boxes, float* stability, int32_t* area, cudaStream_t st, bool force_generic,
-                    const float* thr_arr) {
+                    const float* thr_arr, const float* lazy_iou, float lazy_iou_thresh, uint8_t* lazy_done) {
   PostGeom g;
   if (make_geom(in_h, in_w, out_h, out_w, &g)) return -1;
   if (n <= 0) return 0;
+  const LazyStats lazy{lazy_iou, lazy_iou_thresh, lazy_done};
   prof_begin(st, "mask_stats", 0.0, (double)n * (65536.0 * 4 + 24));
   if (g.identity2 && in_h == 1024 && in_w == 1024 && !force_generic) {
-    mask_stats_x4_kernel<<<n, 512, 0, st>>>(low_res, g, thr, thr_arr, off, boxes, stability, area);
+    mask_stats_x4_kernel<<<n, 512, 0, st>>>(low_res, g, thr, thr_arr, off, boxes, stability, area, lazy);
   } else {
-    mask_stats_kernel<<<n, 256, 0, st>>>(low_res, g, thr, thr_arr, off, boxes, stability, area);
+    mask_stats_kernel<<<n, 256, 0, st>>>(low_res, g, thr, thr_arr, off, boxes, stability, area, lazy);
   }
   prof_end(st);
   LAUNCH_CHECK("mask_stats");

@@ -2,9 +2,12 @@
 (micro_sam/instance_segmentation.py:65-680), re-expressed so that no full-resolution logit, bool mask or RLE ever leaves
 the GPU unless asked for:
 
-* initialize(): encoder -> decoder over the point grid -> `msam_mask_stats` (fused upsample + stability + threshold + box
-  + area).  The per-crop state keeps the 256x256 low-res logits on the device instead of CPU RLEs (the reference's
-  `_to_mask_data` D2H-copies every mask for CPU RLE, instance_segmentation.py:229-255).
+* initialize(): encoder -> decoder over the point grid.  The per-crop state keeps the 256x256 low-res logits on the device
+  instead of CPU RLEs (the reference's `_to_mask_data` D2H-copies every mask for CPU RLE, instance_segmentation.py:229-255).
+  The per-mask statistics (`msam_mask_stats`: fused upsample + stability + threshold + box + area) are evaluated LAZILY:
+  `_postprocess_batch` (:99-132) filters by predicted IoU first, so generate() computes them -- once, cached in the state --
+  only for the masks that pass that filter; `crop_list` / `get_state()` materialise all of them, so the state a caller sees
+  is always complete.
 * generate(): `msam_amg_filter_nms` (pred-IoU / stability / crop-edge filters + box NMS, one kernel) -> survivors are
   painted straight from their low-res logits (`msam_paint`), then connected components / background removal / relabel
   on the host like the reference (util.py:1831-1848).  RLEs / binary masks are produced lazily for the survivors only.
@@ -20,7 +23,6 @@ import torch
 
 from . import _amg_utils as amg_utils
 from . import _lib, util
-from .sam import mask_stats
 
 DEFAULT_SEGMENTATION_MODE_WITH_DECODER = "ais"
 
@@ -40,7 +42,39 @@ class AMGBase(ABC):
 
     @property
     def crop_list(self):
+        """The per-crop state with every statistic materialised (pending lazy statistics are computed first)."""
+        if self._crop_list is not None and getattr(self, "_predictor", None) is not None:
+            lo = getattr(self, "_tile_lo", 0)      # multi-rank tiled state: this rank's tiles are crop_boxes[lo : lo + n]
+            for k, data in enumerate(self._crop_list):
+                self._ensure_stats(data, self._crop_boxes[lo + k], 0.0)
         return self._crop_list
+
+    def _geom_of(self, crop_box):
+        from .sam import get_preprocess_shape
+        H, W = self.original_size
+        x0, y0, x1, y1 = crop_box
+        h, w = min(int(y1), H) - int(y0), min(int(x1), W) - int(x0)
+        return dict(inp=get_preprocess_shape(h, w, self._predictor.transform.target_length), orig=(h, w))
+
+    def _ensure_stats(self, data, crop_box, pred_iou_thresh: float) -> None:
+        """Compute the pending mask statistics of a crop for the masks with iou_pred > pred_iou_thresh (<= 0: all of them);
+        no host synchronisation (`msam_mask_stats_lazy` skips per mask on the device)."""
+        done = data["stats_done"] if "stats_done" in data else None
+        if done is None or getattr(data, "_all_done", False):
+            return
+        low = data["low_res"]
+        if low.device != done.device:      # offloaded state: statistics were completed before the logits left the device
+            return
+        g = self._geom_of(crop_box)
+        n = int(low.shape[0])
+        if n:
+            _lib.check(_lib.lib().msam_mask_stats_lazy(
+                _lib.ptr(low), n, int(g["inp"][0]), int(g["inp"][1]), int(g["orig"][0]), int(g["orig"][1]),
+                float(self._predictor.model.mask_threshold), float(getattr(self, "_stability_score_offset", 1.0)),
+                _lib.ptr(data["iou_preds"]), float(pred_iou_thresh), _lib.ptr(done), _lib.ptr(data["boxes"]),
+                _lib.ptr(data["stability_score"]), _lib.ptr(data["area"]), _lib.cur_stream()))
+        if pred_iou_thresh <= 0.0:
+            data._all_done = True
 
     @property
     def crop_boxes(self):
@@ -56,6 +90,7 @@ class AMGBase(ABC):
         orig_h, orig_w = original_size
         n = int(data["iou_preds"].shape[0])
         dev = data["iou_preds"].device
+        self._ensure_stats(data, crop_box, pred_iou_thresh)   # statistics of the masks the predicted-IoU filter lets through
         keep = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         n_keep = torch.zeros(1, dtype=torch.int32, device=dev)
         crop = (ctypes.c_int32 * 4)(*[int(c) for c in crop_box])
@@ -110,13 +145,7 @@ class AMGBase(ABC):
         """Per-crop (input_size, original_size) of the predictor while the crop was decoded -- a pure function of the crop
         boxes (the crop is what `set_image` / the tile embedding saw; input_size = ResizeLongestSide of it), so a state
         restored with set_state() needs nothing beyond the reference's three keys."""
-        from .sam import get_preprocess_shape
-        H, W = self.original_size
-        geoms = []
-        for x0, y0, x1, y1 in self.crop_boxes:
-            h, w = min(int(y1), H) - int(y0), min(int(x1), W) - int(x0)
-            geoms.append(dict(inp=get_preprocess_shape(h, w, self._predictor.transform.target_length), orig=(h, w)))
-        return geoms
+        return [self._geom_of(cb) for cb in self.crop_boxes]
 
     @staticmethod
     def _logits_rows(data, rows: torch.Tensor, device):
@@ -129,10 +158,11 @@ class AMGBase(ABC):
         picked = low.index_select(0, rows.to("cpu", torch.long))
         return picked.to(device, non_blocking=True), torch.arange(len(rows), dtype=torch.int32, device=device)
 
-    def _offload(self, data) -> None:
+    def _offload(self, data, crop_box) -> None:
         """Move a crop's low-res logits (805 MB per 32x32-grid tile) to pinned host memory; the small per-mask statistics stay
         on the device.  This is the reference's memory model (its state holds CPU RLEs, instance_segmentation.py:229-255)."""
         low = data["low_res"]
+        self._ensure_stats(data, crop_box, 0.0)   # the statistics need the logits on the device: complete them first
         host = torch.empty(low.shape, dtype=low.dtype, pin_memory=True)
         host.copy_(low, non_blocking=False)
         data["low_res"] = host
@@ -188,9 +218,13 @@ class AutomaticMaskGenerator(AMGBase):
         low, iou = pred.decode_low_res(in_points[:, None, :], in_labels[:, None], None, multimask_output=True)
         P, M = low.shape[:2]
         low = low.view(P * M, 256, 256)
-        boxes, stab, area = mask_stats(low, pred.input_size, pred.original_size, pred.model.mask_threshold,
-                                       self._stability_score_offset)
-        data = amg_utils.MaskData(low_res=low, iou_preds=iou.reshape(-1), stability_score=stab, boxes=boxes, area=area)
+        dev = low.device
+        # statistics pending: filled by _ensure_stats for the masks a generate() call actually looks at
+        data = amg_utils.MaskData(low_res=low, iou_preds=iou.reshape(-1),
+                                  stability_score=torch.zeros(P * M, dtype=torch.float32, device=dev),
+                                  boxes=torch.zeros(P * M, 4, dtype=torch.int32, device=dev),
+                                  area=torch.zeros(P * M, dtype=torch.int32, device=dev),
+                                  stats_done=torch.zeros(P * M, dtype=torch.uint8, device=dev))
         data["points"] = torch.as_tensor(points.repeat(M, axis=0), dtype=torch.float)
         return data
 
@@ -252,8 +286,8 @@ class AutomaticMaskGenerator(AMGBase):
         if min_mask_region_area > 0:
             return self._generate_small_regions(pred_iou_thresh, stability_score_thresh, box_nms_thresh, crop_nms_thresh,
                                                 min_mask_region_area, output_mode, with_background, geoms)
-        if output_mode == "instance_segmentation" and len(self.crop_list) == 1 and geoms and \
-                self.crop_list[0]["low_res"].device == self.crop_list[0]["iou_preds"].device and \
+        if output_mode == "instance_segmentation" and len(self._crop_list) == 1 and geoms and \
+                self._crop_list[0]["low_res"].device == self._crop_list[0]["iou_preds"].device and \
                 tuple(self.crop_boxes[0]) == (0, 0, self.original_size[1], self.original_size[0]):
             out = self.generate_device(pred_iou_thresh, stability_score_thresh, box_nms_thresh, with_background)
             return out.cpu().numpy().view(np.uint32)
@@ -267,7 +301,7 @@ class AutomaticMaskGenerator(AMGBase):
         H, W = self.original_size
         dev = self._predictor.device
         keeps, gboxes, crop_id = [], [], []
-        for ci, (data, crop_box) in enumerate(zip(self.crop_list, self.crop_boxes)):
+        for ci, (data, crop_box) in enumerate(zip(self._crop_list, self.crop_boxes)):
             keep = self._filter_nms(data, crop_box, self.original_size, pred_iou_thresh, stability_score_thresh,
                                     box_nms_thresh)
             keeps.append(keep)
@@ -293,7 +327,7 @@ class AutomaticMaskGenerator(AMGBase):
         n = len(order)
         if output_mode != "instance_segmentation":
             out = [None] * n
-            for ci, (data, crop_box) in enumerate(zip(self.crop_list, self.crop_boxes)):
+            for ci, (data, crop_box) in enumerate(zip(self._crop_list, self.crop_boxes)):
                 pos = (crop_id == ci).nonzero()[:, 0]
                 if len(pos) == 0:
                     continue
@@ -314,7 +348,7 @@ class AutomaticMaskGenerator(AMGBase):
             return out
         canvas = torch.full((H, W), -1, dtype=torch.int64, device=dev)
         L = _lib.lib()
-        for ci, (data, crop_box) in enumerate(zip(self.crop_list, self.crop_boxes)):
+        for ci, (data, crop_box) in enumerate(zip(self._crop_list, self.crop_boxes)):
             pos = (crop_id == ci).nonzero()[:, 0]
             if len(pos) == 0:
                 continue
@@ -407,7 +441,7 @@ class AutomaticMaskGenerator(AMGBase):
             raise RuntimeError("AutomaticMaskGenerator has not been initialized. Call initialize first.")
         if len(self.crop_list) != 1:
             raise NotImplementedError("device-side generate supports a single crop")
-        data, crop_box, geom = self.crop_list[0], self.crop_boxes[0], self._crop_geoms()[0]
+        data, crop_box, geom = self._crop_list[0], self.crop_boxes[0], self._crop_geoms()[0]
         H, W = self.original_size
         dev = data["iou_preds"].device
         if data["low_res"].device != dev:
@@ -461,7 +495,7 @@ class TiledAutomaticMaskGenerator(AutomaticMaskGenerator):
         dev = self._predictor.device
         geoms = self._crop_geoms()
         tabs = dict(gbox=[], lbox=[], area=[], tile=[], low=[])
-        for k, data in enumerate(self.crop_list):
+        for k, data in enumerate(self._crop_list):
             ci = self._tile_lo + k
             crop_box = self.crop_boxes[ci]
             keep = self._filter_nms(data, crop_box, self.original_size, pred_iou_thresh, stability_score_thresh, box_nms_thresh)
@@ -566,7 +600,7 @@ class TiledAutomaticMaskGenerator(AutomaticMaskGenerator):
                                                    "original_size": f.attrs["original_size"]}, i)
             mask_data.append(self._process_crop(original_size, crop_boxes[idx], 0))
             if offload_state:
-                self._offload(mask_data[-1])
+                self._offload(mask_data[-1], crop_boxes[idx])
             pbar_update(1)
         pbar_close()
         self._is_initialized = True
