@@ -439,7 +439,7 @@ class AutomaticMaskGenerator(AMGBase):
         removal / consecutive relabel (msam_finish_segmentation).  Returns a uint32-valued int32 (H, W) device tensor."""
         if not self.is_initialized:
             raise RuntimeError("AutomaticMaskGenerator has not been initialized. Call initialize first.")
-        if len(self.crop_list) != 1:
+        if len(self._crop_list) != 1:
             raise NotImplementedError("device-side generate supports a single crop")
         data, crop_box, geom = self._crop_list[0], self.crop_boxes[0], self._crop_geoms()[0]
         H, W = self.original_size
