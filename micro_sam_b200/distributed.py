@@ -56,7 +56,10 @@ def gather_instance_tables(tables: dict, group=None) -> Tuple[dict, List[int]]:
     out, counts = {}, None
     for k in sorted(tables):
         t = tables[k]
-        flat = t.reshape(t.shape[0], -1) if t.ndim > 1 else t.reshape(-1, 1)
+        width = 1
+        for d in t.shape[1:]:
+            width *= int(d)
+        flat = t.reshape(t.shape[0], width)   # explicit width: reshape(0, -1) is ambiguous for a rank without instances
         g, c = all_gather_tables(flat.contiguous(), group)
         if counts is not None and c != counts:
             raise RuntimeError(f"gather_instance_tables: inconsistent row counts for {k}: {c} != {counts}")

@@ -126,6 +126,9 @@ def _dist_worker(rank, world, port, ret):
         assert c == counts and g["gbox"].shape == (11, 4) and g["low"].shape == (11, 2, 3) and g["tile"].dtype == torch.int32
         assert g["gbox"][:, 0].tolist() == list(range(11)) and g["low"][:, 1, 2].tolist() == list(map(float, range(11)))
         assert g["tile"].tolist() == [0] * counts[0] + [1] * counts[1]
+        # a rank that owns no instance at all still takes part in the exchange
+        e, ce = D.gather_instance_tables({"low": torch.zeros(3 if rank == 1 else 0, 2, 3), "tile": torch.zeros(3 if rank == 1 else 0, dtype=torch.int32)})
+        assert ce == [0, 3] and e["low"].shape == (3, 2, 3) and e["tile"].shape == (3,)
         ret[rank] = (lo, hi, full.tolist(), counts, offs.tolist())
     finally:
         dist.destroy_process_group()
