@@ -40,9 +40,30 @@ def get_device(device: Optional[Union[str, torch.device]] = None) -> torch.devic
     return dev
 
 
+class _TolerantPickle:
+    """`pickle_module` for torch.load that resolves classes it cannot import to placeholders instead of failing (util.py:246-257):
+    torch_em training checkpoints pickle trainer / loss / logger objects next to the weights, and only the weights are
+    wanted here.  A private namespace instead of the reference's in-place patch of `pickle.Unpickler`."""
+    import pickle as _p
+    __name__ = "pickle"
+    load, loads, dump, dumps = _p.load, _p.loads, _p.dump, _p.dumps
+    HIGHEST_PROTOCOL, DEFAULT_PROTOCOL, Pickler = _p.HIGHEST_PROTOCOL, _p.DEFAULT_PROTOCOL, _p.Pickler
+    PickleError, UnpicklingError, PicklingError = _p.PickleError, _p.UnpicklingError, _p.PicklingError
+
+    class Unpickler(_p.Unpickler):
+        def find_class(self, module, name):
+            try:
+                return super().find_class(module, name)
+            except (AttributeError, ModuleNotFoundError) as e:
+                warnings.warn(f"Did not find {module}:{name} and will skip it, due to error {e}")
+                # a placeholder class (the reference returns None, which fails for pickled INSTANCES of the class)
+                return type(name, (), {"__init__": lambda self, *a, **k: None, "__setstate__": lambda self, state: None,
+                                       "__reduce_ex__": None, "__module__": module})
+
+
 def _load_checkpoint(checkpoint_path):
     """util.py:273-290: torch_em checkpoints carry {"model_state": {"sam.<key>": ...}, "decoder_state": ...}."""
-    state = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+    state = torch.load(checkpoint_path, map_location="cpu", weights_only=False, pickle_module=_TolerantPickle)
     if "model_state" in state:
         model_state = state["model_state"]
         model_state = {k[len("module."):] if k.startswith("module.") else k: v for k, v in model_state.items()}

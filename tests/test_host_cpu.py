@@ -207,3 +207,31 @@ def test_tiled_prompt_routing_matches_oracle_loop():
         pin = (pts[k, 0] - np.array(t.begin)[::-1])[None, None]
         refp[tid] = np.concatenate([refp[tid], pin]) if tid in refp else pin
     assert ids == sorted(refp) and all(np.array_equal(p2t[t], refp[t]) and len(l2t[t]) == len(refp[t]) for t in ids)
+
+
+def test_checkpoint_loading_tolerates_missing_training_classes(tmp_path):
+    """util._load_checkpoint (util.py:246-290): torch_em checkpoints pickle trainer objects whose classes need not be
+    importable; only the weights are wanted.  `sam.` / `module.` prefixes are stripped."""
+    import sys
+    import types
+    import warnings
+    from micro_sam_b200 import util
+    mod = types.ModuleType("ghost_trainer_mod")
+    sys.modules["ghost_trainer_mod"] = mod
+
+    class Trainer:
+        def __init__(self):
+            self.lr = 1e-4
+    Trainer.__module__, Trainer.__qualname__ = "ghost_trainer_mod", "Trainer"
+    mod.Trainer = Trainer
+    p = str(tmp_path / "best.pt")
+    torch.save({"model_state": {"sam.image_encoder.pos_embed": torch.ones(2), "module.sam.x": torch.zeros(1)}, "trainer": Trainer(),
+                "epoch": 3}, p)
+    del sys.modules["ghost_trainer_mod"]
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        state, model_state = util._load_checkpoint(p)
+    assert sorted(model_state) == ["image_encoder.pos_embed", "x"] and state["epoch"] == 3
+    assert any("ghost_trainer_mod" in str(x.message) for x in w)
+    torch.save({"image_encoder.pos_embed": torch.ones(2)}, p)
+    assert sorted(util._load_checkpoint(p)[1]) == ["image_encoder.pos_embed"]
