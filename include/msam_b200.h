@@ -186,6 +186,9 @@ int msam_op_gemm(const void* A, const void* W, int M, int N, int K, const float*
 /* Weight gradient of a linear layer (first piece of msam_*_backward, cfg 5): out[M,N] fp32 = A[K,M]^T B[K,N], A = dY
  * (tokens x out-features), B = X (tokens x in-features), both bf16 row-major -- torch autograd's dW = dY^T X. */
 int msam_op_gemm_tn(const void* A, const void* B, int M, int N, int K, float* out, void* stream);
+/* Input gradient of the same layer: out[M,N] fp32 = A[M,K] B[K,N], A = dY (tokens x out-features), B = W (out-features x
+ * in-features, the forward weight as stored) -- torch autograd's dX = dY W. */
+int msam_op_gemm_nn(const void* A, const void* B, int M, int N, int K, float* out, void* stream);
 /* LayerNorm over rows of fp32 x[rows, D] -> bf16; window_mode=1 scatters into the 14x14 window-partitioned layout. */
 int msam_op_layernorm(const float* x, int rows, int D, const float* gamma, const float* beta, float eps, void* out_bf16,
                       int window_mode, void* stream);

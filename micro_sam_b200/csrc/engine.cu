@@ -606,6 +606,11 @@ int msam_op_gemm_tn(const void* A, const void* B, int M, int N, int K, float* ou
   return launch_gemm_tn((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, M, N, K, M, N, out, N, (cudaStream_t)stream);
 }
 
+int msam_op_gemm_nn(const void* A, const void* B, int M, int N, int K, float* out, void* stream) {
+  if (!A || !B || !out) return set_error("msam_op_gemm_nn: null argument");
+  return launch_gemm_nn((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, M, N, K, K, N, out, N, (cudaStream_t)stream);
+}
+
 int msam_op_layernorm(const float* x, int rows, int D, const float* gamma, const float* beta, float eps, void* out_bf16,
                       int window_mode, void* stream) {
   LnArgs l;

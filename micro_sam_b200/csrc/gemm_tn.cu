@@ -1,7 +1,9 @@
-// Weight-gradient GEMM of the fine-tuning step (first piece of the backward pass, cfg 5):
-//     dW[M, N] (fp32) = A^T B,   A = dY [K, M] bf16 (tokens x out-features),  B = X [K, N] bf16 (tokens x in-features)
-// i.e. the contraction runs over the SLOW dimension of both operands (the token index), so neither operand is K-major in
-// memory.  Instead of materialising transposes, both operands are fed to tcgen05.mma as MN-major tiles: TMA loads
+// Backward GEMMs of a linear layer y = x W^T (first pieces of the backward pass, cfg 5), without materialising a transpose:
+//   wgrad (A_MN = true):   dW[M, N] (fp32) = A^T B,  A = dY [K, M] bf16 (tokens x out-features), B = X [K, N] (tokens x in-features)
+//   dgrad (A_MN = false):  dX[M, N] (fp32) = A B,    A = dY [M, K] bf16 (tokens x out-features, K-major as in the forward GEMM),
+//                                                    B = W [K, N] (out-features x in-features: the forward weight as stored)
+// In both the B operand -- and in wgrad also A -- is contracted over its SLOW dimension:
+// such operands are fed to tcgen05.mma as MN-major tiles: TMA loads
 // [64 tokens x 64 features] boxes (SWIZZLE_128B, 128-byte rows along the feature = M/N dimension) and the UMMA descriptors
 // carry a_major = b_major = MN (leading-dimension byte offset = distance between 64-feature blocks, stride = 8 token rows).
 // One CTA per 128 x 128 output tile, 4-stage TMA ring over 64-token K blocks, fp32 accumulator in TMEM, row-per-thread
@@ -23,11 +25,12 @@ constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
 constexpr int THREADS = 256;
 }  // namespace wg
 
-// kind::f16, BF16 x BF16 -> FP32, both operands MN-major (bit 15: A major, bit 16: B major)
-__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+// kind::f16, BF16 x BF16 -> FP32; bit 15: A major (1 = MN), bit 16: B major (1 = MN)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(uint32_t M, uint32_t N, uint32_t a_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+template <bool A_MN>
 __global__ void __launch_bounds__(wg::THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ out,
                int M, int N, int K, int ldc) {
@@ -62,15 +65,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&empty_bar[stage], phase ^ 1, 50);
         uint8_t* sa = smem + stage * STAGE_BYTES;
         mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+        if constexpr (A_MN) {
 #pragma unroll
-        for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * SUB, &tmA, &full_bar[stage], m0 + 64 * j, kb * BK);
+          for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * SUB, &tmA, &full_bar[stage], m0 + 64 * j, kb * BK);
+        } else {   // K-major A: one [128 rows x 64 K] box
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+        }
 #pragma unroll
         for (int j = 0; j < BN / 64; ++j) tma_load_2d(sa + A_BYTES + j * SUB, &tmB, &full_bar[stage], n0 + 64 * j, kb * BK);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16_mn(BM, BN);
+    constexpr uint32_t idesc = make_idesc_bf16_mn(BM, BN, A_MN ? 1u : 0u);
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = 0; kb < k_blocks; ++kb) {
@@ -80,7 +87,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < BK / 16; ++kk) {  // 16 token rows = 2048 B further down the MN-major tile
-          const uint64_t da = make_desc_sw128(sa + kk * 2048, SUB, 1024), db = make_desc_sw128(sb + kk * 2048, SUB, 1024);
+          const uint64_t da = A_MN ? make_desc_sw128(sa + kk * 2048, SUB, 1024) : make_desc_sw128(sa + kk * 32, 0, 1024);
+          const uint64_t db = make_desc_sw128(sb + kk * 2048, SUB, 1024);
           umma_bf16(tmem_base, da, db, idesc, (kb | kk) != 0);
         }
         umma_commit(&empty_bar[stage]);
@@ -116,28 +124,39 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-int launch_gemm_tn(const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K, int lda, int ldb, float* out, int ldc,
-                   cudaStream_t stream) {
+template <bool A_MN>
+static int launch_gemm_mn(const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K, int lda, int ldb, float* out, int ldc,
+                          cudaStream_t stream) {
   using namespace wg;
   if (M <= 0 || N <= 0 || K <= 0) return set_error("gemm_tn: empty problem M=%d N=%d K=%d", M, N, K);
-  if (M % 8 || N % 8 || lda % 8 || ldb % 8 || ldc % 4) return set_error("gemm_tn: M, N, lda, ldb must be multiples of 8, ldc of 4");
+  if (M % 8 || N % 8 || K % 8 || lda % 8 || ldb % 8 || ldc % 4)
+    return set_error("gemm_tn: M, N, K, lda, ldb must be multiples of 8, ldc of 4");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<A_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return set_error("gemm_tn: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  CUtensorMap tmA, tmB;   // rows = tokens (K), inner (contiguous) dimension = features; box = 64 features x 64 tokens
-  if (make_tmap_bf16_2d(&tmA, A, K, M, lda, BK)) return -1;
+  CUtensorMap tmA, tmB;   // MN-major operand: rows = contraction index, inner (contiguous) dimension = features, box 64 x 64
+  if (A_MN ? make_tmap_bf16_2d(&tmA, A, K, M, lda, BK) : make_tmap_bf16_2d(&tmA, A, M, K, lda, BM)) return -1;
   if (make_tmap_bf16_2d(&tmB, B, K, N, ldb, BK)) return -1;
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
-  prof_begin(stream, "gemm_tn (wgrad)", 2.0 * M * N * K, (double)K * (M + N) * 2 + (double)M * N * 4);
-  gemm_tn_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, out, M, N, K, ldc);
+  prof_begin(stream, A_MN ? "gemm_tn (wgrad)" : "gemm_nn (dgrad)", 2.0 * M * N * K, (double)K * (M + N) * 2 + (double)M * N * 4);
+  gemm_tn_kernel<A_MN><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, out, M, N, K, ldc);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm_tn launch failed: %s", cudaGetErrorString(e));
   count_launch();
   return 0;
+}
+
+int launch_gemm_tn(const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K, int lda, int ldb, float* out, int ldc,
+                   cudaStream_t stream) {
+  return launch_gemm_mn<true>(A, B, M, N, K, lda, ldb, out, ldc, stream);
+}
+int launch_gemm_nn(const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K, int lda, int ldb, float* out, int ldc,
+                   cudaStream_t stream) {
+  return launch_gemm_mn<false>(A, B, M, N, K, lda, ldb, out, ldc, stream);
 }
 
 }  // namespace msam

@@ -39,6 +39,9 @@ int launch_gemm_2sm(const GemmArgs& a, int num_sms, cudaStream_t stream);
 // ---- gemm_tn.cu : out[M,N] fp32 = A[K,M]^T B[K,N]  (weight gradient dW = dY^T X; both operands MN-major)
 int launch_gemm_tn(const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K, int lda, int ldb, float* out, int ldc,
                    cudaStream_t stream);
+// out[M,N] fp32 = A[M,K] B[K,N]  (input gradient dX = dY W; A K-major, B = the forward weight [out, in] consumed MN-major)
+int launch_gemm_nn(const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K, int lda, int ldb, float* out, int ldc,
+                   cudaStream_t stream);
 
 // ---- upscale_fused.cu : conv-transpose 1 + LayerNorm2d + GELU + conv-transpose 2 + GELU + hyper-network product in one pass
 struct UpscaleFusedArgs {

@@ -742,9 +742,13 @@ paint_min_area_x4_kernel(const float* __restrict__ low_res, const int32_t* __res
                          const int32_t* __restrict__ area, PostGeom g, float thr, int32_t* __restrict__ label, int ld_label) {
   __shared__ unsigned long long skey[PAINT_SORT_MAX];
   __shared__ float patch[2][10][12];
-  const int n_sel = *n_sel_ptr;
+  __shared__ unsigned cand_bits[PAINT_SORT_MAX / 32], cand_off[PAINT_SORT_MAX / 32 + 1];
+  __shared__ unsigned short cand[PAINT_SORT_MAX];
+  const int n_all = *n_sel_ptr;
   const int tid = threadIdx.x;
-  const bool sorted = n_sel <= PAINT_SORT_MAX;
+  const bool sorted = n_all <= PAINT_SORT_MAX;
+  const int X0 = blockIdx.x * 32, Y0 = blockIdx.y * 32;
+  int n_sel = n_all;
   if (sorted) {
     int npow2 = 1;
     while (npow2 < n_sel) npow2 <<= 1;
@@ -763,8 +767,43 @@ paint_min_area_x4_kernel(const float* __restrict__ low_res, const int32_t* __res
         __syncthreads();
       }
     }
+    // Candidates of THIS region, in sorted order: survivors whose box misses the 32 x 32 region are dropped up front (with
+    // localised masks a region sees a handful of the survivors instead of all of them).  Order-preserving compaction:
+    // ballot words -> exclusive scan of their popcounts by warp 0 -> scatter.
+    for (int k0 = 0; k0 < npow2; k0 += 256) {
+      const int k = k0 + tid;
+      bool hit = false;
+      if (k < n_all) {
+        const int mi = sel[(int)(0xFFFFFFFFu - (unsigned)(skey[k] & 0xFFFFFFFFull))];
+        const int4 b = *reinterpret_cast<const int4*>(boxes + 4L * mi);
+        hit = b.x <= X0 + 31 && b.z >= X0 && b.y <= Y0 + 31 && b.w >= Y0;
+      }
+      const unsigned w = __ballot_sync(0xffffffffu, hit);
+      if ((tid & 31) == 0 && k < npow2) cand_bits[k >> 5] = w;
+    }
+    __syncthreads();
+    const int n_words = (npow2 + 31) >> 5;
+    if (tid < 32) {
+      unsigned run = 0;
+      for (int w0 = 0; w0 < n_words; w0 += 32) {
+        const int w = w0 + tid;
+        const unsigned c = w < n_words ? __popc(cand_bits[w]) : 0u;
+        unsigned incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += t; }
+        if (w < n_words) cand_off[w] = run + incl - c;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (tid == 0) cand_off[n_words] = run;
+    }
+    __syncthreads();
+    for (int k = tid; k < n_all; k += 256) {
+      const unsigned w = cand_bits[k >> 5];
+      if ((w >> (k & 31)) & 1u) cand[cand_off[k >> 5] + __popc(w & ((1u << (k & 31)) - 1u))] = (unsigned short)k;
+    }
+    n_sel = (int)cand_off[n_words];
+    __syncthreads();
   }
-  const int X0 = blockIdx.x * 32, Y0 = blockIdx.y * 32;
   const int py0 = (Y0 >> 2) - 1, px0 = (X0 >> 2) - 1;          // low-res origin of the patch (may be -1: never referenced)
   const int y = Y0 + (tid >> 3), xb = X0 + (tid & 7) * 4;       // this thread: pixels (y, xb .. xb+3)
   const Interp iy = interp_axis(y, g.s1, g.lr);
@@ -774,7 +813,7 @@ paint_min_area_x4_kernel(const float* __restrict__ low_res, const int32_t* __res
   unsigned long long best[4] = {~0ull, ~0ull, ~0ull, ~0ull};
   const int pr = tid / 10, pc = tid % 10;                        // patch element fetched by threads 0..99
   const int gy = min(max(py0 + pr, 0), g.lr - 1), gx = min(max(px0 + pc, 0), g.lr - 1);
-  auto pos_of = [&](int k) -> int { return sorted ? (int)(0xFFFFFFFFu - (unsigned)(skey[k] & 0xFFFFFFFFull)) : k; };
+  auto pos_of = [&](int k) -> int { return sorted ? (int)(0xFFFFFFFFu - (unsigned)(skey[cand[k]] & 0xFFFFFFFFull)) : k; };
   float nxt = 0.f;
   if (n_sel > 0 && tid < 100) nxt = __ldg(low_res + (long)sel[pos_of(0)] * g.lr * g.lr + gy * g.lr + gx);
   for (int k = 0; k < n_sel; ++k) {

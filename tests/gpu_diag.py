@@ -134,6 +134,18 @@ def sec_wgrad():
             print(f"[BAD] wgrad T={T} O={O} I={I}: EXCEPTION {e}", flush=True)
             continue
         report(f"wgrad dW = dY^T X  T={T} O={O} I={I} (vs autograd)", out, lin.weight.grad, 1e-5)
+        # dgrad through the same kernel family: dX = dY W with W = the forward weight [O, I] (bf16), vs autograd
+        xg = x.float().requires_grad_(True)
+        wb = lin.weight.detach().bfloat16()
+        (xg @ wb.float().t()).backward(dy.float())
+        dx = torch.empty(T, I, device=DEV, dtype=torch.float32)
+        try:
+            _lib.check(_lib.lib().msam_op_gemm_nn(_lib.ptr(dy), _lib.ptr(wb.contiguous()), T, I, O, _lib.ptr(dx), _lib.cur_stream()))
+            torch.cuda.synchronize()
+            report(f"dgrad dX = dY W    T={T} O={O} I={I} (vs autograd)", dx, xg.grad, 1e-5)
+        except Exception as e:  # noqa: BLE001
+            RESULTS.append(False)
+            print(f"[BAD] dgrad T={T} O={O} I={I}: EXCEPTION {e}", flush=True)
     T, O, I = 16 * 4096, 3072, 768
     x, dy = torch.randn(T, I, device=DEV).bfloat16(), torch.randn(T, O, device=DEV).bfloat16()
     out = torch.empty(O, I, device=DEV, dtype=torch.float32)
