@@ -19,7 +19,7 @@ typedef struct msam_handle msam_handle;
 /* Architecture, mirrors the constructor arguments of micro_sam/models/build_sam.py:87-142 (_build_sam). */
 typedef struct msam_config {
   int32_t embed_dim;          /* 768 / 1024 / 1280 */
-  int32_t depth;              /* 12 / 24 / 32 */
+  int32_t depth;              /* 12 / 24 / 32; 0 selects MobileSAM's TinyViT encoder (vit_t: embed_dim 320, num_heads 10) */
   int32_t num_heads;          /* 12 / 16 / 16  (head_dim must be 64 or 80) */
   int32_t global_attn[8];     /* indexes of global-attention blocks, -1 terminated */
   int32_t window_size;        /* 14 */
@@ -60,6 +60,7 @@ int msam_encode_u8(msam_handle* h, const uint8_t* hwc, int B, int hh, int ww, fl
 /* Parity localisation (tests): patch embedding + the first n_blocks transformer blocks of msam_encode_u8; x_out receives the
  * fp32 residual stream [B*4096, embed_dim] (token-major), to be compared with the oracle's activations block by block. */
 int msam_encode_u8_blocks(msam_handle* h, const uint8_t* hwc, int B, int hh, int ww, int n_blocks, float* x_out, void* stream);
+/* (vit_t: n_blocks counts TinyViT stages 1..4; x_out = the token stream [B*H*H, dim] after layers.{n_blocks-1}.) */
 
 /* SamPredictor.features assignment (util.py:676-679 / set_precomputed util.py:1248-1256): bind a (256,64,64) fp32
  * NCHW image embedding as the decoder's current image; precomputes the prompt-independent layer-0 projections. */

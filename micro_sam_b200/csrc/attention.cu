@@ -7,6 +7,7 @@
 #include "kernels.h"
 #include "ptx.cuh"
 #include "tensormap.h"
+#include <stdlib.h>
 #include <type_traits>
 
 namespace msam {
@@ -19,7 +20,10 @@ struct AttParams {
   int d_model;   // heads * D
   int grid;      // 64
   float scale_log2;
+  unsigned long long* trace;
 };
+
+#define ATT_TRACE(slot) do { if (tr) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tr[slot] = t_; } } while (0)
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -90,6 +94,9 @@ attn_window_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, head = blockIdx.y, group = blockIdx.z;
+  unsigned long long* tr = nullptr;
+  if (p.trace && threadIdx.x == 0 && qt == 0 && head == 0 && group < 64) tr = p.trace + group * 16;
+  ATT_TRACE(0);
 
   if (warp == 4 && lane == 0) {
     prefetch_tmap(&tmQ);
@@ -110,6 +117,7 @@ attn_window_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int row0 = group * G;
+  ATT_TRACE(1);
 
   if (warp == 4) {
     if (lane == 0) {
@@ -172,6 +180,7 @@ attn_window_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     float yh[S], yw[S];
     mbar_wait(t_full, 0, 50);
     tc_fence_after();
+    ATT_TRACE(2);
     {
       int qh = qi / S;
       const int qw = qi % S;
@@ -195,10 +204,12 @@ attn_window_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     tc_fence_before();
     mbar_arrive(t_done);
+    ATT_TRACE(3);
 
     const float sl2 = p.scale_log2;
     mbar_wait(s_full, 0, 51);
     tc_fence_after();
+    ATT_TRACE(4);
     // pass A: row max over the 196 valid keys (S stays in TMEM)
     float m = -INFINITY;
 #pragma unroll
@@ -215,6 +226,7 @@ attn_window_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (key < G) m = fmaxf(m, fmaf(__uint_as_float(v[i]), sl2, yh[key / S] + yw[key % S]));
       }
     }
+    ATT_TRACE(5);
     // pass B: p = exp2(s - m) -> bf16 P tile (K-major SW128 blocks of 64 keys) over the dead Q|K buffers
     float l = 0.f;
     float ptail[4] = {0.f, 0.f, 0.f, 0.f};  // compact layout: probabilities of keys 192..195
@@ -246,12 +258,15 @@ attn_window_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         *reinterpret_cast<uint4*>(prow + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
       }
     }
+    ATT_TRACE(6);
     tc_fence_before();
     fence_proxy_async_smem();
     mbar_arrive(p_full);
+    ATT_TRACE(7);
 
     mbar_wait(o_full, 0, 52);
     tc_fence_after();
+    ATT_TRACE(8);
     const float inv = 1.0f / l;
     long out_row = -1;
     {
@@ -299,6 +314,7 @@ attn_window_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       __syncwarp();
     }
+    ATT_TRACE(9);
   }
   tc_fence_before();
   __syncthreads();
@@ -327,6 +343,7 @@ static int launch_attn_window(const AttnArgs& a, cudaStream_t stream) {
   if (make_tmap_bf16_2d(&tmRT, a.rel_table, 64, C::NB * 64, C::NB * 64, 64)) return -1;
   AttParams p;
   p.out = a.out; p.d_model = d_model; p.grid = a.grid; p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.trace = get_attn_trace();
   prof_begin(stream, D == 64 ? "attn_window<64>" : "attn_window<80>", (double)groups * a.heads * (4.0 * 196 * 196 * D + 4.0 * 196 * S * D),
              (double)groups * 196 * a.heads * D * 2 * 4);
   attn_window_kernel<D><<<dim3(2, a.heads, groups), ATT_THREADS, C::SMEM_BYTES, stream>>>(tmQ, tmKV, tmRT, p);
@@ -343,7 +360,10 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     return launch_attention_global(a, stream);
   } else if (a.window == 14) {
     if (a.head_dim == 64) return launch_attn_window<64>(a, stream);
-    if (a.head_dim == 80) return launch_attn_window<80>(a, stream);
+    if (a.head_dim == 80) {
+      static const bool v1 = getenv("MSAM_WIN_V1") != nullptr;   // first-generation kernel, kept for A/B timing
+      return v1 ? launch_attn_window<80>(a, stream) : launch_attn_window80(a, stream);
+    }
   }
   return set_error("attention: unsupported head_dim=%d window=%d", a.head_dim, a.window);
 }

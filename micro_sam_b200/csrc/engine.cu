@@ -239,6 +239,7 @@ int Engine::alloc_encoder_ws() {
 // ------------------------------------------------------------------------------------------------ encoder forward
 int Engine::encode(const uint8_t* u8, const float* f32, int B, int hh, int ww, float* out, cudaStream_t st, int stop_after,
                    float* x_out) {
+  if (is_tinyvit()) return encode_tinyvit(u8, f32, B, hh, ww, out, st, stop_after, x_out);
   if (!finalized) return set_error("msam_encode: weights not finalized");
   if (B <= 0) return set_error("msam_encode: empty batch");
   const int D = cfg.embed_dim, hd = D / cfg.num_heads, g = cfg.image_size / cfg.patch_size, T = g * g, C = cfg.out_chans;
@@ -389,9 +390,13 @@ int msam_create(const msam_config* cfg, int device, msam_handle** out) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   if (prop.major != 10) return set_error("msam_create: device %d is sm_%d%d; this library is sm_100a only", device, prop.major, prop.minor);
-  if (cfg->embed_dim % cfg->num_heads != 0) return set_error("embed_dim %% num_heads != 0");
-  const int hd = cfg->embed_dim / cfg->num_heads;
-  if (hd != 64 && hd != 80) return set_error("head_dim %d unsupported (64 or 80)", hd);
+  if (cfg->depth == 0) {   // MobileSAM TinyViT (vit_t): fixed architecture, see csrc/tinyvit.cu
+    if (cfg->embed_dim != 320 || cfg->num_heads != 10) return set_error("vit_t (depth 0) takes embed_dim 320 / num_heads 10");
+  } else {
+    if (cfg->num_heads <= 0 || cfg->embed_dim % cfg->num_heads != 0) return set_error("embed_dim %% num_heads != 0");
+    const int hd = cfg->embed_dim / cfg->num_heads;
+    if (hd != 64 && hd != 80) return set_error("head_dim %d unsupported (64 or 80)", hd);
+  }
   if (cfg->image_size != 1024 || cfg->patch_size != 16 || cfg->window_size != 14 || cfg->out_chans != 256)
     return set_error("only image_size 1024 / patch 16 / window 14 / out_chans 256 are supported");
   if (cfg->embed_dim % 32 != 0 || cfg->embed_dim > 1280) return set_error("embed_dim %d unsupported", cfg->embed_dim);
@@ -428,8 +433,13 @@ int msam_load_weight(msam_handle* h, const char* name, const float* host_data, c
 int msam_finalize_weights(msam_handle* h) {
   if (!h) return set_error("null handle");
   cudaSetDevice(h->eng.device);
-  if (h->eng.finalize_encoder()) return -1;
-  if (h->eng.alloc_encoder_ws()) return -1;
+  if (h->eng.is_tinyvit()) {
+    if (h->eng.finalize_tinyvit()) return -1;
+    if (h->eng.alloc_tinyvit_ws()) return -1;
+  } else {
+    if (h->eng.finalize_encoder()) return -1;
+    if (h->eng.alloc_encoder_ws()) return -1;
+  }
   if (h->eng.finalize_decoder()) return -1;
   h->eng.host_weights.clear();
   if (cudaDeviceSynchronize() != cudaSuccess) return set_error("finalize: %s", cudaGetErrorString(cudaGetLastError()));
@@ -625,6 +635,12 @@ int msam_op_attention(const void* qkv, const void* rel_table, void* out, int bat
   a.qkv = (const __nv_bfloat16*)qkv; a.rel_table = (const __nv_bfloat16*)rel_table; a.out = (__nv_bfloat16*)out;
   a.batch = batch; a.heads = heads; a.head_dim = head_dim; a.grid = 64; a.window = window; a.scale = scale;
   return launch_attention(a, (cudaStream_t)stream);
+}
+
+// debug hook (profiles/scripts/win_attn_probe.py): device buffer of 64 x 16 uint64 phase timestamps, or NULL to switch off
+int msam_debug_attn_trace(void* dev_buf) {
+  set_attn_trace((unsigned long long*)dev_buf);
+  return 0;
 }
 
 }  // extern "C"

@@ -40,6 +40,31 @@ struct EncoderWorkspace {
   __nv_bfloat16 *neck1b = nullptr, *neck_col = nullptr;
 };
 
+// ---- TinyViT (vit_t) encoder, tinyvit.cu
+struct TvConv {                       // Conv2d_BN with the BatchNorm folded in
+  __nv_bfloat16* w = nullptr;         // dense / 1x1: GEMM operand [out, in * k * k]
+  float* wf = nullptr;                // depth-wise 3x3: [9][C]; stem conv 1: [27][32]
+  float* b = nullptr;
+};
+struct TvMBConv { TvConv conv1, conv2, conv3; };
+struct TvMerge { TvConv conv1, conv2, conv3; };
+struct TvBlock {
+  float *an_g = nullptr, *an_b = nullptr, *mn_g = nullptr, *mn_b = nullptr, *bias_tab = nullptr;
+  __nv_bfloat16 *qkv_w = nullptr, *proj_w = nullptr, *fc1_w = nullptr, *fc2_w = nullptr;
+  float *qkv_b = nullptr, *proj_b = nullptr, *fc1_b = nullptr, *fc2_b = nullptr;
+  TvConv local;
+};
+struct TvStage { int dim = 0, heads = 0, ws = 0; std::vector<TvBlock> blocks; };
+struct TinyVit {
+  TvConv stem1, stem2;
+  TvMBConv mb[2];
+  TvMerge merge[3];
+  TvStage stage[4];                   // [1..3] used
+  __nv_bfloat16 *s1 = nullptr, *col = nullptr, *a0 = nullptr, *a1 = nullptr, *h1 = nullptr, *h2 = nullptr, *xw = nullptr,
+                *qkv = nullptr, *attn = nullptr, *xn = nullptr;
+  float *x = nullptr, *x2 = nullptr;
+};
+
 struct DecoderState;  // decoder.cu
 
 struct Engine {
@@ -50,6 +75,8 @@ struct Engine {
   std::vector<void*> allocs;
   EncoderWeights enc;
   EncoderWorkspace ws;
+  TinyVit tv;
+  bool is_tinyvit() const { return cfg.depth == 0; }
   DecoderState* dec = nullptr;
 
   void* dalloc(size_t bytes, bool zero = false);
@@ -63,6 +90,10 @@ struct Engine {
   int finalize_encoder();
   int alloc_encoder_ws();
   int finalize_decoder();  // decoder.cu
+  int finalize_tinyvit();   // tinyvit.cu
+  int alloc_tinyvit_ws();
+  int encode_tinyvit(const uint8_t* u8, const float* f32, int B, int hh, int ww, float* out, cudaStream_t st, int stop_after = -1,
+                     float* x_out = nullptr);
   int encode(const uint8_t* u8, const float* f32, int B, int hh, int ww, float* out, cudaStream_t st, int stop_after = -1,
              float* x_out = nullptr);
   int set_image_embedding(const float* feat, cudaStream_t st);  // decoder.cu

@@ -52,6 +52,7 @@ struct GemmParams {
   int res_tma;            // fp32 residual fetched by TMA into the staging tile (fp32 output, res_rows % 128 == 0)
   int out_fp32;
   int act;                // 0 none, 1 GELU(erf), 2 ReLU
+  int act_after_res;      // apply act after the residual add
   const float* ln_gamma;  // fused LayerNorm epilogues
   const float* ln_beta;
   float ln_eps;
@@ -328,7 +329,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
               }
             }
-            if (p.act == 1 && !p.out_fp32) {  // bf16 output: the fast erf is exact to well below the output rounding
+            if (p.act_after_res) {
+              // activation applied below, after the residual
+            } else if (p.act == 1 && !p.out_fp32) {  // bf16 output: the fast erf is exact to well below the output rounding
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
             } else if (p.act) {
@@ -349,6 +352,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int q = 0; q < 8; ++q) f[j + q] += r8[q];
               }
+            }
+            if (p.act_after_res && p.act) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
             }
           }
           if (p.out_fp32) {  // 32 fp32 columns fill the 128-B staging row: one store per chunk
@@ -465,7 +472,7 @@ static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   if (make_tmap_2d(&tmC, a.out, a.out_fp32 ? 4 : 2, a.M, a.N, ldc, GEMM_BM)) return -1;
   GemmParams p;
   const int res_rows = a.res_rows > 0 ? a.res_rows : a.M, ldr = a.ldr > 0 ? a.ldr : a.N;
-  p.res_tma = (EPI == EPI_PLAIN && a.residual && !a.res_bf16 && a.out_fp32 && res_rows % GEMM_BM == 0 && ldr % 4 == 0) ? 1 : 0;
+  p.res_tma = (EPI == EPI_PLAIN && a.residual && !a.res_bf16 && a.out_fp32 && res_rows % GEMM_BM == 0 && ldr % 4 == 0 && !a.act_after_res) ? 1 : 0;
   if (p.res_tma) {
     if (make_tmap_2d(&tmR, a.residual, 4, res_rows, a.N, ldr, GEMM_BM)) return -1;
   } else {
@@ -479,6 +486,7 @@ static int launch_gemm_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   p.ldr = a.ldr > 0 ? a.ldr : a.N;
   p.out_fp32 = a.out_fp32;
   p.act = a.act;
+  p.act_after_res = a.act_after_res;
   p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;
   const int tiles = ((a.M + GEMM_BM - 1) / GEMM_BM) * ((a.N + BN - 1) / BN);
   const int max_ctas = num_sms * Cfg::MIN_CTAS;

@@ -279,7 +279,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 int launch_gemm_2sm(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   using namespace g2;
   const int res_rows = a.res_rows > 0 ? a.res_rows : a.M, ldr = a.ldr > 0 ? a.ldr : a.N;
-  if (a.epi != 0 || a.N % BN != 0 || a.K % BK != 0 || a.K < 512 || a.M < 4096) return 0;
+  if (a.epi != 0 || a.act_after_res || a.N % BN != 0 || a.K % BK != 0 || a.K < 512 || a.M < 4096) return 0;
   if (a.residual && (a.res_bf16 || !a.out_fp32 || res_rows % BM != 0 || ldr % 4 != 0)) return 0;
   static bool attr_set = false;
   if (!attr_set) {

@@ -26,6 +26,7 @@ struct GemmArgs {
   int ldc = 0;
   int out_fp32 = 0;
   int act = 0;  // 0 none, 1 GELU(erf), 2 ReLU
+  int act_after_res = 0;  // apply `act` after the residual add (MBConv: act3(conv3(x) + shortcut)); bf16 / strided-residual path only
   // fused row epilogue (gemm.cu): 0 plain, 1 LayerNorm over N=256
   int epi = 0;
   const float* ln_gamma = nullptr;
@@ -109,6 +110,10 @@ struct AttnArgs {
 };
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
 int launch_attention_global(const AttnArgs& a, cudaStream_t stream);  // attention_global.cu (window == 0)
+int launch_attn_window80(const AttnArgs& a, cudaStream_t stream);     // attention_w80.cu (window 14, head_dim 80)
+// debug: per-CTA phase timestamps (%globaltimer, 16 slots x 64 windows) of the window-attention kernels; nullptr = off
+void set_attn_trace(unsigned long long* dev_buf);
+unsigned long long* get_attn_trace();
 
 // ---- elementwise.cu
 int launch_patchify(const uint8_t* u8, const float* f32, int B, int h, int w, int img, const float* mean,

@@ -21,6 +21,8 @@ ARCH = {
     "vit_b": dict(embed_dim=768, depth=12, num_heads=12, global_attn_indexes=(2, 5, 8, 11)),
     "vit_l": dict(embed_dim=1024, depth=24, num_heads=16, global_attn_indexes=(5, 11, 17, 23)),
     "vit_h": dict(embed_dim=1280, depth=32, num_heads=16, global_attn_indexes=(7, 15, 23, 31)),
+    # MobileSAM (micro_sam/util.py:35-43,436-441): TinyViT encoder, fixed architecture (csrc/tinyvit.cu); depth 0 selects it
+    "vit_t": dict(embed_dim=320, depth=0, num_heads=10, global_attn_indexes=()),
     # tiny shapes for tests only
     "vit_test": dict(embed_dim=128, depth=2, num_heads=2, global_attn_indexes=(1,)),
     "vit_test80": dict(embed_dim=160, depth=2, num_heads=2, global_attn_indexes=(1,)),

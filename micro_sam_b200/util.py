@@ -92,8 +92,8 @@ def get_sam_model(model_type: str = "vit_b", device: Optional[Union[str, torch.d
     detected = validate_model_type(state_dict)
     if detected in ARCH and detected != abbrev and abbrev in ("vit_b", "vit_l", "vit_h"):
         raise RuntimeError(f"model_type {model_type!r} does not match the checkpoint ({detected!r})")
-    if detected == "vit_t":
-        raise NotImplementedError("vit_t (MobileSAM / TinyViT) has no B200 kernels yet (SURVEY.md 8f-4)")
+    if detected == "vit_t" and abbrev in ("vit_b", "vit_l", "vit_h"):
+        raise RuntimeError(f"model_type {model_type!r} does not match the checkpoint (MobileSAM 'vit_t')")
     sam = B200Sam(detected, state_dict, device=device, max_batch=max_batch, max_prompts=max_prompts)
     predictor = B200SamPredictor(sam)
     predictor.model_type = model_type

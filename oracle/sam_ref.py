@@ -589,14 +589,19 @@ class SamPredictor:
 
 # ------------------------------------ builders -----------------------------------------------
 def build_sam(model_type: str = "vit_b", image_size: int = 1024, num_multimask_outputs: int = 3) -> Sam:
-    a = ARCH[model_type]
     prompt_embed_dim, patch = 256, 16
     g = image_size // patch
+    if model_type == "vit_t":   # MobileSAM: TinyViT encoder, segment_anything's prompt encoder / mask decoder (util.py:436-441)
+        from .tinyvit_ref import TinyViT
+        encoder = TinyViT(img_size=image_size)
+    else:
+        a = ARCH[model_type]
+        encoder = ImageEncoderViT(img_size=image_size, patch_size=patch, embed_dim=a["embed_dim"],
+                                  depth=a["depth"], num_heads=a["num_heads"], mlp_ratio=4,
+                                  out_chans=prompt_embed_dim, window_size=14,
+                                  global_attn_indexes=a["global_attn_indexes"])
     sam = Sam(
-        image_encoder=ImageEncoderViT(img_size=image_size, patch_size=patch, embed_dim=a["embed_dim"],
-                                      depth=a["depth"], num_heads=a["num_heads"], mlp_ratio=4,
-                                      out_chans=prompt_embed_dim, window_size=14,
-                                      global_attn_indexes=a["global_attn_indexes"]),
+        image_encoder=encoder,
         prompt_encoder=PromptEncoder(prompt_embed_dim, (g, g), (image_size, image_size), 16),
         mask_decoder=MaskDecoder(prompt_embed_dim,
                                  TwoWayTransformer(depth=2, embedding_dim=prompt_embed_dim, mlp_dim=2048,
@@ -615,12 +620,21 @@ def seeded_state_dict(model_type: str = "vit_b", seed: int = 0, image_size: int 
     logits to ~0 which would make mask parity vacuous)."""
     sam = build_sam(model_type, image_size)
     g = torch.Generator().manual_seed(seed)
-    ln_mods = {n for n, m in sam.named_modules() if isinstance(m, (nn.LayerNorm, LayerNorm2d))}
+    ln_mods = {n for n, m in sam.named_modules()
+               if isinstance(m, (nn.LayerNorm, nn.BatchNorm2d)) or type(m).__name__ == "LayerNorm2d"}
     sd = {}
     for k, v in sam.state_dict().items():
         mod, leaf = k.rsplit(".", 1) if "." in k else ("", k)
         if k.endswith("positional_encoding_gaussian_matrix"):
             sd[k] = torch.randn(v.shape, generator=g)
+        elif leaf == "num_batches_tracked":
+            sd[k] = torch.zeros((), dtype=torch.long)
+        elif leaf == "running_mean":      # BatchNorm statistics (vit_t): non-trivial so the folding is exercised
+            sd[k] = 0.1 * torch.randn(v.shape, generator=g)
+        elif leaf == "running_var":
+            sd[k] = 0.5 + torch.rand(v.shape, generator=g)
+        elif leaf == "attention_biases":
+            sd[k] = 0.5 * torch.randn(v.shape, generator=g)
         elif mod in ln_mods:
             sd[k] = (1.0 if leaf == "weight" else 0.0) + 0.1 * torch.randn(v.shape, generator=g)
         elif v.ndim == 1:  # biases

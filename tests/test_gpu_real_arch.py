@@ -193,3 +193,63 @@ def test_vit_b_full_amg_tile_against_oracle():
     # the full 3072-mask state: deterministic and consistent with the subset statistics
     full = amg.generate(pred_iou_thresh=q_iou, stability_score_thresh=q_stab)
     assert np.array_equal(full, amg.generate(pred_iou_thresh=q_iou, stability_score_thresh=q_stab))
+
+
+def test_vit_t_encoder_against_oracle():
+    """MobileSAM's TinyViT (BASELINE.json configs[0]): stage-by-stage token streams and the final embedding against
+    oracle/tinyvit_ref.py (parity unpinned: no second TinyViT source in this image), then the cfg-1 flow -- one 512 x 512 tile
+    through precompute_image_embeddings -- and one box-prompt decode on that embedding against the oracle predictor."""
+    from oracle import sam_ref
+    from micro_sam_b200 import _lib, util
+    from micro_sam_b200.sample_data import lm_tile
+    torch.set_num_threads(min(64, os.cpu_count() or 8))
+    sd = sam_ref.seeded_state_dict("vit_t", seed=0)
+    osam = sam_ref.build_sam("vit_t")
+    osam.load_state_dict(sd)
+    pred = util.get_sam_model("vit_t", state_dict=sd, max_batch=2, max_prompts=64)
+    sam = pred.model
+    img = util._to_image(lm_tile((1024, 1024), 150, seed=0))
+    u8 = torch.from_numpy(np.stack([img, img[::-1].copy()])).cuda()
+    x_pre = osam.preprocess(torch.from_numpy(img).permute(2, 0, 1)[None].float())
+    enc = osam.image_encoder
+    stage_out = []
+    with torch.no_grad():
+        x = enc.patch_embed(x_pre)
+        for layer in enc.layers:
+            x = layer(x)
+            stage_out.append(x[0].clone())
+        feat = enc.neck(x.view(1, 64, 64, -1).permute(0, 3, 1, 2))
+    assert feat.std() > 0.3, f"degenerate oracle embedding (std {feat.std():.3g})"
+    per_stage = []
+    for n, ref in enumerate(stage_out, start=1):
+        got = torch.empty(2 * ref.shape[0], ref.shape[1], device="cuda")
+        _lib.check(_lib.lib().msam_encode_u8_blocks(sam._h, _lib.ptr(u8), 2, 1024, 1024, n, _lib.ptr(got), _lib.cur_stream()))
+        per_stage.append(_rel(got[: ref.shape[0]].cpu(), ref))
+    got = sam.encode_u8(u8)
+    rel = _rel(got[0:1].cpu(), feat)
+    print(f"vit_t: encoder rel-L2 {rel:.3e} (oracle std {feat.std():.3f}); token stream after stages 0..3: "
+          + ", ".join(f"{v:.2e}" for v in per_stage))
+    for v in per_stage:
+        assert v < 2e-2, per_stage
+    assert rel < 2e-2, rel
+    alone = sam.encode_u8(u8[1:2])
+    assert _rel(got[1:2].cpu(), feat) > 0.05 and _rel(got[1:2].cpu(), alone.cpu()) < 1e-5
+    # fp32 NCHW entry point (what image_encoder(...) receives)
+    got_f = sam.image_encoder(x_pre.cuda())
+    assert _rel(got_f.cpu(), feat) < 2e-2
+
+    # cfg 1: vit_t precompute_image_embeddings on one 512 x 512 tile, then a decode on it
+    tile = lm_tile((512, 512), 40, seed=0)
+    emb = util.precompute_image_embeddings(pred, tile, ndim=2)
+    opred = sam_ref.SamPredictor(osam)
+    opred.set_image(util._to_image(tile))
+    rel1 = _rel(torch.from_numpy(np.asarray(emb["features"])), opred.features)
+    assert emb["features"].shape == (1, 256, 64, 64) and tuple(emb["input_size"]) == (1024, 1024) and tuple(emb["original_size"]) == (512, 512)
+    assert rel1 < 2e-2, rel1
+    util.set_precomputed(pred, emb)
+    boxes = torch.tensor([[100.0, 120.0, 300.0, 360.0], [500.0, 40.0, 900.0, 420.0]])
+    masks, iou, low = pred.predict_torch(None, None, boxes=boxes.cuda(), multimask_output=True, return_logits=True)
+    with torch.no_grad():
+        omasks, oiou, olow = opred.predict_torch(None, None, boxes=boxes, multimask_output=True, return_logits=True)
+    print(f"vit_t cfg1: embedding rel-L2 {rel1:.3e}; decoder iou err {(iou.cpu() - oiou).abs().max():.2e}, low-res rel-L2 {_rel(low.cpu(), olow):.2e}")
+    assert (iou.cpu() - oiou).abs().max() < 2e-2 and _rel(low.cpu(), olow) < 3e-2
