@@ -1,5 +1,10 @@
-"""bench.py --config cfg3 | cfg4: the other GPU configurations of BASELINE.json, as extra JSON lines with bench.py's contract
+"""bench.py --config cfg1 | cfg3 | cfg4: the other configurations of BASELINE.json, as extra JSON lines with bench.py's contract
 (one rank per GPU under torchrun, barrier + CUDA events + max over ranks, `--impl reference` = the oracle port on host cores).
+
+cfg1  vit_t (MobileSAM / TinyViT) precompute_image_embeddings on 512 x 512 float32 LM tiles (the reference's CPU-runnable
+      case): a step = 16 tiles, one call per tile as the reference does it (util.py:902 _compute_2d).  `value` = device-resident
+      (resized uint8 tiles in HBM, batch of 16 through the encoder), `e2e` = host float32 tile -> host embedding through
+      precompute_image_embeddings (normalise + PIL resize 512 -> 1024 + H2D + encoder + D2H per tile).
 
 cfg3  vit_l tiled 3-D embedding precompute: uint8 EM volume 64 x 2048 x 2048, tile_shape (1024, 1024), halo (128, 128)
       -> 4 outer tiles of 1152^2 per plane, 256 encoder tiles, written to a zarr container (1 GiB of embeddings).
@@ -28,7 +33,15 @@ CFG3 = dict(shape=(64, 2048, 2048), tile_shape=(1024, 1024), halo=(128, 128), ba
 CFG4 = dict(n_tiles=128, n_boxes=256, tile=1024, enc_batch=8)
 
 
+CFG1 = dict(n_tiles=16, tile=512)
+
+
 def _config(args):
+    if args.config == "cfg1":
+        return {"workload": f"{args.model} (MobileSAM TinyViT) precompute_image_embeddings, 16 synthetic 512x512 float32 LM tiles, one call "
+                            "per tile (BASELINE.json configs[0]); seeded random-init weights",
+                "tiles_per_step_per_gpu": CFG1["n_tiles"], "l2": "flushed between steps (256 MB buffer write)",
+                "parallelism": "tile shards, one process per GPU, no collective (reference arm: host threads of rank 0)"}
     if args.config == "cfg3":
         return {"workload": f"{args.model} tiled 3d embedding precompute, 64x2048x2048 uint8 EM-like volume, tile_shape=(1024,1024) "
                             "halo=(128,128) -> 256 tiles of 1152^2, zarr container (BASELINE.json configs[2]); seeded random-init weights",
@@ -145,6 +158,63 @@ def run_cfg3(args):
         dist.destroy_process_group()
 
 
+def run_cfg1(args):
+    from bench import ClockSampler, peaks
+    from oracle import sam_ref
+    from micro_sam_b200 import _lib, util
+    from micro_sam_b200.sam import ResizeLongestSide
+    from micro_sam_b200.sample_data import lm_tile
+    dist, world, rank, local, device = _dist()
+    pk, _ = peaks()
+    sd = {k: v for k, v in sam_ref.seeded_state_dict(args.model, seed=0).items() if k.startswith("image_encoder.")}
+    pred = util.get_sam_model(args.model, device=device, state_dict=sd, max_batch=CFG1["n_tiles"], max_prompts=1)
+    n = CFG1["n_tiles"]
+    tiles = [lm_tile((CFG1["tile"],) * 2, 40, seed=rank * n + t).astype(np.float32) for t in range(n)]
+    rs = ResizeLongestSide(1024)
+    tiles_u8 = torch.from_numpy(np.stack([rs.apply_image(util._to_image(t)) for t in tiles])).to(device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def step_device():
+        flush.fill_(1)
+        return pred.model.encode_u8(tiles_u8)
+
+    def step_e2e():
+        flush.fill_(1)
+        return [util.precompute_image_embeddings(pred, t, ndim=2)["features"] for t in tiles]
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = _lib.launch_count()
+    ms = _timed(dist, world, device, step_device, args.steps, args.warmup)
+    launches = (_lib.launch_count() - l0) / (args.steps + args.warmup)
+    ms_e2e = _timed(dist, world, device, step_e2e, args.steps, 1)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        L = _lib.lib()
+        L.msam_profile(1)
+        pred.model.encode_u8(tiles_u8)
+        rep = sorted(_lib.profile_report(), key=lambda r: -r["ms"])
+        L.msam_profile(0)
+        dom = rep[0]
+        tf, gbs = dom["flops"] / (dom["ms"] * 1e-3) / 1e12, dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
+        bound = "tensor" if tf / pk["bf16_tflops_sustained"] >= gbs / pk["hbm_gbs"] else "hbm"
+        feats = step_e2e()
+        out = {"metric": "512x512 tiles/s, vit_t precompute_image_embeddings", "value": n * world * args.steps / (ms / 1e3), "unit": "tiles/s",
+               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": _config(args),
+               "e2e": {"value": n * world * args.steps / (ms_e2e / 1e3), "unit": "tiles/s", "ms_per_step": ms_e2e / args.steps,
+                       "h2d_bytes_per_step": n * 1024 * 1024 * 3, "d2h_bytes_per_step": n * 256 * 64 * 64 * 4},
+               "gpu_launches": launches, "clocks": clocks, "embedding_shape": list(np.asarray(feats[-1]).shape),
+               "roofline": {"bound": bound, "kernel": dom["name"], "achieved": tf if bound == "tensor" else gbs,
+                            "peak": pk["bf16_tflops_sustained"] if bound == "tensor" else pk["hbm_gbs"],
+                            "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                            "frac": tf / pk["bf16_tflops_sustained"] if bound == "tensor" else gbs / pk["hbm_gbs"], "traffic": None,
+                            "share_of_step": dom["ms"] / (ms / args.steps),
+                            "kernels_ms_per_tile": {r["name"]: round(r["ms"] / n, 4) for r in rep}}}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def _cfg4_inputs(rank, world):
     from micro_sam_b200.sample_data import lm_tile, random_boxes
     lo, hi = (CFG4["n_tiles"] * rank) // world, (CFG4["n_tiles"] * (rank + 1)) // world
@@ -220,8 +290,9 @@ def run_cfg4(args):
 
 
 def run_reference(args):
-    """The oracle port on the host cores, bounded sample: cfg3 = one 1152^2 tile (normalise + resize + vit_l encoder);
-    cfg4 = one tile (vit_h encoder) + 32 of its 256 boxes through batched_inference (decoder part scaled x8)."""
+    """The oracle port on the host cores, bounded sample: cfg1 = 4 of the 16 tiles (normalise + resize + TinyViT encoder each);
+    cfg3 = one 1152^2 tile (normalise + resize + vit_l encoder); cfg4 = one tile (vit_h encoder) + 32 of its 256 boxes through
+    batched_inference (decoder part scaled x8)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     from bench import best_cpu_threads
@@ -232,7 +303,15 @@ def run_reference(args):
     pred = sam_ref.SamPredictor(sam)
     vals, t_all = [], time.perf_counter()
     for it in range(args.steps + (1 if args.warmup > 0 else 0)):
-        if args.config == "cfg3":
+        if args.config == "cfg1":
+            from micro_sam_b200.sample_data import lm_tile
+            tiles = [lm_tile((CFG1["tile"],) * 2, 40, seed=t).astype(np.float32) for t in range(4)]
+            t0 = time.perf_counter()
+            for t in tiles:
+                amg_ref.precompute_image_embeddings_2d(pred, t)
+            per_tile = (time.perf_counter() - t0) / len(tiles)
+            sample = f"4 of 16 tiles (512^2 -> 1024^2, {args.model} encoder) {per_tile:.2f}s each"
+        elif args.config == "cfg3":
             from scipy import ndimage
             v = ndimage.gaussian_filter(np.random.default_rng(0).standard_normal((1152, 1152)).astype(np.float32), 3)
             tile = ((v - v.min()) / (v.max() - v.min() + 1e-7) * 255).astype(np.uint8)
@@ -255,7 +334,7 @@ def run_reference(args):
             vals.append(1.0 / per_tile)
     v = float(np.mean(vals))
     cb = {"value": v, "unit": "tiles/s", "cores": threads, "kind": "port", "sample": sample}
-    print(json.dumps({"impl": "reference", "metric": "1024x1024 tiles/s", "value": v, "unit": "tiles/s", "n_gpus": args.gpus,
+    print(json.dumps({"impl": "reference", "metric": "512x512 tiles/s" if args.config == "cfg1" else "1024x1024 tiles/s", "value": v, "unit": "tiles/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (time.perf_counter() - t_all) / max(args.steps, 1),
                       "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": _config(args), "cpu_baseline": cb,
@@ -267,4 +346,4 @@ def main(args):
         return run_reference(args)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback; use --impl reference)")
-    return run_cfg3(args) if args.config == "cfg3" else run_cfg4(args)
+    return {"cfg1": run_cfg1, "cfg3": run_cfg3, "cfg4": run_cfg4}[args.config](args)

@@ -359,10 +359,10 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   if (a.window == 0) {
     return launch_attention_global(a, stream);
   } else if (a.window == 14) {
-    if (a.head_dim == 64) return launch_attn_window<64>(a, stream);
-    if (a.head_dim == 80) {
-      static const bool v1 = getenv("MSAM_WIN_V1") != nullptr;   // first-generation kernel, kept for A/B timing
-      return v1 ? launch_attn_window<80>(a, stream) : launch_attn_window80(a, stream);
+    if (a.head_dim == 64 || a.head_dim == 80) {
+      static const bool v1 = getenv("MSAM_WIN_V1") != nullptr;   // first-generation kernel (below), kept for A/B timing
+      if (!v1) return launch_attn_window2(a, stream);
+      return a.head_dim == 64 ? launch_attn_window<64>(a, stream) : launch_attn_window<80>(a, stream);
     }
   }
   return set_error("attention: unsupported head_dim=%d window=%d", a.head_dim, a.window);

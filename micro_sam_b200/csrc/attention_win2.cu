@@ -1,4 +1,4 @@
-// Windowed ViT-H attention (head_dim 80, 14x14 windows, 196 keys incl. the zero-pad tokens), second generation.
+// Windowed ViT attention (head_dim 64 / 80, 14x14 windows, 196 keys incl. the zero-pad tokens), second generation.
 // Restates segment_anything's Attention.forward + add_decomposed_rel_pos (oracle/sam_ref.py:Attention) like attention.cu,
 // but moves everything except max / exp off the CUDA cores (profiles/r1_ncu_attn_window_d80.txt: the first kernel spends
 // ~10 instructions per logit and holds 28 bias values per thread; 168 registers, 30 % issue slots, 12.7 us per CTA):
@@ -13,8 +13,11 @@
 //     (box 1, columns 32..47), instead of 320 CUDA-core FMAs per row in the epilogue;
 //   * row max with 3-input max (0.5 instructions / logit), exp pass = fma + ex2 + half a pack;
 //   * TMEM loads double buffered (the next 32 columns are in flight while the current ones are processed).
-// Layout (compact, as attention.cu's D = 80 path): [Q 2 x 16 KB | R 2 x 8 KB | K 2 x 26 KB]; P (keys 0..191, 3 boxes)
-// goes over Q | R once S is complete, V is loaded over K; keys 192..195 are added on the CUDA cores in the epilogue.
+// Layout: [box A0 16 KB | box A1 16 KB | R 16 KB | box B0 26 KB | box B1 26 KB]; P (keys 0..191, 3 boxes) goes over A0 | A1 | R
+// once S is complete, V is loaded over K (B0 / B1).  head_dim 80: A0 | A1 = Q (80 of 128 columns), the bias columns sit in A1
+// columns 16..47, the one-hot columns in B1 (= K box 1) columns 16..47, the ones column in V box 1 column 16.  head_dim 64:
+// A0 = Q, A1 = the bias tile (columns 0..31), B0 = K / V, B1 = the one-hot tile (columns 0..31; column 0 becomes the ones
+// column once S is complete): the same byte offsets, only the column offset inside box 1 differs.
 // Warp roles: warps 0-3 softmax / epilogue (thread r <-> query row r <-> TMEM lane r), warp 4 TMA, warp 5 TMEM + MMA.
 #include "kernels.h"
 #include "ptx.cuh"
@@ -25,7 +28,6 @@ namespace msam {
 namespace {
 
 constexpr int W8_THREADS = 192;
-constexpr int W8_D = 80;
 constexpr int W8_QBOX = 128 * 128;   // 128 rows x 64 bf16
 constexpr int W8_NK = 208;           // keys padded to a multiple of 16
 constexpr int W8_KBOX = W8_NK * 128;
@@ -83,10 +85,15 @@ __device__ __forceinline__ void lane_shift14(float (&x)[32], int sh) {
 
 #define W8_TRACE(slot) do { if (tr) tr[slot] = gtimer(); } while (0)
 
+template <int D>
 __global__ void __launch_bounds__(W8_THREADS, 2)
-attn_window80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+attn_window2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                      const __grid_constant__ CUtensorMap tmRT, const W8Params p) {
-  constexpr int S = 14, G = 196, D = W8_D;
+  constexpr int S = 14, G = 196;
+  constexpr int NB = (D + 63) / 64;          // TMA boxes per operand
+  constexpr int KS = D / 16;                 // k-steps of Q K^T
+  constexpr int AUGC = (D == 80) ? 2 : 0;    // first 16-byte chunk of the bias / one-hot columns inside box 1
+  constexpr int NO = D + 16;                 // P V columns: values + the ones column (+ 15 unused)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -127,21 +134,21 @@ attn_window80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp == 4) {
     if (lane == 0) {
       const int qcol = head * D, kcol = p.d_model + head * D, vcol = 2 * p.d_model + head * D;
-      mbar_expect_tx(q_full, 2 * W8_QBOX + 2 * W8_RTBOX);   // T = Q R^T can start before K has landed
-      for (int b = 0; b < 2; ++b) {
+      mbar_expect_tx(q_full, NB * (W8_QBOX + W8_RTBOX));   // T = Q R^T can start before K has landed
+      for (int b = 0; b < NB; ++b) {
         tma_load_2d(sQ + b * W8_QBOX, &tmQ, q_full, qcol + b * 64, row0 + qt * 128);
         tma_load_2d(sRT + b * W8_RTBOX, &tmRT, q_full, b * 64, 0);
       }
-      mbar_expect_tx(ld_full, 2 * W8_KBOX);
-      for (int b = 0; b < 2; ++b) tma_load_2d(sK + b * W8_KBOX, &tmKV, ld_full, kcol + b * 64, row0);
+      mbar_expect_tx(ld_full, NB * W8_KBOX);
+      for (int b = 0; b < NB; ++b) tma_load_2d(sK + b * W8_KBOX, &tmKV, ld_full, kcol + b * 64, row0);
       mbar_wait(s_full, 0, 44);  // S has been computed: V goes over the dead K tile
-      mbar_expect_tx(v_full, 2 * W8_KBOX);
-      for (int b = 0; b < 2; ++b) tma_load_2d(sK + b * W8_KBOX, &tmKV, v_full, vcol + b * 64, row0);
+      mbar_expect_tx(v_full, NB * W8_KBOX);
+      for (int b = 0; b < NB; ++b) tma_load_2d(sK + b * W8_KBOX, &tmKV, v_full, vcol + b * 64, row0);
     }
   } else if (warp == 5) {
     constexpr uint32_t idescT = make_idesc_bf16(128, 64);
     constexpr uint32_t idescS = make_idesc_bf16(128, W8_NK);
-    constexpr uint32_t idescO = make_idesc_bf16(128, 96, 1);   // 80 value columns + the ones column (+ 15 unused)
+    constexpr uint32_t idescO = make_idesc_bf16(128, NO, 1);   // D value columns + the ones column (+ 15 unused)
     const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aRT = smem_u32(sRT);
     auto kdesc = [](uint32_t base, uint32_t box_bytes, int ks) {
       return make_desc_sw128(base + (uint32_t)(ks >> 2) * box_bytes + (uint32_t)(ks & 3) * 32u, 0, 1024);
@@ -150,7 +157,7 @@ attn_window80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tc_fence_after();
     if (elect_one()) {
 #pragma unroll
-      for (int ks = 0; ks < 5; ++ks) umma_bf16(tmem, kdesc(aQ, W8_QBOX, ks), kdesc(aRT, W8_RTBOX, ks), idescT, ks > 0);
+      for (int ks = 0; ks < KS; ++ks) umma_bf16(tmem, kdesc(aQ, W8_QBOX, ks), kdesc(aRT, W8_RTBOX, ks), idescT, ks > 0);
       umma_commit(t_full);
     }
     __syncwarp();
@@ -159,10 +166,13 @@ attn_window80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tc_fence_after();
     if (elect_one()) {
 #pragma unroll
-      for (int ks = 0; ks < 7; ++ks) umma_bf16(tmem, kdesc(aQ, W8_QBOX, ks), kdesc(aK, W8_KBOX, ks), idescS, ks > 0);
+      for (int ks = 0; ks < KS; ++ks) umma_bf16(tmem, kdesc(aQ, W8_QBOX, ks), kdesc(aK, W8_KBOX, ks), idescS, ks > 0);
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks)   // rounding residuals of the bias against the same one-hot columns
-        umma_bf16(tmem, make_desc_sw128(aRT + (uint32_t)ks * 32u, 0, 1024), kdesc(aK, W8_KBOX, 5 + ks), idescS, 1);
+      for (int ks = 0; ks < 2; ++ks) {   // bias (hi, then its rounding residuals) against the one-hot columns of box 1
+        const uint64_t de = make_desc_sw128(aK + W8_KBOX + (uint32_t)(AUGC * 16 + ks * 32), 0, 1024);
+        umma_bf16(tmem, make_desc_sw128(aQ + W8_QBOX + (uint32_t)(AUGC * 16 + ks * 32), 0, 1024), de, idescS, 1);
+        umma_bf16(tmem, make_desc_sw128(aRT + (uint32_t)ks * 32u, 0, 1024), de, idescS, 1);
+      }
       umma_commit(s_full);
     }
     __syncwarp();
@@ -174,7 +184,7 @@ attn_window80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int ks = 0; ks < 12; ++ks) {
         const uint64_t da = make_desc_sw128(aQ + (uint32_t)(ks >> 2) * W8_QBOX + (uint32_t)(ks & 3) * 32u, 0, 1024);
         const uint64_t db = make_desc_sw128(aK + (uint32_t)ks * 2048u, W8_KBOX, 1024);
-        umma_bf16(tmem, da, db, idescO, ks > 0);   // O over the dead S columns [0, 96)
+        umma_bf16(tmem, da, db, idescO, ks > 0);   // O over the dead S columns [0, NO)
       }
       // keys 192..207: A = the tail probabilities parked in V box 1 columns 32..47, B = V rows 192..207
       umma_bf16(tmem, make_desc_sw128(aK + W8_KBOX + 64u, 0, 1024), make_desc_sw128(aK + 12u * 2048u, W8_KBOX, 1024), idescO, 1);
@@ -221,11 +231,13 @@ attn_window80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t lrow = smem_u32(sRT) + (uint32_t)r * 128u;         // lo: its own tile over the dead R table, columns 0..31
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        st_shared_v4(qrow + ((uint32_t)((c + 2) ^ (r & 7)) << 4), make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+        st_shared_v4(qrow + ((uint32_t)((c + AUGC) ^ (r & 7)) << 4), make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
         st_shared_v4(lrow + ((uint32_t)(c ^ (r & 7)) << 4), make_uint4(wl[4 * c], wl[4 * c + 1], wl[4 * c + 2], wl[4 * c + 3]));
       }
     }
-    // one-hot key columns: rows r and r + 128 of the K tile (box 1, columns 16..47)
+    // one-hot key columns: rows r and r + 128 of box B1.  head_dim 80: B1 is K box 1 -- wait until the K tile has landed (its
+    // TMA box covers these columns with the next head's data); head_dim 64: B1 is a tile of its own
+    if constexpr (D == 80) mbar_wait(ld_full, 0, 54);
     for (int k = r; k < W8_NK; k += 128) {
       unsigned long long bits = 0ull;
       if (k < G) {
@@ -241,7 +253,7 @@ attn_window80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const int col = 2 * (4 * c + j);
           e[j] = (((bits >> col) & 1ull) ? 0x3F80u : 0u) | (((bits >> (col + 1)) & 1ull) ? 0x3F800000u : 0u);
         }
-        st_shared_v4(krow + ((uint32_t)((c + 2) ^ (k & 7)) << 4), make_uint4(e[0], e[1], e[2], e[3]));
+        st_shared_v4(krow + ((uint32_t)((c + AUGC) ^ (k & 7)) << 4), make_uint4(e[0], e[1], e[2], e[3]));
       }
     }
     fence_proxy_async_smem();
@@ -301,7 +313,7 @@ attn_window80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // beyond 195) into box 1 columns 32..47 = the K-major A tile of the 13th k-step
     mbar_wait(v_full, 0, 53);
     for (int k = r; k < W8_NK; k += 128) {
-      const uint32_t a = aK + W8_KBOX + (uint32_t)k * 128u + ((uint32_t)(2 ^ (k & 7)) << 4);
+      const uint32_t a = aK + W8_KBOX + (uint32_t)k * 128u + ((uint32_t)(AUGC ^ (k & 7)) << 4);
       asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)0x3F80) : "memory");
     }
     {
@@ -327,10 +339,10 @@ attn_window80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (live) {
       __nv_bfloat16* orow = p.out + (out_row < 0 ? 0 : out_row) * p.d_model + head * D;
       uint32_t va[32], vb[32];
-      tmem_ld32(tlane + 64, va);   // columns 64..95: 16 value columns + the row sum at column 80
+      tmem_ld32(tlane + 64, va);   // head_dim 80: 16 value columns + the row sum at column 80; head_dim 64: the row sum at column 64
       tmem_ld_wait();
       tmem_ld32(tlane + 0, vb);
-      const float inv = 1.0f / __uint_as_float(va[16]);
+      const float inv = 1.0f / __uint_as_float(va[D - 64]);
       auto store = [&](const uint32_t(&v)[32], int c0, int n) {
         if (out_row < 0) return;
 #pragma unroll
@@ -344,7 +356,7 @@ attn_window80_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           *reinterpret_cast<uint4*>(orow + c0 + cc) = u;
         }
       };
-      store(va, 64, 16);
+      if constexpr (D == 80) store(va, 64, 16);
       tmem_ld_wait();
       tmem_ld32(tlane + 32, va);
       store(vb, 0, 32);
@@ -368,32 +380,38 @@ unsigned long long* g_attn_trace = nullptr;
 void set_attn_trace(unsigned long long* dev_buf) { g_attn_trace = dev_buf; }
 unsigned long long* get_attn_trace() { return g_attn_trace; }
 
-int launch_attn_window80(const AttnArgs& a, cudaStream_t stream) {
+template <int D>
+static int launch_attn_window2_t(const AttnArgs& a, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_window80_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W8_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_window2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, W8_SMEM);
     if (e != cudaSuccess) return set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int d_model = a.heads * W8_D, S = 14;
+  constexpr int NB = (D + 63) / 64;
+  const int d_model = a.heads * D, S = 14;
   const int wpr = (a.grid + S - 1) / S;
   const int groups = a.batch * wpr * wpr;
   const long rows = (long)groups * 196;
   CUtensorMap tmQ, tmKV, tmRT;
   if (make_tmap_bf16_2d(&tmQ, a.qkv, rows, 3 * d_model, 3 * d_model, 128)) return -1;
   if (make_tmap_bf16_2d(&tmKV, a.qkv, rows, 3 * d_model, 3 * d_model, W8_NK)) return -1;
-  if (make_tmap_bf16_2d(&tmRT, a.rel_table, 64, 128, 128, 64)) return -1;
+  if (make_tmap_bf16_2d(&tmRT, a.rel_table, 64, NB * 64, NB * 64, 64)) return -1;
   W8Params p;
   p.out = a.out; p.d_model = d_model; p.grid = a.grid; p.sl2 = a.scale * 1.4426950408889634f; p.inv_scale = 1.0f / a.scale;
   p.trace = g_attn_trace;
-  prof_begin(stream, "attn_window<80>", (double)groups * a.heads * (4.0 * 196 * 196 * W8_D + 4.0 * 196 * S * W8_D),
-             (double)groups * 196 * a.heads * W8_D * 2 * 4);
-  attn_window80_kernel<<<dim3(2, a.heads, groups), W8_THREADS, W8_SMEM, stream>>>(tmQ, tmKV, tmRT, p);
+  prof_begin(stream, D == 64 ? "attn_window<64>" : "attn_window<80>",
+             (double)groups * a.heads * (4.0 * 196 * 196 * D + 4.0 * 196 * S * D), (double)groups * 196 * a.heads * D * 2 * 4);
+  attn_window2_kernel<D><<<dim3(2, a.heads, groups), W8_THREADS, W8_SMEM, stream>>>(tmQ, tmKV, tmRT, p);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("window attention launch failed: %s", cudaGetErrorString(e));
   count_launch();
   return 0;
+}
+
+int launch_attn_window2(const AttnArgs& a, cudaStream_t stream) {
+  return a.head_dim == 64 ? launch_attn_window2_t<64>(a, stream) : launch_attn_window2_t<80>(a, stream);
 }
 
 }  // namespace msam

@@ -110,7 +110,7 @@ struct AttnArgs {
 };
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
 int launch_attention_global(const AttnArgs& a, cudaStream_t stream);  // attention_global.cu (window == 0)
-int launch_attn_window80(const AttnArgs& a, cudaStream_t stream);     // attention_w80.cu (window 14, head_dim 80)
+int launch_attn_window2(const AttnArgs& a, cudaStream_t stream);      // attention_win2.cu (window 14, head_dim 64 / 80)
 // debug: per-CTA phase timestamps (%globaltimer, 16 slots x 64 windows) of the window-attention kernels; nullptr = off
 void set_attn_trace(unsigned long long* dev_buf);
 unsigned long long* get_attn_trace();
