@@ -197,6 +197,25 @@ int msam_op_layernorm(const float* x, int rows, int D, const float* gamma, const
 int msam_op_attention(const void* qkv_bf16, const void* rel_table_bf16, void* out_bf16, int batch, int heads, int head_dim,
                       int window, float scale, void* stream);
 
+/* ---- fine-tuning (BASELINE.json configs[4], micro_sam/training/sam_trainer.py:393: loss.backward() through the image encoder).
+ * msam_encode_train = msam_encode_f32 that keeps the activations of B <= max_batch images (ViT encoders only);
+ * msam_encode_backward takes dL/d(embedding) (B,256,64,64) fp32 NCHW and fills one fp32 gradient per encoder parameter;
+ * msam_encoder_grad copies the gradient of the parameter with upstream key `name` (e.g. "image_encoder.blocks.0.attn.qkv.weight",
+ * n = its element count, upstream layout) into a device buffer.  The decoder-side backward (dL/d embedding from the mask loss) is
+ * not part of this library yet. */
+int msam_encode_train(msam_handle* h, const float* nchw, int B, float* out, void* stream);
+int msam_encode_backward(msam_handle* h, const float* d_out_nchw, void* stream);
+int msam_encoder_grad(msam_handle* h, const char* name, float* dst, int64_t n, void* stream);
+/* Batched GEMM of the attention backward pass (csrc/bgemm.cu), exposed for the op-level parity tests. */
+int msam_op_bgemm(const void* A, const void* B, int a_mn, int b_mn, int M, int N, int K, int lda, int ldb, int64_t a_hstride,
+                  int64_t a_wstride, int64_t b_hstride, int64_t b_wstride, int heads, int outer, float* out, int ldc,
+                  int64_t o_hstride, int64_t o_wstride, float alpha, int accumulate, void* stream);
+/* LayerNorm backward over fp32 rows (csrc/backward.cu); dgamma / dbeta are ACCUMULATED into (zero them first). */
+int msam_op_layernorm_bwd(const float* x, int rows, int D, const float* gamma, float eps, const float* dy, int window_mode,
+                          int accumulate, float* dx, float* dgamma, float* dbeta, void* stream);
+/* debug: device buffer of 64 x 16 uint64 %globaltimer stamps written by the window-attention kernels, NULL = off */
+int msam_debug_attn_trace(void* dev_buf);
+
 #ifdef __cplusplus
 }
 #endif

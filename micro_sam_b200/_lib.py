@@ -84,6 +84,14 @@ def lib() -> ctypes.CDLL:
         L.msam_profile.argtypes = [c_int]
         L.msam_profile_report.argtypes = [ctypes.c_char_p, c_int]
         L.msam_encode_u8_blocks.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+        L.msam_encode_train.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+        L.msam_encode_backward.argtypes = [c_void_p, c_void_p, c_void_p]
+        L.msam_encoder_grad.argtypes = [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]
+        L.msam_op_bgemm.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64,
+                                    c_int64, c_int, c_int, c_void_p, c_int, c_int64, c_int64, c_float, c_int, c_void_p]
+        L.msam_op_layernorm_bwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                            c_void_p, c_void_p]
+        L.msam_debug_attn_trace.argtypes = [c_void_p]
         _lib = L
     return _lib
 

@@ -110,6 +110,8 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
   uint8_t* sQ = smem + C::OFF_Q;
   uint8_t* sK = smem + C::OFF_K;
   uint8_t* sV = smem + C::OFF_V;
@@ -416,7 +418,7 @@ int launch_global_t(const AttnArgs& a, cudaStream_t stream) {
   p.out = a.out; p.d_model = d_model; p.scale_log2 = a.scale * 1.4426950408889634f;
   prof_begin(stream, D == 64 ? "attn_global<64>" : "attn_global<80>", (double)a.batch * a.heads * (4.0 * 4096 * 4096 * D + 4.0 * 4096 * 64 * D),
              (double)a.batch * 4096 * a.heads * D * 2 * 4);
-  attn_global_kernel<D><<<dim3(32, a.heads, a.batch), 384, C::SMEM_BYTES, stream>>>(tmQKV, tmRTh, tmRTw, p);
+  launch_pdl(attn_global_kernel<D>, dim3(32, a.heads, a.batch), dim3(384), C::SMEM_BYTES, stream, tmQKV, tmRTh, tmRTw, p);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("global attention launch failed: %s", cudaGetErrorString(e));

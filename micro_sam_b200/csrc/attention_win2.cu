@@ -129,6 +129,8 @@ attn_window2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int row0 = group * G;
+  pdl_wait();
+  pdl_trigger();
   W8_TRACE(1);
 
   if (warp == 4) {
@@ -402,7 +404,7 @@ static int launch_attn_window2_t(const AttnArgs& a, cudaStream_t stream) {
   p.trace = g_attn_trace;
   prof_begin(stream, D == 64 ? "attn_window<64>" : "attn_window<80>",
              (double)groups * a.heads * (4.0 * 196 * 196 * D + 4.0 * 196 * S * D), (double)groups * 196 * a.heads * D * 2 * 4);
-  attn_window2_kernel<D><<<dim3(2, a.heads, groups), W8_THREADS, W8_SMEM, stream>>>(tmQ, tmKV, tmRT, p);
+  launch_pdl(attn_window2_kernel<D>, dim3(2, a.heads, groups), dim3(W8_THREADS), W8_SMEM, stream, tmQ, tmKV, tmRT, p);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("window attention launch failed: %s", cudaGetErrorString(e));

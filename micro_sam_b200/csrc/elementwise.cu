@@ -2,6 +2,7 @@
 // fp32->bf16 casts, 3x3 im2col.  All are simple coalesced streaming kernels; the heavy lifting is in gemm.cu /
 // attention.cu.
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace msam {
 
@@ -79,6 +80,8 @@ __global__ void layernorm_rows_kernel(const float* __restrict__ x, int rows, int
                                       __nv_bfloat16* __restrict__ out2, float* __restrict__ out_f32, int act) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_trigger();
   if (warp >= rows) return;
   const float4* src = reinterpret_cast<const float4*>(x + (long)warp * D);
   const int nv = D >> 2;
@@ -150,9 +153,8 @@ int launch_layernorm(const LnArgs& a, cudaStream_t stream) {
   const int warps_per_block = 8;
   const unsigned blocks = (unsigned)((a.rows + warps_per_block - 1) / warps_per_block);
   prof_begin(stream, "layernorm_rows", 0.0, (double)a.rows * a.D * (4 + (a.out ? 2 : 0) + (a.out2 ? 2 : 0) + (a.out_f32 ? 4 : 0)));
-  layernorm_rows_kernel<<<blocks, warps_per_block * 32, 0, stream>>>(a.x, a.rows, a.D, a.gamma, a.beta, a.eps, a.out,
-                                                                    a.window_mode, a.grid, a.ws, a.add, a.add_rows,
-                                                                    a.out2, a.out_f32, a.act);
+  launch_pdl(layernorm_rows_kernel, dim3(blocks), dim3(warps_per_block * 32), 0, stream, a.x, a.rows, a.D, a.gamma, a.beta, a.eps,
+             a.out, a.window_mode, a.grid, a.ws, a.add, a.add_rows, a.out2, a.out_f32, a.act);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("layernorm launch failed: %s", cudaGetErrorString(e));

@@ -3,6 +3,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace msam {
@@ -19,6 +20,12 @@ int set_error(const char* fmt, ...) {
   return -1;
 }
 void count_launch() { ++g_launches; }
+bool pdl_enabled() {
+  // measured on B200 (profiles/r3_pdl_ab.txt): no gain for this chain (every kernel needs its predecessor's output at once, so only
+  // the ~2 us prologues overlap, and the 2-SM GEMMs occupy a whole SM each) -> off unless MSAM_PDL=1
+  static const bool on = getenv("MSAM_PDL") != nullptr;
+  return on;
+}
 
 struct ProfRec { cudaEvent_t a, b; const char* name; double flops, bytes; };
 static bool g_prof_on = false;
@@ -635,6 +642,33 @@ int msam_op_attention(const void* qkv, const void* rel_table, void* out, int bat
   a.qkv = (const __nv_bfloat16*)qkv; a.rel_table = (const __nv_bfloat16*)rel_table; a.out = (__nv_bfloat16*)out;
   a.batch = batch; a.heads = heads; a.head_dim = head_dim; a.grid = 64; a.window = window; a.scale = scale;
   return launch_attention(a, (cudaStream_t)stream);
+}
+
+int msam_encode_train(msam_handle* h, const float* nchw, int B, float* out, void* stream) {
+  if (!h || !nchw || !out) return set_error("msam_encode_train: null argument");
+  return h->eng.encode_train(nchw, B, out, (cudaStream_t)stream);
+}
+int msam_encode_backward(msam_handle* h, const float* d_out, void* stream) {
+  if (!h || !d_out) return set_error("msam_encode_backward: null argument");
+  return h->eng.encode_backward(d_out, (cudaStream_t)stream);
+}
+int msam_encoder_grad(msam_handle* h, const char* name, float* dst, int64_t n, void* stream) {
+  if (!h || !name || !dst) return set_error("msam_encoder_grad: null argument");
+  return h->eng.encoder_grad(name, dst, n, (cudaStream_t)stream);
+}
+int msam_op_bgemm(const void* A, const void* B, int a_mn, int b_mn, int M, int N, int K, int lda, int ldb, int64_t a_hstride,
+                  int64_t a_wstride, int64_t b_hstride, int64_t b_wstride, int heads, int outer, float* out, int ldc,
+                  int64_t o_hstride, int64_t o_wstride, float alpha, int accumulate, void* stream) {
+  BGemmArgs a;
+  a.A = (const __nv_bfloat16*)A; a.B = (const __nv_bfloat16*)B; a.a_mn = a_mn; a.b_mn = b_mn; a.M = M; a.N = N; a.K = K;
+  a.lda = lda; a.ldb = ldb; a.a_hstride = a_hstride; a.a_wstride = a_wstride; a.b_hstride = b_hstride; a.b_wstride = b_wstride;
+  a.heads = heads; a.outer = outer; a.out = out; a.ldc = ldc; a.o_hstride = o_hstride; a.o_wstride = o_wstride; a.alpha = alpha;
+  a.accumulate = accumulate;
+  return launch_bgemm(a, (cudaStream_t)stream);
+}
+int msam_op_layernorm_bwd(const float* x, int rows, int D, const float* gamma, float eps, const float* dy, int window_mode,
+                          int accumulate, float* dx, float* dgamma, float* dbeta, void* stream) {
+  return launch_layernorm_bwd(x, rows, D, gamma, eps, dy, window_mode, 64, 14, accumulate, dx, dgamma, dbeta, (cudaStream_t)stream);
 }
 
 // debug hook (profiles/scripts/win_attn_probe.py): device buffer of 64 x 16 uint64 phase timestamps, or NULL to switch off

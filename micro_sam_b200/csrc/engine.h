@@ -66,6 +66,7 @@ struct TinyVit {
 };
 
 struct DecoderState;  // decoder.cu
+struct TrainState;    // encoder_train.cu
 
 struct Engine {
   msam_config cfg{};
@@ -78,6 +79,7 @@ struct Engine {
   TinyVit tv;
   bool is_tinyvit() const { return cfg.depth == 0; }
   DecoderState* dec = nullptr;
+  TrainState* train = nullptr;
 
   void* dalloc(size_t bytes, bool zero = false);
   const std::vector<float>* host(const std::string& name, std::initializer_list<int64_t> shape);
@@ -96,6 +98,12 @@ struct Engine {
                      float* x_out = nullptr);
   int encode(const uint8_t* u8, const float* f32, int B, int hh, int ww, float* out, cudaStream_t st, int stop_after = -1,
              float* x_out = nullptr);
+  // encoder_train.cu (cfg 5): forward keeping activations, backward, gradient read-out by upstream key name
+  int train_setup();
+  int encode_train(const float* f32, int B, float* out, cudaStream_t st);
+  int encode_backward(const float* d_out, cudaStream_t st);
+  int encoder_grad(const char* name, float* dst, int64_t n, cudaStream_t st);
+  void train_invalidate();
   int set_image_embedding(const float* feat, cudaStream_t st);  // decoder.cu
   int decode(const float* points, const float* labels, int np, const float* boxes, const float* mask_in, int P, int multimask,
              float* low_res, float* iou, cudaStream_t st);  // decoder.cu

@@ -119,6 +119,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // the previous kernel's outputs (A, residual) are complete and visible from here on
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (one per CTA: its A rows, its half of W)
@@ -305,7 +307,7 @@ int launch_gemm_2sm(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   prof_begin(stream, "gemm2_bf16 (2-SM, encoder)", 2.0 * a.M * a.N * a.K,
              (double)a.M * a.K * 2 + (double)a.N * a.K * 2 + (double)a.M * a.N * (a.out_fp32 ? 4 : 2) * (a.residual ? 2 : 1));
-  gemm2_bf16_kernel<<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmR, p);
+  launch_pdl(gemm2_bf16_kernel, dim3(2 * clusters), dim3(THREADS), SMEM_BYTES, stream, tmA, tmB, tmC, tmR, p);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm2 launch failed: %s", cudaGetErrorString(e));

@@ -129,8 +129,9 @@ static int launch_gemm_mn(const __nv_bfloat16* A, const __nv_bfloat16* B, int M,
                           cudaStream_t stream) {
   using namespace wg;
   if (M <= 0 || N <= 0 || K <= 0) return set_error("gemm_tn: empty problem M=%d N=%d K=%d", M, N, K);
-  if (M % 8 || N % 8 || K % 8 || lda % 8 || ldb % 8 || ldc % 4)
-    return set_error("gemm_tn: M, N, K, lda, ldb must be multiples of 8, ldc of 4");
+  // an MN-major operand is contracted over its rows: any K works (the K tail is zero-filled); a K-major A needs 16-byte rows
+  if (M % 8 || N % 8 || (!A_MN && K % 8) || lda % 8 || ldb % 8 || ldc % 4)
+    return set_error("gemm_tn: M, N (and K of a K-major operand), lda, ldb must be multiples of 8, ldc of 4");
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<A_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);

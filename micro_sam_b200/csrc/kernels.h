@@ -4,7 +4,23 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 namespace msam {
+
+// Launch with programmatic dependent launch allowed (see ptx.cuh:pdl_wait).  ONLY for kernels in which every thread executes
+// pdl_wait() before touching global memory.  The attribute is only set when MSAM_PDL=1 (measured: no gain, see engine.cu).
+bool pdl_enabled();   // engine.cu
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 int set_error(const char* fmt, ...);  // records msam_last_error(); returns -1
 void count_launch();                  // per-thread launch counter (msam_launch_count)
@@ -43,6 +59,44 @@ int launch_gemm_tn(const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N,
 // out[M,N] fp32 = A[M,K] B[K,N]  (input gradient dX = dY W; A K-major, B = the forward weight [out, in] consumed MN-major)
 int launch_gemm_nn(const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K, int lda, int ldb, float* out, int ldc,
                    cudaStream_t stream);
+
+// ---- bgemm.cu : batched GEMM over (outer = window | image, head) pairs, fp32 out: C[w,h] (+)= alpha * op(A[w,h]) op(B[w,h])
+struct BGemmArgs {
+  const __nv_bfloat16* A = nullptr;
+  const __nv_bfloat16* B = nullptr;
+  int a_mn = 0, b_mn = 0;       // 0: K-major (contraction along the contiguous features), 1: MN-major (contraction along the rows)
+  int M = 0, N = 0, K = 0;
+  int lda = 0, ldb = 0;         // row pitch of A / B (elements)
+  long a_hstride = 0, a_wstride = 0, b_hstride = 0, b_wstride = 0;   // element offsets per head / per outer index; 0 = shared
+  int heads = 1, outer = 1;
+  float* out = nullptr;         // [outer, heads, M, ldc] through o_wstride / o_hstride
+  int ldc = 0;
+  long o_hstride = 0, o_wstride = 0;
+  float alpha = 1.f;
+  int accumulate = 0;
+};
+int launch_bgemm(const BGemmArgs& a, cudaStream_t stream);
+
+// ---- backward.cu : HBM-bound pieces of the encoder backward pass (cfg 5)
+// LayerNorm backward over rows: dx (+)= d LN(x) ; dgamma / dbeta += (atomics into zero-initialised fp32 [D]).
+// window_mode: dy is indexed in the window-partitioned row order of the forward LayerNorm (pad rows are skipped).
+int launch_layernorm_bwd(const float* x, int rows, int D, const float* gamma, float eps, const float* dy, int window_mode, int grid,
+                         int ws, int accumulate, float* dx, float* dgamma, float* dbeta, cudaStream_t stream);
+int launch_gelu_fwd(const __nv_bfloat16* pre, long n, __nv_bfloat16* out, cudaStream_t stream);
+int launch_gelu_bwd(const __nv_bfloat16* dh, const __nv_bfloat16* pre, long n, __nv_bfloat16* dpre, cudaStream_t stream);
+int launch_colsum(const __nv_bfloat16* x, long rows, int N, float* out, cudaStream_t stream);   // out[N] += column sums
+int launch_window_gather(const __nv_bfloat16* x, int B, int grid, int ws, int D, __nv_bfloat16* out_win, cudaStream_t stream);
+struct AttnBwdGeom { int side = 14, n_tok = 196, nt = 64, woff = 32; };   // window: 14 / 196 / 64 / 32; global: 64 / 4096 / 256 / 128
+int launch_attn_probs(const float* S, const float* T, long n_batch, AttnBwdGeom g, int pitch_s, int pitch_p, float scale,
+                      __nv_bfloat16* P, cudaStream_t stream);
+int launch_attn_ds(const __nv_bfloat16* P, const float* dP, long n_batch, AttnBwdGeom g, int pitch_s, int pitch_p,
+                   __nv_bfloat16* dS, __nv_bfloat16* dT, cudaStream_t stream);
+int launch_pack_dqkv(const float* dq, const float* dk, const float* dv, int outer, int heads, int T, int d, __nv_bfloat16* dqkv,
+                     cudaStream_t stream);
+int launch_sum_batch(const float* x, long n_batch, long n, float* out, int accumulate, cudaStream_t stream);   // out[n] (+)= sum_b x[b, n]
+int launch_nchw_to_tok(const float* nchw, int B, int C, int T, float* tok, cudaStream_t stream);
+int launch_col2im3x3(const __nv_bfloat16* dcol, int B, int g, int C, float* out, cudaStream_t stream);
+int launch_cast_f32(const __nv_bfloat16* x, long n, float* out, cudaStream_t stream);
 
 // ---- upscale_fused.cu : conv-transpose 1 + LayerNorm2d + GELU + conv-transpose 2 + GELU + hyper-network product in one pass
 struct UpscaleFusedArgs {

@@ -21,6 +21,14 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every kernel of the encoder chain is launched with the programmatic-stream-serialization attribute (kernels.h:launch_pdl): its
+// CTAs may become resident while the previous kernel of the stream is still draining, run their prologue (barrier init,
+// tensor-map prefetch, TMEM allocation) and then block here until the previous grid has completed and flushed -- every thread
+// executes the wait before its first global-memory access, so the memory semantics are those of ordinary stream order.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

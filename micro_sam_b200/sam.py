@@ -84,6 +84,27 @@ class ResizeLongestSide:
         return self.apply_coords_torch(boxes.reshape(-1, 2, 2), original_size).reshape(-1, 4)
 
 
+class _EncoderFn(torch.autograd.Function):
+    """image_encoder with a backward pass (cfg 5): forward = msam_encode_train (keeps the activations in the engine), backward =
+    msam_encode_backward, which fills the engine's per-parameter gradients (read them with `B200Sam.encoder_grads()`); the image
+    itself gets no gradient (trainable_sam.py never asks for one)."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, sam):
+        x = x.to(device=sam.device, dtype=torch.float32).contiguous()
+        out = torch.empty(x.shape[0], 256, 64, 64, device=sam.device, dtype=torch.float32)
+        _lib.check(_lib.lib().msam_encode_train(sam._h, _lib.ptr(x), x.shape[0], _lib.ptr(out), _lib.cur_stream()))
+        ctx.sam = sam
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g = grad_out.to(torch.float32).contiguous()
+        _lib.check(_lib.lib().msam_encode_backward(ctx.sam._h, _lib.ptr(g), _lib.cur_stream()))
+        ctx.sam._encoder_grads_valid = True
+        return None, torch.zeros((), device=g.device), None
+
+
 class _ImageEncoder:
     """Callable stand-in for `sam.image_encoder`: (B,3,1024,1024) fp32 preprocessed -> (B,256,64,64) fp32."""
 
@@ -95,6 +116,10 @@ class _ImageEncoder:
         sam = self._sam
         if x.ndim != 4 or x.shape[1] != 3 or x.shape[2] != self.img_size or x.shape[3] != self.img_size:
             raise ValueError(f"image_encoder expects (B,3,{self.img_size},{self.img_size}), got {tuple(x.shape)}")
+        if torch.is_grad_enabled() and sam.training:
+            if getattr(sam, "_grad_anchor", None) is None:   # a leaf that makes the output part of the autograd graph
+                sam._grad_anchor = torch.zeros((), device=sam.device, requires_grad=True)
+            return _EncoderFn.apply(x, sam._grad_anchor, sam)
         x = x.to(device=sam.device, dtype=torch.float32).contiguous()
         out = torch.empty(x.shape[0], 256, 64, 64, device=sam.device, dtype=torch.float32)
         _lib.check(_lib.lib().msam_encode_f32(sam._h, _lib.ptr(x), x.shape[0], _lib.ptr(out), _lib.cur_stream()))
@@ -274,13 +299,33 @@ class B200Sam:
         for _, p in self.named_parameters():
             yield p
 
+    training = False
+
     def eval(self):
+        self.training = False
         return self
 
     def train(self, mode: bool = True):
-        if mode:
-            raise NotImplementedError("micro_sam_b200 has no backward kernels yet (cfg 5, DESIGN.md)")
+        """Training mode switches `image_encoder(x)` (under grad mode) to the activation-keeping forward with a backward pass
+        (csrc/encoder_train.cu).  The prompt encoder / mask decoder stay forward-only (decoder backward not built)."""
+        if mode and self.model_type == "vit_t":
+            raise NotImplementedError("the TinyViT encoder has no backward pass")
+        self.training = bool(mode)
         return self
+
+    def encoder_grads(self, names=None) -> Dict[str, torch.Tensor]:
+        """fp32 gradients of the image-encoder parameters after a backward pass, keyed and shaped like the upstream state dict."""
+        if not getattr(self, "_encoder_grads_valid", False):
+            raise RuntimeError("no encoder gradients: run image_encoder(x) in train() mode and call backward() first")
+        out = {}
+        L = _lib.lib()
+        for k, v in self._state.items():
+            if not k.startswith("image_encoder.") or (names is not None and k not in names):
+                continue
+            g = torch.empty(v.shape, device=self.device, dtype=torch.float32)
+            _lib.check(L.msam_encoder_grad(self._h, k.encode(), _lib.ptr(g), g.numel(), _lib.cur_stream()))
+            out[k] = g
+        return out
 
     def bind_embedding(self, f: torch.Tensor) -> None:
         """Bind a (1,256,64,64) image embedding as the decoder's current image (SamPredictor.features assignment).  The
