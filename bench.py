@@ -5,7 +5,7 @@ tensor-core roofline.
 
   python bench.py --gpus N --steps K --warmup W            # ours (torchrun for N > 1, one rank per GPU, weak scaling)
   python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm's CPU path (oracle port) on host cores
-  python bench.py --config cfg1|cfg3|cfg4 ...                   # the other BASELINE.json GPU configurations (extra JSON lines)
+  python bench.py --config cfg1|cfg3|cfg4|cfg5 ...                   # the other BASELINE.json GPU configurations (extra JSON lines)
 
 One "step" = one pass of the hot path over one batch of 16 tiles per GPU.  BOTH arms run the same workload
 (`workload_config`): same tiles, same seeded weights, same point grid and the same generate() thresholds, chosen so that
@@ -445,7 +445,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--config", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--model", default=None)
     ap.add_argument("--max-prompts", type=int, default=1024)
     ap.add_argument("--enc-batch", type=int, default=16, help="tiles per encoder pass (the engine chunks the 16-tile batch)")
@@ -456,7 +456,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.model is None:
-        args.model = {"cfg1": "vit_t", "cfg2": "vit_b", "cfg3": "vit_l", "cfg4": "vit_h"}[args.config]
+        args.model = {"cfg1": "vit_t", "cfg2": "vit_b", "cfg3": "vit_l", "cfg4": "vit_h", "cfg5": "vit_b"}[args.config]
     if args.config != "cfg2":
         import bench_configs
         return bench_configs.main(args)

@@ -6,6 +6,11 @@ cfg1  vit_t (MobileSAM / TinyViT) precompute_image_embeddings on 512 x 512 float
       (resized uint8 tiles in HBM, batch of 16 through the encoder), `e2e` = host float32 tile -> host embedding through
       precompute_image_embeddings (normalise + PIL resize 512 -> 1024 + H2D + encoder + D2H per tile).
 
+cfg5  vit_b fine-tuning step on LIVECell-shaped batches (2 images of 512 x 512 per GPU, 25 box-prompted objects each): preprocess
+      (torch resize) + encoder forward keeping activations + mask decoder forward + loss (dice + IoU MSE) + ENCODER BACKWARD +
+      gradient all-reduce over the ranks (NCCL, one flat fp32 buffer).  The decoder has no backward pass yet, so the gradient
+      entering the encoder is a fixed synthetic dL/d embedding: the line reports `"complete_step": false` and is the cost of every
+      piece of the step that exists, not a training throughput claim.  metric: images/s.
 cfg3  vit_l tiled 3-D embedding precompute: uint8 EM volume 64 x 2048 x 2048, tile_shape (1024, 1024), halo (128, 128)
       -> 4 outer tiles of 1152^2 per plane, 256 encoder tiles, written to a zarr container (1 GiB of embeddings).
       The volume is FIXED (strong scaling): ranks take contiguous shards of the (z, tile) list, each writes its own chunks,
@@ -34,6 +39,7 @@ CFG4 = dict(n_tiles=128, n_boxes=256, tile=1024, enc_batch=8)
 
 
 CFG1 = dict(n_tiles=16, tile=512)
+CFG5 = dict(batch=2, tile=512, n_obj=25)
 
 
 def _config(args):
@@ -42,6 +48,13 @@ def _config(args):
                             "per tile (BASELINE.json configs[0]); seeded random-init weights",
                 "tiles_per_step_per_gpu": CFG1["n_tiles"], "l2": "flushed between steps (256 MB buffer write)",
                 "parallelism": "tile shards, one process per GPU, no collective (reference arm: host threads of rank 0)"}
+    if args.config == "cfg5":
+        return {"workload": f"{args.model} fine-tuning step, batch of 2 synthetic 512x512 images per GPU with 25 box-prompted objects each "
+                            "(BASELINE.json configs[4]); seeded random-init weights; encoder fwd + decoder fwd + loss + encoder bwd + "
+                            "gradient all-reduce; decoder bwd NOT built (synthetic dL/d embedding)",
+                "images_per_step_per_gpu": CFG5["batch"], "objects_per_image": CFG5["n_obj"], "complete_step": False,
+                "l2": "working_set_exceeds_l2 (GBs of saved activations per step)",
+                "parallelism": "data parallel replicas, one process per GPU, one NCCL all-reduce of the flat gradient buffer per step"}
     if args.config == "cfg3":
         return {"workload": f"{args.model} tiled 3d embedding precompute, 64x2048x2048 uint8 EM-like volume, tile_shape=(1024,1024) "
                             "halo=(128,128) -> 256 tiles of 1152^2, zarr container (BASELINE.json configs[2]); seeded random-init weights",
@@ -215,6 +228,90 @@ def run_cfg1(args):
         dist.destroy_process_group()
 
 
+def _cfg5_batch(seed0):
+    """LIVECell-like: 512 x 512 uint8 images with non-overlapping disks; the first n_obj disks become box prompts + targets."""
+    rng = np.random.default_rng(seed0)
+    S, n = CFG5["tile"], CFG5["n_obj"]
+    recs, targets = [], []
+    yy, xx = np.mgrid[:S, :S]
+    for b in range(CFG5["batch"]):
+        img = rng.normal(60, 8, (S, S)).astype(np.float32)
+        boxes, masks, tries = [], [], 0
+        while len(boxes) < n and tries < 5000:
+            tries += 1
+            r = rng.integers(8, 22)
+            cy, cx = rng.integers(r + 1, S - r - 1, 2)
+            if any((cy - py) ** 2 + (cx - px) ** 2 < (r + pr + 2) ** 2 for py, px, pr in masks):
+                continue
+            masks.append((cy, cx, r))
+            boxes.append([cx - r, cy - r, cx + r, cy + r])
+            img[(yy - cy) ** 2 + (xx - cx) ** 2 < r * r] += 90
+        img = np.clip(img, 0, 255)
+        tg = np.stack([((yy - cy) ** 2 + (xx - cx) ** 2 < r * r)[None] for cy, cx, r in masks]).astype(np.float32)
+        recs.append({"image": torch.from_numpy(np.repeat(img[None], 3, 0)), "original_size": (S, S),
+                     "boxes": torch.tensor(boxes, dtype=torch.float32) * (1024.0 / S)})
+        targets.append(torch.from_numpy(tg))
+    return recs, targets
+
+
+def run_cfg5(args):
+    from bench import ClockSampler, peaks, ENC_FLOPS
+    from oracle import sam_ref
+    from micro_sam_b200 import _lib, training, util
+    dist, world, rank, local, device = _dist()
+    pk, _ = peaks()
+    pred = util.get_sam_model(args.model, device=device, state_dict=sam_ref.seeded_state_dict(args.model, seed=0),
+                              max_batch=CFG5["batch"], max_prompts=64)
+    sam = pred.model.train()
+    m = training.TrainableSAM(sam)
+    recs, targets = _cfg5_batch(100 + rank)
+    d_emb = (torch.randn(CFG5["batch"], 256, 64, 64, generator=torch.Generator().manual_seed(rank)) * 1e-3).to(device)
+    state = {}
+
+    def step():
+        rr = [dict(r) for r in recs]
+        emb, rr = m.image_embeddings_oft(rr)                      # encoder forward, activations kept
+        out = m(rr, emb.detach(), multimask_output=True, return_masks=False)
+        loss = training.compute_loss(out, targets)                # a number: the decoder has no backward pass
+        emb.backward(d_emb)                                       # encoder backward
+        g = sam.encoder_grads()
+        flat = torch.cat([v.reshape(-1) for v in g.values()])
+        if world > 1:
+            dist.all_reduce(flat)
+            flat /= world
+        state["loss"], state["n"] = float(loss[0]), flat.numel()
+        return flat
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = _lib.launch_count()
+    ms = _timed(dist, world, device, step, args.steps, args.warmup)
+    launches = (_lib.launch_count() - l0) / (args.steps + args.warmup)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        L = _lib.lib()
+        L.msam_profile(1)
+        step()
+        rep = sorted(_lib.profile_report(), key=lambda r: -r["ms"])
+        L.msam_profile(0)
+        dom = rep[0]
+        tf = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
+        n_img = CFG5["batch"] * world
+        enc_flops = 3 * ENC_FLOPS[args.model] * CFG5["batch"]     # forward + ~2x backward, algorithmic
+        out = {"metric": "images/s, fine-tuning step without the decoder backward pass", "value": n_img * args.steps / (ms / 1e3), "unit": "images/s",
+               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": _config(args),
+               "e2e": {"value": n_img * args.steps / (ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": CFG5["batch"] * 3 * 512 * 512 * 4,
+                       "d2h_bytes_per_step": 4, "note": "host float images -> device every step; the loss value is read back"},
+               "gpu_launches": launches, "clocks": clocks, "loss": state.get("loss"), "gradient_elements": state.get("n"),
+               "roofline": {"bound": "tensor", "kernel": dom["name"], "achieved": tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                            "frac": tf / pk["bf16_tflops_sustained"], "traffic": None, "share_of_step": dom["ms"] / (ms / args.steps),
+                            "encoder_fwd_bwd_tflops": enc_flops / (ms / args.steps * 1e-3) / 1e12,
+                            "kernels_ms_per_step": {r["name"]: round(r["ms"], 3) for r in rep}}}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def _cfg4_inputs(rank, world):
     from micro_sam_b200.sample_data import lm_tile, random_boxes
     lo, hi = (CFG4["n_tiles"] * rank) // world, (CFG4["n_tiles"] * (rank + 1)) // world
@@ -303,7 +400,22 @@ def run_reference(args):
     pred = sam_ref.SamPredictor(sam)
     vals, t_all = [], time.perf_counter()
     for it in range(args.steps + (1 if args.warmup > 0 else 0)):
-        if args.config == "cfg1":
+        if args.config == "cfg5":
+            from oracle import train_ref
+            recs, targets = _cfg5_batch(100)
+            recs, targets = recs[:1], targets[:1]
+            om = train_ref.TrainableSAM(sam)
+            for p in sam.image_encoder.parameters():
+                p.requires_grad_(True)
+            t0 = time.perf_counter()
+            emb, rr = om.image_embeddings_oft([dict(r) for r in recs])
+            with torch.no_grad():
+                loss = train_ref.compute_loss(om(rr, emb.detach(), multimask_output=True), targets)
+            emb.backward(torch.randn(emb.shape, generator=torch.Generator().manual_seed(0)) * 1e-3)
+            per_tile = time.perf_counter() - t0
+            sam.zero_grad(set_to_none=True)
+            sample = f"1 of 2 images: encoder fwd + decoder fwd + loss ({float(loss[0]):.3f}) + encoder bwd (autograd) {per_tile:.1f}s"
+        elif args.config == "cfg1":
             from micro_sam_b200.sample_data import lm_tile
             tiles = [lm_tile((CFG1["tile"],) * 2, 40, seed=t).astype(np.float32) for t in range(4)]
             t0 = time.perf_counter()
@@ -334,11 +446,13 @@ def run_reference(args):
             vals.append(1.0 / per_tile)
     v = float(np.mean(vals))
     cb = {"value": v, "unit": "tiles/s", "cores": threads, "kind": "port", "sample": sample}
-    print(json.dumps({"impl": "reference", "metric": "512x512 tiles/s" if args.config == "cfg1" else "1024x1024 tiles/s", "value": v, "unit": "tiles/s", "n_gpus": args.gpus,
+    unit = "images/s" if args.config == "cfg5" else "tiles/s"
+    cb["unit"] = unit
+    print(json.dumps({"impl": "reference", "metric": {"cfg1": "512x512 tiles/s", "cfg5": "images/s, fine-tuning step without the decoder backward pass"}.get(args.config, "1024x1024 tiles/s"), "value": v, "unit": unit, "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (time.perf_counter() - t_all) / max(args.steps, 1),
                       "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": _config(args), "cpu_baseline": cb,
-                      "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                      "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 def main(args):
@@ -346,4 +460,4 @@ def main(args):
         return run_reference(args)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback; use --impl reference)")
-    return {"cfg1": run_cfg1, "cfg3": run_cfg3, "cfg4": run_cfg4}[args.config](args)
+    return {"cfg1": run_cfg1, "cfg3": run_cfg3, "cfg4": run_cfg4, "cfg5": run_cfg5}[args.config](args)

@@ -8,9 +8,11 @@ minimum over the 1 / 3 predicted masks, + MSE between predicted and true IoU) fr
 `msam_mask_loss_stats` accumulates straight from the low-res logits, so the (n_obj, M, H, W) logits are only materialised
 when the caller asks for `masks`.
 
-There are no backward kernels yet: `forward` runs under no_grad and the loss is a number, not a graph.  The backward plan
-(dgrad / wgrad GEMMs with MN-major operand descriptors, recompute-based attention backward, DDP all-reduce of the packed
-gradient buffer) is in DESIGN.md; `msam_op_gemm_tn` is its first piece (wgrad GEMM, checked against autograd in the tests).
+Backward: the image encoder has one (csrc/encoder_train.cu): with `sam.train()` the embeddings returned by
+`image_embeddings_oft` are part of the autograd graph, `embeddings.backward(dL/d embeddings)` runs the encoder backward pass on
+the device and `sam.encoder_grads()` hands out one fp32 gradient per encoder parameter (upstream keys / shapes).  The prompt
+encoder / mask decoder are forward-only: `forward` runs under no_grad and the loss is a number, so dL/d embeddings has to come
+from elsewhere (decoder backward not built).
 """
 from __future__ import annotations
 
@@ -37,12 +39,12 @@ class TrainableSAM:
         s = self.sam.image_encoder.img_size
         return torch.nn.functional.pad(x, (0, s - x.shape[-1], 0, s - x.shape[-2])), input_size
 
-    @torch.no_grad()
     def image_embeddings_oft(self, batched_inputs: List[Dict[str, Any]]):
-        images, input_size = self.preprocess(torch.stack([x["image"] for x in batched_inputs], dim=0))
-        for rec in batched_inputs:
-            rec["input_size"] = input_size
-        return self.sam.image_encoder(images), batched_inputs
+        with torch.set_grad_enabled(bool(getattr(self.sam, "training", False)) and torch.is_grad_enabled()):
+            images, input_size = self.preprocess(torch.stack([x["image"] for x in batched_inputs], dim=0))
+            for rec in batched_inputs:
+                rec["input_size"] = input_size
+            return self.sam.image_encoder(images), batched_inputs
 
     @torch.no_grad()
     def forward(self, batched_inputs: List[Dict[str, Any]], image_embeddings: torch.Tensor, multimask_output: bool = False,
