@@ -206,6 +206,22 @@ int msam_op_attention(const void* qkv_bf16, const void* rel_table_bf16, void* ou
 int msam_encode_train(msam_handle* h, const float* nchw, int B, float* out, void* stream);
 int msam_encode_backward(msam_handle* h, const float* d_out_nchw, void* stream);
 int msam_encoder_grad(msam_handle* h, const char* name, float* dst, int64_t n, void* stream);
+/* Mask decoder + prompt encoder in training mode (micro_sam/training/trainable_sam.py:62-114): MaskDecoder.forward for the P prompts of
+ * ONE image keeping the activations in `slot` (0..7), and its backward pass.  sparse = prompt_encoder's sparse embeddings
+ * [P, n_sparse, 256] (msam_prompt_encode), emb_index [P, n_sparse] int32 = the embedding-table row behind each sparse token (0..3 =
+ * point_embeddings.{0..3}, 4 = not_a_point_embed) so that their gradients can be formed; the dense prompt is no_mask_embed.
+ * backward: d_low_res [P, M, 256, 256] / d_iou [P, M] (either may be NULL) -> parameter gradients ACCUMULATE (msam_decoder_zero_grads),
+ * d_emb_nchw [256, 64, 64] = dL/d(image embedding) is overwritten.  msam_decoder_grad reads a gradient by upstream key
+ * ("....weight@gemm" / "@stack" keys carry packed layouts that micro_sam_b200/sam.py:decoder_grads folds back). */
+int msam_decoder_train_forward(msam_handle* h, int slot, const float* emb_nchw, const float* sparse, const int32_t* emb_index, int n_sparse,
+                               int P, int multimask, float* low_res, float* iou, void* stream);
+int msam_decoder_train_backward(msam_handle* h, int slot, const float* d_low_res, const float* d_iou, float* d_emb_nchw, void* stream);
+int msam_decoder_grad(msam_handle* h, const char* name, float* dst, int64_t n, void* stream);
+int msam_decoder_zero_grads(msam_handle* h, void* stream);
+/* Adjoint of msam_mask_loss_stats w.r.t. the low-res logits: d_stats [n_obj*M, 5] (only columns 0, 1 = dL/d sum(p t), dL/d sum(p^2)
+ * matter) -> d_low_res [n_obj*M, 256, 256] accumulated (zero it first).  sam_trainer.py:131-172 backward. */
+int msam_mask_loss_backward(const float* low_res, const uint8_t* targets, const float* d_stats, int n_obj, int M, int in_h, int in_w,
+                            int orig_h, int orig_w, float* d_low_res, void* stream);
 /* Batched GEMM of the attention backward pass (csrc/bgemm.cu), exposed for the op-level parity tests. */
 int msam_op_bgemm(const void* A, const void* B, int a_mn, int b_mn, int M, int N, int K, int lda, int ldb, int64_t a_hstride,
                   int64_t a_wstride, int64_t b_hstride, int64_t b_wstride, int heads, int outer, float* out, int ldc,

@@ -92,6 +92,12 @@ def lib() -> ctypes.CDLL:
         L.msam_op_layernorm_bwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                             c_void_p, c_void_p]
         L.msam_debug_attn_trace.argtypes = [c_void_p]
+        L.msam_decoder_train_forward.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                                 c_void_p]
+        L.msam_decoder_train_backward.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+        L.msam_decoder_grad.argtypes = [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]
+        L.msam_decoder_zero_grads.argtypes = [c_void_p, c_void_p]
+        L.msam_mask_loss_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
         _lib = L
     return _lib
 

@@ -196,8 +196,8 @@ static int launch_bgemm_t(const BGemmArgs& a, cudaStream_t stream) {
   // the map extents are the logical (feature, row) extents of ONE batch entry: features = the operand's contiguous dimension
   // (K when K-major, M / N when MN-major), rows = the other one
   CUtensorMap tmA, tmB;
-  const uint64_t a_feats = A_MN ? a.M : a.K, a_rows = A_MN ? a.K : a.M;
-  const uint64_t b_feats = B_MN ? a.N : a.K, b_rows = B_MN ? a.K : a.N;
+  const uint64_t a_feats = A_MN ? a.M : a.K, a_rows = a.a_rows_valid > 0 ? a.a_rows_valid : (A_MN ? a.K : a.M);
+  const uint64_t b_feats = B_MN ? a.N : a.K, b_rows = a.b_rows_valid > 0 ? a.b_rows_valid : (B_MN ? a.K : a.N);
   if (make_tmap_bf16_4d(&tmA, a.A, a_feats, a.a_hstride ? a.heads : 1, a_rows, a.a_wstride ? a.outer : 1, a.a_hstride, a.lda,
                         a.a_wstride)) return -1;
   if (make_tmap_bf16_4d(&tmB, a.B, b_feats, a.b_hstride ? a.heads : 1, b_rows, a.b_wstride ? a.outer : 1, a.b_hstride, a.ldb,

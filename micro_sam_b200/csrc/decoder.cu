@@ -794,6 +794,8 @@ int Engine::decode(const float* points, const float* labels, int np, const float
 
 // PromptEncoder.forward as a stand-alone call: sparse [P, n_sparse, 256] (points incl. the padding point when no box is
 // given, then the two box corners) and, for mask prompts, the dense embedding [P, 256, 64, 64] (NCHW fp32).
+const float* Engine::dec_pos() { return dec ? dec->pos : nullptr; }
+
 int Engine::prompt_encode(const float* points, const float* labels, int np, const float* boxes, const float* mask_in, int P,
                           float* sparse_out, float* dense_out, cudaStream_t st) {
   if (!finalized || !dec) return set_error("prompt_encode: decoder weights not loaded");

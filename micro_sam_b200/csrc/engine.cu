@@ -448,6 +448,8 @@ int msam_finalize_weights(msam_handle* h) {
     if (h->eng.alloc_encoder_ws()) return -1;
   }
   if (h->eng.finalize_decoder()) return -1;
+  for (auto& kv : h->eng.host_weights)
+    if (kv.first.rfind("mask_decoder.", 0) == 0 || kv.first.rfind("prompt_encoder.", 0) == 0) h->eng.dec_host[kv.first] = std::move(kv.second);
   h->eng.host_weights.clear();
   if (cudaDeviceSynchronize() != cudaSuccess) return set_error("finalize: %s", cudaGetErrorString(cudaGetLastError()));
   h->eng.finalized = true;
@@ -655,6 +657,27 @@ int msam_encode_backward(msam_handle* h, const float* d_out, void* stream) {
 int msam_encoder_grad(msam_handle* h, const char* name, float* dst, int64_t n, void* stream) {
   if (!h || !name || !dst) return set_error("msam_encoder_grad: null argument");
   return h->eng.encoder_grad(name, dst, n, (cudaStream_t)stream);
+}
+int msam_decoder_train_forward(msam_handle* h, int slot, const float* emb_nchw, const float* sparse, const int32_t* emb_index, int n_sparse,
+                               int P, int multimask, float* low_res, float* iou, void* stream) {
+  if (!h || !emb_nchw || !low_res || !iou) return set_error("msam_decoder_train_forward: null argument");
+  return h->eng.decoder_train_forward(slot, emb_nchw, sparse, emb_index, n_sparse, P, multimask, low_res, iou, (cudaStream_t)stream);
+}
+int msam_decoder_train_backward(msam_handle* h, int slot, const float* d_low_res, const float* d_iou, float* d_emb_nchw, void* stream) {
+  if (!h || !d_emb_nchw) return set_error("msam_decoder_train_backward: null argument");
+  return h->eng.decoder_train_backward(slot, d_low_res, d_iou, d_emb_nchw, (cudaStream_t)stream);
+}
+int msam_decoder_grad(msam_handle* h, const char* name, float* dst, int64_t n, void* stream) {
+  if (!h || !name || !dst) return set_error("msam_decoder_grad: null argument");
+  return h->eng.decoder_grad(name, dst, n, (cudaStream_t)stream);
+}
+int msam_decoder_zero_grads(msam_handle* h, void* stream) {
+  if (!h) return set_error("msam_decoder_zero_grads: null handle");
+  return h->eng.decoder_zero_grads((cudaStream_t)stream);
+}
+int msam_mask_loss_backward(const float* low_res, const uint8_t* targets, const float* d_stats, int n_obj, int M, int in_h, int in_w,
+                            int orig_h, int orig_w, float* d_low_res, void* stream) {
+  return post_mask_loss_backward(low_res, targets, d_stats, n_obj, M, in_h, in_w, orig_h, orig_w, d_low_res, (cudaStream_t)stream);
 }
 int msam_op_bgemm(const void* A, const void* B, int a_mn, int b_mn, int M, int N, int K, int lda, int ldb, int64_t a_hstride,
                   int64_t a_wstride, int64_t b_hstride, int64_t b_wstride, int heads, int outer, float* out, int ldc,

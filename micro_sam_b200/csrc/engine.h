@@ -67,6 +67,7 @@ struct TinyVit {
 
 struct DecoderState;  // decoder.cu
 struct TrainState;    // encoder_train.cu
+struct DecTrain;      // decoder_train.cu
 
 struct Engine {
   msam_config cfg{};
@@ -80,6 +81,8 @@ struct Engine {
   bool is_tinyvit() const { return cfg.depth == 0; }
   DecoderState* dec = nullptr;
   TrainState* train = nullptr;
+  DecTrain* dtrain = nullptr;
+  std::unordered_map<std::string, HostTensor> dec_host;   // prompt_encoder.* / mask_decoder.* host copies (decoder_train.cu packs its own operands)
 
   void* dalloc(size_t bytes, bool zero = false);
   const std::vector<float>* host(const std::string& name, std::initializer_list<int64_t> shape);
@@ -104,6 +107,14 @@ struct Engine {
   int encode_backward(const float* d_out, cudaStream_t st);
   int encoder_grad(const char* name, float* dst, int64_t n, cudaStream_t st);
   void train_invalidate();
+  // decoder_train.cu (cfg 5): mask decoder forward keeping activations (one image's prompts per call and slot) + backward
+  int dec_train_setup();
+  int decoder_train_forward(int slot, const float* emb_nchw, const float* sparse, const int* emb_index, int Ts, int P, int multimask,
+                            float* low_res, float* iou, cudaStream_t st);
+  int decoder_train_backward(int slot, const float* d_low_res, const float* d_iou, float* d_emb_nchw, cudaStream_t st);
+  int decoder_grad(const char* name, float* dst, int64_t n, cudaStream_t st);
+  int decoder_zero_grads(cudaStream_t st);
+  const float* dec_pos();   // decoder.cu: dense positional encoding, token-major [4096, 256] fp32
   int set_image_embedding(const float* feat, cudaStream_t st);  // decoder.cu
   int decode(const float* points, const float* labels, int np, const float* boxes, const float* mask_in, int P, int multimask,
              float* low_res, float* iou, cudaStream_t st);  // decoder.cu
@@ -143,6 +154,8 @@ int post_paint_canvas(const float* low_res, const int32_t* sel, const int32_t* g
 int post_canvas_to_label(const unsigned long long* canvas, long n, int32_t* label, cudaStream_t st);
 int post_mask_loss_stats(const float* low_res, const uint8_t* targets, int n_obj, int M, int in_h, int in_w, int out_h, int out_w,
                          float* out, cudaStream_t st);
+int post_mask_loss_backward(const float* low_res, const uint8_t* targets, const float* d_stats, int n_obj, int M, int in_h, int in_w,
+                            int out_h, int out_w, float* d_low_res, cudaStream_t st);
 int post_filter_nms(const int32_t* boxes, const float* scores, const float* stab, int n, int use_filters, float iou_thresh,
                     float stab_thresh, float nms_thresh, const int32_t* crop_box, const int32_t* orig_box, int32_t* keep,
                     int32_t* n_keep, cudaStream_t st);

@@ -33,7 +33,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_mn(uint32_t M, uint32_t N
 template <bool A_MN>
 __global__ void __launch_bounds__(wg::THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ out,
-               int M, int N, int K, int ldc) {
+               int M, int N, int K, int ldc, int accumulate) {
   using namespace wg;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -110,9 +110,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* dst = out + (size_t)row * ldc + n0 + 32 * c;
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          if (n0 + 32 * c + j < N)
-            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          if (n0 + 32 * c + j < N) {
+            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            if (accumulate) {   // gradient accumulation over images / sub-iterations (decoder_train.cu)
+              const float4 t = *reinterpret_cast<const float4*>(dst + j);
+              o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+            }
+            *reinterpret_cast<float4*>(dst + j) = o;
+          }
       }
     }
   }
@@ -126,7 +131,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 template <bool A_MN>
 static int launch_gemm_mn(const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K, int lda, int ldb, float* out, int ldc,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, int accumulate = 0) {
   using namespace wg;
   if (M <= 0 || N <= 0 || K <= 0) return set_error("gemm_tn: empty problem M=%d N=%d K=%d", M, N, K);
   // an MN-major operand is contracted over its rows: any K works (the K tail is zero-filled); a K-major A needs 16-byte rows
@@ -143,7 +148,7 @@ static int launch_gemm_mn(const __nv_bfloat16* A, const __nv_bfloat16* B, int M,
   if (make_tmap_bf16_2d(&tmB, B, K, N, ldb, BK)) return -1;
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
   prof_begin(stream, A_MN ? "gemm_tn (wgrad)" : "gemm_nn (dgrad)", 2.0 * M * N * K, (double)K * (M + N) * 2 + (double)M * N * 4);
-  gemm_tn_kernel<A_MN><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, out, M, N, K, ldc);
+  gemm_tn_kernel<A_MN><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, out, M, N, K, ldc, accumulate);
   prof_end(stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm_tn launch failed: %s", cudaGetErrorString(e));
@@ -152,8 +157,8 @@ static int launch_gemm_mn(const __nv_bfloat16* A, const __nv_bfloat16* B, int M,
 }
 
 int launch_gemm_tn(const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K, int lda, int ldb, float* out, int ldc,
-                   cudaStream_t stream) {
-  return launch_gemm_mn<true>(A, B, M, N, K, lda, ldb, out, ldc, stream);
+                   cudaStream_t stream, int accumulate) {
+  return launch_gemm_mn<true>(A, B, M, N, K, lda, ldb, out, ldc, stream, accumulate);
 }
 int launch_gemm_nn(const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K, int lda, int ldb, float* out, int ldc,
                    cudaStream_t stream) {

@@ -55,7 +55,7 @@ int launch_gemm_2sm(const GemmArgs& a, int num_sms, cudaStream_t stream);
 
 // ---- gemm_tn.cu : out[M,N] fp32 = A[K,M]^T B[K,N]  (weight gradient dW = dY^T X; both operands MN-major)
 int launch_gemm_tn(const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K, int lda, int ldb, float* out, int ldc,
-                   cudaStream_t stream);
+                   cudaStream_t stream, int accumulate = 0);
 // out[M,N] fp32 = A[M,K] B[K,N]  (input gradient dX = dY W; A K-major, B = the forward weight [out, in] consumed MN-major)
 int launch_gemm_nn(const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K, int lda, int ldb, float* out, int ldc,
                    cudaStream_t stream);
@@ -74,6 +74,7 @@ struct BGemmArgs {
   long o_hstride = 0, o_wstride = 0;
   float alpha = 1.f;
   int accumulate = 0;
+  int a_rows_valid = 0, b_rows_valid = 0;   // row extent of an operand if smaller than its tile extent (rows beyond are read as zeros)
 };
 int launch_bgemm(const BGemmArgs& a, cudaStream_t stream);
 

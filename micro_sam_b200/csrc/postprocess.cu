@@ -656,6 +656,58 @@ mask_loss_stats_kernel(const float* __restrict__ low_res, const uint8_t* __restr
   }
 }
 
+// Adjoint of mask_loss_stats_kernel w.r.t. the low-res logits: the loss reaches them only through  pt = sum sigmoid(v) t  and
+// pp = sum sigmoid(v)^2  (the counts are piecewise constant), so with a = dL/dpt, b = dL/dpp per predicted mask
+//   dL/dv(y, x) = (a t + 2 b p) p (1 - p),  p = sigmoid(v),
+// scattered to the low-res taps with the weights of the two bilinear stages (the transpose of full_res()).  d_low_res is
+// ACCUMULATED into with atomics (zero it first).
+__device__ __forceinline__ void stage1_scatter(float* __restrict__ dlr, const PostGeom& g, int Y, int X, float w) {
+  const Interp iy = interp_axis(Y, g.s1, g.lr), ix = interp_axis(X, g.s1, g.lr);
+  atomicAdd(dlr + iy.i0 * g.lr + ix.i0, w * iy.l0 * ix.l0);
+  atomicAdd(dlr + iy.i0 * g.lr + ix.i1, w * iy.l0 * ix.l1);
+  atomicAdd(dlr + iy.i1 * g.lr + ix.i0, w * iy.l1 * ix.l0);
+  atomicAdd(dlr + iy.i1 * g.lr + ix.i1, w * iy.l1 * ix.l1);
+}
+__global__ void __launch_bounds__(256)
+mask_loss_backward_kernel(const float* __restrict__ low_res, const uint8_t* __restrict__ targets, const float* __restrict__ d_stats,
+                          int M, PostGeom g, float* __restrict__ d_low_res) {
+  const long mi = blockIdx.x;
+  const float a = d_stats[mi * 5 + 0], b = d_stats[mi * 5 + 1];
+  if (a == 0.f && b == 0.f) return;   // masks that lost the min over the candidates
+  const float* lr = low_res + mi * g.lr * g.lr;
+  float* dlr = d_low_res + mi * g.lr * g.lr;
+  const uint8_t* tg = targets + (mi / M) * (long)g.out_h * g.out_w;
+  for (int y = threadIdx.x >> 5; y < g.out_h; y += 8) {
+    for (int x = threadIdx.x & 31; x < g.out_w; x += 32) {
+      const float v = full_res(lr, g, y, x);
+      const float t = tg[(long)y * g.out_w + x] != 0 ? 1.f : 0.f;
+      const float p = 1.0f / (1.0f + __expf(-v));
+      const float gv = (a * t + 2.f * b * p) * p * (1.f - p);
+      if (g.identity2) {
+        stage1_scatter(dlr, g, y, x, gv);
+      } else {
+        const Interp iy = interp_axis(y, g.s2y, g.in_h), ix = interp_axis(x, g.s2x, g.in_w);
+        stage1_scatter(dlr, g, iy.i0, ix.i0, gv * iy.l0 * ix.l0);
+        stage1_scatter(dlr, g, iy.i0, ix.i1, gv * iy.l0 * ix.l1);
+        stage1_scatter(dlr, g, iy.i1, ix.i0, gv * iy.l1 * ix.l0);
+        stage1_scatter(dlr, g, iy.i1, ix.i1, gv * iy.l1 * ix.l1);
+      }
+    }
+  }
+}
+
+int post_mask_loss_backward(const float* low_res, const uint8_t* targets, const float* d_stats, int n_obj, int M, int in_h, int in_w,
+                            int out_h, int out_w, float* d_low_res, cudaStream_t st) {
+  PostGeom g;
+  if (make_geom(in_h, in_w, out_h, out_w, &g)) return -1;
+  if (n_obj <= 0 || M <= 0) return 0;
+  prof_begin(st, "mask_loss_backward", 0.0, (double)n_obj * M * 65536.0 * 8 + (double)n_obj * out_h * out_w);
+  mask_loss_backward_kernel<<<n_obj * M, 256, 0, st>>>(low_res, targets, d_stats, M, g, d_low_res);
+  prof_end(st);
+  LAUNCH_CHECK("mask_loss_backward");
+  return 0;
+}
+
 int post_mask_loss_stats(const float* low_res, const uint8_t* targets, int n_obj, int M, int in_h, int in_w, int out_h, int out_w,
                          float* out, cudaStream_t st) {
   PostGeom g;

@@ -105,6 +105,36 @@ class _EncoderFn(torch.autograd.Function):
         return None, torch.zeros((), device=g.device), None
 
 
+class _DecoderFn(torch.autograd.Function):
+    """prompt encoder + mask decoder of ONE image with a backward pass (csrc/decoder_train.cu): (embedding [256,64,64], sparse prompt
+    embeddings [P,Ts,256]) -> (low-res logits [P,M,256,256], IoU predictions [P,M]).  backward fills / accumulates the decoder and
+    prompt-encoder parameter gradients inside the engine (`B200Sam.decoder_grads()`) and returns dL/d embedding."""
+
+    @staticmethod
+    def forward(ctx, emb, sparse, emb_index, sam, slot, multimask):
+        emb = emb.to(device=sam.device, dtype=torch.float32).contiguous()
+        sparse = sparse.to(device=sam.device, dtype=torch.float32).contiguous()
+        emb_index = emb_index.to(device=sam.device, dtype=torch.int32).contiguous()
+        P, Ts = sparse.shape[:2]
+        M = 3 if multimask else 1
+        low = torch.empty(P, M, 256, 256, device=sam.device, dtype=torch.float32)
+        iou = torch.empty(P, M, device=sam.device, dtype=torch.float32)
+        _lib.check(_lib.lib().msam_decoder_train_forward(sam._h, slot, _lib.ptr(emb), _lib.ptr(sparse), _lib.ptr(emb_index), Ts, P,
+                                                         int(bool(multimask)), _lib.ptr(low), _lib.ptr(iou), _lib.cur_stream()))
+        ctx.sam, ctx.slot = sam, slot
+        return low, iou
+
+    @staticmethod
+    def backward(ctx, d_low, d_iou):
+        sam = ctx.sam
+        d_low = None if d_low is None else d_low.to(torch.float32).contiguous()
+        d_iou = None if d_iou is None else d_iou.to(torch.float32).contiguous()
+        d_emb = torch.empty(256, 64, 64, device=sam.device, dtype=torch.float32)
+        _lib.check(_lib.lib().msam_decoder_train_backward(sam._h, ctx.slot, _lib.ptr(d_low), _lib.ptr(d_iou), _lib.ptr(d_emb), _lib.cur_stream()))
+        sam._decoder_grads_valid = True
+        return d_emb, None, None, None, None, None
+
+
 class _ImageEncoder:
     """Callable stand-in for `sam.image_encoder`: (B,3,1024,1024) fp32 preprocessed -> (B,256,64,64) fp32."""
 
@@ -312,6 +342,65 @@ class B200Sam:
             raise NotImplementedError("the TinyViT encoder has no backward pass")
         self.training = bool(mode)
         return self
+
+    def decoder_train(self, emb: torch.Tensor, points, boxes, multimask_output: bool, slot: int = 0):
+        """mask_decoder(prompt_encoder(points, boxes)) for ONE image in training mode: differentiable w.r.t. `emb` (256,64,64) and the
+        decoder / prompt-encoder parameters.  points = (coords (P,n,2), labels (P,n)) in the 1024 frame or None; boxes (P,4) or None."""
+        if not self.training:
+            raise RuntimeError("decoder_train needs train() mode")
+        with torch.no_grad():
+            sparse, _ = self.prompt_encoder(points=points, boxes=boxes, masks=None)
+        P = sparse.shape[0]
+        idx = []
+        if points is not None:
+            lab = points[1].to(self.device).round().to(torch.int64)
+            if boxes is None:   # a padding point (label -1) is appended when there is no box (prompt_encoder._embed_points(pad=True))
+                lab = torch.cat([lab, torch.full((P, 1), -1, device=self.device, dtype=torch.int64)], dim=1)
+            idx.append(torch.where(lab < 0, torch.full_like(lab, 4), lab.clamp(max=1)))
+        if boxes is not None:
+            idx.append(torch.tensor([[2, 3]], device=self.device, dtype=torch.int64).expand(P, 2))
+        emb_index = torch.cat(idx, dim=1)
+        assert emb_index.shape == sparse.shape[:2], (emb_index.shape, sparse.shape)
+        return _DecoderFn.apply(emb, sparse, emb_index, self, int(slot), bool(multimask_output))
+
+    def zero_decoder_grads(self) -> None:
+        _lib.check(_lib.lib().msam_decoder_zero_grads(self._h, _lib.cur_stream()))
+
+    def decoder_grads(self) -> Dict[str, torch.Tensor]:
+        """fp32 gradients of the mask-decoder / prompt-encoder parameters accumulated since `zero_decoder_grads()`, keyed and shaped
+        like the upstream state dict (parameters the training path does not touch -- mask_downscaling, the PE matrix -- are absent)."""
+        if not getattr(self, "_decoder_grads_valid", False):
+            raise RuntimeError("no decoder gradients: run decoder_train(...) and backward() first")
+        L = _lib.lib()
+
+        def fetch(name, n):
+            g = torch.empty(n, device=self.device, dtype=torch.float32)
+            _lib.check(L.msam_decoder_grad(self._h, name.encode(), _lib.ptr(g), n, _lib.cur_stream()))
+            return g
+        out = {}
+        for k, v in self._state.items():
+            if not (k.startswith("mask_decoder.") or k.startswith("prompt_encoder.")):
+                continue
+            if "mask_downscaling" in k or k.endswith("positional_encoding_gaussian_matrix"):
+                continue
+            if "output_upscaling.0" in k or "output_upscaling.3" in k:       # ConvTranspose2d [ci, co, 2, 2] <- GEMM layout [(dy,dx,co), ci]
+                ci, co = self._state[k.rsplit(".", 1)[0] + ".weight"].shape[:2]
+                if k.endswith(".weight"):
+                    out[k] = fetch(k + "@gemm", 4 * co * ci).view(2, 2, co, ci).permute(3, 2, 0, 1).contiguous()
+                else:
+                    out[k] = fetch(k + "@gemm", 4 * co).view(4, co).sum(0)
+            elif "point_embeddings" in k:
+                i = int(k.split(".")[2])
+                out[k] = fetch("prompt_encoder.point_embeddings@stack", 4 * 256).view(4, 1, 256)[i]
+            elif k == "mask_decoder.iou_token.weight":
+                out[k] = fetch("mask_decoder.output_tokens@stack", 5 * 256).view(5, 256)[:1]
+            elif k == "mask_decoder.mask_tokens.weight":
+                out[k] = fetch("mask_decoder.output_tokens@stack", 5 * 256).view(5, 256)[1:]
+            elif k.startswith("mask_decoder.iou_prediction_head.layers.2."):   # 4 outputs padded to 32 GEMM columns
+                out[k] = (fetch(k, 32 * 256).view(32, 256)[:4] if k.endswith(".weight") else fetch(k, 32)[:4]).contiguous()
+            else:
+                out[k] = fetch(k, v.numel()).view(v.shape)
+        return out
 
     def encoder_grads(self, names=None) -> Dict[str, torch.Tensor]:
         """fp32 gradients of the image-encoder parameters after a backward pass, keyed and shaped like the upstream state dict."""

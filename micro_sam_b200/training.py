@@ -46,11 +46,34 @@ class TrainableSAM:
                 rec["input_size"] = input_size
             return self.sam.image_encoder(images), batched_inputs
 
-    @torch.no_grad()
     def forward(self, batched_inputs: List[Dict[str, Any]], image_embeddings: torch.Tensor, multimask_output: bool = False,
                 return_masks: bool = True) -> List[Dict[str, Any]]:
         """trainable_sam.py:62-114.  `return_masks=False` skips the (n_obj, M, H, W) up-sampled logits (the loss does not need
-        them: `compute_loss` works from `low_res_masks`)."""
+        them: `compute_loss` works from `low_res_masks`).  In train() mode with grad enabled the outputs are part of the autograd
+        graph (point / box prompts; mask prompts are forward-only): image i of the batch uses decoder slot i."""
+        if getattr(self.sam, "training", False) and torch.is_grad_enabled():
+            return self._forward_train(batched_inputs, image_embeddings, multimask_output, return_masks)
+        with torch.no_grad():
+            return self._forward_eval(batched_inputs, image_embeddings, multimask_output, return_masks)
+
+    def _forward_train(self, batched_inputs, image_embeddings, multimask_output, return_masks):
+        sam, dev = self.sam, self.sam.device
+        outputs = []
+        for i, (rec, emb) in enumerate(zip(batched_inputs, image_embeddings)):
+            if "mask_inputs" in rec:
+                raise NotImplementedError("mask prompts have no backward pass (DESIGN.md): train with point / box prompts")
+            points = (rec["point_coords"].to(dev), rec["point_labels"].to(dev)) if "point_coords" in rec else None
+            boxes = rec["boxes"].to(dev) if "boxes" in rec else None
+            low, iou = sam.decoder_train(emb, points, boxes, multimask_output, slot=i % 8)
+            out = {"low_res_masks": low, "iou_predictions": iou, "input_size": tuple(rec["input_size"]),
+                   "original_size": tuple(rec["original_size"])}
+            if return_masks:
+                with torch.no_grad():
+                    out["masks"] = sam.postprocess_masks(low.detach(), input_size=rec["input_size"], original_size=rec["original_size"])
+            outputs.append(out)
+        return outputs
+
+    def _forward_eval(self, batched_inputs, image_embeddings, multimask_output, return_masks):
         sam, dev = self.sam, self.sam.device
         outputs = []
         for rec, emb in zip(batched_inputs, image_embeddings):
@@ -71,16 +94,38 @@ class TrainableSAM:
     __call__ = forward
 
 
+class _LossStatsFn(torch.autograd.Function):
+    """msam_mask_loss_stats with its adjoint (msam_mask_loss_backward): the loss depends on the logits only through the first two
+    sums (sum p t, sum p^2); the three counts are piecewise constant."""
+
+    @staticmethod
+    def forward(ctx, lr, tg, in_h, in_w, H, W):
+        n_obj, M = lr.shape[:2]
+        out = torch.empty(n_obj, M, 5, device=lr.device, dtype=torch.float32)
+        _lib.check(_lib.lib().msam_mask_loss_stats(_lib.ptr(lr), _lib.ptr(tg), n_obj, M, in_h, in_w, H, W, _lib.ptr(out), _lib.cur_stream()))
+        ctx.save_for_backward(lr, tg)
+        ctx.geom = (in_h, in_w, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_stats):
+        lr, tg = ctx.saved_tensors
+        n_obj, M = lr.shape[:2]
+        d_lr = torch.zeros_like(lr)
+        ds = d_stats.to(torch.float32).contiguous()
+        _lib.check(_lib.lib().msam_mask_loss_backward(_lib.ptr(lr), _lib.ptr(tg), _lib.ptr(ds), n_obj, M, *ctx.geom, _lib.ptr(d_lr),
+                                                      _lib.cur_stream()))
+        return d_lr, None, None, None, None, None
+
+
 def mask_loss_stats(low_res: torch.Tensor, targets: torch.Tensor, input_size, original_size) -> torch.Tensor:
-    """`msam_mask_loss_stats`: low_res (n_obj, M, 256, 256) logits + targets (n_obj, 1, H, W) {0,1} -> (n_obj, M, 5)."""
+    """`msam_mask_loss_stats`: low_res (n_obj, M, 256, 256) logits + targets (n_obj, 1, H, W) {0,1} -> (n_obj, M, 5); differentiable
+    w.r.t. `low_res` when it requires grad."""
     n_obj, M = low_res.shape[:2]
     H, W = int(original_size[0]), int(original_size[1])
     lr = low_res.to(torch.float32).contiguous()
     tg = (targets.reshape(n_obj, H, W).to(lr.device) != 0).to(torch.uint8).contiguous()
-    out = torch.empty(n_obj, M, 5, device=lr.device, dtype=torch.float32)
-    _lib.check(_lib.lib().msam_mask_loss_stats(_lib.ptr(lr), _lib.ptr(tg), n_obj, M, int(input_size[0]), int(input_size[1]), H, W,
-                                               _lib.ptr(out), _lib.cur_stream()))
-    return out
+    return _LossStatsFn.apply(lr, tg, int(input_size[0]), int(input_size[1]), H, W)
 
 
 def compute_loss(batched_outputs: List[Dict[str, Any]], y_one_hot, eps_dice: float = 1e-7, eps_iou: float = 1e-7):

@@ -1,7 +1,9 @@
 """`-m gpu` parity of the encoder backward pass (BASELINE.json configs[4], csrc/encoder_train.cu) against torch autograd over the
 fp32 oracle encoder (oracle/sam_ref.py): op level (batched attention-backward GEMM in its four operand layouts, LayerNorm
 backward) and model level (every parameter gradient of the image encoder for a random upstream gradient dL/d embedding).
-Tolerance: rel-L2 <= 3e-2 per gradient tensor (bf16 operands, fp32 accumulation; the forward tolerance is 2e-2)."""
+Tolerance: encoder alone (random upstream gradient) rel-L2 <= 3e-2 per gradient tensor (bf16 operands, fp32 accumulation; the forward
+tolerance is 2e-2); decoder and whole step: rel-L2 <= 1.5e-1 and cosine >= 0.99 per tensor = the measured bf16 noise floor of the
+decoder (see test_decoder_train_against_autograd); the loss-statistics adjoint is exact to 1e-6."""
 import os
 
 import numpy as np
@@ -145,3 +147,158 @@ def test_encoder_backward_small_archs(model_type):
 def test_encoder_backward_vit_b():
     """The architecture cfg 5 names, one image (the fp32 autograd reference needs ~30 GB of host memory for the global blocks)."""
     _encoder_grad_case("vit_b", B=1)
+
+
+# ------------------------------------------------------------------------------------------------ decoder + loss + full step
+def _small_models(max_batch=2):
+    from oracle import sam_ref
+    from micro_sam_b200 import util
+    sd = sam_ref.seeded_state_dict("vit_test", seed=1)
+    osam = sam_ref.build_sam("vit_test")
+    osam.load_state_dict(sd)
+    pred = util.get_sam_model("vit_test", state_dict=sd, max_batch=max_batch, max_prompts=64)
+    return osam, pred.model
+
+
+def _compare_grads(got, ref_named, tol, min_cos=0.0, dump=None):
+    """rel-L2 per gradient tensor.  Gradients that are analytically zero (k_proj biases: softmax is invariant to a constant added to
+    every key's logit; parameters the prompt type does not touch) are compared absolutely against the scale of the largest
+    reference gradient instead."""
+    scale = max(float(p.grad.double().norm()) for p in ref_named.values() if p.grad is not None)
+    rels, bad = {}, {}
+    for k, g in got.items():
+        ref = ref_named[k].grad
+        if ref is None or float(ref.double().norm()) < 1e-6 * scale:
+            if not float(g.double().norm()) < 1e-3 * scale:
+                bad[k] = ("expected ~0", float(g.double().norm()), scale)
+            continue
+        assert tuple(ref.shape) == tuple(g.shape), (k, ref.shape, g.shape)
+        r = _rel(g, ref)
+        cos = float(torch.nn.functional.cosine_similarity(g.double().cpu().flatten(), ref.double().flatten(), dim=0))
+        rels[k] = r
+        if not (r < tol and cos > min_cos):
+            bad[k] = (r, cos)
+    if dump:
+        with open(dump, "w") as f:
+            for k, v in sorted(rels.items(), key=lambda kv: -kv[1]):
+                f.write(f"{v:.3e}  {k}\n")
+    return rels, bad
+
+
+@pytest.mark.parametrize("prompt,multimask", [("boxes", True), ("points", False), ("points+boxes", True)])
+def test_decoder_train_against_autograd(prompt, multimask):
+    """Training-mode mask decoder + prompt encoder (csrc/decoder_train.cu) for one image: forward against the oracle modules, then
+    dL/d embedding and every parameter gradient for a random linear functional of (low_res, iou) against torch autograd."""
+    osam, sam = _small_models()
+    sam.train()
+    gen = torch.Generator().manual_seed(3)
+    P = 6
+    emb = torch.randn(1, 256, 64, 64, generator=gen)
+    boxes = pts = None
+    if "boxes" in prompt:
+        xy = torch.rand(P, 2, generator=gen) * 600 + 50
+        boxes = torch.cat([xy, xy + torch.rand(P, 2, generator=gen) * 300 + 20], 1)
+    if "points" in prompt:
+        coords = torch.rand(P, 3, 2, generator=gen) * 1000
+        labels = torch.tensor([[1, 0, 1]] * (P - 1) + [[1, 1, -1]], dtype=torch.float32)
+        pts = (coords, labels)
+    M = 3 if multimask else 1
+    w_low = torch.randn(P, M, 256, 256, generator=gen) / 256
+    w_iou = torch.randn(P, M, generator=gen)
+    # oracle
+    for p in osam.parameters():
+        p.requires_grad_(True)
+    oemb = emb.clone().requires_grad_(True)
+    sp, de = osam.prompt_encoder(points=pts, boxes=boxes, masks=None)
+    olow, oiou = osam.mask_decoder(image_embeddings=oemb, image_pe=osam.prompt_encoder.get_dense_pe(), sparse_prompt_embeddings=sp,
+                                   dense_prompt_embeddings=de, multimask_output=multimask)
+    ((olow * w_low).sum() + (oiou * w_iou).sum()).backward()
+    # ours
+    gemb = emb.clone().to(DEV).requires_grad_(True)
+    gp = None if pts is None else (pts[0].to(DEV), pts[1].to(DEV))
+    sam.zero_decoder_grads()
+    low, iou = sam.decoder_train(gemb[0], gp, None if boxes is None else boxes.to(DEV), multimask, slot=1)
+    rl, ri = _rel(low.detach(), olow.detach()), float((iou.detach().cpu() - oiou.detach()).abs().max())
+    torch.autograd.backward([low, iou], [w_low.to(DEV), w_iou.to(DEV)])
+    re = _rel(gemb.grad, oemb.grad)
+    # Tolerance = the bf16 noise floor of this decoder, measured with torch itself (tests/bf16_noise_floor.py: the oracle under
+    # autocast(bfloat16) against its own fp32 autograd gives forward 1.5e-2, d emb 1.8e-2, parameter gradients median 8.2e-2, worst
+    # 1.3e-1 -- on the SAME tensors that are worst here: hyper-network MLP 1, norm_final_attn, final attention): the token side is
+    # 42 rows through ~25 bf16 ops and with random weights the attention is near uniform, so dS = P (dP - sum P dP) is a small
+    # difference of bf16-rounded products.  The image side (d emb) sits at 1e-2.
+    os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out"), exist_ok=True)
+    rels, bad = _compare_grads(sam.decoder_grads(), dict(osam.named_parameters()), 1.5e-1, min_cos=0.99,
+                               dump=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", f"decoder_grads_{prompt}.txt"))
+    worst = sorted(rels.items(), key=lambda kv: -kv[1])[:5]
+    print(f"decoder_train {prompt} M={M}: low-res rel-L2 {rl:.2e}, iou err {ri:.2e}, d emb rel-L2 {re:.2e}; {len(rels)} parameter gradients, "
+          f"median {np.median(list(rels.values())):.2e}, worst " + ", ".join(f"{k.split('.', 1)[1]} {v:.2e}" for k, v in worst))
+    assert rl < 3e-2 and ri < 2e-2 and re < 4e-2
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("input_size,original_size", [((768, 1024), (96, 128)), ((1024, 1024), (1024, 1024)), ((1024, 1024), (512, 512))])
+def test_loss_backward_against_autograd(input_size, original_size):
+    """d loss / d low-res logits of compute_loss (dice of sigmoid(postprocess_masks(low_res)) minimised over the candidate masks + IoU
+    MSE): the fused statistics kernel + its adjoint against autograd through the oracle's interpolate / sigmoid / dice."""
+    from oracle import sam_ref, train_ref
+    from micro_sam_b200 import training
+    H, W = original_size
+    gen = torch.Generator().manual_seed(4)
+    n_obj, M = 3, 3
+    low = (torch.randn(n_obj, M, 256, 256, generator=gen) * 2)
+    low = torch.nn.functional.avg_pool2d(low, 9, 1, 4)        # smooth logits: masks with structure
+    iou = torch.rand(n_obj, M, generator=gen)
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    tg = torch.stack([(((yy - H * (0.3 + 0.2 * k)) ** 2 + (xx - W * (0.3 + 0.2 * k)) ** 2) < (min(H, W) * 0.15) ** 2).float()[None] for k in range(n_obj)])
+    osam = sam_ref.build_sam("vit_test")
+    olow = low.clone().requires_grad_(True)
+    oiou = iou.clone().requires_grad_(True)
+    omasks = osam.postprocess_masks(olow, input_size, original_size)
+    oloss = train_ref.compute_loss([{"masks": omasks, "iou_predictions": oiou}], [tg])
+    oloss[0].backward()
+    glow = low.clone().to(DEV).requires_grad_(True)
+    giou = iou.clone().to(DEV).requires_grad_(True)
+    loss = training.compute_loss([{"low_res_masks": glow, "iou_predictions": giou, "input_size": input_size, "original_size": original_size}], [tg])
+    loss[0].backward()
+    assert abs(float(loss[0]) - float(oloss[0])) < 1e-4
+    r1, r2 = _rel(glow.grad, olow.grad), _rel(giou.grad, oiou.grad)
+    print(f"loss backward {input_size}->{original_size}: loss {float(loss[0]):.4f}, d low-res rel-L2 {r1:.2e}, d iou rel-L2 {r2:.2e}")
+    assert r1 < 1e-3 and r2 < 1e-4
+
+
+def test_training_step_end_to_end():
+    """The whole fine-tuning step of cfg 5 on the tiny architecture: TrainableSAM.image_embeddings_oft -> forward (box prompts) ->
+    _compute_loss -> loss.backward(): the loss and every encoder / decoder / prompt-encoder gradient against the oracle TrainableSAM
+    under torch autograd (micro_sam/training/sam_trainer.py:131-172, :393)."""
+    from oracle import train_ref
+    from micro_sam_b200 import training
+    from micro_sam_b200.sample_data import lm_tile
+    osam, sam = _small_models()
+    sam.train()
+    for p in osam.parameters():
+        p.requires_grad_(True)
+    om, m = train_ref.TrainableSAM(osam), training.TrainableSAM(sam)
+    B, n_obj, H, W = 2, 4, 128, 128
+    imgs = [torch.from_numpy(np.repeat(lm_tile((H, W), 12, seed=30 + b, dtype="uint8")[None], 3, 0).astype("float32")) for b in range(B)]
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    cen = [(30 + 22 * k, 28 + 24 * k, 9 + 2 * k) for k in range(n_obj)]
+    y_one_hot = [torch.stack([(((yy - cy) ** 2 + (xx - cx) ** 2) < r * r).float()[None] for cy, cx, r in cen]) for _ in range(B)]
+    boxes = torch.tensor([[cx - r, cy - r, cx + r, cy + r] for cy, cx, r in cen], dtype=torch.float32) * (1024.0 / W)
+
+    def records():
+        return [{"image": im.clone(), "original_size": (H, W), "boxes": boxes.clone()} for im in imgs]
+    oemb, orecs = om.image_embeddings_oft(records())
+    oloss = train_ref.compute_loss(om(orecs, oemb, multimask_output=True), y_one_hot)
+    oloss[0].backward()
+    sam.zero_decoder_grads()
+    emb, recs = m.image_embeddings_oft(records())
+    assert emb.requires_grad
+    loss = training.compute_loss(m(recs, emb, multimask_output=True, return_masks=False), y_one_hot)
+    loss[0].backward()
+    ref = dict(osam.named_parameters())
+    r_enc, bad_enc = _compare_grads(sam.encoder_grads(), ref, 1.5e-1, min_cos=0.99)
+    r_dec, bad_dec = _compare_grads(sam.decoder_grads(), ref, 1.5e-1, min_cos=0.99)
+    print(f"training step: loss {float(loss[0]):.4f} (oracle {float(oloss[0]):.4f}); encoder gradients median rel-L2 {np.median(list(r_enc.values())):.2e} "
+          f"max {max(r_enc.values()):.2e}; decoder gradients median {np.median(list(r_dec.values())):.2e} max {max(r_dec.values()):.2e}")
+    assert abs(float(loss[0]) - float(oloss[0])) < 2e-2
+    assert not bad_enc and not bad_dec, (bad_enc, bad_dec)
