@@ -218,6 +218,12 @@ int msam_decoder_train_forward(msam_handle* h, int slot, const float* emb_nchw, 
 int msam_decoder_train_backward(msam_handle* h, int slot, const float* d_low_res, const float* d_iou, float* d_emb_nchw, void* stream);
 int msam_decoder_grad(msam_handle* h, const char* name, float* dst, int64_t n, void* stream);
 int msam_decoder_zero_grads(msam_handle* h, void* stream);
+/* torch.optim.AdamW semantics (micro_sam/training/training.py:train_sam's default optimizer) over every tensor that has received
+ * gradients through msam_encode_backward / msam_decoder_train_backward: fp32 master weights, moments and decoupled weight decay on the
+ * device, then the bf16 / transposed / packed operands of the training paths are refreshed.  msam_train_param reads a master tensor
+ * (same keys and layouts as the gradient read-outs).  The packed operands of the INFERENCE decoder are refreshed by load_state_dict. */
+int msam_optimizer_step(msam_handle* h, float lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
+int msam_train_param(msam_handle* h, const char* key, float* dst, int64_t n, void* stream);
 /* Adjoint of msam_mask_loss_stats w.r.t. the low-res logits: d_stats [n_obj*M, 5] (only columns 0, 1 = dL/d sum(p t), dL/d sum(p^2)
  * matter) -> d_low_res [n_obj*M, 256, 256] accumulated (zero it first).  sam_trainer.py:131-172 backward. */
 int msam_mask_loss_backward(const float* low_res, const uint8_t* targets, const float* d_stats, int n_obj, int M, int in_h, int in_w,

@@ -795,6 +795,13 @@ int Engine::decode(const float* points, const float* labels, int np, const float
 // PromptEncoder.forward as a stand-alone call: sparse [P, n_sparse, 256] (points incl. the padding point when no box is
 // given, then the two box corners) and, for mask prompts, the dense embedding [P, 256, 64, 64] (NCHW fp32).
 const float* Engine::dec_pos() { return dec ? dec->pos : nullptr; }
+int Engine::dec_set_prompt_tables(const float* point_emb, const float* not_a_point, cudaStream_t st) {
+  if (!dec) return set_error("decoder weights not loaded");
+  if ((point_emb && cudaMemcpyAsync(dec->point_emb, point_emb, 4 * 256 * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) ||
+      (not_a_point && cudaMemcpyAsync(dec->not_a_point, not_a_point, 256 * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess))
+    return set_error("prompt tables: copy failed");
+  return 0;
+}
 
 int Engine::prompt_encode(const float* points, const float* labels, int np, const float* boxes, const float* mask_in, int P,
                           float* sparse_out, float* dense_out, cudaStream_t st) {

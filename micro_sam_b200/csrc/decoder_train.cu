@@ -464,6 +464,11 @@ static int dt_lin(Engine& e, DecTrain& d, const std::string& key, int out, int i
   CHK(L->gb = (float*)e.dalloc((size_t)op * 4, true));
   d.grads[key + ".weight"] = {L->gw, (int64_t)op * in};
   d.grads[key + ".bias"] = {L->gb, op};
+  OptParam pw, pb;
+  pw.key = key + ".weight"; CHK(pw.w = e.upload_f32(wp.data(), wp.size())); pw.g = L->gw; pw.n = (int64_t)op * in;
+  pw.refresh = 2; pw.dst = L->w; pw.dstT = L->wT; pw.rows = op; pw.cols = in;
+  pb.key = key + ".bias"; pb.w = L->bias; pb.g = L->gb; pb.n = op;
+  e.opt_add(pw); e.opt_add(pb);
   return 0;
 }
 static int dt_ln(Engine& e, DecTrain& d, const std::string& key, int D, float eps, DLn* L) {
@@ -474,6 +479,10 @@ static int dt_ln(Engine& e, DecTrain& d, const std::string& key, int D, float ep
   CHK(L->gb = (float*)e.dalloc((size_t)D * 4, true));
   d.grads[key + ".weight"] = {L->gg, D};
   d.grads[key + ".bias"] = {L->gb, D};
+  OptParam pg, pb;
+  pg.key = key + ".weight"; pg.w = L->g; pg.g = L->gg; pg.n = D;
+  pb.key = key + ".bias"; pb.w = L->b; pb.g = L->gb; pb.n = D;
+  e.opt_add(pg); e.opt_add(pb);
   return 0;
 }
 static int dt_attn(Engine& e, DecTrain& d, const std::string& key, int inner, DAttn* A) {
@@ -504,6 +513,11 @@ static int dt_convT(Engine& e, DecTrain& d, const std::string& key, int ci, int 
   CHK(L->gb = (float*)e.dalloc(bg.size() * 4, true));
   d.grads[key + ".weight@gemm"] = {L->gw, (int64_t)wg.size()};
   d.grads[key + ".bias@gemm"] = {L->gb, (int64_t)bg.size()};
+  OptParam pw, pb;
+  pw.key = key + ".weight@gemm"; CHK(pw.w = e.upload_f32(wg.data(), wg.size())); pw.g = L->gw; pw.n = (int64_t)wg.size();
+  pw.refresh = 2; pw.dst = L->w; pw.dstT = L->wT; pw.rows = 4 * co; pw.cols = ci;
+  pb.key = key + ".bias@gemm"; pb.w = L->bias; pb.g = L->gb; pb.n = (int64_t)bg.size(); pb.refresh = 6;
+  e.opt_add(pw); e.opt_add(pb);
   return 0;
 }
 
@@ -564,6 +578,11 @@ int Engine::dec_train_setup() {
     d.grads["mask_decoder.output_tokens@stack"] = {d.g_out_tokens, 5 * 256};
     d.grads["prompt_encoder.not_a_point_embed.weight"] = {d.g_nap, 256};
     d.grads["prompt_encoder.no_mask_embed.weight"] = {d.g_no_mask, 256};
+    OptParam p;
+    p.key = "prompt_encoder.point_embeddings@stack"; p.w = d.point_emb; p.g = d.g_point_emb; p.n = 4 * 256; p.refresh = 5; opt_add(p);
+    p.key = "prompt_encoder.not_a_point_embed.weight"; p.w = d.not_a_point; p.g = d.g_nap; p.n = 256; p.refresh = 5; opt_add(p);
+    p.key = "mask_decoder.output_tokens@stack"; p.w = d.out_tokens; p.g = d.g_out_tokens; p.n = 5 * 256; p.refresh = 0; opt_add(p);
+    p.key = "prompt_encoder.no_mask_embed.weight"; p.w = d.no_mask; p.g = d.g_no_mask; p.n = 256; p.refresh = 0; opt_add(p);
     return 0;
   };
   rc = go();

@@ -119,6 +119,28 @@ int Engine::train_setup() {
     CHK(s.g_fc2_b = galloc(*this, t, p + "mlp.lin2.bias", D));
     CHK(s.g_rel_h = galloc(*this, t, p + "attn.rel_pos_h", (int64_t)(2 * S - 1) * hd));
     CHK(s.g_rel_w = galloc(*this, t, p + "attn.rel_pos_w", (int64_t)(2 * S - 1) * hd));
+    // optimizer registry (train_opt.cu): fp32 parameters are updated in place, bf16 operands from fp32 masters
+    EncBlock& b = enc.blocks[i];
+    auto inplace = [&](const std::string& k, float* w, float* g, int64_t n) { OptParam q; q.key = k; q.w = w; q.g = g; q.n = n; opt_add(q); };
+    auto casted = [&](const std::string& k, float* g, int64_t n, __nv_bfloat16* dst) -> int {
+      OptParam q; q.key = k; q.g = g; q.n = n; q.refresh = 1; q.dst = dst;
+      CHK(q.w = opt_master_from_host(k, n));
+      opt_add(q);
+      return 0;
+    };
+    inplace(p + "norm1.weight", b.ln1_g, s.g_ln1_g, D); inplace(p + "norm1.bias", b.ln1_b, s.g_ln1_b, D);
+    inplace(p + "norm2.weight", b.ln2_g, s.g_ln2_g, D); inplace(p + "norm2.bias", b.ln2_b, s.g_ln2_b, D);
+    RUN(casted(p + "attn.qkv.weight", s.g_qkv_w, (int64_t)3 * D * D, b.qkv_w)); inplace(p + "attn.qkv.bias", b.qkv_b, s.g_qkv_b, 3 * D);
+    RUN(casted(p + "attn.proj.weight", s.g_proj_w, (int64_t)D * D, b.proj_w)); inplace(p + "attn.proj.bias", b.proj_b, s.g_proj_b, D);
+    RUN(casted(p + "mlp.lin1.weight", s.g_fc1_w, (int64_t)4 * D * D, b.fc1_w)); inplace(p + "mlp.lin1.bias", b.fc1_b, s.g_fc1_b, 4 * D);
+    RUN(casted(p + "mlp.lin2.weight", s.g_fc2_w, (int64_t)4 * D * D, b.fc2_w)); inplace(p + "mlp.lin2.bias", b.fc2_b, s.g_fc2_b, D);
+    for (int hw = 0; hw < 2; ++hw) {
+      OptParam q;
+      q.key = p + (hw ? "attn.rel_pos_w" : "attn.rel_pos_h"); q.g = hw ? s.g_rel_w : s.g_rel_h; q.n = (int64_t)(2 * S - 1) * hd;
+      q.refresh = 3; q.dst = b.rel_table; q.rows = 2 * S - 1; q.cols = hd; q.cols_pad = ((hd + 63) / 64) * 64; q.row_off = hw ? (glob ? 128 : 32) : 0;
+      CHK(q.w = opt_master_from_host(q.key, q.n));
+      opt_add(q);
+    }
   }
   CHK(t.neck1_wT = (__nv_bfloat16*)dalloc((size_t)C * D * 2));
   CHK(t.neck2_wT = (__nv_bfloat16*)dalloc((size_t)9 * C * C * 2));
@@ -132,6 +154,20 @@ int Engine::train_setup() {
   CHK(t.g_neck2_w_up = galloc(*this, t, e + "neck.2.weight", (int64_t)9 * C * C));
   CHK(t.g_neck_ln2_g = galloc(*this, t, e + "neck.3.weight", C));
   CHK(t.g_neck_ln2_b = galloc(*this, t, e + "neck.3.bias", C));
+  {
+    auto inplace = [&](const std::string& k, float* w, float* g, int64_t n) { OptParam q; q.key = k; q.w = w; q.g = g; q.n = n; opt_add(q); };
+    OptParam q;
+    q.key = e + "patch_embed.proj.weight"; q.g = t.g_patch_w; q.n = (int64_t)D * 768; q.refresh = 1; q.dst = enc.patch_w;
+    CHK(q.w = opt_master_from_host(q.key, q.n)); opt_add(q);
+    inplace(e + "patch_embed.proj.bias", enc.patch_b, t.g_patch_b, D);
+    inplace(e + "pos_embed", enc.pos_embed, t.g_pos, (int64_t)T * D);
+    q = OptParam(); q.key = e + "neck.0.weight"; q.g = t.g_neck1_w; q.n = (int64_t)C * D; q.refresh = 1; q.dst = enc.neck_conv1;
+    CHK(q.w = opt_master_from_host(q.key, q.n)); opt_add(q);
+    inplace(e + "neck.1.weight", enc.neck_ln1_g, t.g_neck_ln1_g, C); inplace(e + "neck.1.bias", enc.neck_ln1_b, t.g_neck_ln1_b, C);
+    q = OptParam(); q.key = e + "neck.2.weight"; q.g = t.g_neck2_w_up; q.n = (int64_t)9 * C * C; q.refresh = 4; q.dst = enc.neck_conv2; q.rows = C;
+    CHK(q.w = opt_master_from_host(q.key, q.n)); opt_add(q);
+    inplace(e + "neck.3.weight", enc.neck_ln2_g, t.g_neck_ln2_g, C); inplace(e + "neck.3.bias", enc.neck_ln2_b, t.g_neck_ln2_b, C);
+  }
   // scratch
   const size_t Dm = D > C ? D : C;
   CHK(t.dx = (float*)dalloc(M * Dm * 4));

@@ -448,8 +448,7 @@ int msam_finalize_weights(msam_handle* h) {
     if (h->eng.alloc_encoder_ws()) return -1;
   }
   if (h->eng.finalize_decoder()) return -1;
-  for (auto& kv : h->eng.host_weights)
-    if (kv.first.rfind("mask_decoder.", 0) == 0 || kv.first.rfind("prompt_encoder.", 0) == 0) h->eng.dec_host[kv.first] = std::move(kv.second);
+  h->eng.dec_host = std::move(h->eng.host_weights);   // kept: fp32 masters / training-path operands are built from them on demand
   h->eng.host_weights.clear();
   if (cudaDeviceSynchronize() != cudaSuccess) return set_error("finalize: %s", cudaGetErrorString(cudaGetLastError()));
   h->eng.finalized = true;
@@ -678,6 +677,14 @@ int msam_decoder_zero_grads(msam_handle* h, void* stream) {
 int msam_mask_loss_backward(const float* low_res, const uint8_t* targets, const float* d_stats, int n_obj, int M, int in_h, int in_w,
                             int orig_h, int orig_w, float* d_low_res, void* stream) {
   return post_mask_loss_backward(low_res, targets, d_stats, n_obj, M, in_h, in_w, orig_h, orig_w, d_low_res, (cudaStream_t)stream);
+}
+int msam_optimizer_step(msam_handle* h, float lr, float beta1, float beta2, float eps, float weight_decay, void* stream) {
+  if (!h) return set_error("msam_optimizer_step: null handle");
+  return h->eng.optimizer_step(lr, beta1, beta2, eps, weight_decay, (cudaStream_t)stream);
+}
+int msam_train_param(msam_handle* h, const char* key, float* dst, int64_t n, void* stream) {
+  if (!h || !key || !dst) return set_error("msam_train_param: null argument");
+  return h->eng.train_param(key, dst, n, (cudaStream_t)stream);
 }
 int msam_op_bgemm(const void* A, const void* B, int a_mn, int b_mn, int M, int N, int K, int lda, int ldb, int64_t a_hstride,
                   int64_t a_wstride, int64_t b_hstride, int64_t b_wstride, int heads, int outer, float* out, int ldc,

@@ -65,6 +65,18 @@ struct TinyVit {
   float *x = nullptr, *x2 = nullptr;
 };
 
+// One trainable tensor of the optimizer (train_opt.cu): fp32 master weights (the live parameter buffer itself when the kernels read
+// fp32: biases, LayerNorm, embedding tables), its gradient, AdamW moments, and how the packed operands are refreshed after an update.
+struct OptParam {
+  std::string key;              // gradient key: upstream name, or "<name>@gemm" / "@stack" for packed layouts
+  float *w = nullptr, *g = nullptr, *m = nullptr, *v = nullptr;
+  int64_t n = 0;
+  int refresh = 0;              // 0 none | 1 cast -> dst | 2 cast -> dst + transpose -> dstT | 3 rows of a rel-pos table | 4 neck 3x3 conv
+                                // relayout | 5 prompt-encoder tables of the inference decoder | 6 conv-transpose bias (fold the 4 tiles first)
+  __nv_bfloat16 *dst = nullptr, *dstT = nullptr;
+  int rows = 0, cols = 0, cols_pad = 0, row_off = 0;
+};
+
 struct DecoderState;  // decoder.cu
 struct TrainState;    // encoder_train.cu
 struct DecTrain;      // decoder_train.cu
@@ -82,7 +94,9 @@ struct Engine {
   DecoderState* dec = nullptr;
   TrainState* train = nullptr;
   DecTrain* dtrain = nullptr;
-  std::unordered_map<std::string, HostTensor> dec_host;   // prompt_encoder.* / mask_decoder.* host copies (decoder_train.cu packs its own operands)
+  std::unordered_map<std::string, HostTensor> dec_host;   // host fp32 copies of every weight, kept for the training paths (masters, decoder_train.cu operands)
+  std::vector<OptParam> opt;
+  int64_t opt_step_count = 0;
 
   void* dalloc(size_t bytes, bool zero = false);
   const std::vector<float>* host(const std::string& name, std::initializer_list<int64_t> shape);
@@ -115,6 +129,12 @@ struct Engine {
   int decoder_grad(const char* name, float* dst, int64_t n, cudaStream_t st);
   int decoder_zero_grads(cudaStream_t st);
   const float* dec_pos();   // decoder.cu: dense positional encoding, token-major [4096, 256] fp32
+  int dec_set_prompt_tables(const float* point_emb_4x256, const float* not_a_point, cudaStream_t st);   // decoder.cu
+  // train_opt.cu: AdamW over every registered tensor + refresh of the packed operands; read-out of the master weights
+  float* opt_master_from_host(const std::string& key, int64_t n);
+  void opt_add(const OptParam& p) { opt.push_back(p); }
+  int optimizer_step(float lr, float beta1, float beta2, float eps, float weight_decay, cudaStream_t st);
+  int train_param(const char* key, float* dst, int64_t n, cudaStream_t st);
   int set_image_embedding(const float* feat, cudaStream_t st);  // decoder.cu
   int decode(const float* points, const float* labels, int np, const float* boxes, const float* mask_in, int P, int multimask,
              float* low_res, float* iou, cudaStream_t st);  // decoder.cu

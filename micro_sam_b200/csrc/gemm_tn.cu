@@ -43,7 +43,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int k_blocks = (K + BK - 1) / BK;   // the K tail is zero-filled by TMA (out-of-bounds rows)
+  // split-K over gridDim.z: the token dimension is long (8192 .. 400k rows) and the output weight-sized, so one CTA per tile would
+  // leave most SMs idle; partial sums are added with atomics (the host zeroes the output first unless it accumulates anyway)
+  const int k_blocks_all = (K + BK - 1) / BK;   // the K tail is zero-filled by TMA (out-of-bounds rows)
+  const int kb_per = (k_blocks_all + gridDim.z - 1) / gridDim.z;
+  const int kb0 = blockIdx.z * kb_per;
+  const int kb1 = (kb0 + kb_per < k_blocks_all) ? kb0 + kb_per : k_blocks_all;
+  const bool atomic_out = gridDim.z > 1;
 
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
   if (warp == 1 && lane == 0) {
@@ -61,7 +67,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1, 50);
         uint8_t* sa = smem + stage * STAGE_BYTES;
         mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
@@ -80,7 +86,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t idesc = make_idesc_bf16_mn(BM, BN, A_MN ? 1u : 0u);
     int stage = 0;
     uint32_t phase = 0;
-    for (int kb = 0; kb < k_blocks; ++kb) {
+    for (int kb = kb0; kb < kb1; ++kb) {
       mbar_wait(&full_bar[stage], phase, 51);
       tc_fence_after();
       const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
@@ -89,10 +95,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kk = 0; kk < BK / 16; ++kk) {  // 16 token rows = 2048 B further down the MN-major tile
           const uint64_t da = A_MN ? make_desc_sw128(sa + kk * 2048, SUB, 1024) : make_desc_sw128(sa + kk * 32, 0, 1024);
           const uint64_t db = make_desc_sw128(sb + kk * 2048, SUB, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (kb | kk) != 0);
+          umma_bf16(tmem_base, da, db, idesc, (kb > kb0) || (kk != 0));
         }
         umma_commit(&empty_bar[stage]);
-        if (kb == k_blocks - 1) umma_commit(acc_full);
+        if (kb == kb1 - 1) umma_commit(acc_full);
       }
       __syncwarp();
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -112,6 +118,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < 32; j += 4)
           if (n0 + 32 * c + j < N) {
             float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            if (atomic_out) {
+              atomicAdd(dst + j, o.x); atomicAdd(dst + j + 1, o.y); atomicAdd(dst + j + 2, o.z); atomicAdd(dst + j + 3, o.w);
+              continue;
+            }
             if (accumulate) {   // gradient accumulation over images / sub-iterations (decoder_train.cu)
               const float4 t = *reinterpret_cast<const float4*>(dst + j);
               o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
@@ -147,6 +157,18 @@ static int launch_gemm_mn(const __nv_bfloat16* A, const __nv_bfloat16* B, int M,
   if (A_MN ? make_tmap_bf16_2d(&tmA, A, K, M, lda, BK) : make_tmap_bf16_2d(&tmA, A, M, K, lda, BM)) return -1;
   if (make_tmap_bf16_2d(&tmB, B, K, N, ldb, BK)) return -1;
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
+  {   // split-K until ~2 CTAs per SM, at least 8 k-blocks per split
+    const int k_blocks = (K + BK - 1) / BK, tiles = grid.x * grid.y;
+    int splits = (296 + tiles - 1) / tiles;
+    if (splits > (k_blocks + 7) / 8) splits = (k_blocks + 7) / 8;
+    if (splits < 1) splits = 1;
+    const int per = (k_blocks + splits - 1) / splits;
+    splits = (k_blocks + per - 1) / per;       // no empty split
+    grid.z = splits;
+    if (splits > 1 && !accumulate &&
+        cudaMemset2DAsync(out, (size_t)ldc * 4, 0, (size_t)N * 4, M, stream) != cudaSuccess)
+      return set_error("gemm_tn: memset failed");
+  }
   prof_begin(stream, A_MN ? "gemm_tn (wgrad)" : "gemm_nn (dgrad)", 2.0 * M * N * K, (double)K * (M + N) * 2 + (double)M * N * 4);
   gemm_tn_kernel<A_MN><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, out, M, N, K, ldc, accumulate);
   prof_end(stream);

@@ -371,11 +371,13 @@ class B200Sam:
         like the upstream state dict (parameters the training path does not touch -- mask_downscaling, the PE matrix -- are absent)."""
         if not getattr(self, "_decoder_grads_valid", False):
             raise RuntimeError("no decoder gradients: run decoder_train(...) and backward() first")
-        L = _lib.lib()
+        return self._decoder_tensors(_lib.lib().msam_decoder_grad)
 
+    def _decoder_tensors(self, getter, params: bool = False) -> Dict[str, torch.Tensor]:
+        """Decoder / prompt-encoder tensors (gradients or master weights) from the engine's packed layouts to upstream keys / shapes."""
         def fetch(name, n):
             g = torch.empty(n, device=self.device, dtype=torch.float32)
-            _lib.check(L.msam_decoder_grad(self._h, name.encode(), _lib.ptr(g), n, _lib.cur_stream()))
+            _lib.check(getter(self._h, name.encode(), _lib.ptr(g), n, _lib.cur_stream()))
             return g
         out = {}
         for k, v in self._state.items():
@@ -388,7 +390,8 @@ class B200Sam:
                 if k.endswith(".weight"):
                     out[k] = fetch(k + "@gemm", 4 * co * ci).view(2, 2, co, ci).permute(3, 2, 0, 1).contiguous()
                 else:
-                    out[k] = fetch(k + "@gemm", 4 * co).view(4, co).sum(0)
+                    t4 = fetch(k + "@gemm", 4 * co).view(4, co)      # the bias is kept as 4 identical tiles, its gradient as 4 partial sums
+                    out[k] = t4[0].clone() if params else t4.sum(0)
             elif "point_embeddings" in k:
                 i = int(k.split(".")[2])
                 out[k] = fetch("prompt_encoder.point_embeddings@stack", 4 * 256).view(4, 1, 256)[i]
@@ -400,6 +403,26 @@ class B200Sam:
                 out[k] = (fetch(k, 32 * 256).view(32, 256)[:4] if k.endswith(".weight") else fetch(k, 32)[:4]).contiguous()
             else:
                 out[k] = fetch(k, v.numel()).view(v.shape)
+        return out
+
+    def optimizer_step(self, lr: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01) -> None:
+        """One AdamW update (torch.optim.AdamW semantics, the reference trainer's default) of every tensor that has gradients, on the
+        device (csrc/train_opt.cu): fp32 master weights + moments, then the operands of the training paths are refreshed.  The fused
+        inference decoder keeps its old operands until `load_state_dict(self.trained_state_dict())`."""
+        _lib.check(_lib.lib().msam_optimizer_step(self._h, lr, betas[0], betas[1], eps, weight_decay, _lib.cur_stream()))
+
+    def trained_state_dict(self) -> Dict[str, torch.Tensor]:
+        """Upstream-keyed state dict with the fp32 master weights of the optimizer (CPU tensors); untouched tensors as loaded."""
+        L = _lib.lib()
+        out = dict(self._state)
+        if getattr(self, "_decoder_grads_valid", False):
+            out.update({k: v.cpu() for k, v in self._decoder_tensors(L.msam_train_param, params=True).items()})
+        if getattr(self, "_encoder_grads_valid", False):
+            for k, v in self._state.items():
+                if k.startswith("image_encoder."):
+                    g = torch.empty(v.shape, device=self.device, dtype=torch.float32)
+                    _lib.check(L.msam_train_param(self._h, k.encode(), _lib.ptr(g), g.numel(), _lib.cur_stream()))
+                    out[k] = g.cpu()
         return out
 
     def encoder_grads(self, names=None) -> Dict[str, torch.Tensor]:

@@ -302,3 +302,52 @@ def test_training_step_end_to_end():
           f"max {max(r_enc.values()):.2e}; decoder gradients median {np.median(list(r_dec.values())):.2e} max {max(r_dec.values()):.2e}")
     assert abs(float(loss[0]) - float(oloss[0])) < 2e-2
     assert not bad_enc and not bad_dec, (bad_enc, bad_dec)
+
+
+def test_optimizer_steps_reduce_the_loss_and_match_torch_adamw():
+    """AdamW on the device (csrc/train_opt.cu): (1) one step from zero moments equals torch.optim.AdamW applied to the same gradients,
+    tensor by tensor (fp32 masters, incl. the packed conv-transpose / table layouts folded back); (2) repeated steps on a fixed batch
+    reduce the loss, i.e. forward, backward, update and operand refresh work together."""
+    from micro_sam_b200 import training
+    from micro_sam_b200.sample_data import lm_tile
+    _, sam = _small_models()
+    sam.train()
+    m = training.TrainableSAM(sam)
+    B, n_obj, H, W = 2, 4, 128, 128
+    imgs = [torch.from_numpy(np.repeat(lm_tile((H, W), 12, seed=40 + b, dtype="uint8")[None], 3, 0).astype("float32")) for b in range(B)]
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    cen = [(30 + 22 * k, 28 + 24 * k, 9 + 2 * k) for k in range(n_obj)]
+    y_one_hot = [torch.stack([(((yy - cy) ** 2 + (xx - cx) ** 2) < r * r).float()[None] for cy, cx, r in cen]) for _ in range(B)]
+    boxes = torch.tensor([[cx - r, cy - r, cx + r, cy + r] for cy, cx, r in cen], dtype=torch.float32) * (1024.0 / W)
+
+    def step():
+        sam.zero_decoder_grads()
+        emb, recs = m.image_embeddings_oft([{"image": im.clone(), "original_size": (H, W), "boxes": boxes.clone()} for im in imgs])
+        loss = training.compute_loss(m(recs, emb, multimask_output=True, return_masks=False), y_one_hot)
+        loss[0].backward()
+        return float(loss[0])
+
+    kw = dict(lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    l0 = step()
+    grads = dict(sam.encoder_grads())
+    grads.update(sam.decoder_grads())
+    before = {k: v.to(DEV) for k, v in sam.state_dict().items() if k in grads}
+    sam.optimizer_step(**kw)
+    after = sam.trained_state_dict()
+    worst = 0.0
+    for k, g in grads.items():
+        p = torch.nn.Parameter(before[k].clone())
+        p.grad = g.reshape(p.shape).clone()
+        torch.optim.AdamW([p], **kw).step()
+        d_ref, d_got = (p.detach() - before[k]).double().cpu(), (after[k].to(torch.float64) - before[k].double().cpu())
+        if float(d_ref.norm()) > 0:
+            worst = max(worst, float((d_got - d_ref).norm() / d_ref.norm()))
+    losses = [l0] + [0.0] * 6
+    for i in range(1, 7):
+        losses[i] = step()
+        sam.optimizer_step(**kw)
+    print(f"AdamW: update vs torch.optim.AdamW worst rel-L2 {worst:.2e} over {len(grads)} tensors; losses " + " ".join(f"{v:.4f}" for v in losses))
+    assert worst < 1e-3
+    assert losses[-1] < losses[0] - 0.02, losses
+    # the inference engine can be rebuilt from the trained weights
+    sam.load_state_dict(sam.trained_state_dict())
