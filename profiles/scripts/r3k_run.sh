@@ -1,0 +1,11 @@
+mkdir -p gpurun_out
+(time timeout 1500 python -m pytest tests/test_gpu_backward.py -q -s -m gpu -k "optimizer or small_archs") > gpurun_out/r3k_bwd.log 2>&1
+(time python bench.py --config cfg5 --steps 5 --warmup 3) > gpurun_out/r3k_cfg5.log 2>&1
+grep -n "AdamW\|vit_test\|passed\|failed" gpurun_out/r3k_bwd.log | cut -c1-1500 | head
+python - <<'PY'
+import json
+l=[x for x in open("gpurun_out/r3k_cfg5.log") if x.startswith('{')]
+if l:
+    d=json.loads(l[-1]); print(d['value'], d['ms_per_step'], d['roofline']['kernels_ms_per_step'])
+else: print(open("gpurun_out/r3k_cfg5.log").read()[-1500:])
+PY

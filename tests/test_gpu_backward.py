@@ -334,14 +334,18 @@ def test_optimizer_steps_reduce_the_loss_and_match_torch_adamw():
     before = {k: v.to(DEV) for k, v in sam.state_dict().items() if k in grads}
     sam.optimizer_step(**kw)
     after = sam.trained_state_dict()
-    worst = 0.0
+    worst, per = 0.0, {}
     for k, g in grads.items():
         p = torch.nn.Parameter(before[k].clone())
         p.grad = g.reshape(p.shape).clone()
         torch.optim.AdamW([p], **kw).step()
         d_ref, d_got = (p.detach() - before[k]).double().cpu(), (after[k].to(torch.float64) - before[k].double().cpu())
         if float(d_ref.norm()) > 0:
-            worst = max(worst, float((d_got - d_ref).norm() / d_ref.norm()))
+            # tensors without gradient (unused mask token 0, unused point embeddings) only see the weight decay: an update of 2e-6 |w|,
+            # i.e. ~30 fp32 ulps of w -- compare against a floor of 1e-4 |w| so that its rounding does not count
+            per[k] = float((d_got - d_ref).norm() / max(float(d_ref.norm()), 1e-4 * float(before[k].double().norm())))
+            worst = max(worst, per[k])
+    print("AdamW worst tensors: " + ", ".join(f"{k} {v:.2e}" for k, v in sorted(per.items(), key=lambda kv: -kv[1])[:8]))
     losses = [l0] + [0.0] * 6
     for i in range(1, 7):
         losses[i] = step()
