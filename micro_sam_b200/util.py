@@ -728,6 +728,47 @@ def batched_mask_nms(masks: torch.Tensor, boxes_xyxy: torch.Tensor, scores: torc
     return (out, mat.view(n, n)) if return_matrix else out
 
 
+def _tiled_mask_nms_sparse(predictions, idx, scores, nms_thresh: float, intersection_over_min: bool, areas, device=None):
+    """Greedy mask NMS over tiled predictions WITHOUT the dense (N, H, W) canvas (util.py:1697-1770 compares overlap windows
+    only): intersections are evaluated on the overlap window of the two global boxes, for box-overlapping pairs only -- pairs whose
+    boxes are disjoint have IoU 0 and never suppress.  Same order and rule as `batched_mask_nms` (descending score, keep
+    `iou <= thresh`).  Used when the canvas would not fit (`apply_nms`)."""
+    n = len(idx)
+    gb = np.array([predictions[k]["global_bbox"] for k in idx], dtype=np.int64)    # xywh, global
+    lb = np.array([predictions[k]["bbox"] for k in idx], dtype=np.int64)           # xywh, tile-local
+    x0, y0, x1, y1 = gb[:, 0], gb[:, 1], gb[:, 0] + gb[:, 2], gb[:, 1] + gb[:, 3]
+    order = np.argsort(-np.asarray(scores, dtype=np.float64), kind="stable")
+    masks = [torch.as_tensor(predictions[k]["segmentation"]).to(device).bool() if device is not None
+             else torch.as_tensor(predictions[k]["segmentation"]).bool() for k in idx]
+    a = np.asarray([float(areas[k]) for k in idx], dtype=np.float32)
+    alive = np.ones(n, dtype=bool)
+    keep = []
+    for pos, i in enumerate(order):
+        if not alive[i]:
+            continue
+        keep.append(int(i))
+        rest = order[pos + 1:]
+        rest = rest[alive[rest]]
+        if len(rest) == 0:
+            break
+        ov = rest[(x0[rest] < x1[i]) & (x1[rest] > x0[i]) & (y0[rest] < y1[i]) & (y1[rest] > y0[i])]
+        oi = (gb[i, 1] - lb[i, 1], gb[i, 0] - lb[i, 0])                                # global offset of tile-local (0, 0)
+        for j in ov:
+            wx0, wy0, wx1, wy1 = max(x0[i], x0[j]), max(y0[i], y0[j]), min(x1[i], x1[j]), min(y1[i], y1[j])
+            oj = (gb[j, 1] - lb[j, 1], gb[j, 0] - lb[j, 0])
+            mi = masks[i][wy0 - oi[0]:wy1 - oi[0], wx0 - oi[1]:wx1 - oi[1]]
+            mj = masks[j][wy0 - oj[0]:wy1 - oj[0], wx0 - oj[1]:wx1 - oj[1]]
+            inter = np.float32(int((mi & mj).sum()))
+            den = np.float32(min(a[i], a[j])) if intersection_over_min else np.float32(a[i] + a[j] - inter)
+            if den > 0 and np.float32(inter / den) > np.float32(nms_thresh):
+                alive[j] = False
+    return torch.as_tensor(keep, dtype=torch.long)
+
+
+# dense canvases above this many bytes (N x H x W uint8) switch the tiled mask NMS to the box-overlap formulation
+_DENSE_NMS_BYTES = 8 << 30
+
+
 def apply_nms(predictions: List[Dict[str, Any]], min_size: int, shape: Optional[Tuple[int, int]] = None,
               perform_box_nms: bool = False, nms_thresh: float = 0.9, max_size: Optional[int] = None,
               intersection_over_min: bool = False) -> np.ndarray:
@@ -747,6 +788,18 @@ def apply_nms(predictions: List[Dict[str, Any]], min_size: int, shape: Optional[
     if shape is None:
         shape = tuple(predictions[0]["segmentation"].shape)
     dev = torch.device("cuda")
+    if is_tiled and len(predictions) * int(shape[0]) * int(shape[1]) > _DENSE_NMS_BYTES and not perform_box_nms:
+        # large tiled images: no (N, H, W) canvas / N x N matrix (1000 masks on 10k x 10k would need 100 GB)
+        area_l = [int(np.asarray(p["segmentation"]).sum()) for p in predictions]
+        idx_l = [k for k in range(len(predictions)) if area_l[k] > min_size and (max_size is None or area_l[k] < max_size)] \
+            if min_size > 0 or max_size is not None else list(range(len(predictions)))
+        if not idx_l:
+            return np.zeros(shape, dtype="uint32")
+        sc = [predictions[k]["predicted_iou"] * predictions[k]["stability_score"] for k in idx_l]
+        keep = _tiled_mask_nms_sparse(predictions, idx_l, sc, nms_thresh, intersection_over_min, area_l, device=dev)
+        mask_data = [{"segmentation": predictions[idx_l[k]]["segmentation"], "area": area_l[idx_l[k]], "bbox": list(predictions[idx_l[k]]["bbox"]),
+                      "global_bbox": list(predictions[idx_l[k]]["global_bbox"])} for k in keep.tolist()]
+        return mask_data_to_segmentation(mask_data, shape=shape, min_object_size=min_size)
     if is_tiled:
         masks = torch.zeros((len(predictions),) + tuple(shape), dtype=torch.uint8, device=dev)
         for k, pred in enumerate(predictions):

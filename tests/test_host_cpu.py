@@ -235,3 +235,43 @@ def test_checkpoint_loading_tolerates_missing_training_classes(tmp_path):
     assert any("ghost_trainer_mod" in str(x.message) for x in w)
     torch.save({"image_encoder.pos_embed": torch.ones(2)}, p)
     assert sorted(util._load_checkpoint(p)[1]) == ["image_encoder.pos_embed"]
+
+
+def test_tiled_mask_nms_without_the_dense_canvas_equals_the_dense_rule():
+    """util._tiled_mask_nms_sparse (large tiled images: intersections on box-overlap windows only) keeps exactly the set the dense
+    greedy rule keeps (descending score, keep iou <= thresh), for IoU and intersection-over-min."""
+    from micro_sam_b200 import util
+    rng = np.random.default_rng(0)
+    H, W, tile = 96, 128, 64
+    preds, dense = [], []
+    for k in range(40):
+        ty, tx = int(rng.integers(0, H - tile + 1)), int(rng.integers(0, W - tile + 1))       # tile origin in the image
+        m = np.zeros((tile, tile), bool)
+        cy, cx, r = rng.integers(8, tile - 8), rng.integers(8, tile - 8), rng.integers(3, 9)
+        yy, xx = np.mgrid[:tile, :tile]
+        m[(yy - cy) ** 2 + (xx - cx) ** 2 < r * r] = True
+        ys, xs = np.where(m)
+        bbox = [int(xs.min()), int(ys.min()), int(xs.max() - xs.min() + 1), int(ys.max() - ys.min() + 1)]
+        gb = [bbox[0] + tx, bbox[1] + ty, bbox[2], bbox[3]]
+        preds.append({"segmentation": m, "bbox": bbox, "global_bbox": gb, "predicted_iou": float(rng.random()), "stability_score": 1.0})
+        full = np.zeros((H, W), bool)
+        full[ty:ty + tile, tx:tx + tile] = m
+        dense.append(full)
+    dense = np.stack(dense)
+    areas = [int(d.sum()) for d in dense]
+    scores = [p["predicted_iou"] for p in preds]
+    for iomin in (False, True):
+        for thr in (0.1, 0.5):
+            order = np.argsort(-np.asarray(scores), kind="stable")
+            alive, ref = np.ones(len(preds), bool), []
+            for pos, i in enumerate(order):
+                if not alive[i]:
+                    continue
+                ref.append(int(i))
+                for j in order[pos + 1:]:
+                    inter = np.float32((dense[i] & dense[j]).sum())
+                    den = np.float32(min(areas[i], areas[j])) if iomin else np.float32(areas[i] + areas[j] - inter)
+                    if np.float32(inter / den) > np.float32(thr):
+                        alive[j] = False
+            got = util._tiled_mask_nms_sparse(preds, list(range(len(preds))), scores, thr, iomin, areas).tolist()
+            assert got == ref and len(ref) < len(preds), (iomin, thr, got, ref)
