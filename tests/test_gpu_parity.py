@@ -622,3 +622,27 @@ def test_large_inputs_beyond_the_former_size_caps():
     ws = torch.empty(util.finish_ws_size(H, W), dtype=torch.int32, device="cuda")
     _lib.check(_lib.lib().msam_finish_segmentation(_lib.ptr(d), H, W, 50, 1, _lib.ptr(out), _lib.ptr(ws), _lib.cur_stream()))
     assert np.array_equal(out.cpu().numpy().view(np.uint32), util._finish_segmentation(seg.astype(np.uint32), 50, True, True))
+
+
+def test_precompute_state_round_trip(models, tmp_path):
+    """precompute_state.precompute_state: embeddings container + cached AMG state for a folder of images; a second generator built from
+    the cache (cache_amg_state load path) segments exactly like the one that computed it."""
+    from micro_sam_b200 import precompute_state as ps, util
+    from micro_sam_b200.sample_data import lm_tile
+    _, pred = models
+    os.makedirs(tmp_path / "in")
+    imgs = [lm_tile((200, 240), 12, seed=50 + k) for k in range(2)]
+    for k, im in enumerate(imgs):
+        np.save(tmp_path / "in" / f"im{k}.npy", im)
+    ps.precompute_state(str(tmp_path / "in"), str(tmp_path / "out"), pattern="*.npy", predictor=pred, precompute_amg_state=True)
+    for k, im in enumerate(imgs):
+        zpath = str(tmp_path / "out" / f"im{k}.zarr")
+        assert os.path.exists(os.path.join(zpath, "amg_state.pickle"))
+        emb = util.precompute_image_embeddings(pred, im, zpath)                 # loads: the signature matches
+        amg = ps.cache_amg_state(pred, im, emb, zpath, verbose=False)     # loads the pickle (32 x 32 grid, the default)
+        kw = dict(pred_iou_thresh=0.5, stability_score_thresh=0.5, box_nms_thresh=0.7)
+        seg = amg.generate(**kw)
+        from micro_sam_b200 import instance_segmentation as iseg
+        ref = iseg.AutomaticMaskGenerator(pred)
+        ref.initialize(im, image_embeddings=emb)
+        assert np.array_equal(seg, ref.generate(**kw))

@@ -275,3 +275,28 @@ def test_tiled_mask_nms_without_the_dense_canvas_equals_the_dense_rule():
                         alive[j] = False
             got = util._tiled_mask_nms_sparse(preds, list(range(len(preds))), scores, thr, iomin, areas).tolist()
             assert got == ref and len(ref) < len(preds), (iomin, thr, got, ref)
+
+
+def test_precompute_state_loads_a_cached_amg_state_without_a_gpu(tmp_path):
+    """precompute_state.cache_amg_state: an existing `amg_state.pickle` / `amg_state/state-<i>.pkl` is loaded instead of recomputed
+    (reference file names, micro_sam/precompute_state.py:52-64), and the pickle holds CPU tensors only."""
+    import pickle
+    import torch
+    from micro_sam_b200 import precompute_state as ps
+
+    class _Pred:    # the generator's constructor only stores the predictor
+        device = "cpu"
+    state = {"crop_list": [{"iou_preds": torch.rand(6), "boxes": torch.zeros(6, 4)}], "crop_boxes": [[0, 0, 8, 8]], "original_size": (8, 8)}
+    with open(tmp_path / "amg_state.pickle", "wb") as f:
+        pickle.dump(ps._state_to_cpu(state), f)
+    amg = ps.cache_amg_state(_Pred(), np.zeros((8, 8)), {"input_size": (8, 8)}, str(tmp_path), verbose=False)
+    assert amg.is_initialized and amg.get_state()["original_size"] == (8, 8)
+    os.makedirs(tmp_path / "amg_state")
+    with open(tmp_path / "amg_state" / "state-3.pkl", "wb") as f:
+        pickle.dump(ps._state_to_cpu(state), f)
+    amg = ps.cache_amg_state(_Pred(), np.zeros((5, 8, 8)), {"input_size": (8, 8)}, str(tmp_path), verbose=False, i=3)
+    assert torch.equal(amg.get_state()["crop_list"][0]["iou_preds"], state["crop_list"][0]["iou_preds"])
+    np.save(tmp_path / "img.npy", np.arange(12).reshape(3, 4))
+    assert ps.load_image_data(str(tmp_path / "img.npy")).shape == (3, 4)
+    with pytest.raises(NotImplementedError):
+        ps.cache_is_state()
