@@ -9,8 +9,8 @@ cfg1  vit_t (MobileSAM / TinyViT) precompute_image_embeddings on 512 x 512 float
 cfg5  vit_b fine-tuning step on LIVECell-shaped batches (2 images of 512 x 512 per GPU, 25 box-prompted objects each): preprocess
       (torch resize) + encoder forward keeping activations + prompt encoder / mask decoder forward (training mode) + loss (dice +
       IoU MSE) + loss.backward() through the decoder and the encoder + gradient all-reduce over the ranks (NCCL, one flat fp32
-      buffer, averaged).  One prompting iteration per step (the reference's further sub-iterations feed mask prompts, which have
-      no backward pass here); the optimizer update is not part of the library.  metric: images/s.
+      buffer, averaged) + AdamW update on the device.  One prompting iteration per step (the reference's further sub-iterations
+      feed mask prompts, which have no backward pass here).  metric: images/s.
 cfg3  vit_l tiled 3-D embedding precompute: uint8 EM volume 64 x 2048 x 2048, tile_shape (1024, 1024), halo (128, 128)
       -> 4 outer tiles of 1152^2 per plane, 256 encoder tiles, written to a zarr container (1 GiB of embeddings).
       The volume is FIXED (strong scaling): ranks take contiguous shards of the (z, tile) list, each writes its own chunks,
@@ -51,7 +51,7 @@ def _config(args):
     if args.config == "cfg5":
         return {"workload": f"{args.model} fine-tuning step, batch of 2 synthetic 512x512 images per GPU with 25 box-prompted objects each "
                             "(BASELINE.json configs[4]); seeded random-init weights; encoder + decoder forward, dice + IoU loss, backward through "
-                            "decoder and encoder, gradient all-reduce; one prompting iteration, no optimizer update",
+                            "decoder and encoder, gradient all-reduce, AdamW update; one prompting iteration",
                 "images_per_step_per_gpu": CFG5["batch"], "objects_per_image": CFG5["n_obj"], "sub_iterations": 1,
                 "l2": "working_set_exceeds_l2 (GBs of saved activations per step)",
                 "parallelism": "data parallel replicas, one process per GPU, one NCCL all-reduce of the flat gradient buffer per step"}
@@ -274,13 +274,10 @@ def run_cfg5(args):
         out = m(rr, emb, multimask_output=True, return_masks=False)   # prompt encoder + mask decoder, training mode
         loss = training.compute_loss(out, targets)
         loss[0].backward()                                        # loss -> decoder -> encoder
-        g = list(sam.encoder_grads().values()) + list(sam.decoder_grads().values())
-        flat = torch.cat([v.reshape(-1) for v in g])
-        if world > 1:
-            dist.all_reduce(flat)
-            flat /= world
-        state["loss"], state["n"] = float(loss[0]), flat.numel()
-        return flat
+        n = sam.allreduce_grads(world)                            # one NCCL all-reduce of the flat gradient buffer, averaged
+        sam.optimizer_step(lr=1e-5)                               # AdamW on the device + operand refresh
+        state["loss"], state["n"] = float(loss[0]), n
+        return n
 
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = _lib.launch_count()

@@ -224,6 +224,11 @@ int msam_decoder_zero_grads(msam_handle* h, void* stream);
  * (same keys and layouts as the gradient read-outs).  The packed operands of the INFERENCE decoder are refreshed by load_state_dict. */
 int msam_optimizer_step(msam_handle* h, float lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
 int msam_train_param(msam_handle* h, const char* key, float* dst, int64_t n, void* stream);
+/* Enumeration of the trainable tensors (after the first training forward passes): key, DEVICE pointers of the fp32 gradient and master
+ * buffers, element count -- so that a data-parallel driver can all-reduce the gradients in place (torch.distributed / NCCL on views of
+ * these buffers) before msam_optimizer_step. */
+int msam_train_tensor_count(msam_handle* h);
+int msam_train_tensor_info(msam_handle* h, int i, char* key_buf, int cap, void** grad, void** master, int64_t* n);
 /* Adjoint of msam_mask_loss_stats w.r.t. the low-res logits: d_stats [n_obj*M, 5] (only columns 0, 1 = dL/d sum(p t), dL/d sum(p^2)
  * matter) -> d_low_res [n_obj*M, 256, 256] accumulated (zero it first).  sam_trainer.py:131-172 backward. */
 int msam_mask_loss_backward(const float* low_res, const uint8_t* targets, const float* d_stats, int n_obj, int M, int in_h, int in_w,

@@ -99,6 +99,8 @@ def lib() -> ctypes.CDLL:
         L.msam_decoder_zero_grads.argtypes = [c_void_p, c_void_p]
         L.msam_optimizer_step.argtypes = [c_void_p, c_float, c_float, c_float, c_float, c_float, c_void_p]
         L.msam_train_param.argtypes = [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]
+        L.msam_train_tensor_count.argtypes = [c_void_p]
+        L.msam_train_tensor_info.argtypes = [c_void_p, c_int, ctypes.c_char_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64)]
         L.msam_mask_loss_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
         _lib = L
     return _lib

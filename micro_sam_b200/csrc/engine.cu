@@ -686,6 +686,16 @@ int msam_train_param(msam_handle* h, const char* key, float* dst, int64_t n, voi
   if (!h || !key || !dst) return set_error("msam_train_param: null argument");
   return h->eng.train_param(key, dst, n, (cudaStream_t)stream);
 }
+int msam_train_tensor_count(msam_handle* h) { return h ? (int)h->eng.opt.size() : -1; }
+int msam_train_tensor_info(msam_handle* h, int i, char* key_buf, int cap, void** grad, void** master, int64_t* n) {
+  if (!h || i < 0 || i >= (int)h->eng.opt.size() || !key_buf || cap < 2) return set_error("msam_train_tensor_info: bad argument");
+  const OptParam& p = h->eng.opt[i];
+  snprintf(key_buf, cap, "%s", p.key.c_str());
+  if (grad) *grad = p.g;
+  if (master) *master = p.w;
+  if (n) *n = p.n;
+  return 0;
+}
 int msam_op_bgemm(const void* A, const void* B, int a_mn, int b_mn, int M, int N, int K, int lda, int ldb, int64_t a_hstride,
                   int64_t a_wstride, int64_t b_hstride, int64_t b_wstride, int heads, int outer, float* out, int ldc,
                   int64_t o_hstride, int64_t o_wstride, float alpha, int accumulate, void* stream) {

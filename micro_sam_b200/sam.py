@@ -105,6 +105,17 @@ class _EncoderFn(torch.autograd.Function):
         return None, torch.zeros((), device=g.device), None
 
 
+class _DevBuf:
+    """Exposes a raw device allocation through __cuda_array_interface__ so that torch can wrap it without a copy."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def _device_view(ptr: int, n: int, device) -> torch.Tensor:
+    return torch.as_tensor(_DevBuf(ptr, n), device=device)
+
+
 class _DecoderFn(torch.autograd.Function):
     """prompt encoder + mask decoder of ONE image with a backward pass (csrc/decoder_train.cu): (embedding [256,64,64], sparse prompt
     embeddings [P,Ts,256]) -> (low-res logits [P,M,256,256], IoU predictions [P,M]).  backward fills / accumulates the decoder and
@@ -404,6 +415,34 @@ class B200Sam:
             else:
                 out[k] = fetch(k, v.numel()).view(v.shape)
         return out
+
+    def grad_views(self):
+        """Zero-copy torch views of the engine's fp32 gradient buffers [(key, tensor)] (keys as in the C API: a few carry packed
+        layouts, `@gemm` / `@stack`).  In-place operations on them (all-reduce, clipping, scaling) are seen by `optimizer_step()`."""
+        L = _lib.lib()
+        n = L.msam_train_tensor_count(self._h)
+        out = []
+        buf = ctypes.create_string_buffer(256)
+        for i in range(max(n, 0)):
+            g, w, cnt = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+            _lib.check(L.msam_train_tensor_info(self._h, i, buf, 256, ctypes.byref(g), ctypes.byref(w), ctypes.byref(cnt)))
+            out.append((buf.value.decode(), _device_view(g.value, cnt.value, self.device)))
+        return out
+
+    def allreduce_grads(self, world_size: int) -> int:
+        """DDP semantics (micro_sam/training/training.py:train_sam): average every gradient over the ranks with ONE all-reduce of a
+        flat fp32 buffer, written back into the engine's gradient buffers.  Returns the number of gradient elements."""
+        views = [v for _, v in self.grad_views()]
+        flat = torch.cat([v.reshape(-1) for v in views])
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(flat)
+            flat /= world_size
+            off = 0
+            for v in views:
+                v.copy_(flat[off:off + v.numel()])
+                off += v.numel()
+        return flat.numel()
 
     def optimizer_step(self, lr: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01) -> None:
         """One AdamW update (torch.optim.AdamW semantics, the reference trainer's default) of every tensor that has gradients, on the

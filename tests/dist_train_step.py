@@ -34,8 +34,7 @@ def step(sam, m, seed):
     emb, rr = m.image_embeddings_oft([dict(r) for r in recs])
     loss = training.compute_loss(m(rr, emb, multimask_output=True, return_masks=False), targets)
     loss[0].backward()
-    g = list(sam.encoder_grads().values()) + list(sam.decoder_grads().values())
-    return torch.cat([v.reshape(-1) for v in g]), float(loss[0])
+    return torch.cat([v.reshape(-1).clone() for _, v in sam.grad_views()]), float(loss[0])
 
 
 def main():
@@ -48,9 +47,9 @@ def main():
     pred = util.get_sam_model("vit_test", device=f"cuda:{local}", state_dict=sd, max_batch=2, max_prompts=64)
     sam = pred.model.train()
     m = training.TrainableSAM(sam)
-    flat, loss = step(sam, m, rank)
-    dist.all_reduce(flat)
-    flat /= world
+    _, loss = step(sam, m, rank)
+    sam.allreduce_grads(world)
+    flat = torch.cat([v.reshape(-1).clone() for _, v in sam.grad_views()])
     ok, rel = 1, 0.0
     if rank == 0:
         ref = sum(step(sam, m, r)[0] for r in range(world)) / world
