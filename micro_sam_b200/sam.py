@@ -105,6 +105,24 @@ class _EncoderFn(torch.autograd.Function):
         return None, torch.zeros((), device=g.device), None
 
 
+def prompt_table_index(point_labels: Optional[torch.Tensor], has_boxes: bool, n_prompts: int) -> torch.Tensor:
+    """Which learned embedding sits behind each sparse prompt token (PromptEncoder._embed_points / _embed_boxes): label 0 / 1 ->
+    point_embeddings[0 / 1], label -1 -> not_a_point_embed (index 4; a padding point with label -1 is appended when no box is given),
+    box corners -> point_embeddings[2], [3].  (n_prompts, n_sparse) int64 -- the gradient routing table of the training decoder."""
+    idx = []
+    if point_labels is not None:
+        lab = torch.as_tensor(point_labels).round().to(torch.int64).reshape(n_prompts, -1)
+        if not has_boxes:
+            lab = torch.cat([lab, torch.full((n_prompts, 1), -1, dtype=torch.int64, device=lab.device)], dim=1)
+        idx.append(torch.where(lab < 0, torch.full_like(lab, 4), lab.clamp(max=1)))
+    if has_boxes:
+        dev = idx[0].device if idx else "cpu"
+        idx.append(torch.tensor([[2, 3]], dtype=torch.int64, device=dev).expand(n_prompts, 2))
+    if not idx:
+        raise ValueError("training needs point and / or box prompts")
+    return torch.cat(idx, dim=1)
+
+
 class _DevBuf:
     """Exposes a raw device allocation through __cuda_array_interface__ so that torch can wrap it without a copy."""
 
@@ -362,15 +380,7 @@ class B200Sam:
         with torch.no_grad():
             sparse, _ = self.prompt_encoder(points=points, boxes=boxes, masks=None)
         P = sparse.shape[0]
-        idx = []
-        if points is not None:
-            lab = points[1].to(self.device).round().to(torch.int64)
-            if boxes is None:   # a padding point (label -1) is appended when there is no box (prompt_encoder._embed_points(pad=True))
-                lab = torch.cat([lab, torch.full((P, 1), -1, device=self.device, dtype=torch.int64)], dim=1)
-            idx.append(torch.where(lab < 0, torch.full_like(lab, 4), lab.clamp(max=1)))
-        if boxes is not None:
-            idx.append(torch.tensor([[2, 3]], device=self.device, dtype=torch.int64).expand(P, 2))
-        emb_index = torch.cat(idx, dim=1)
+        emb_index = prompt_table_index(None if points is None else points[1], boxes is not None, P).to(self.device)
         assert emb_index.shape == sparse.shape[:2], (emb_index.shape, sparse.shape)
         return _DecoderFn.apply(emb, sparse, emb_index, self, int(slot), bool(multimask_output))
 

@@ -300,3 +300,33 @@ def test_precompute_state_loads_a_cached_amg_state_without_a_gpu(tmp_path):
     assert ps.load_image_data(str(tmp_path / "img.npy")).shape == (3, 4)
     with pytest.raises(NotImplementedError):
         ps.cache_is_state()
+
+
+def test_prompt_table_index_follows_the_prompt_encoder():
+    """sam.prompt_table_index (gradient routing of the training decoder) against the oracle PromptEncoder: a sparse token minus its
+    positional part equals the embedding row the index names."""
+    import torch
+    from oracle import sam_ref
+    from micro_sam_b200.sam import prompt_table_index
+    osam = sam_ref.build_seeded_sam("vit_test", seed=1)
+    pe = osam.prompt_encoder
+    tables = torch.cat([pe.point_embeddings[i].weight for i in range(4)] + [pe.not_a_point_embed.weight]).detach()
+    g = torch.Generator().manual_seed(0)
+    P = 3
+    coords = torch.rand(P, 2, 2, generator=g) * 1000
+    labels = torch.tensor([[1.0, 0.0], [0.0, -1.0], [1.0, 1.0]])
+    boxes = torch.rand(P, 4, generator=g) * 500 + torch.tensor([0.0, 0.0, 500.0, 500.0])
+    for pts, bx in (((coords, labels), None), (None, boxes), ((coords, labels), boxes)):
+        with torch.no_grad():
+            sparse, _ = pe(points=pts, boxes=bx, masks=None)
+        idx = prompt_table_index(None if pts is None else pts[1], bx is not None, P)
+        assert idx.shape == sparse.shape[:2]
+        # positional part: what the encoder produces with zeroed tables
+        saved = [p.detach().clone() for p in (*[e.weight for e in pe.point_embeddings], pe.not_a_point_embed.weight)]
+        with torch.no_grad():
+            for p in (*[e.weight for e in pe.point_embeddings], pe.not_a_point_embed.weight):
+                p.zero_()
+            pos, _ = pe(points=pts, boxes=bx, masks=None)
+            for p, s in zip((*[e.weight for e in pe.point_embeddings], pe.not_a_point_embed.weight), saved):
+                p.copy_(s)
+        assert torch.allclose(sparse - pos, tables[idx], atol=1e-6)
