@@ -284,10 +284,13 @@ def run_cfg5(args):
     ms = _timed(dist, world, device, step, args.steps, args.warmup)
     launches = (_lib.launch_count() - l0) / (args.steps + args.warmup)
     clocks = sampler.stop() if sampler else None
+    # the instrumented step contains the gradient all-reduce: EVERY rank runs it (a rank-0-only step would wait for its peers until
+    # the NCCL timeout), only rank 0 records the kernel events
+    L = _lib.lib()
     if rank == 0:
-        L = _lib.lib()
         L.msam_profile(1)
-        step()
+    step()
+    if rank == 0:
         rep = sorted(_lib.profile_report(), key=lambda r: -r["ms"])
         L.msam_profile(0)
         dom = rep[0]

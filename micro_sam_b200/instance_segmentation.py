@@ -491,9 +491,13 @@ class TiledAutomaticMaskGenerator(AutomaticMaskGenerator):
         NMS that prefers smaller tiles (:511-521) and the painting (util.py:1799-1829) on the gathered list, identically
         on every rank (so every rank returns the full label image)."""
         from . import distributed as D
-        H, W = self.original_size
+        local = self._local_instance_tables(pred_iou_thresh, stability_score_thresh, box_nms_thresh)
+        tab, _ = D.gather_instance_tables(local, group)          # <- the one collective of the stitched path
+        return self._stitch_gathered(tab, crop_nms_thresh, with_background)
+
+    def _local_instance_tables(self, pred_iou_thresh, stability_score_thresh, box_nms_thresh):
+        """This rank's contribution to the exchange: per-tile filters + box NMS on the tiles it owns."""
         dev = self._predictor.device
-        geoms = self._crop_geoms()
         tabs = dict(gbox=[], lbox=[], area=[], tile=[], low=[])
         for k, data in enumerate(self._crop_list):
             ci = self._tile_lo + k
@@ -506,9 +510,14 @@ class TiledAutomaticMaskGenerator(AutomaticMaskGenerator):
             tabs["tile"].append(torch.full((len(keep),), ci, dtype=torch.int32, device=dev))
             tabs["low"].append(self._logits_rows(data, keep, dev)[0] if data["low_res"].device != dev else data["low_res"][keep])
         empty = dict(gbox=(0, 4), lbox=(0, 4), area=(0,), tile=(0,), low=(0, 256, 256))
-        local = {k: (torch.cat(v) if v else torch.zeros(empty[k], dtype=torch.float32 if k == "low" else torch.int32, device=dev))
-                 for k, v in tabs.items()}
-        tab, _ = D.gather_instance_tables(local, group)          # <- the one collective of the stitched path
+        return {k: (torch.cat(v) if v else torch.zeros(empty[k], dtype=torch.float32 if k == "low" else torch.int32, device=dev))
+                for k, v in tabs.items()}
+
+    def _stitch_gathered(self, tab, crop_nms_thresh, with_background):
+        """Cross-tile NMS + painting on the gathered instance tables (rank order = tile order), identical on every rank."""
+        H, W = self.original_size
+        dev = self._predictor.device
+        geoms = self._crop_geoms()
         n = int(tab["gbox"].shape[0])
         crop_id = tab["tile"].long()
         order = torch.arange(n, device=dev)

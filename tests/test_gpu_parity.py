@@ -646,3 +646,36 @@ def test_precompute_state_round_trip(models, tmp_path):
         ref = iseg.AutomaticMaskGenerator(pred)
         ref.initialize(im, image_embeddings=emb)
         assert np.array_equal(seg, ref.generate(**kw))
+
+
+def test_rank_sharded_tiled_amg_emulated_on_one_gpu(models):
+    """The multi-rank tiled AMG (instance_segmentation._generate_distributed) without a second GPU: every 'rank' initialises its tile
+    shard in this process, the instance tables are concatenated in rank order (= what the all-gather returns) and stitched; the result
+    must equal the single-process label image bit for bit, for 1, 2 and 4 ranks.  (tests/test_gpu_multi.py runs the same over NCCL.)"""
+    from micro_sam_b200 import instance_segmentation as iseg
+    from micro_sam_b200.sample_data import lm_tile
+    _, pred = models
+    img = lm_tile((500, 700), 40, seed=13)
+    tile_shape, halo = (200, 256), (24, 24)
+    ref_amg = iseg.TiledAutomaticMaskGenerator(pred, points_per_side=4)
+    ref_amg.initialize(img, tile_shape=tile_shape, halo=halo, batch_size=2)
+    ref = ref_amg.generate(pred_iou_thresh=0.0, stability_score_thresh=0.5, crop_nms_thresh=0.3)
+    assert ref.max() > 0
+    tabs1 = None
+    for world in (1, 2, 4):
+        gens, locs = [], []
+        for r in range(world):
+            a = iseg.TiledAutomaticMaskGenerator(pred, points_per_side=4)
+            a.initialize(img, tile_shape=tile_shape, halo=halo, batch_size=2, rank=r, world_size=world)
+            gens.append(a)
+            locs.append(a._local_instance_tables(0.0, 0.5, 0.7))
+        tab = {k: torch.cat([l[k] for l in locs]) for k in locs[0]}
+        if tabs1 is None:
+            tabs1 = tab
+        same_tab = {k: bool(tab[k].shape == tabs1[k].shape and torch.equal(tab[k], tabs1[k])) for k in tab}
+        seg = gens[0]._stitch_gathered(tab, 0.3, True)
+        ndiff = int((seg != ref).sum())
+        print(f"world {world}: {int(tab['gbox'].shape[0])} gathered instances, tables equal to world 1: {same_tab}, "
+              f"{int(seg.max())} labels (single process {int(ref.max())}), {ndiff} differing pixels")
+        assert all(same_tab.values()), (world, same_tab)
+        assert ndiff == 0, (world, ndiff)
