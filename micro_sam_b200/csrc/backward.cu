@@ -205,40 +205,17 @@ __global__ void attn_probs_kernel(const float* __restrict__ S, const float* __re
   const float* t = T + row * g.nt;
   __nv_bfloat16* p = P + row * pitch_p;
   const int oh = qh + g.side - 1, ow = g.woff + qw + g.side - 1;
-  // keys as (kh, kw): no integer division per logit (ncu of the first version: 79 % issue-slot utilisation, 25 % of HBM peak), and the
-  // column part of the bias stays in registers (kw = lane, lane + 32)
-  float tw[2];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) tw[i] = (lane + 32 * i < g.side) ? t[ow - (lane + 32 * i)] : 0.f;
+  // flat key loop, all 32 lanes busy for every geometry.  Measured alternatives (profiles/r3_bench_cfg5*.json.log): a (kh, kw) double loop
+  // without the integer divisions is SLOWER (11.1 vs 9.0 ms per step: idle lanes for the 14-wide windows, twice the loop overhead for
+  // the 64-wide rows); 128 logits per lane in registers is slower still (255 registers, 23 ms).
   float m = -INFINITY;
-  for (int kh = 0; kh < g.side; ++kh) {
-    const float th = t[oh - kh];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int kw = lane + 32 * i;
-      if (kw < g.side) m = fmaxf(m, fmaf(s[kh * g.side + kw], scale, th + tw[i]));
-    }
-  }
+  for (int k = lane; k < g.n_tok; k += 32) m = fmaxf(m, fmaf(s[k], scale, t[oh - k / g.side] + t[ow - k % g.side]));
   m = warp_max(m);
   float l = 0.f;
-  for (int kh = 0; kh < g.side; ++kh) {
-    const float th = t[oh - kh];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int kw = lane + 32 * i;
-      if (kw < g.side) l += __expf(fmaf(s[kh * g.side + kw], scale, th + tw[i]) - m);
-    }
-  }
+  for (int k = lane; k < g.n_tok; k += 32) l += __expf(fmaf(s[k], scale, t[oh - k / g.side] + t[ow - k % g.side]) - m);
   const float inv = 1.0f / warp_sum(l);
-  for (int kh = 0; kh < g.side; ++kh) {
-    const float th = t[oh - kh];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int kw = lane + 32 * i;
-      if (kw < g.side) p[kh * g.side + kw] = __float2bfloat16(__expf(fmaf(s[kh * g.side + kw], scale, th + tw[i]) - m) * inv);
-    }
-  }
-  for (int k = g.n_tok + lane; k < pitch_p; k += 32) p[k] = __float2bfloat16(0.f);
+  for (int k = lane; k < pitch_p; k += 32)
+    p[k] = __float2bfloat16(k < g.n_tok ? __expf(fmaf(s[k], scale, t[oh - k / g.side] + t[ow - k % g.side]) - m) * inv : 0.f);
 }
 
 // dS = P o (dP - delta), delta = sum_k P dP;  dT[q, j] = the bias gradients scattered to the table-row index j (zero elsewhere)
@@ -396,7 +373,6 @@ int launch_window_gather(const __nv_bfloat16* x, int B, int grid, int ws, int D,
 }
 int launch_attn_probs(const float* S, const float* T, long n_batch, AttnBwdGeom g, int pitch_s, int pitch_p, float scale,
                       __nv_bfloat16* P, cudaStream_t stream) {
-  if (g.side > 64) return set_error("attn_probs: side %d > 64", g.side);
   const long rows = n_batch * g.n_tok;
   prof_begin(stream, "attn_bwd softmax", 0.0, (double)rows * (pitch_s * 4.0 + pitch_p * 2.0));
   attn_probs_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(S, T, rows, g, pitch_s, pitch_p, scale, P);
