@@ -24,7 +24,7 @@ def main():
     pred = util.get_sam_model("vit_test", device=f"cuda:{local}", state_dict=sd, max_batch=4, max_prompts=64)
     img = lm_tile((500, 700), 40, seed=13)
     tile_shape, halo = (200, 256), (24, 24)      # 3 x 3 = 9 tiles: uneven shards for 2 and 4 ranks
-    kw = dict(pred_iou_thresh=0.0, stability_score_thresh=0.5, crop_nms_thresh=0.3)
+    kw = dict(pred_iou_thresh=0.0, stability_score_thresh=0.0, crop_nms_thresh=0.3, with_background=False)   # keeps masks for any seeded noise model
     amg = iseg.TiledAutomaticMaskGenerator(pred, points_per_side=4)
     amg.initialize(img, tile_shape=tile_shape, halo=halo, batch_size=2, rank=rank, world_size=world)
     assert len(amg.crop_list) == (9 * (rank + 1)) // world - (9 * rank) // world

@@ -659,7 +659,9 @@ def test_rank_sharded_tiled_amg_emulated_on_one_gpu(models):
     tile_shape, halo = (200, 256), (24, 24)
     ref_amg = iseg.TiledAutomaticMaskGenerator(pred, points_per_side=4)
     ref_amg.initialize(img, tile_shape=tile_shape, halo=halo, batch_size=2)
-    ref = ref_amg.generate(pred_iou_thresh=0.0, stability_score_thresh=0.5, crop_nms_thresh=0.3)
+    # thresholds that keep masks whatever the seeded noise model predicts (a stability threshold of 0.5 left none once the
+    # window-attention kernel changed the last bits of the embeddings)
+    ref = ref_amg.generate(pred_iou_thresh=0.0, stability_score_thresh=0.0, crop_nms_thresh=0.3, with_background=False)
     assert ref.max() > 0
     tabs1 = None
     for world in (1, 2, 4):
@@ -668,12 +670,12 @@ def test_rank_sharded_tiled_amg_emulated_on_one_gpu(models):
             a = iseg.TiledAutomaticMaskGenerator(pred, points_per_side=4)
             a.initialize(img, tile_shape=tile_shape, halo=halo, batch_size=2, rank=r, world_size=world)
             gens.append(a)
-            locs.append(a._local_instance_tables(0.0, 0.5, 0.7))
+            locs.append(a._local_instance_tables(0.0, 0.0, 0.7))
         tab = {k: torch.cat([l[k] for l in locs]) for k in locs[0]}
         if tabs1 is None:
             tabs1 = tab
         same_tab = {k: bool(tab[k].shape == tabs1[k].shape and torch.equal(tab[k], tabs1[k])) for k in tab}
-        seg = gens[0]._stitch_gathered(tab, 0.3, True)
+        seg = gens[0]._stitch_gathered(tab, 0.3, False)
         ndiff = int((seg != ref).sum())
         print(f"world {world}: {int(tab['gbox'].shape[0])} gathered instances, tables equal to world 1: {same_tab}, "
               f"{int(seg.max())} labels (single process {int(ref.max())}), {ndiff} differing pixels")
