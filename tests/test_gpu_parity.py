@@ -656,11 +656,12 @@ def test_rank_sharded_tiled_amg_emulated_on_one_gpu(models):
     from micro_sam_b200.sample_data import lm_tile
     _, pred = models
     img = lm_tile((500, 700), 40, seed=13)
-    tile_shape, halo = (200, 256), (24, 24)
+    # 2 x 2 tiles whose halo reaches the image border on every side: the random-init model predicts near-full-crop masks, which the
+    # near-crop-edge filter (instance_segmentation.py:99-132) removes at every INTERIOR tile edge -- with ordinary halos nothing
+    # survives and the comparison would be vacuous
+    tile_shape, halo = (250, 350), (250, 350)
     ref_amg = iseg.TiledAutomaticMaskGenerator(pred, points_per_side=4)
     ref_amg.initialize(img, tile_shape=tile_shape, halo=halo, batch_size=2)
-    # thresholds that keep masks whatever the seeded noise model predicts (a stability threshold of 0.5 left none once the
-    # window-attention kernel changed the last bits of the embeddings)
     ref = ref_amg.generate(pred_iou_thresh=0.0, stability_score_thresh=0.0, crop_nms_thresh=0.3, with_background=False)
     assert ref.max() > 0
     tabs1 = None
