@@ -53,6 +53,12 @@ class ResizeLongestSide:
         if (th, tw) == tuple(image.shape[:2]):
             return np.ascontiguousarray(image)
         from PIL import Image  # same PIL bilinear(+antialias) uint8 resize the reference reaches via torchvision
+        if image.ndim == 3 and image.shape[2] == 3 and image.dtype == np.uint8 and \
+                np.array_equal(image[..., 0], image[..., 1]) and np.array_equal(image[..., 0], image[..., 2]):
+            # gray image replicated to RGB by _to_image (the usual microscopy input): PIL resamples the bands independently with the
+            # same coefficients, so one band is resized and replicated -- bit-identical, a third of the work (host-bound e2e paths)
+            band = np.asarray(Image.fromarray(np.ascontiguousarray(image[..., 0])).resize((tw, th), Image.BILINEAR))
+            return np.stack([band, band, band], axis=2)      # (measured: 1 ms; a broadcast assignment takes 5 ms)
         return np.array(Image.fromarray(image).resize((tw, th), Image.BILINEAR))
 
     def apply_image_torch(self, image: torch.Tensor) -> torch.Tensor:

@@ -330,3 +330,22 @@ def test_prompt_table_index_follows_the_prompt_encoder():
             for p, s in zip((*[e.weight for e in pe.point_embeddings], pe.not_a_point_embed.weight), saved):
                 p.copy_(s)
         assert torch.allclose(sparse - pos, tables[idx], atol=1e-6)
+
+
+def test_resize_of_replicated_gray_images_is_bit_identical_to_the_rgb_resize():
+    """ResizeLongestSide.apply_image: the single-band shortcut for gray images (3 equal channels) against PIL's RGB resize, up- and
+    down-scaling (antialiased) and non-square shapes; true RGB inputs take the ordinary path."""
+    from PIL import Image
+    from micro_sam_b200.sam import ResizeLongestSide, get_preprocess_shape
+    rng = np.random.default_rng(0)
+    rs = ResizeLongestSide(1024)
+    for shape in ((512, 512), (1152, 1152), (300, 500), (2048, 1536), (1024, 1024)):
+        g = rng.integers(0, 256, shape, dtype=np.uint8)
+        img = np.repeat(g[..., None], 3, axis=2)
+        th, tw = get_preprocess_shape(shape[0], shape[1], 1024)
+        ref = np.array(Image.fromarray(img).resize((tw, th), Image.BILINEAR))
+        out = rs.apply_image(img)
+        assert out.shape == (th, tw, 3) and out.flags["C_CONTIGUOUS"] and np.array_equal(out, ref), shape
+    rgb = rng.integers(0, 256, (400, 640, 3), dtype=np.uint8)
+    th, tw = get_preprocess_shape(400, 640, 1024)
+    assert np.array_equal(rs.apply_image(rgb), np.array(Image.fromarray(rgb).resize((tw, th), Image.BILINEAR)))
