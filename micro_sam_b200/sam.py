@@ -327,6 +327,7 @@ class B200Sam:
             L.msam_destroy(self._h)
         self._h = ctypes.c_void_p()
         self._bound_key = self._bound_src = self._bound_tensor = None
+        self._encoder_grads_valid = self._decoder_grads_valid = False   # a rebuilt engine has no training state yet
         with torch.cuda.device(self.device):
             _lib.check(L.msam_create(ctypes.byref(self._cfg), self.device.index, ctypes.byref(self._h)))
             self._state = {}
