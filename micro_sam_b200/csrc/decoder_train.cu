@@ -766,6 +766,14 @@ int Engine::decoder_grad(const char* name, float* dst, int64_t n, cudaStream_t s
   return 0;
 }
 
+void Engine::dec_train_free() {
+  if (!dtrain) return;
+  for (DecSlot& s : dtrain->slot)
+    if (s.arena) cudaFree(s.arena);
+  delete dtrain;
+  dtrain = nullptr;
+}
+
 int Engine::decoder_zero_grads(cudaStream_t st) {
   if (!dtrain) return 0;
   for (auto& kv : dtrain->grads)

@@ -463,6 +463,11 @@ int Engine::encoder_grad(const char* name, float* dst, int64_t n, cudaStream_t s
   return 0;
 }
 
+void Engine::train_free() {
+  delete train;
+  train = nullptr;
+}
+
 void Engine::train_invalidate() {
   if (train) { train->transposed = false; train->B = 0; }
 }

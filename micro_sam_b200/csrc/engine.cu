@@ -422,6 +422,8 @@ int msam_destroy(msam_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->eng.device);
   cudaDeviceSynchronize();
+  h->eng.dec_train_free();
+  h->eng.train_free();
   for (void* p : h->eng.allocs) cudaFree(p);
   delete h;
   return 0;

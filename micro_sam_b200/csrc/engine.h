@@ -121,6 +121,8 @@ struct Engine {
   int encode_backward(const float* d_out, cudaStream_t st);
   int encoder_grad(const char* name, float* dst, int64_t n, cudaStream_t st);
   void train_invalidate();
+  void train_free();       // encoder_train.cu: host-side training state (device buffers are in `allocs`)
+  void dec_train_free();   // decoder_train.cu: per-slot arenas + host-side state
   // decoder_train.cu (cfg 5): mask decoder forward keeping activations (one image's prompts per call and slot) + backward
   int dec_train_setup();
   int decoder_train_forward(int slot, const float* emb_nchw, const float* sparse, const int* emb_index, int Ts, int P, int multimask,
