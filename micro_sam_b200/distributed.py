@@ -37,6 +37,23 @@ def all_gather_tables(table: torch.Tensor, group=None) -> Tuple[torch.Tensor, Li
     return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0), counts
 
 
+def allreduce_average_(tensors: List[torch.Tensor], group=None) -> int:
+    """Data-parallel gradient exchange (training): average the given tensors over the ranks IN PLACE with one
+    all-reduce of a flat buffer (NCCL over NVLink on GPUs, gloo on CPU); returns the number of elements.  torch DDP's semantics
+    (micro_sam/training/training.py:train_sam).  Without an initialised process group / with one rank it only counts."""
+    n = sum(int(t.numel()) for t in tensors)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1 or n == 0:
+        return n
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat, group=group)
+    flat /= dist.get_world_size(group)
+    off = 0
+    for t in tensors:
+        t.copy_(flat[off:off + t.numel()].view_as(t))
+        off += t.numel()
+    return n
+
+
 def exclusive_id_offsets(local_max_ids: torch.Tensor, group=None) -> torch.Tensor:
     """Per-unit id offsets for slice-wise segmentation: exclusive scan over ALL units (in rank order) of their max ids.
     `local_max_ids` [n_r] int64 -> offsets [n_r] for this rank's units."""

@@ -449,17 +449,8 @@ class B200Sam:
     def allreduce_grads(self, world_size: int) -> int:
         """DDP semantics (micro_sam/training/training.py:train_sam): average every gradient over the ranks with ONE all-reduce of a
         flat fp32 buffer, written back into the engine's gradient buffers.  Returns the number of gradient elements."""
-        views = [v for _, v in self.grad_views()]
-        flat = torch.cat([v.reshape(-1) for v in views])
-        if world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(flat)
-            flat /= world_size
-            off = 0
-            for v in views:
-                v.copy_(flat[off:off + v.numel()])
-                off += v.numel()
-        return flat.numel()
+        from .distributed import allreduce_average_
+        return allreduce_average_([v for _, v in self.grad_views()])
 
     def optimizer_step(self, lr: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01) -> None:
         """One AdamW update (torch.optim.AdamW semantics, the reference trainer's default) of every tensor that has gradients, on the

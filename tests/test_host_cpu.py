@@ -129,6 +129,10 @@ def _dist_worker(rank, world, port, ret):
         # a rank that owns no instance at all still takes part in the exchange
         e, ce = D.gather_instance_tables({"low": torch.zeros(3 if rank == 1 else 0, 2, 3), "tile": torch.zeros(3 if rank == 1 else 0, dtype=torch.int32)})
         assert ce == [0, 3] and e["low"].shape == (3, 2, 3) and e["tile"].shape == (3,)
+        # the gradient exchange of the data-parallel training step: in-place average of tensors of different shapes
+        gs = [torch.full((3, 2), float(rank + 1)), torch.arange(5, dtype=torch.float32) * (rank + 1)]
+        assert D.allreduce_average_(gs) == 11
+        assert torch.allclose(gs[0], torch.full((3, 2), 1.5)) and torch.allclose(gs[1], torch.arange(5, dtype=torch.float32) * 1.5)
         ret[rank] = (lo, hi, full.tolist(), counts, offs.tolist())
     finally:
         dist.destroy_process_group()
