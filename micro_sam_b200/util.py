@@ -670,30 +670,30 @@ def mask_data_to_segmentation(masks: List[Dict[str, Any]], shape: Optional[Tuple
                               with_background: bool = False, merge_exclusively: bool = True) -> np.ndarray:
     """util.mask_data_to_segmentation (util.py:1773-1848) for host-side binary-mask records (API parity; the AMG /
     batched-inference fast path paints on the device instead, see instance_segmentation.py)."""
-    masks = sorted(masks, key=(lambda x: x["area"]), reverse=True)
+    # paint in descending-area order (stable for equal areas): with merge_exclusively the first -- largest -- mask owns a pixel,
+    # without it later -- smaller -- masks overwrite (what AMG asks for, instance_segmentation.py:527-529)
+    order = sorted(range(len(masks)), key=lambda i: -masks[i]["area"])
     if shape is None:
-        shape = next(iter(masks))["segmentation"].shape
-    segmentation = np.zeros(shape, dtype="uint32")
-    seg_id = 1
-    for mask_data in masks:
-        area = mask_data["area"]
-        if (area < min_object_size) or (max_object_size is not None and area > max_object_size):
+        shape = masks[order[0]]["segmentation"].shape
+    label = np.zeros(shape, dtype=np.uint32)
+    next_id = 1
+    for i in order:
+        rec = masks[i]
+        if rec["area"] < min_object_size or (max_object_size is not None and rec["area"] > max_object_size):
             continue
-        this_mask = mask_data["segmentation"]
-        this_mask = this_mask.cpu().numpy() if torch.is_tensor(this_mask) else np.asarray(this_mask)
-        this_seg_id = mask_data.get("seg_id", seg_id)
-        if "global_bbox" in mask_data:
-            bb = mask_data["bbox"]
-            bb = np.s_[bb[1]:bb[1] + bb[3], bb[0]:bb[0] + bb[2]]
-            gbb = mask_data["global_bbox"]
-            gbb = np.s_[gbb[1]:gbb[1] + gbb[3], gbb[0]:gbb[0] + gbb[2]]
-            this_mask = np.logical_and(this_mask[bb], segmentation[gbb] == 0) if merge_exclusively else this_mask[bb]
-            segmentation[gbb][this_mask] = this_seg_id
+        m = rec["segmentation"]
+        m = (m.cpu().numpy() if torch.is_tensor(m) else np.asarray(m)).astype(bool, copy=False)
+        sid = rec.get("seg_id", next_id)
+        if "global_bbox" in rec:     # tiled records: the tile-local box content goes to the global box position
+            x, y, w, h = (int(v) for v in rec["bbox"])
+            gx, gy, gw, gh = (int(v) for v in rec["global_bbox"])
+            window = label[gy:gy + gh, gx:gx + gw]
+            piece = m[y:y + h, x:x + w]
+            window[piece & (window == 0) if merge_exclusively else piece] = sid
         else:
-            if merge_exclusively:
-                this_mask = np.logical_and(this_mask, segmentation == 0)
-            segmentation[this_mask] = this_seg_id
-        seg_id = this_seg_id + 1
+            label[m & (label == 0) if merge_exclusively else m] = sid
+        next_id = sid + 1
+    segmentation = label
     return _finish_segmentation(segmentation, min_object_size, label_masks, with_background)
 
 

@@ -353,3 +353,26 @@ def test_resize_of_replicated_gray_images_is_bit_identical_to_the_rgb_resize():
     rgb = rng.integers(0, 256, (400, 640, 3), dtype=np.uint8)
     th, tw = get_preprocess_shape(400, 640, 1024)
     assert np.array_equal(rs.apply_image(rgb), np.array(Image.fromarray(rgb).resize((tw, th), Image.BILINEAR)))
+
+
+def test_mask_data_to_segmentation_tiled_records_against_the_oracle():
+    """Tiled records (tile-local mask + bbox, global_bbox): the host painter against the oracle restatement of util.py:1799-1829."""
+    from micro_sam_b200 import util
+    from oracle import amg_ref
+    rng = np.random.default_rng(3)
+    H, W, tile = 120, 160, 64
+    recs = []
+    yy, xx = np.mgrid[:tile, :tile]
+    for k in range(25):
+        ty, tx = int(rng.integers(0, H - tile + 1)), int(rng.integers(0, W - tile + 1))
+        cy, cx, r = rng.integers(6, tile - 6), rng.integers(6, tile - 6), rng.integers(3, 14)
+        m = (yy - cy) ** 2 + (xx - cx) ** 2 < r * r
+        ys, xs = np.where(m)
+        bbox = [int(xs.min()), int(ys.min()), int(xs.max() - xs.min() + 1), int(ys.max() - ys.min() + 1)]
+        recs.append({"segmentation": m, "area": int(m.sum()), "bbox": bbox, "global_bbox": [bbox[0] + tx, bbox[1] + ty, bbox[2], bbox[3]]})
+    for kw in (dict(), dict(merge_exclusively=False), dict(min_object_size=40, with_background=True)):
+        a = util.mask_data_to_segmentation(recs, shape=(H, W), **kw)
+        b = amg_ref.mask_data_to_segmentation(recs, shape=(H, W), **kw)
+        assert np.array_equal(a == 0, b == 0) and a.max() > 0
+        pairs = np.unique(np.stack([a.ravel(), b.ravel()], 1), axis=0)
+        assert len(pairs) == len(np.unique(a)) == len(np.unique(b)), kw
