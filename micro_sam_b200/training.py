@@ -58,6 +58,8 @@ class TrainableSAM:
 
     def _forward_train(self, batched_inputs, image_embeddings, multimask_output, return_masks):
         sam, dev = self.sam, self.sam.device
+        if len(batched_inputs) > 8:
+            raise ValueError("training forward: at most 8 images per call (one decoder slot per image until its backward pass has run)")
         outputs = []
         for i, (rec, emb) in enumerate(zip(batched_inputs, image_embeddings)):
             if "mask_inputs" in rec:
